@@ -1,0 +1,218 @@
+/*
+ * pcx_abi.h -- C ABI of libpancax_b200.so: the B200 (sm_100a) implementation of pancax's
+ * training hot path (deep-energy / FE-residual PINN loss + parameter gradient over every
+ * quadrature point of a finite-element mesh).
+ *
+ * Plain C, plain pointers and sizes.  Every `const double*` / `const int32_t*` argument that
+ * is documented "device" is a CUDA device pointer on the handle's device; the caller (XLA,
+ * torch, ...) owns every input and output buffer, the library owns only the handle's workspace.
+ * Compute calls enqueue work on `stream` (a cudaStream_t passed as void*); they never allocate,
+ * never synchronise and never read results back to the host.  Outputs are fully overwritten.
+ *
+ * Return value: 0 on success, a negative PCX_ERR_* code otherwise; pcx_last_error() returns a
+ * thread-local message.  There is no CPU fallback: an unsupported element / model / network
+ * shape is an error, never a silently different code path.
+ *
+ * Each entry point cites the reference interface (pancax 0.0.16) it replaces.
+ */
+#ifndef PCX_ABI_H
+#define PCX_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCX_ABI_VERSION 1
+
+/* error codes */
+#define PCX_OK               0
+#define PCX_ERR_INVALID     -1  /* bad argument / unsupported shape            */
+#define PCX_ERR_CUDA        -2  /* CUDA runtime error (message has the detail) */
+#define PCX_ERR_STATE       -3  /* call order violated (e.g. model not set)    */
+#define PCX_ERR_UNSUPPORTED -4  /* valid pancax input this library refuses (no fallback) */
+
+/* element types: pancax/fem/read_exodus_mesh.py:28-55 */
+#define PCX_ELEM_HEX8  0
+#define PCX_ELEM_QUAD4 1
+#define PCX_ELEM_TRI3  2
+
+/* physics: pancax/physics_kernels/{poisson.py:8-19, solid_mechanics.py:86-109} */
+#define PCX_PHYS_POISSON 0
+#define PCX_PHYS_SOLID   1
+
+/* formulations: pancax/physics_kernels/solid_mechanics.py:20-29 (PlaneStrain), :74-83 (ThreeDimensional) */
+#define PCX_FORM_PLANE_STRAIN      0
+#define PCX_FORM_THREE_DIMENSIONAL 1
+
+/* constitutive models: pancax/constitutive_models/mechanics/hyperelasticity/*.py
+ * property order = dataclass field order of the reference classes:
+ *   NEOHOOKEAN  : bulk_modulus, shear_modulus                        (neohookean.py:17-18)
+ *   GENT        : bulk_modulus, shear_modulus, Jm_parameter          (gent.py:18-20)
+ *   SWANSON     : bulk_modulus, A1, P1, B1, Q1, C1, R1, cutoff_strain (swanson.py:18-26; cutoff static)
+ *   HENCKY      : bulk_modulus, shear_modulus                        (hencky.py:7-8)
+ */
+#define PCX_MODEL_NONE       0
+#define PCX_MODEL_NEOHOOKEAN 1
+#define PCX_MODEL_GENT       2
+#define PCX_MODEL_SWANSON    3
+#define PCX_MODEL_HENCKY     4
+#define PCX_MAX_PROPS        8
+
+/* loss kinds: pancax/loss_functions/weak_form_loss_functions.py */
+#define PCX_LOSS_ENERGY                   0  /* EnergyLoss.path_independent_call            :74-88   */
+#define PCX_LOSS_ENERGY_RESIDUAL          1  /* EnergyAndResidualLoss.path_independent_call :194-205 */
+#define PCX_LOSS_ENERGY_RESIDUAL_REACTION 2  /* EnergyResidualAndReactionLoss               :278-300 */
+
+typedef struct pcx_handle pcx_handle;
+
+/* Static inputs of the path: what VariationalDomain + ForwardProblem build
+ * (pancax/domains.py:132-156, pancax/problems.py:34-96, pancax/fem/dof_manager.py:31-42,
+ *  pancax/data.py:222-243). */
+typedef struct {
+  int32_t elem_type;          /* PCX_ELEM_*                                                   */
+  int32_t q_order;            /* quadrature degree (pancax/fem/quadrature_rules.py)           */
+  int32_t ndof;               /* field dofs per node (physics.n_dofs)                         */
+  int32_t reaction_dof;       /* GlobalData.reaction_dof                                       */
+  int64_t ne;                 /* elements                                                      */
+  int64_t nn;                 /* nodes                                                         */
+  int64_t n_unknown;          /* len(dof_manager.unknownIndices); 0 if residual losses unused  */
+  int64_t n_reaction;         /* len(global_data.reaction_nodes); 0 if unused                  */
+  const double*  coords;      /* device, f64 [nn*nd] row-major (mesh.coords)                   */
+  const int32_t* conns;       /* device, i32 [ne*nnpe] row-major, 0-based (mesh.conns)          */
+  const int64_t* unknown_idx; /* device, i64 [n_unknown], dof id = node*ndof+comp, or NULL      */
+  const int32_t* reaction_nodes; /* device, i32 [n_reaction], or NULL                          */
+  int32_t nt;                 /* number of time steps (len(domain.times))                       */
+  int32_t deterministic;      /* 1: node-centric fixed-order force assembly; 0: fp64 atomics    */
+  const double* times;        /* HOST, f64 [nt]                                                 */
+} pcx_mesh_desc;
+
+/* Field = input normalisation + MLP + Dirichlet wrapper: pancax/networks/fields.py:10-101,
+ * pancax/networks/mlp.py:49-85 (equinox.nn.MLP, tanh hidden activation, identity final one).
+ * Weights travel as ONE flat f64 device vector in equinox leaf order
+ *   [W0 (width,n_in), b0 (width), W1 (width,width), b1, ..., Wout (n_out,width) (, bout)].
+ * The Dirichlet wrapper g(x,t,z) is a Python callable in pancax (fields.py:101); it must be
+ * diagonal-affine in z (all shipped pancax/bvps are) and is passed tabulated at the mesh nodes:
+ *   u[t][n][i] = bc_a[t][n][i] + bc_b[t][n][i] * z[n][i]
+ * with bc_a = g(x,t,0), bc_b = g(x,t,e_i)_i - bc_a.  NULL tables mean g = identity. */
+typedef struct {
+  int32_t n_in;               /* nd + 1                                                         */
+  int32_t n_out;              /* ndof                                                           */
+  int32_t width;              /* n_neurons                                                      */
+  int32_t depth;              /* n_layers (hidden layers)                                       */
+  int32_t use_final_bias;     /* mlp.py:61 (default False)                                      */
+  int32_t normalize_time;     /* fields.py:72-76                                                */
+  double  x_min[3], x_max[3]; /* fields.py:70-71                                                */
+  double  t_min, t_max;       /* fields.py:68-69                                                */
+  const double* bc_a;         /* device, f64 [nt*nn*ndof] or NULL                               */
+  const double* bc_b;         /* device, f64 [nt*nn*ndof] or NULL                               */
+} pcx_field_desc;
+
+/* Constitutive properties.  Property k is either fixed (value[k]) or a trainable
+ * BoundedProperty (pancax/constitutive_models/properties.py:10-38):
+ *   p = prop_min + (prop_max - prop_min) * sigmoid(raw)
+ * Trainable raw values travel in a device vector `prop_raw` in property order, skipping fixed ones. */
+typedef struct {
+  int32_t physics;            /* PCX_PHYS_*                                                     */
+  int32_t model;              /* PCX_MODEL_* (PCX_MODEL_NONE for Poisson)                       */
+  int32_t formulation;        /* PCX_FORM_*                                                     */
+  int32_t nprops;
+  double  value[PCX_MAX_PROPS];
+  int32_t bounded[PCX_MAX_PROPS];
+  double  prop_min[PCX_MAX_PROPS];
+  double  prop_max[PCX_MAX_PROPS];
+  const double* source_q;     /* Poisson: device f64 [ne*nq], f evaluated at the quadrature
+                                 points (poisson.py:17; Python callable tabulated once) or NULL */
+} pcx_physics_desc;
+
+typedef struct {
+  int32_t kind;               /* PCX_LOSS_*                                                     */
+  double  energy_weight;
+  double  residual_weight;
+  double  reaction_weight;
+  const double* global_outputs; /* HOST f64 [nt] (problem.global_data.outputs) or NULL          */
+} pcx_loss_desc;
+
+/* aux layout written by pcx_loss_and_grad (device f64 [PCX_AUX_FIXED + nt]):
+ *   [0] energy  [1] residual  [2] global_data_loss  [3] flags (0 = ok; bit0: det(F)<=0 or NaN seen)
+ *   [4 .. 4+nt) reactions[t]
+ * (keys of the reference's aux dicts: weak_form_loss_functions.py:88,205,297-300) */
+#define PCX_AUX_ENERGY      0
+#define PCX_AUX_RESIDUAL    1
+#define PCX_AUX_GLOBAL_DATA 2
+#define PCX_AUX_FLAGS       3
+#define PCX_AUX_FIXED       4
+
+int pcx_abi_version(void);
+const char* pcx_last_error(void);
+
+/* lifetime */
+int pcx_create(pcx_handle** out, const pcx_mesh_desc* mesh);
+int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* phys);
+int pcx_set_field(pcx_handle* h, const pcx_field_desc* field);
+int pcx_destroy(pcx_handle* h);
+
+/* sizes the caller needs to allocate outputs */
+int64_t pcx_num_weights(const pcx_handle* h);     /* flat MLP parameter count          */
+int64_t pcx_num_trainable_props(const pcx_handle* h);
+int64_t pcx_num_qp(const pcx_handle* h);          /* ne * nq                            */
+int32_t pcx_nq(const pcx_handle* h);
+int32_t pcx_nnpe(const pcx_handle* h);
+int32_t pcx_nd(const pcx_handle* h);
+
+/* (1) element gather / geometry -- NonAllocatedFunctionSpace.{shape_function_gradients,JxWs}
+ *     pancax/fem/function_space.py:63-89 and x_q of base.py:322.
+ *     grad_N [ne*nq*nnpe*nd], JxW [ne*nq], x_q [ne*nq*nd] (any may be NULL). */
+int pcx_element_geometry(pcx_handle* h, double* grad_N, double* JxW, double* x_q, void* stream);
+
+/* (2) field at the mesh nodes -- BasePhysics.vmap_field_values, pancax/physics_kernels/base.py:248-250.
+ *     us [nn*ndof] at times[t_idx]. */
+int pcx_field_forward(pcx_handle* h, const double* weights, int32_t t_idx, double* us, void* stream);
+
+/* (4) its adjoint: g_weights [pcx_num_weights] = d<g_us, us>/d weights (VJP of (2)). */
+int pcx_field_backward(pcx_handle* h, const double* weights, int32_t t_idx, const double* g_us,
+                       double* g_weights, void* stream);
+
+/* field at arbitrary points (FullFieldDataLoss, data_loss_functions.py:13-24):
+ *   pts [n*(nd+1)] rows (x..., t);  u = a + b*z with optional tables a,b [n*ndof];  u [n*ndof]. */
+int pcx_points_forward(pcx_handle* h, const double* weights, const double* pts, const double* a,
+                       const double* b, int64_t n, double* u, void* stream);
+int pcx_points_backward(pcx_handle* h, const double* weights, const double* pts, const double* b,
+                        const double* g_u, int64_t n, double* g_weights, void* stream);
+
+/* (3)+(5) potential energy and internal force -- BaseEnergyFormPhysics.potential_energy /
+ *     potential_energy_and_internal_force, base.py:349-361.
+ *     Pi: device scalar; f [nn*ndof] or NULL; g_props [n_trainable] = dPi/d prop_raw or NULL. */
+int pcx_energy_force(pcx_handle* h, const double* prop_raw, const double* us, double* Pi,
+                     double* f, double* g_props, void* stream);
+
+/* tangent-stiffness action Kv = d/d(eps) f(us + eps v): the second-order term the reference gets
+ * by differentiating through value_and_grad in base.py:363-385.  g_props = d<f,v>/d prop_raw or NULL. */
+int pcx_stiffness_action(pcx_handle* h, const double* prop_raw, const double* us, const double* v,
+                         double* Kv, double* g_props, void* stream);
+
+/* residual norm and reaction force of an assembled f -- base.py:369-371, :381-384.
+ *   out[0] = ||f[unknown]||_2, out[1] = sum f[reaction_nodes, reaction_dof]. */
+int pcx_residual_reaction(pcx_handle* h, const double* f, double* out, void* stream);
+
+/* fused fast path: loss, aux and d loss / d (weights, prop_raw) for the built-in weak-form losses --
+ * eqx.filter_value_and_grad(loss.filtered_loss), pancax/optimizers.py:77-88.
+ *   loss: device scalar; aux: device [PCX_AUX_FIXED+nt]; g_weights [num_weights]; g_props [n_trainable] or NULL. */
+int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* loss, const double* weights,
+                      const double* prop_raw, double* loss_out, double* aux, double* g_weights,
+                      double* g_props, void* stream);
+
+/* FullFieldDataLoss value + weight gradient on one batch -- data_loss_functions.py:13-24.
+ *   loss: device scalar = weight * mean((u - outputs)^2). */
+int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const double* pts,
+                                 const double* a, const double* b, const double* outputs, int64_t n,
+                                 double weight, double* loss_out, double* g_weights, void* stream);
+
+/* number of kernels this library has launched on the handle so far (for bench.py "gpu_launches") */
+int64_t pcx_launch_count(const pcx_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCX_ABI_H */

@@ -1,0 +1,931 @@
+// pcx_api.cu -- the C ABI (include/pcx_abi.h) over the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pcx_abi.h"
+#include "pcx_element.cuh"
+#include "pcx_mlp.cuh"
+
+using namespace pcx;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail(PCX_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCH_CHECK(h)                                                                               \
+  do {                                                                                                \
+    (h)->launches++;                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess) return fail(PCX_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ handle
+struct pcx_handle {
+  int device = 0;
+  // mesh
+  int elem_type = 0, q_order = 0, nd = 0, nnpe = 0, ndof = 0, nq = 0, nt = 0, reaction_dof = 0, deterministic = 1;
+  long long ne = 0, nn = 0, n_unknown = 0, n_reaction = 0;
+  const double* coords = nullptr;
+  const int32_t* conns = nullptr;
+  const long long* unknown_idx = nullptr;
+  const int32_t* reaction_nodes = nullptr;
+  std::vector<double> times;
+  ParentTab tab;
+  // physics
+  bool have_phys = false;
+  pcx_physics_desc phys;
+  int ntrain = 0;
+  // field
+  bool have_field = false;
+  MlpShape ms;
+  const double* bc_a = nullptr;
+  const double* bc_b = nullptr;
+  // workspace (device)
+  int T = 1;                    // time steps processed per batch
+  long long rows_cap = 0;       // activation rows
+  int nblk_el = 0;              // element-kernel blocks per time step
+  int bwd_grid = 0;
+  long long part_stride = 0;
+  double *pk = nullptr, *act = nullptr, *part = nullptr;
+  double *us = nullptr, *fe = nullptr, *f = nullptr, *v = nullptr, *ubar = nullptr;
+  double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
+  double *scal = nullptr;       // see SC_* offsets
+  double *props_dev = nullptr;  // effective properties [PCX_MAX_PROPS] + d p/d raw [PCX_MAX_PROPS]
+  double *times_dev = nullptr, *gout_dev = nullptr;
+  double *gtmp = nullptr;       // [nweights] scratch
+  int* flags = nullptr;
+  long long* adj_ptr = nullptr;
+  int32_t* adj_idx = nullptr;
+  long long launches = 0;
+  int sm_count = 148;
+};
+
+// device scalar block layout (per handle), all sized by nt
+//  SC_PI[nt] SC_R[nt] SC_REACT[nt] SC_C1[nt] SC_C2[nt] SC_DPI[nt*8] SC_DFV[nt*8]
+static inline long long SC_PI(const pcx_handle*) { return 0; }
+static inline long long SC_R(const pcx_handle* h) { return h->nt; }
+static inline long long SC_REACT(const pcx_handle* h) { return 2LL * h->nt; }
+static inline long long SC_C1(const pcx_handle* h) { return 3LL * h->nt; }
+static inline long long SC_C2(const pcx_handle* h) { return 4LL * h->nt; }
+static inline long long SC_DPI(const pcx_handle* h) { return 5LL * h->nt; }
+static inline long long SC_DFV(const pcx_handle* h) { return 5LL * h->nt + 8LL * h->nt; }
+static inline long long SC_RR(const pcx_handle* h) { return 5LL * h->nt + 16LL * h->nt; }  // [nt*2] raw (R^2, react)
+static inline long long SC_SIZE(const pcx_handle* h) { return 5LL * h->nt + 18LL * h->nt + 16; }
+
+// ------------------------------------------------------------------------------------------ parent tables
+// pancax/fem/quadrature_rules.py:109-180,206-245 and elements/{hex8,quad4,simplex_tri}_element.py
+static int build_tab(int elem, int q_order, ParentTab& t) {
+  memset(&t, 0, sizeof(t));
+  static const double hs[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+  static const double qs[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+  double xi[TAB_MAX_NQ][3];
+  memset(xi, 0, sizeof(xi));
+  if (elem == PCX_ELEM_HEX8) {
+    t.nnpe = 8; t.nd = 3;
+    if (q_order == 1) { t.nq = 1; t.w[0] = 8.0; }
+    else if (q_order == 2) {
+      t.nq = 8;
+      const double s = sqrt(1.0 / 3.0);
+      for (int q = 0; q < 8; q++) { t.w[q] = 1.0; for (int j = 0; j < 3; j++) xi[q][j] = s * hs[q][j]; }
+    } else return fail(PCX_ERR_INVALID, "Unsupported quadrature degree %d on hex element.", q_order);
+    for (int q = 0; q < t.nq; q++)
+      for (int a = 0; a < 8; a++) {
+        const double fx = 1.0 + hs[a][0] * xi[q][0], fy = 1.0 + hs[a][1] * xi[q][1], fz = 1.0 + hs[a][2] * xi[q][2];
+        t.N[q * TAB_MAX_NNPE + a] = 0.125 * (fx * fy * fz);
+        t.dN[(q * TAB_MAX_NNPE + a) * 3 + 0] = 0.125 * (hs[a][0] * fy * fz);
+        t.dN[(q * TAB_MAX_NNPE + a) * 3 + 1] = 0.125 * (hs[a][1] * fx * fz);
+        t.dN[(q * TAB_MAX_NNPE + a) * 3 + 2] = 0.125 * (hs[a][2] * fx * fy);
+      }
+  } else if (elem == PCX_ELEM_QUAD4) {
+    t.nnpe = 4; t.nd = 2;
+    if (q_order == 1) { t.nq = 1; t.w[0] = 4.0; }
+    else if (q_order == 2) {
+      t.nq = 4;
+      const double s = sqrt(1.0 / 3.0);
+      for (int q = 0; q < 4; q++) { t.w[q] = 1.0; for (int j = 0; j < 2; j++) xi[q][j] = s * qs[q][j]; }
+    } else if (q_order == 3) {
+      t.nq = 9;
+      const double s = sqrt(3.0 / 5.0);
+      const double px[3] = {-s, 0.0, s};
+      for (int q = 0; q < 9; q++) { xi[q][0] = px[q % 3]; xi[q][1] = px[q / 3]; }
+      // the last weight is 25/80 in the reference (quadrature_rules.py:174); replicated on purpose
+      const double w9[9] = {25.0 / 81.0, 40.0 / 81.0, 25.0 / 81.0, 40.0 / 81.0, 64.0 / 81.0, 40.0 / 81.0, 25.0 / 81.0, 40.0 / 81.0, 25.0 / 80.0};
+      for (int q = 0; q < 9; q++) t.w[q] = w9[q];
+    } else return fail(PCX_ERR_INVALID, "Invalid quadrature degree: %d", q_order);
+    for (int q = 0; q < t.nq; q++)
+      for (int a = 0; a < 4; a++) {
+        const double fx = 1.0 + qs[a][0] * xi[q][0], fy = 1.0 + qs[a][1] * xi[q][1];
+        t.N[q * TAB_MAX_NNPE + a] = 0.25 * (fx * fy);
+        t.dN[(q * TAB_MAX_NNPE + a) * 3 + 0] = 0.25 * (qs[a][0] * fy);
+        t.dN[(q * TAB_MAX_NNPE + a) * 3 + 1] = 0.25 * (qs[a][1] * fx);
+      }
+  } else if (elem == PCX_ELEM_TRI3) {
+    t.nnpe = 3; t.nd = 2;
+    if (q_order == 1) { t.nq = 1; t.w[0] = 5.00000000000000000e-01; xi[0][0] = xi[0][1] = 3.33333333333333333e-01; }
+    else if (q_order == 2) {
+      t.nq = 3;
+      const double a = 6.66666666666666667e-01, b = 1.66666666666666667e-01;
+      xi[0][0] = a; xi[0][1] = b; xi[1][0] = b; xi[1][1] = a; xi[2][0] = b; xi[2][1] = b;
+      t.w[0] = 1.66666666666666666e-01; t.w[1] = 1.66666666666666667e-01; t.w[2] = 1.66666666666666667e-01;
+    } else return fail(PCX_ERR_INVALID, "Unsupported quadrature degree %d on tri3 element.", q_order);
+    // degree-1 simplex, nodal order (1,0),(0,1),(0,0): N = (x, y, 1-x-y)
+    for (int q = 0; q < t.nq; q++) {
+      t.N[q * TAB_MAX_NNPE + 0] = xi[q][0];
+      t.N[q * TAB_MAX_NNPE + 1] = xi[q][1];
+      t.N[q * TAB_MAX_NNPE + 2] = 1.0 - xi[q][0] - xi[q][1];
+      const double g[3][2] = {{1, 0}, {0, 1}, {-1, -1}};
+      for (int a = 0; a < 3; a++) for (int j = 0; j < 2; j++) t.dN[(q * TAB_MAX_NNPE + a) * 3 + j] = g[a][j];
+    }
+  } else return fail(PCX_ERR_INVALID, "Unsupported element type: %d", elem);
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+// effective properties from raw trainables: properties.py:33-38
+__global__ void k_props(pcx_physics_desc d, const double* __restrict__ raw, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int k = 0;
+  for (int i = 0; i < PCX_MAX_PROPS; i++) {
+    double p = 0.0, dp = 0.0;
+    if (i < d.nprops) {
+      if (d.bounded[i]) {
+        const double s = 1.0 / (1.0 + exp(-raw[k++]));
+        p = d.prop_min[i] + (d.prop_max[i] - d.prop_min[i]) * s;
+        dp = (d.prop_max[i] - d.prop_min[i]) * s * (1.0 - s);
+      } else p = d.value[i];
+    }
+    out[i] = p;
+    out[PCX_MAX_PROPS + i] = dp;
+  }
+}
+
+// after the residual/reaction reductions: R_t, r_t and the coefficients of v_t
+//   v_t = c1 * m.f_t + c2 * 1_{S,d},  c1 = (w_r/nt)/R_t (0 if R_t == 0),  c2 = (2 w_g/nt)(r_t - rhat_t)
+__global__ void k_resid_coeffs(int t0, int T, int nt, double wr, double wg, const double* __restrict__ rr,
+                               const double* __restrict__ gout, double* __restrict__ R, double* __restrict__ react,
+                               double* __restrict__ c1, double* __restrict__ c2) {
+  const int i = threadIdx.x;
+  if (i >= T) return;
+  const int t = t0 + i;
+  const double r2 = rr[2 * i], re = rr[2 * i + 1];
+  const double Rt = r2 > 0.0 ? sqrt(r2) : 0.0;
+  R[t] = Rt;
+  react[t] = re;
+  // convention shared with the oracle: below the rounding-noise floor the direction
+  // f/||f|| is meaningless (jnp.linalg.norm would yield NaN / noise) -> zero gradient
+  c1[t] = Rt > 1.0e-10 ? (wr / nt) / Rt : 0.0;
+  c2[t] = gout ? (2.0 * wg / nt) * (re - gout[t]) : 0.0;
+}
+
+// v[t][dof] over unknown dofs and reaction nodes (v pre-zeroed)
+__global__ void k_make_v(int t0, long long nn, int ndof, const double* __restrict__ f, const long long* __restrict__ uidx,
+                         long long nu, const int32_t* __restrict__ rnodes, long long nr, int rdof,
+                         const double* __restrict__ c1, const double* __restrict__ c2, double* __restrict__ v, int phase) {
+  const int ti = blockIdx.y;
+  const long long base = (long long)ti * nn * ndof;
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (phase == 0) {
+    if (k < nu) v[base + uidx[k]] = c1[t0 + ti] * f[base + uidx[k]];
+  } else {
+    if (k < nr) v[base + (long long)rnodes[k] * ndof + rdof] += c2[t0 + ti];
+  }
+}
+
+__global__ void k_finish(int kind, int nt, double we, double wr, double wg, const double* __restrict__ sc_pi,
+                         const double* __restrict__ sc_R, const double* __restrict__ sc_re, const double* __restrict__ gout,
+                         const double* __restrict__ dpi, const double* __restrict__ dfv, const double* __restrict__ props_dev,
+                         pcx_physics_desc d, const int* __restrict__ flags, double* __restrict__ loss, double* __restrict__ aux,
+                         double* __restrict__ g_props) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double e = 0.0, R = 0.0, gl = 0.0;
+  for (int t = 0; t < nt; t++) e += sc_pi[t];
+  double L = we * e;
+  if (kind != PCX_LOSS_ENERGY) {
+    for (int t = 0; t < nt; t++) R += sc_R[t];
+    R /= nt;  // mean (EnergyAndResidual :203) == sum/nt (EnergyResidualAndReaction :289)
+    L += wr * R;
+  }
+  if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) {
+    for (int t = 0; t < nt; t++) { const double dd = sc_re[t] - gout[t]; gl += dd * dd; }
+    gl /= nt;
+    L += wg * gl;
+  }
+  *loss = L;
+  aux[PCX_AUX_ENERGY] = e;
+  aux[PCX_AUX_RESIDUAL] = R;
+  aux[PCX_AUX_GLOBAL_DATA] = gl;
+  aux[PCX_AUX_FLAGS] = (double)(*flags);
+  for (int t = 0; t < nt; t++) aux[PCX_AUX_FIXED + t] = (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) ? sc_re[t] : 0.0;
+  if (g_props) {
+    int k = 0;
+    for (int i = 0; i < d.nprops; i++) {
+      if (!d.bounded[i]) continue;
+      double s = 0.0;
+      for (int t = 0; t < nt; t++) {
+        s += we * dpi[t * PCX_MAX_PROPS + i];
+        if (kind != PCX_LOSS_ENERGY) s += dfv[t * PCX_MAX_PROPS + i];
+      }
+      g_props[k++] = s * props_dev[PCX_MAX_PROPS + i];
+    }
+  }
+}
+
+// data loss: g_u = (2 w / (n*n_out)) (u - y); loss partials
+__global__ void __launch_bounds__(256) k_data_loss(long long n, const double* __restrict__ u, const double* __restrict__ y,
+                                                   double scale, double* __restrict__ g_u, double* __restrict__ part) {
+  __shared__ double sh[8];
+  double s = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += stride) {
+    const double d = u[k] - y[k];
+    s = fma(d, d, s);
+    g_u[k] = 2.0 * scale * d;
+  }
+  const double t = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = t * scale;
+}
+
+__global__ void k_chain_props(pcx_physics_desc d, const double* __restrict__ props_dev, const double* __restrict__ dp,
+                              double* __restrict__ g_props) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int k = 0;
+  for (int i = 0; i < d.nprops; i++)
+    if (d.bounded[i]) g_props[k++] = dp[i] * props_dev[PCX_MAX_PROPS + i];
+}
+
+// ------------------------------------------------------------------------------------------ dispatch helpers
+template <int NNPE, int ND, int NDOF, int MODEL>
+static void launch_element_t(bool tangent, dim3 grid, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+  if (tangent) k_element<NNPE, ND, NDOF, MODEL, true><<<grid, 128, 0, st>>>(tab, a);
+  else k_element<NNPE, ND, NDOF, MODEL, false><<<grid, 128, 0, st>>>(tab, a);
+}
+template <int NNPE, int ND, int NDOF>
+static int launch_element_m(int model, bool tangent, dim3 grid, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+  switch (model) {
+    case PCX_MODEL_NEOHOOKEAN: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_NEOHOOKEAN>(tangent, grid, st, tab, a); return 0;
+    case PCX_MODEL_GENT: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_GENT>(tangent, grid, st, tab, a); return 0;
+    case PCX_MODEL_SWANSON: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_SWANSON>(tangent, grid, st, tab, a); return 0;
+    case PCX_MODEL_HENCKY: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_HENCKY>(tangent, grid, st, tab, a); return 0;
+  }
+  return -1;
+}
+
+static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, const ElemArgs& a) {
+  dim3 grid(h->nblk_el, T);
+  int rc = -1;
+  if (h->phys.physics == PCX_PHYS_POISSON) {
+    if (h->elem_type == PCX_ELEM_HEX8) { launch_element_t<8, 3, 1, 0>(tangent, grid, st, h->tab, a); rc = 0; }
+    else if (h->elem_type == PCX_ELEM_QUAD4) { launch_element_t<4, 2, 1, 0>(tangent, grid, st, h->tab, a); rc = 0; }
+    else { launch_element_t<3, 2, 1, 0>(tangent, grid, st, h->tab, a); rc = 0; }
+  } else {
+    if (h->elem_type == PCX_ELEM_HEX8) rc = launch_element_m<8, 3, 3>(h->phys.model, tangent, grid, st, h->tab, a);
+    else if (h->elem_type == PCX_ELEM_QUAD4) rc = launch_element_m<4, 2, 2>(h->phys.model, tangent, grid, st, h->tab, a);
+    else rc = launch_element_m<3, 2, 2>(h->phys.model, tangent, grid, st, h->tab, a);
+  }
+  if (rc) return fail(PCX_ERR_INVALID, "no element kernel for this element/physics/model combination");
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+template <int NT>
+static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, const MlpIO& io) {
+#define PCX_BWD_CASE(dh)                                                                                     \
+  case dh: {                                                                                                 \
+    const size_t smem = sizeof(BwdSmem<NT, dh>);                                                            \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, dh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    k_mlp_backward<NT, dh><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);                                   \
+    break;                                                                                                   \
+  }
+  switch (DH) {
+    PCX_BWD_CASE(0)
+    PCX_BWD_CASE(1)
+    PCX_BWD_CASE(2)
+    PCX_BWD_CASE(3)
+    PCX_BWD_CASE(4)
+    default: return fail(PCX_ERR_UNSUPPORTED, "MLP depth %d not supported (1..5 hidden layers)", DH + 1);
+  }
+#undef PCX_BWD_CASE
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  const long long groups = (io.n + 15) / 16;
+  long long blocks = (groups + 7) / 8;
+  const long long maxb = (long long)h->sm_count * 2;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  switch (h->ms.NT) {
+    case 2: k_mlp_forward<2, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
+    case 4: k_mlp_forward<4, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
+    case 7: k_mlp_forward<7, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
+    case 8: k_mlp_forward<8, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
+    default: return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
+  }
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+static int bwd_rows_per_cta(const pcx_handle* h) { return 8 * (h->ms.NT + 1); }
+
+static int launch_mlp_bwd(pcx_handle* h, cudaStream_t st, const MlpIO& io, int* grid_out) {
+  const long long ntiles = (io.n + bwd_rows_per_cta(h) - 1) / bwd_rows_per_cta(h);
+  int grid = (int)(ntiles < h->bwd_grid ? ntiles : h->bwd_grid);
+  if (grid < 1) grid = 1;
+  *grid_out = grid;
+  const int DH = h->ms.depth - 1;
+  switch (h->ms.NT) {
+    case 2: return launch_mlp_bwd_nt<2>(h, DH, grid, st, io);
+    case 4: return launch_mlp_bwd_nt<4>(h, DH, grid, st, io);
+    case 7: return launch_mlp_bwd_nt<7>(h, DH, grid, st, io);
+    case 8: return launch_mlp_bwd_nt<8>(h, DH, grid, st, io);
+  }
+  return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
+}
+
+static int pack_weights(pcx_handle* h, const double* w, cudaStream_t st) {
+  const int thr = 256;
+  const int blocks = (int)((h->ms.npacked + thr - 1) / thr);
+  k_pack_weights<<<blocks, thr, 0, st>>>(h->ms, w, h->pk);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+static int reduce_wgrad(pcx_handle* h, int nparts, double* g, cudaStream_t st) {
+  const int thr = 128;
+  const int blocks = (int)((h->ms.nweights + thr - 1) / thr);
+  k_reduce_wgrad<<<blocks, thr, 0, st>>>(h->ms, h->part, h->part_stride, nparts, g);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+static void free_ws(pcx_handle* h) {
+  double** ptrs[] = {&h->pk, &h->act, &h->part, &h->us, &h->fe, &h->f, &h->v, &h->ubar, &h->epart, &h->ppart,
+                     &h->rpart, &h->scal, &h->props_dev, &h->times_dev, &h->gout_dev, &h->gtmp};
+  for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (h->flags) cudaFree(h->flags);
+  h->flags = nullptr;
+}
+
+static int alloc_ws(pcx_handle* h) {
+  // called once both physics and field are known
+  free_ws(h);
+  const MlpShape& s = h->ms;
+  const long long act_per_row = (long long)s.depth * s.NT * 8 * sizeof(double);
+  const long long fe_per_t = h->ne * h->nnpe * h->ndof * (long long)sizeof(double);
+  const long long per_t = act_per_row * h->nn + fe_per_t + 4LL * h->nn * h->ndof * 8;
+  long long budget = 32LL << 30;
+  if (const char* e = getenv("PCX_WORKSPACE_GB")) budget = (long long)(atof(e) * (1LL << 30));
+  long long T = budget / (per_t > 0 ? per_t : 1);
+  if (T < 1) T = 1;
+  if (T > h->nt) T = h->nt;
+  if (const char* e = getenv("PCX_TCHUNK")) { long long v = atoll(e); if (v >= 1 && v <= h->nt) T = v; }
+  h->T = (int)T;
+  h->rows_cap = T * h->nn;
+  if (h->rows_cap < 16384) h->rows_cap = 16384;
+  h->rows_cap = (h->rows_cap + 63) / 64 * 64;
+  h->nblk_el = (int)((h->ne + 127) / 128);
+  h->bwd_grid = h->sm_count;
+  const long long WPd = 8LL * s.NT;
+  h->part_stride = WPd * 8 + (long long)(s.depth - 1) * WPd * WPd + 8 * WPd;
+  const long long ndofs = h->nn * h->ndof;
+  CUDA_TRY(cudaMalloc(&h->pk, s.npacked * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->act, act_per_row * h->rows_cap));
+  CUDA_TRY(cudaMalloc(&h->part, h->part_stride * h->bwd_grid * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->us, h->rows_cap * h->ndof * sizeof(double)));   // rows_cap >= T*nn
+  CUDA_TRY(cudaMalloc(&h->f, T * ndofs * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->v, T * ndofs * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->ubar, h->rows_cap * h->ndof * sizeof(double)));
+  if (h->deterministic) CUDA_TRY(cudaMalloc(&h->fe, T * fe_per_t));
+  CUDA_TRY(cudaMalloc(&h->epart, (long long)T * h->nblk_el * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->ppart, (long long)T * h->nblk_el * PCX_MAX_PROPS * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->rpart, (long long)T * 256 * 2 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->scal, SC_SIZE(h) * sizeof(double)));
+  CUDA_TRY(cudaMemset(h->scal, 0, SC_SIZE(h) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->props_dev, 2 * PCX_MAX_PROPS * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->times_dev, h->nt * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(h->times_dev, h->times.data(), h->nt * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&h->gout_dev, h->nt * sizeof(double)));
+  CUDA_TRY(cudaMemset(h->gout_dev, 0, h->nt * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->gtmp, s.nweights * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->flags, sizeof(int)));
+  CUDA_TRY(cudaMemset(h->flags, 0, sizeof(int)));
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: lifetime
+extern "C" int pcx_abi_version(void) { return PCX_ABI_VERSION; }
+extern "C" const char* pcx_last_error(void) { return g_err; }
+
+extern "C" int pcx_create(pcx_handle** out, const pcx_mesh_desc* m) {
+  if (!out || !m) return fail(PCX_ERR_INVALID, "pcx_create: null argument");
+  if (!m->coords || !m->conns) return fail(PCX_ERR_INVALID, "pcx_create: coords/conns must be device pointers");
+  if (m->ne <= 0 || m->nn <= 0 || m->nt <= 0 || !m->times) return fail(PCX_ERR_INVALID, "pcx_create: empty mesh or times");
+  pcx_handle* h = new pcx_handle();
+  int rc = build_tab(m->elem_type, m->q_order, h->tab);
+  if (rc) { delete h; return rc; }
+  CUDA_TRY(cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major < 10) { delete h; return fail(PCX_ERR_UNSUPPORTED, "libpancax_b200 requires an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor); }
+  h->sm_count = prop.multiProcessorCount;
+  h->elem_type = m->elem_type; h->q_order = m->q_order;
+  h->nd = h->tab.nd; h->nnpe = h->tab.nnpe; h->nq = h->tab.nq;
+  h->ndof = m->ndof; h->ne = m->ne; h->nn = m->nn; h->nt = m->nt;
+  h->n_unknown = m->unknown_idx ? m->n_unknown : 0;
+  h->n_reaction = m->reaction_nodes ? m->n_reaction : 0;
+  h->reaction_dof = m->reaction_dof;
+  h->deterministic = m->deterministic ? 1 : 0;
+  h->coords = m->coords; h->conns = m->conns;
+  h->unknown_idx = (const long long*)m->unknown_idx; h->reaction_nodes = m->reaction_nodes;
+  h->times.assign(m->times, m->times + m->nt);
+  if (h->ndof < 1 || h->ndof > 3) { delete h; return fail(PCX_ERR_INVALID, "ndof must be 1..3"); }
+
+  // node -> (element, local node) adjacency in ascending (element, local) order: the fixed summation
+  // order of the deterministic force assembly.  Built on the host once (static mesh data).
+  if (h->deterministic) {
+    const long long nent = h->ne * h->nnpe;
+    if (nent > 2147483647LL) { delete h; return fail(PCX_ERR_UNSUPPORTED, "ne*nnpe exceeds int32 range; shard the mesh"); }
+    std::vector<int32_t> hc((size_t)nent);
+    CUDA_TRY(cudaMemcpy(hc.data(), m->conns, nent * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<long long> ptr((size_t)h->nn + 1, 0);
+    for (long long k = 0; k < nent; k++) {
+      const int32_t n = hc[(size_t)k];
+      if (n < 0 || n >= h->nn) { delete h; return fail(PCX_ERR_INVALID, "connectivity entry %lld = %d out of range [0,%lld)", k, n, h->nn); }
+      ptr[(size_t)n + 1]++;
+    }
+    for (long long n = 0; n < h->nn; n++) ptr[(size_t)n + 1] += ptr[(size_t)n];
+    std::vector<int32_t> idx((size_t)nent);
+    std::vector<long long> cur(ptr.begin(), ptr.end() - 1);
+    for (long long k = 0; k < nent; k++) idx[(size_t)cur[(size_t)hc[(size_t)k]]++] = (int32_t)k;
+    CUDA_TRY(cudaMalloc(&h->adj_ptr, (h->nn + 1) * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&h->adj_idx, nent * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(h->adj_ptr, ptr.data(), (h->nn + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->adj_idx, idx.data(), nent * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  *out = h;
+  return PCX_OK;
+}
+
+extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
+  if (!h || !p) return fail(PCX_ERR_INVALID, "pcx_set_physics: null argument");
+  if (p->physics == PCX_PHYS_POISSON) {
+    if (h->ndof != 1) return fail(PCX_ERR_INVALID, "Poisson needs ndof == 1");
+  } else if (p->physics == PCX_PHYS_SOLID) {
+    if (p->model < PCX_MODEL_NEOHOOKEAN || p->model > PCX_MODEL_HENCKY) return fail(PCX_ERR_INVALID, "unknown constitutive model %d", p->model);
+    const int need[5] = {0, 2, 3, 8, 2};
+    if (p->nprops != need[p->model]) return fail(PCX_ERR_INVALID, "model %d takes %d properties, got %d", p->model, need[p->model], p->nprops);
+    if (p->formulation == PCX_FORM_PLANE_STRAIN) { if (h->nd != 2 || h->ndof != 2) return fail(PCX_ERR_INVALID, "PlaneStrain needs a 2D mesh and ndof == 2"); }
+    else if (p->formulation == PCX_FORM_THREE_DIMENSIONAL) { if (h->nd != 3 || h->ndof != 3) return fail(PCX_ERR_INVALID, "ThreeDimensional needs a 3D mesh and ndof == 3"); }
+    else return fail(PCX_ERR_UNSUPPORTED, "formulation %d is not on the B200 path (PlaneStress needs a per-qp root find)", p->formulation);
+    if (p->model == PCX_MODEL_SWANSON && p->bounded[7]) return fail(PCX_ERR_INVALID, "Swanson cutoff_strain is static in pancax (swanson.py:26)");
+  } else return fail(PCX_ERR_INVALID, "unknown physics %d", p->physics);
+  h->phys = *p;
+  h->ntrain = 0;
+  for (int i = 0; i < p->nprops; i++) if (p->bounded[i]) h->ntrain++;
+  h->have_phys = true;
+  if (h->have_field) return alloc_ws(h);
+  return PCX_OK;
+}
+
+extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
+  if (!h || !f) return fail(PCX_ERR_INVALID, "pcx_set_field: null argument");
+  if (f->n_in != h->nd + 1) return fail(PCX_ERR_INVALID, "field n_in must be nd+1 = %d (fields.py:88), got %d", h->nd + 1, f->n_in);
+  if (f->n_out != h->ndof) return fail(PCX_ERR_INVALID, "field n_out must equal ndof = %d, got %d", h->ndof, f->n_out);
+  if (f->depth < 1 || f->depth > 5) return fail(PCX_ERR_UNSUPPORTED, "MLP n_layers must be 1..5, got %d", f->depth);
+  if (f->width < 1 || f->width > 63) return fail(PCX_ERR_UNSUPPORTED, "MLP n_neurons must be 1..63, got %d", f->width);
+  MlpShape& s = h->ms;
+  memset(&s, 0, sizeof(s));
+  s.n_in = f->n_in; s.n_out = f->n_out; s.width = f->width; s.depth = f->depth; s.use_final_bias = f->use_final_bias;
+  const int need_nt = (f->width + 1 + 7) / 8;
+  s.NT = need_nt <= 2 ? 2 : need_nt <= 4 ? 4 : need_nt <= 7 ? 7 : 8;
+  s.KS = (f->width + 3) / 4;
+  long long o = 0;
+  for (int i = 0; i <= s.depth; i++) {
+    const int fin = i == 0 ? s.n_in : s.width, fout = i == s.depth ? s.n_out : s.width;
+    s.offW[i] = o; o += (long long)fin * fout;
+    if (i < s.depth || s.use_final_bias) { s.offB[i] = o; o += fout; } else s.offB[i] = -1;
+  }
+  s.nweights = o;
+  const long long NT = s.NT, KSP = 2 * NT;
+  long long p = 0;
+  s.pF0 = p; p += NT * 32;
+  s.pFB = p; p += (long long)s.depth * NT * 64;
+  s.pFH = p; p += (long long)(s.depth - 1) * KSP * NT * 32;
+  s.pFO = p; p += KSP * 32;
+  s.pFOB = p; p += 64;
+  s.pBO = p; p += NT * 32;
+  s.pBH = p; p += (long long)(s.depth - 1) * KSP * NT * 32;
+  s.npacked = p;
+  s.nd = h->nd;
+  for (int j = 0; j < h->nd; j++) { s.x_min[j] = f->x_min[j]; s.x_scale[j] = f->x_max[j] - f->x_min[j]; }
+  s.t_min = f->t_min; s.t_scale = f->t_max - f->t_min; s.normalize_time = f->normalize_time;
+  h->bc_a = f->bc_a; h->bc_b = f->bc_b;
+  h->have_field = true;
+  if (h->have_phys) return alloc_ws(h);
+  return PCX_OK;
+}
+
+extern "C" int pcx_destroy(pcx_handle* h) {
+  if (!h) return PCX_OK;
+  free_ws(h);
+  if (h->adj_ptr) cudaFree(h->adj_ptr);
+  if (h->adj_idx) cudaFree(h->adj_idx);
+  delete h;
+  return PCX_OK;
+}
+
+extern "C" int64_t pcx_num_weights(const pcx_handle* h) { return h && h->have_field ? h->ms.nweights : -1; }
+extern "C" int64_t pcx_num_trainable_props(const pcx_handle* h) { return h && h->have_phys ? h->ntrain : -1; }
+extern "C" int64_t pcx_num_qp(const pcx_handle* h) { return h ? h->ne * h->nq : -1; }
+extern "C" int32_t pcx_nq(const pcx_handle* h) { return h ? h->nq : -1; }
+extern "C" int32_t pcx_nnpe(const pcx_handle* h) { return h ? h->nnpe : -1; }
+extern "C" int32_t pcx_nd(const pcx_handle* h) { return h ? h->nd : -1; }
+extern "C" int64_t pcx_launch_count(const pcx_handle* h) { return h ? h->launches : -1; }
+
+#define NEED_READY(h)                                                                                    \
+  do {                                                                                                   \
+    if (!(h)) return fail(PCX_ERR_INVALID, "null handle");                                               \
+    if (!(h)->have_phys || !(h)->have_field) return fail(PCX_ERR_STATE, "call pcx_set_physics and pcx_set_field first"); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ ABI: geometry
+extern "C" int pcx_element_geometry(pcx_handle* h, double* grad_N, double* JxW, double* x_q, void* stream) {
+  if (!h) return fail(PCX_ERR_INVALID, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int epb = 64;
+  const int grid = (int)((h->ne + epb - 1) / epb);
+  const size_t smem = (size_t)epb * h->nnpe * sizeof(int32_t);
+  if (h->elem_type == PCX_ELEM_HEX8) k_geometry<8, 3><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, grad_N, JxW, x_q, epb);
+  else if (h->elem_type == PCX_ELEM_QUAD4) k_geometry<4, 2><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, grad_N, JxW, x_q, epb);
+  else k_geometry<3, 2><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, grad_N, JxW, x_q, epb);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ internals shared by the ops
+static MlpIO node_io(pcx_handle* h, int t0, int T) {
+  MlpIO io;
+  memset(&io, 0, sizeof(io));
+  io.x = h->coords; io.x_stride = h->nd; io.trow = nullptr; io.t = 0.0;
+  io.n = (long long)T * h->nn;
+  io.nn_mod = h->nn; io.times = h->times_dev + t0;
+  io.bc_a = h->bc_a ? h->bc_a + (long long)t0 * h->nn * h->ndof : nullptr;
+  io.bc_b = h->bc_b ? h->bc_b + (long long)t0 * h->nn * h->ndof : nullptr;
+  io.act = h->act; io.rows_cap = h->rows_cap; io.pk = h->pk; io.part = h->part; io.part_stride = h->part_stride;
+  return io;
+}
+
+// energy (+force) sweep over T time steps of `us` -> f (assembled, scaled by alpha, + beta*add)
+static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const double* v, double* out, double alpha,
+                 const double* add, double beta, bool want_energy, bool want_dp, bool want_force, cudaStream_t st) {
+  ElemArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ne = h->ne; a.coords = h->coords; a.conns = h->conns; a.us = us; a.v = v;
+  a.src_q = h->phys.source_q;
+  a.props_dev = h->props_dev; a.nprops = h->phys.nprops; a.flags = h->flags;
+  a.nn = h->nn;
+  a.epart = want_energy ? h->epart : nullptr;
+  a.ppart = want_dp ? h->ppart : nullptr;
+  a.want_force = want_force ? 1 : 0;
+  const long long ndofs = h->nn * h->ndof;
+  if (want_force) {
+    if (h->deterministic) { a.fe = h->fe; a.f_atomic = nullptr; }
+    else {
+      a.fe = nullptr; a.f_atomic = out;
+      CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)T * ndofs * sizeof(double), st));
+    }
+  }
+  int rc = launch_element(h, tangent, T, st, a);
+  if (rc) return rc;
+  if (want_force) {
+    const long long n = (long long)T * ndofs;
+    const int thr = 256;
+    const int blocks = (int)((n + thr - 1) / thr);
+    if (h->deterministic) {
+      k_assemble<<<blocks, thr, 0, st>>>(h->nn, h->ndof, T, h->ne * h->nnpe, h->adj_ptr, h->adj_idx, h->fe, alpha, add, beta, out);
+      LAUNCH_CHECK(h);
+    } else if (alpha != 1.0 || add) {
+      k_axpby<<<blocks, thr, 0, st>>>(n, alpha, out, beta, add, out);
+      LAUNCH_CHECK(h);
+    }
+  }
+  return PCX_OK;
+}
+
+static int reduce_rows(pcx_handle* h, const double* part, long long n_per_row, int stride, int ncomp, int rows,
+                       double* out, int out_stride, cudaStream_t st) {
+  k_reduce_partials<<<rows, 256, 0, st>>>(part, n_per_row, stride, ncomp, out, out_stride);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+static int set_props(pcx_handle* h, const double* prop_raw, cudaStream_t st) {
+  if (h->ntrain > 0 && !prop_raw) return fail(PCX_ERR_INVALID, "prop_raw is required: %d trainable properties", h->ntrain);
+  k_props<<<1, 32, 0, st>>>(h->phys, prop_raw, h->props_dev);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+static int check_tangent_supported(pcx_handle* h) {
+  if (h->phys.physics == PCX_PHYS_SOLID && h->phys.model == PCX_MODEL_HENCKY)
+    return fail(PCX_ERR_UNSUPPORTED,
+                "Hencky: the second derivative of the log-strain rule (tensor_math.py:343-424) is not on the B200 path; "
+                "residual losses / stiffness action are refused (no fallback)");
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: field ops
+extern "C" int pcx_field_forward(pcx_handle* h, const double* weights, int32_t t_idx, double* us, void* stream) {
+  NEED_READY(h);
+  if (t_idx < 0 || t_idx >= h->nt) return fail(PCX_ERR_INVALID, "t_idx out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pack_weights(h, weights, st);
+  if (rc) return rc;
+  MlpIO io = node_io(h, t_idx, 1);
+  io.u = us;
+  return launch_mlp_fwd(h, st, io);
+}
+
+extern "C" int pcx_field_backward(pcx_handle* h, const double* weights, int32_t t_idx, const double* g_us,
+                                  double* g_weights, void* stream) {
+  NEED_READY(h);
+  if (t_idx < 0 || t_idx >= h->nt) return fail(PCX_ERR_INVALID, "t_idx out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pack_weights(h, weights, st);
+  if (rc) return rc;
+  MlpIO io = node_io(h, t_idx, 1);
+  io.u = nullptr;  // recompute activations only
+  rc = launch_mlp_fwd(h, st, io);
+  if (rc) return rc;
+  io.g_u = g_us;
+  int grid = 0;
+  rc = launch_mlp_bwd(h, st, io, &grid);
+  if (rc) return rc;
+  return reduce_wgrad(h, grid, g_weights, st);
+}
+
+static MlpIO points_io(pcx_handle* h, const double* pts, const double* a, const double* b, long long n) {
+  MlpIO io;
+  memset(&io, 0, sizeof(io));
+  io.x = pts; io.x_stride = h->nd + 1; io.trow = pts + h->nd; io.n = n;
+  io.nn_mod = 0; io.times = nullptr;
+  io.bc_a = a; io.bc_b = b;
+  io.act = h->act; io.rows_cap = h->rows_cap; io.pk = h->pk; io.part = h->part; io.part_stride = h->part_stride;
+  return io;
+}
+
+extern "C" int pcx_points_forward(pcx_handle* h, const double* weights, const double* pts, const double* a,
+                                  const double* b, int64_t n, double* u, void* stream) {
+  NEED_READY(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pack_weights(h, weights, st);
+  if (rc) return rc;
+  for (long long o = 0; o < n; o += h->rows_cap) {
+    const long long m = (n - o < h->rows_cap) ? n - o : h->rows_cap;
+    MlpIO io = points_io(h, pts + o * (h->nd + 1), a ? a + o * h->ndof : nullptr, b ? b + o * h->ndof : nullptr, m);
+    io.u = u + o * h->ndof;
+    io.act = nullptr;
+    rc = launch_mlp_fwd(h, st, io);
+    if (rc) return rc;
+  }
+  return PCX_OK;
+}
+
+static int points_backward_impl(pcx_handle* h, const double* pts, const double* b, const double* g_u, long long n,
+                                double* g_weights, cudaStream_t st) {
+  int rc;
+  bool first = true;
+  for (long long o = 0; o < n; o += h->rows_cap) {
+    const long long m = (n - o < h->rows_cap) ? n - o : h->rows_cap;
+    MlpIO io = points_io(h, pts + o * (h->nd + 1), nullptr, b ? b + o * h->ndof : nullptr, m);
+    io.u = nullptr;
+    rc = launch_mlp_fwd(h, st, io);
+    if (rc) return rc;
+    io.g_u = g_u + o * h->ndof;
+    int grid = 0;
+    rc = launch_mlp_bwd(h, st, io, &grid);
+    if (rc) return rc;
+    rc = reduce_wgrad(h, grid, first ? g_weights : h->gtmp, st);
+    if (rc) return rc;
+    if (!first) {
+      const int thr = 256;
+      k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);
+      LAUNCH_CHECK(h);
+    }
+    first = false;
+  }
+  return PCX_OK;
+}
+
+extern "C" int pcx_points_backward(pcx_handle* h, const double* weights, const double* pts, const double* b,
+                                   const double* g_u, int64_t n, double* g_weights, void* stream) {
+  NEED_READY(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pack_weights(h, weights, st);
+  if (rc) return rc;
+  return points_backward_impl(h, pts, b, g_u, n, g_weights, st);
+}
+
+extern "C" int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const double* pts, const double* a,
+                                            const double* b, const double* outputs, int64_t n, double weight,
+                                            double* loss_out, double* g_weights, void* stream) {
+  NEED_READY(h);
+  if (n <= 0) return fail(PCX_ERR_INVALID, "empty batch");
+  if (n > h->rows_cap)
+    return fail(PCX_ERR_INVALID, "batch of %lld rows exceeds the workspace (%lld rows)", (long long)n, h->rows_cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pack_weights(h, weights, st);
+  if (rc) return rc;
+  // forward (stores activations), loss + cotangent, backward
+  MlpIO io = points_io(h, pts, a, b, n);
+  io.u = h->us;
+  rc = launch_mlp_fwd(h, st, io);
+  if (rc) return rc;
+  const long long nv = n * h->ndof;
+  const double scale = weight / (double)nv;  // w * mean over (rows, dofs): data_loss_functions.py:22-24
+  const int grid = 128;
+  k_data_loss<<<grid, 256, 0, st>>>(nv, h->us, outputs, scale, h->ubar, h->rpart);
+  LAUNCH_CHECK(h);
+  rc = reduce_rows(h, h->rpart, grid, 1, 1, 1, loss_out, 1, st);
+  if (rc) return rc;
+  io.g_u = h->ubar;
+  int bgrid = 0;
+  rc = launch_mlp_bwd(h, st, io, &bgrid);
+  if (rc) return rc;
+  return reduce_wgrad(h, bgrid, g_weights, st);
+}
+
+// ------------------------------------------------------------------------------------------ ABI: energy / force ops
+extern "C" int pcx_energy_force(pcx_handle* h, const double* prop_raw, const double* us, double* Pi, double* f,
+                                double* g_props, void* stream) {
+  NEED_READY(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = set_props(h, prop_raw, st);
+  if (rc) return rc;
+  const bool want_dp = g_props != nullptr && h->ntrain > 0;
+  rc = sweep(h, false, 1, us, nullptr, f, 1.0, nullptr, 0.0, true, want_dp, f != nullptr, st);
+  if (rc) return rc;
+  rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, 1, Pi, 1, st);
+  if (rc) return rc;
+  if (want_dp) {
+    rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, 1, h->scal + SC_DPI(h), PCX_MAX_PROPS, st);
+    if (rc) return rc;
+    k_chain_props<<<1, 32, 0, st>>>(h->phys, h->props_dev, h->scal + SC_DPI(h), g_props);
+    LAUNCH_CHECK(h);
+  }
+  return PCX_OK;
+}
+
+extern "C" int pcx_stiffness_action(pcx_handle* h, const double* prop_raw, const double* us, const double* v,
+                                    double* Kv, double* g_props, void* stream) {
+  NEED_READY(h);
+  int rc = check_tangent_supported(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = set_props(h, prop_raw, st);
+  if (rc) return rc;
+  const bool want_dp = g_props != nullptr && h->ntrain > 0;
+  rc = sweep(h, true, 1, us, v, Kv, 1.0, nullptr, 0.0, false, want_dp, true, st);
+  if (rc) return rc;
+  if (want_dp) {
+    rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, 1, h->scal + SC_DFV(h), PCX_MAX_PROPS, st);
+    if (rc) return rc;
+    k_chain_props<<<1, 32, 0, st>>>(h->phys, h->props_dev, h->scal + SC_DFV(h), g_props);
+    LAUNCH_CHECK(h);
+  }
+  return PCX_OK;
+}
+
+static int resid_react(pcx_handle* h, int T, const double* f, double* out_rr /* [T][2] raw (R^2, react) */, cudaStream_t st) {
+  dim3 grid(256, T);
+  k_resid_react_partials<<<grid, 256, 0, st>>>(f, h->nn * h->ndof, h->unknown_idx, h->n_unknown, h->reaction_nodes,
+                                               h->n_reaction, h->ndof, h->reaction_dof, h->rpart);
+  LAUNCH_CHECK(h);
+  return reduce_rows(h, h->rpart, 256, 2, 2, T, out_rr, 2, st);
+}
+
+__global__ void k_sqrt0(double* p) { if (threadIdx.x == 0 && blockIdx.x == 0) p[0] = p[0] > 0.0 ? sqrt(p[0]) : 0.0; }
+
+extern "C" int pcx_residual_reaction(pcx_handle* h, const double* f, double* out, void* stream) {
+  NEED_READY(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = resid_react(h, 1, f, out, st);
+  if (rc) return rc;
+  k_sqrt0<<<1, 32, 0, st>>>(out);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: fused loss + grad
+extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
+                                 double* loss_out, double* aux, double* g_weights, double* g_props, void* stream) {
+  NEED_READY(h);
+  if (!L || !weights || !loss_out || !aux || !g_weights) return fail(PCX_ERR_INVALID, "pcx_loss_and_grad: null argument");
+  const int kind = L->kind;
+  if (kind < PCX_LOSS_ENERGY || kind > PCX_LOSS_ENERGY_RESIDUAL_REACTION) return fail(PCX_ERR_INVALID, "unknown loss kind %d", kind);
+  const bool resid = kind != PCX_LOSS_ENERGY;
+  if (resid) {
+    int rc = check_tangent_supported(h);
+    if (rc) return rc;
+    if (!h->unknown_idx) return fail(PCX_ERR_STATE, "residual losses need unknown_idx in pcx_mesh_desc");
+  }
+  if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) {
+    if (!h->reaction_nodes || !L->global_outputs) return fail(PCX_ERR_STATE, "reaction loss needs reaction_nodes and global_outputs");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const double we = L->energy_weight, wr = resid ? L->residual_weight : 0.0;
+  const double wg = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->reaction_weight : 0.0;
+  int rc;
+  if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION)
+    CUDA_TRY(cudaMemcpyAsync(h->gout_dev, L->global_outputs, h->nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+  if ((rc = set_props(h, prop_raw, st))) return rc;
+  if ((rc = pack_weights(h, weights, st))) return rc;
+  const bool want_dp = g_props != nullptr && h->ntrain > 0;
+  const long long ndofs = h->nn * h->ndof;
+  bool first = true;
+  for (int t0 = 0; t0 < h->nt; t0 += h->T) {
+    const int T = (h->nt - t0 < h->T) ? h->nt - t0 : h->T;
+    // (2) field at the nodes for T time steps
+    MlpIO io = node_io(h, t0, T);
+    io.u = h->us;
+    if ((rc = launch_mlp_fwd(h, st, io))) return rc;
+    // (1)+(3)+(5) energy, force; ubar = we * f for the energy loss
+    if (!resid) {
+      if ((rc = sweep(h, false, T, h->us, nullptr, h->ubar, we, nullptr, 0.0, true, want_dp, true, st))) return rc;
+    } else {
+      if ((rc = sweep(h, false, T, h->us, nullptr, h->f, 1.0, nullptr, 0.0, true, want_dp, true, st))) return rc;
+    }
+    if ((rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, T, h->scal + SC_PI(h) + t0, 1, st))) return rc;
+    if (want_dp)
+      if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T,
+                            h->scal + SC_DPI(h) + (long long)t0 * PCX_MAX_PROPS, PCX_MAX_PROPS, st))) return rc;
+    if (resid) {
+      // residual norm, reaction, v_t, tangent action, ubar = we f + K v
+      if ((rc = resid_react(h, T, h->f, h->scal + SC_RR(h), st))) return rc;
+      k_resid_coeffs<<<1, 64, 0, st>>>(t0, T, h->nt, wr, wg, h->scal + SC_RR(h),
+                                       kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? h->gout_dev : nullptr,
+                                       h->scal + SC_R(h), h->scal + SC_REACT(h), h->scal + SC_C1(h), h->scal + SC_C2(h));
+      LAUNCH_CHECK(h);
+      CUDA_TRY(cudaMemsetAsync(h->v, 0, (size_t)T * ndofs * sizeof(double), st));
+      {
+        dim3 g0((unsigned)((h->n_unknown + 255) / 256), T);
+        if (h->n_unknown > 0) {
+          k_make_v<<<g0, 256, 0, st>>>(t0, h->nn, h->ndof, h->f, h->unknown_idx, h->n_unknown, h->reaction_nodes,
+                                       h->n_reaction, h->reaction_dof, h->scal + SC_C1(h), h->scal + SC_C2(h), h->v, 0);
+          LAUNCH_CHECK(h);
+        }
+        if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION && h->n_reaction > 0) {
+          dim3 g1((unsigned)((h->n_reaction + 255) / 256), T);
+          k_make_v<<<g1, 256, 0, st>>>(t0, h->nn, h->ndof, h->f, h->unknown_idx, h->n_unknown, h->reaction_nodes,
+                                       h->n_reaction, h->reaction_dof, h->scal + SC_C1(h), h->scal + SC_C2(h), h->v, 1);
+          LAUNCH_CHECK(h);
+        }
+      }
+      if ((rc = sweep(h, true, T, h->us, h->v, h->ubar, 1.0, h->f, we, false, want_dp, true, st))) return rc;
+      if (want_dp)
+        if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T,
+                              h->scal + SC_DFV(h) + (long long)t0 * PCX_MAX_PROPS, PCX_MAX_PROPS, st))) return rc;
+    }
+    // (4) adjoint through the field
+    io.u = nullptr;
+    io.g_u = h->ubar;
+    int grid = 0;
+    if ((rc = launch_mlp_bwd(h, st, io, &grid))) return rc;
+    if ((rc = reduce_wgrad(h, grid, first ? g_weights : h->gtmp, st))) return rc;
+    if (!first) {
+      const int thr = 256;
+      k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);
+      LAUNCH_CHECK(h);
+    }
+    first = false;
+  }
+  k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
+                             h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
+                             want_dp ? g_props : nullptr);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}

@@ -1,0 +1,445 @@
+// pcx_element.cuh -- element sweeps: gather, geometry, constitutive update, energy reduction,
+// internal-force / tangent-action scatter.
+//
+// Replaces pancax/physics_kernels/base.py:297-361 (element_integral, element_interpolants,
+// potential_energy_on_block, potential_energy_and_internal_force) with
+// pancax/fem/function_space.py:63-89 inlined, for all elements of the mesh in one launch.
+//
+// One thread = one element (all its quadrature points), everything in registers:
+//   J[k][j]   = sum_a dN[q][a][k] X[a][j]                 (function_space.py:64,83)
+//   Gu[i][k]  = sum_a U[a][i] dN[q][a][k]                 parent-space gradient of u
+//   H         = Gu Jinv^T   (= U^T gradN, base.py:323-325 with gradN = (Jinv dN^T)^T, fs:87-89)
+//   fe[a][i] += sum_k (JxW * P Jinv)[i][k] dN[q][a][k]     (the VJP JAX derives for base.py:356-361)
+// so the (nq, nnpe, nd) shape-gradient tensor XLA materialises (3.2 GB at 16.7 M qp) never exists.
+// Energy: per-thread fixed-order sum over q, warp shuffle tree, fixed-order block partial;
+// k_reduce_partials finishes in fixed order -> bit-reproducible Pi.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pcx_models.cuh"
+
+namespace pcx {
+
+constexpr int TAB_MAX_NQ = 9;
+constexpr int TAB_MAX_NNPE = 8;
+
+struct ParentTab {
+  int nq, nnpe, nd;
+  double w[TAB_MAX_NQ];
+  double N[TAB_MAX_NQ * TAB_MAX_NNPE];        // [q][a]
+  double dN[TAB_MAX_NQ * TAB_MAX_NNPE * 3];   // [q][a][k]
+};
+
+// blockIdx.y = time step within the batch: per-step arrays are offset by t * (their per-step size).
+struct ElemArgs {
+  long long ne;
+  long long nn;
+  const double* coords;    // [nn][ND]
+  const int32_t* conns;    // [ne][NNPE]
+  const double* us;        // [nn][NDOF]
+  const double* v;         // tangent direction [nn][NDOF] (TANGENT mode)
+  const double* src_q;     // Poisson source at qps [ne][nq] or nullptr
+  double* fe;              // [ne][NNPE][NDOF] element vectors (deterministic mode) or nullptr
+  double* f_atomic;        // [nn][NDOF] atomic target (fast mode) or nullptr
+  double* epart;           // [gridDim] energy partials (FORCE mode) or nullptr
+  double* ppart;           // [gridDim][PCX_MAX_PROPS] property-gradient partials or nullptr
+  int* flags;              // device flag word: bit0 = det(F) <= 0 or non-finite energy seen
+  const double* props_dev; // effective properties [PCX_MAX_PROPS] (device: trainable ones change every step)
+  int nprops;
+  int want_force;
+};
+
+template <int ND>
+__device__ __forceinline__ double inv_det(const double* J, double* Ji) {
+  if constexpr (ND == 2) {
+    const double det = J[0] * J[3] - J[1] * J[2];
+    const double id = 1.0 / det;
+    Ji[0] = J[3] * id; Ji[1] = -J[1] * id; Ji[2] = -J[2] * id; Ji[3] = J[0] * id;
+    return det;
+  } else {
+    double cof[9];
+    cofactor3(J, cof);
+    const double det = J[0] * cof[0] + J[1] * cof[1] + J[2] * cof[2];
+    const double id = 1.0 / det;
+    // inverse = cof^T / det
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Ji[3 * i + j] = cof[3 * j + i] * id;
+    return det;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide deterministic sum; result valid in thread 0
+template <int NTHREADS>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NTHREADS / 32; i++) t += sh[i];
+  }
+  return t;
+}
+
+// MODEL: 0 = Poisson, else PCX_MODEL_*.  TANGENT: false -> energy + internal force,
+// true -> stiffness action K v (forward-mode duals through the same constitutive source).
+template <int NNPE, int ND, int NDOF, int MODEL, bool TANGENT>
+__global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+  constexpr int NTH = 128;
+  __shared__ double sh[NTH / 32];
+  const long long e = blockIdx.x * (long long)NTH + threadIdx.x;
+  // per-time-step views
+  struct {
+    long long ne; const double* coords; const int32_t* conns; const double* us; const double* v; const double* src_q;
+    double* fe; double* f_atomic; double* epart; double* ppart; int* flags; Props props; int nprops; int want_force;
+  } A;
+  {
+    const long long ts = blockIdx.y;
+    A.ne = A0.ne; A.coords = A0.coords; A.conns = A0.conns; A.src_q = A0.src_q; A.flags = A0.flags;
+    A.nprops = A0.nprops; A.want_force = A0.want_force;
+    A.us = A0.us + ts * A0.nn * NDOF;
+    A.v = A0.v ? A0.v + ts * A0.nn * NDOF : nullptr;
+    A.fe = A0.fe ? A0.fe + ts * A0.ne * (NNPE * NDOF) : nullptr;
+    A.f_atomic = A0.f_atomic ? A0.f_atomic + ts * A0.nn * NDOF : nullptr;
+    A.epart = A0.epart ? A0.epart + ts * gridDim.x : nullptr;
+    A.ppart = A0.ppart ? A0.ppart + ts * (long long)gridDim.x * PCX_MAX_PROPS : nullptr;
+#pragma unroll
+    for (int k = 0; k < PCX_MAX_PROPS; k++) A.props.p[k] = (MODEL != 0 && k < A0.nprops) ? __ldg(A0.props_dev + k) : 0.0;
+  }
+  const bool live = e < A.ne;
+  double Wsum = 0.0;
+  double dps[PCX_MAX_PROPS];
+#pragma unroll
+  for (int k = 0; k < PCX_MAX_PROPS; k++) dps[k] = 0.0;
+  const bool want_dp = A.ppart != nullptr;
+  bool bad = false;
+
+  if (live) {
+    int32_t cn[NNPE];
+    if constexpr (NNPE % 4 == 0) {
+      const int4* cp = reinterpret_cast<const int4*>(A.conns + e * NNPE);
+#pragma unroll
+      for (int q = 0; q < NNPE / 4; q++) {
+        int4 t = __ldg(cp + q);
+        cn[4 * q] = t.x; cn[4 * q + 1] = t.y; cn[4 * q + 2] = t.z; cn[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < NNPE; a++) cn[a] = __ldg(A.conns + e * NNPE + a);
+    }
+    double X[NNPE][ND], U[NNPE][NDOF], acc[NNPE][NDOF];
+    double V[TANGENT ? NNPE : 1][NDOF];
+#pragma unroll
+    for (int a = 0; a < NNPE; a++) {
+#pragma unroll
+      for (int j = 0; j < ND; j++) X[a][j] = __ldg(A.coords + (long long)cn[a] * ND + j);
+#pragma unroll
+      for (int i = 0; i < NDOF; i++) {
+        U[a][i] = __ldg(A.us + (long long)cn[a] * NDOF + i);
+        acc[a][i] = 0.0;
+        if constexpr (TANGENT) V[a][i] = __ldg(A.v + (long long)cn[a] * NDOF + i);
+      }
+    }
+
+    for (int q = 0; q < tab.nq; q++) {
+      const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
+      double J[ND * ND], Ji[ND * ND];
+#pragma unroll
+      for (int k = 0; k < ND; k++)
+#pragma unroll
+        for (int j = 0; j < ND; j++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < NNPE; a++) s = fma(dN[a * 3 + k], X[a][j], s);
+          J[k * ND + j] = s;
+        }
+      const double detJ = inv_det<ND>(J, Ji);
+      const double JxW = detJ * tab.w[q];
+      // parent-space gradient of u (and of v)
+      double Gu[NDOF][ND];
+      double Gv[TANGENT ? NDOF : 1][ND];
+#pragma unroll
+      for (int i = 0; i < NDOF; i++)
+#pragma unroll
+        for (int k = 0; k < ND; k++) {
+          double s = 0.0, sv = 0.0;
+#pragma unroll
+          for (int a = 0; a < NNPE; a++) {
+            s = fma(U[a][i], dN[a * 3 + k], s);
+            if constexpr (TANGENT) sv = fma(V[a][i], dN[a * 3 + k], sv);
+          }
+          Gu[i][k] = s;
+          if constexpr (TANGENT) Gv[i][k] = sv;
+        }
+      // H[i][j] = sum_k Gu[i][k] Ji[j][k]
+      double H[NDOF][ND], dH[TANGENT ? NDOF : 1][ND];
+#pragma unroll
+      for (int i = 0; i < NDOF; i++)
+#pragma unroll
+        for (int j = 0; j < ND; j++) {
+          double s = 0.0, sv = 0.0;
+#pragma unroll
+          for (int k = 0; k < ND; k++) {
+            s = fma(Gu[i][k], Ji[j * ND + k], s);
+            if constexpr (TANGENT) sv = fma(Gv[i][k], Ji[j * ND + k], sv);
+          }
+          H[i][j] = s;
+          if constexpr (TANGENT) dH[i][j] = sv;
+        }
+
+      // physics: stress-like output S[i][j] (P or dP) and, for Poisson, the u-conjugate term
+      double S[NDOF][ND];
+      double su = 0.0;  // d(density)/du_q (Poisson: -f)
+      if constexpr (MODEL == 0) {
+        // poisson.py:16-19: 0.5 grad_u.grad_u - f u
+        const double fq = A.src_q ? A.src_q[e * tab.nq + q] : 0.0;
+        if constexpr (!TANGENT) {
+          double uq = 0.0, w = 0.0;
+#pragma unroll
+          for (int a = 0; a < NNPE; a++) uq = fma(tab.N[q * TAB_MAX_NNPE + a], U[a][0], uq);
+#pragma unroll
+          for (int j = 0; j < ND; j++) { w = fma(H[0][j], H[0][j], w); S[0][j] = H[0][j]; }
+          Wsum = fma(JxW, 0.5 * w - fq * uq, Wsum);
+          su = -fq;
+        } else {
+#pragma unroll
+          for (int j = 0; j < ND; j++) S[0][j] = dH[0][j];
+        }
+      } else {
+        // solid_mechanics.py:102-109: plane strain embeds the 2x2 gradient in a 3x3 of zeros
+        // (tensor_math.py:64-65); F = grad_u + I (mechanics/base.py:19-21)
+        if constexpr (!TANGENT) {
+          double F[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+#pragma unroll
+          for (int i = 0; i < NDOF; i++)
+#pragma unroll
+            for (int j = 0; j < ND; j++) F[3 * i + j] += H[i][j];
+          double W, P[9], dp[PCX_MAX_PROPS];
+          model_eval<MODEL, double>(F, A.props, W, P, dp, want_dp);
+          if (!(W == W) || fabs(W) > 1.0e300) bad = true;
+          Wsum = fma(JxW, W, Wsum);
+          if (want_dp) {
+#pragma unroll
+            for (int k = 0; k < PCX_MAX_PROPS; k++)
+              if (k < A.nprops) dps[k] = fma(JxW, dp[k], dps[k]);
+          }
+#pragma unroll
+          for (int i = 0; i < NDOF; i++)
+#pragma unroll
+            for (int j = 0; j < ND; j++) S[i][j] = P[3 * i + j];
+        } else {
+          Dual F[9];
+#pragma unroll
+          for (int i = 0; i < 9; i++) F[i] = Dual((i % 4 == 0) ? 1.0 : 0.0, 0.0);
+#pragma unroll
+          for (int i = 0; i < NDOF; i++)
+#pragma unroll
+            for (int j = 0; j < ND; j++) { F[3 * i + j].v += H[i][j]; F[3 * i + j].d = dH[i][j]; }
+          Dual W, P[9], dp[PCX_MAX_PROPS];
+          model_eval<MODEL, Dual>(F, A.props, W, P, dp, want_dp);
+          if (want_dp) {
+            // d(P:dH)/dp = tangent of dW/dp along dH
+#pragma unroll
+            for (int k = 0; k < PCX_MAX_PROPS; k++)
+              if (k < A.nprops) dps[k] = fma(JxW, dp[k].d, dps[k]);
+          }
+#pragma unroll
+          for (int i = 0; i < NDOF; i++)
+#pragma unroll
+            for (int j = 0; j < ND; j++) S[i][j] = P[3 * i + j].d;
+        }
+      }
+      if (A.want_force) {
+        // Q[i][k] = JxW sum_j S[i][j] Ji[j][k];  acc[a][i] += sum_k Q[i][k] dN[a][k]
+        double Q[NDOF][ND];
+#pragma unroll
+        for (int i = 0; i < NDOF; i++)
+#pragma unroll
+          for (int k = 0; k < ND; k++) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < ND; j++) s = fma(S[i][j], Ji[j * ND + k], s);
+            Q[i][k] = s * JxW;
+          }
+#pragma unroll
+        for (int a = 0; a < NNPE; a++)
+#pragma unroll
+          for (int i = 0; i < NDOF; i++) {
+            double s = acc[a][i];
+#pragma unroll
+            for (int k = 0; k < ND; k++) s = fma(Q[i][k], dN[a * 3 + k], s);
+            if constexpr (MODEL == 0 && !TANGENT) s = fma(JxW * su, tab.N[q * TAB_MAX_NNPE + a], s);
+            acc[a][i] = s;
+          }
+      }
+    }
+    if (A.want_force) {
+      if (A.fe) {
+        double* o = A.fe + e * (NNPE * NDOF);
+#pragma unroll
+        for (int a = 0; a < NNPE; a++)
+#pragma unroll
+          for (int i = 0; i < NDOF; i++) o[a * NDOF + i] = acc[a][i];
+      } else {
+#pragma unroll
+        for (int a = 0; a < NNPE; a++)
+#pragma unroll
+          for (int i = 0; i < NDOF; i++) atomicAdd(A.f_atomic + (long long)cn[a] * NDOF + i, acc[a][i]);
+      }
+    }
+  }
+  if (bad) atomicOr(A.flags, 1);
+  if (A.epart) {
+    const double t = block_sum<NTH>(Wsum, sh);
+    if (threadIdx.x == 0) A.epart[blockIdx.x] = t;
+  }
+  if (A.ppart) {
+    for (int k = 0; k < A.nprops; k++) {
+      const double t = block_sum<NTH>(dps[k], sh);
+      if (threadIdx.x == 0) A.ppart[(long long)blockIdx.x * PCX_MAX_PROPS + k] = t;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Standalone geometry kernel (north_star item 1): gradN (ne,nq,nnpe,nd), JxW (ne,nq), x_q (ne,nq,nd).
+// function_space.py:63-89 and base.py:322.  HBM-bound (writes ~ (nnpe*nd + 1 + nd) * 8 B per qp).
+// One thread per (element, qp); the element's connectivity row is staged through shared memory
+// with a coalesced block load.
+// ----------------------------------------------------------------------------------------------
+template <int NNPE, int ND>
+__global__ void __launch_bounds__(256) k_geometry(const __grid_constant__ ParentTab tab, long long ne,
+                                                  const double* __restrict__ coords, const int32_t* __restrict__ conns,
+                                                  double* __restrict__ gradN, double* __restrict__ JxW,
+                                                  double* __restrict__ xq, int epb /* elements per block */) {
+  extern __shared__ int32_t s_conn[];  // [epb][NNPE]
+  const long long e0 = (long long)blockIdx.x * epb;
+  const int nloc = (int)min((long long)epb, ne - e0);
+  for (int i = threadIdx.x; i < nloc * NNPE; i += blockDim.x) s_conn[i] = __ldg(conns + e0 * NNPE + i);
+  __syncthreads();
+  const int nq = tab.nq;
+  for (int t = threadIdx.x; t < nloc * nq; t += blockDim.x) {
+    const int el = t / nq, q = t - el * nq;
+    const long long e = e0 + el;
+    double X[NNPE][ND];
+#pragma unroll
+    for (int a = 0; a < NNPE; a++)
+#pragma unroll
+      for (int j = 0; j < ND; j++) X[a][j] = __ldg(coords + (long long)s_conn[el * NNPE + a] * ND + j);
+    const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
+    double J[ND * ND], Ji[ND * ND];
+#pragma unroll
+    for (int k = 0; k < ND; k++)
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; a++) s = fma(dN[a * 3 + k], X[a][j], s);
+        J[k * ND + j] = s;
+      }
+    const double det = inv_det<ND>(J, Ji);
+    const long long qi = e * nq + q;
+    if (JxW) JxW[qi] = det * tab.w[q];
+    if (gradN) {
+#pragma unroll
+      for (int a = 0; a < NNPE; a++)
+#pragma unroll
+        for (int j = 0; j < ND; j++) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < ND; k++) s = fma(Ji[j * ND + k], dN[a * 3 + k], s);
+          gradN[(qi * NNPE + a) * ND + j] = s;
+        }
+    }
+    if (xq) {
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NNPE; a++) s = fma(tab.N[q * TAB_MAX_NNPE + a], X[a][j], s);
+        xq[qi * ND + j] = s;
+      }
+    }
+  }
+}
+
+// node-centric fixed-order assembly for T time steps:
+//   out[ts][n][i] = alpha * sum_{k in adj(n)} fe[ts][adj_idx[k]][i] (+ beta*add[ts][n][i])
+__global__ void k_assemble(long long nn, int ndof, int T, long long nent, const long long* __restrict__ adj_ptr,
+                           const int32_t* __restrict__ adj_idx, const double* __restrict__ fe,
+                           double alpha, const double* __restrict__ add, double beta, double* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)T * nn * ndof) return;
+  const long long ts = t / (nn * ndof);
+  const long long rem = t - ts * nn * ndof;
+  const long long n = rem / ndof;
+  const int i = (int)(rem - n * ndof);
+  fe += ts * nent * ndof;
+  double s = 0.0;
+  for (long long k = adj_ptr[n]; k < adj_ptr[n + 1]; k++) s += fe[(long long)adj_idx[k] * ndof + i];
+  s *= alpha;
+  if (add) s = fma(beta, add[t], s);
+  out[t] = s;
+}
+
+// out = alpha*x + beta*y (y nullable)
+__global__ void k_axpby(long long n, double alpha, const double* __restrict__ x, double beta,
+                        const double* __restrict__ y, double* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double s = alpha * x[t];
+  if (y) s = fma(beta, y[t], s);
+  out[t] = s;
+}
+
+// partial sums for the residual norm and the reaction force (fixed order per block)
+__global__ void __launch_bounds__(256) k_resid_react_partials(const double* __restrict__ f, long long ndofs_per_t,
+                                                              const long long* __restrict__ uidx,
+                                                              long long nu, const int32_t* __restrict__ rnodes, long long nr,
+                                                              int ndof, int rdof, double* __restrict__ part /* [T][grid][2] */) {
+  __shared__ double sh[8];
+  f += (long long)blockIdx.y * ndofs_per_t;
+  part += (long long)blockIdx.y * gridDim.x * 2;
+  double s2 = 0.0, sr = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nu; k += stride) {
+    const double v = f[uidx[k]];
+    s2 = fma(v, v, s2);
+  }
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nr; k += stride)
+    sr += f[(long long)rnodes[k] * ndof + rdof];
+  const double a = block_sum<256>(s2, sh);
+  const double b = block_sum<256>(sr, sh);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// fixed-order reduction of `n` partials with `ncomp` interleaved components, one block per row:
+// out[row*out_stride + c] = sum_i part[(row*n + i)*stride + c]
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ part, long long n, int stride, int ncomp,
+                                                         double* __restrict__ out, int out_stride) {
+  __shared__ double sh[8];
+  part += (long long)blockIdx.x * n * stride;
+  out += (long long)blockIdx.x * out_stride;
+  for (int c = 0; c < ncomp; c++) {
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) s += part[i * stride + c];
+    const double t = block_sum<256>(s, sh);
+    if (threadIdx.x == 0) out[c] = t;
+  }
+}
+
+}  // namespace pcx

@@ -1,0 +1,511 @@
+// pcx_mlp.cuh -- Field (input normalisation + tanh MLP + Dirichlet wrapper) forward and adjoint
+// on the FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64; tcgen05 has no f64 kind).
+//
+// Replaces: pancax/networks/fields.py:79-101 + equinox.nn.MLP (pancax/networks/mlp.py:72-85) vmapped
+// over nodes (pancax/physics_kernels/base.py:248-250) and the reverse-mode pass JAX derives for it.
+//
+// Layout idea (B200-first, not a translation of the vmap):
+//  * a warp owns tiles of 8 rows (nodes); the whole layer chain of a tile stays in registers.
+//    The m8n8k4 accumulator fragment of layer i (lane (r=l/4, c=l%4) holds row r, "slots" 2c,2c+1 of
+//    each 8-wide tile) IS the A fragment of layer i+1 if the K index is permuted consistently:
+//    accumulator register x of tile j, lane c  <->  feature 8j + 4x + c, so k-step ks of the next
+//    layer covers features 4ks..4ks+3.  The weights are pre-packed once per step into B fragments
+//    that follow this permutation (k_pack_weights), so no shuffle / shared-memory round trip sits
+//    between layers.
+//  * activations are written for the backward pass in that same fragment order
+//    act[layer][tile][row][8 slots]  (one fully coalesced 512 B store per warp per tile) instead of
+//    being recomputed (3.4 GB per time step at 2.1 M nodes: HBM is cheap, FP64 flops are not).
+//  * backward: the delta chain runs like the forward pass (DMMA with transposed weight fragments);
+//    the weight-gradient contraction sum_rows d_i^T h_i -- the only true dense contraction of the
+//    path -- needs rows on the K axis, so d_i and h_i tiles are staged through shared memory
+//    (bank-conflict-free stride) and each warp owns a fixed 8-row block of every layer's dW in
+//    registers for the CTA's whole persistent loop; bias gradients come for free from a column of
+//    ones in a padding slot.  Per-CTA partials are summed in fixed order by k_reduce_wgrad.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pcx {
+
+constexpr int MLP_MAX_LAYERS = 8;  // depth <= 7 hidden layers
+
+struct MlpShape {
+  int n_in, n_out, width, depth, use_final_bias;
+  int NT;      // 8-wide feature tiles (width + 1 <= 8*NT: one spare slot carries the bias column)
+  int KS;      // k-steps of 4 features: ceil(width / 4)
+  // offsets (in doubles) into the flat equinox-order weight vector
+  long long offW[MLP_MAX_LAYERS], offB[MLP_MAX_LAYERS];  // offB = -1 if the layer has no bias
+  long long nweights;
+  // offsets into the packed-fragment buffer
+  long long pF0, pFB, pFH, pFO, pFOB, pBO, pBH, npacked;
+  // input normalisation (fields.py:80-86)
+  double x_min[3], x_scale[3];  // x_hat = (x - x_min) / (x_max - x_min); x_scale = x_max - x_min
+  double t_min, t_scale;
+  int normalize_time;
+  int nd;
+};
+
+__host__ __device__ inline int slot_to_feat(int s) { return 8 * (s >> 3) + 4 * (s & 1) + ((s & 7) >> 1); }
+__host__ __device__ inline int feat_to_slot(int f) { return 8 * (f >> 3) + 2 * (f & 3) + ((f & 7) >> 2); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void st_cs_f64x2(double* p, double a, double b) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ double2 ld_cs_f64x2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: flat equinox vector -> B fragments (one double per lane per fragment).
+//   F0  [NT][32]            layer 0:   lane(r',c') = W0[feat(8jn+r')][c']                (c' < n_in)
+//   FB  [depth][NT][32][2]  biases in accumulator layout: b_i[feat(8jn+2c+x)]
+//   FH  [depth-1][KSP][NT][32] hidden i>=1: W_i[feat(8jn+r')][4ks+c']
+//   FO  [KSP][32]           output:    W_out[r'][4ks+c']                                  (r' < n_out)
+//   FOB [32][2]             output bias (if any) in accumulator layout: b_out[2c+x]
+//   BO  [NT][32]            backward top: W_out[c'][feat(8jn+r')]                          (c' < n_out)
+//   BH  [depth-1][KSP][NT][32] backward hidden i>=1: W_i[4ks+c'][feat(8jn+r')]
+// KSP = 2*NT (padded k-step count so offsets do not depend on width).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_weights(MlpShape s, const double* __restrict__ w, double* __restrict__ pk) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (tid >= s.npacked) return;
+  const int NT = s.NT, KSP = 2 * s.NT, W = s.width, D = s.depth;
+  double val = 0.0;
+  long long t = tid;
+  if (t < s.pFB) {  // F0
+    int lane = t & 31, jn = (int)(t >> 5);
+    int r = lane >> 2, c = lane & 3;
+    int o = slot_to_feat(8 * jn + r);
+    if (o < W && c < s.n_in) val = w[s.offW[0] + (long long)o * s.n_in + c];
+  } else if (t < s.pFH) {  // FB
+    t -= s.pFB;
+    int x = t & 1, lane = (t >> 1) & 31;
+    long long q = t >> 6;
+    int jn = (int)(q % NT), i = (int)(q / NT);
+    int c = lane & 3;
+    int o = slot_to_feat(8 * jn + 2 * c + x);
+    if (o < W && s.offB[i] >= 0) val = w[s.offB[i] + o];
+  } else if (t < s.pFO) {  // FH
+    t -= s.pFH;
+    int lane = t & 31;
+    long long q = t >> 5;
+    int jn = (int)(q % NT);
+    q /= NT;
+    int ks = (int)(q % KSP), i = (int)(q / KSP) + 1;
+    int r = lane >> 2, c = lane & 3;
+    int o = slot_to_feat(8 * jn + r), k = 4 * ks + c;
+    if (o < W && k < W) val = w[s.offW[i] + (long long)o * W + k];
+  } else if (t < s.pFOB) {  // FO
+    t -= s.pFO;
+    int lane = t & 31, ks = (int)(t >> 5);
+    int r = lane >> 2, c = lane & 3;
+    int k = 4 * ks + c;
+    if (r < s.n_out && k < W) val = w[s.offW[D] + (long long)r * W + k];
+  } else if (t < s.pBO) {  // FOB
+    t -= s.pFOB;
+    int x = t & 1, lane = (int)(t >> 1);
+    int c = lane & 3;
+    int o = 2 * c + x;
+    if (o < s.n_out && s.offB[D] >= 0) val = w[s.offB[D] + o];
+  } else if (t < s.pBH) {  // BO
+    t -= s.pBO;
+    int lane = t & 31, jn = (int)(t >> 5);
+    int r = lane >> 2, c = lane & 3;
+    int k = slot_to_feat(8 * jn + r);
+    if (c < s.n_out && k < W) val = w[s.offW[D] + (long long)c * W + k];
+  } else {  // BH
+    t -= s.pBH;
+    int lane = t & 31;
+    long long q = t >> 5;
+    int jn = (int)(q % NT);
+    q /= NT;
+    int ks = (int)(q % KSP), i = (int)(q / KSP) + 1;
+    int r = lane >> 2, c = lane & 3;
+    int o = 4 * ks + c, k = slot_to_feat(8 * jn + r);
+    if (o < W && k < W) val = w[s.offW[i] + (long long)o * W + k];
+  }
+  pk[tid] = val;
+}
+
+struct MlpIO {
+  // rows to evaluate
+  const double* x;      // row r input coordinates at x[r*x_stride + j], j < nd
+  long long x_stride;
+  const double* trow;   // per-row time at trow[r*x_stride] or nullptr -> use `t`
+  double t;
+  long long n;          // number of rows
+  long long nn_mod;     // > 0: rows are (time step, node) pairs: x row = r % nn_mod, t = times[r / nn_mod]
+  const double* times;  // device, used when nn_mod > 0
+  const double* bc_a;   // [n*n_out] or nullptr
+  const double* bc_b;   // [n*n_out] or nullptr
+  double* u;            // forward: [n*n_out] out (may be nullptr)
+  const double* g_u;    // backward: [n*n_out] cotangent on u
+  double* act;          // activations [depth][NT][rows_cap][8] (nullptr: do not store)
+  long long rows_cap;
+  const double* pk;     // packed weights
+  double* part;         // backward: per-CTA partial weight gradients [gridDim][part_stride]
+  long long part_stride;
+  // optional fused data loss: g_u = scale * 2 (u - target) computed in the forward pass
+};
+
+__device__ __forceinline__ double mlp_input(const MlpShape& s, const MlpIO& io, long long row, int c) {
+  // fields.py:80-88: inputs = hstack(x_norm, t_norm)
+  if (row >= io.n) return 0.0;
+  const long long xr = io.nn_mod > 0 ? row % io.nn_mod : row;
+  if (c < s.nd) return (io.x[xr * io.x_stride + c] - s.x_min[c]) / s.x_scale[c];
+  if (c == s.nd) {
+    double t = io.nn_mod > 0 ? io.times[row / io.nn_mod] : (io.trow ? io.trow[row * io.x_stride] : io.t);
+    return s.normalize_time ? (t - s.t_min) / s.t_scale : t;
+  }
+  return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward.  One warp = MT tiles of 8 rows; grid-stride over row groups.  No shared memory: the
+// packed weights (<= 90 KB) are read through L1 with coalesced 256 B warp loads; activations are
+// streamed (.cs) so they do not evict them.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int MT>
+__global__ void __launch_bounds__(256) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
+  const int lane = threadIdx.x & 31;
+  const int r = lane >> 2, c = lane & 3;
+  const int KSP = 2 * NT;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long ngroups = (io.n + 8 * MT - 1) / (8 * MT);
+  const double* __restrict__ pk = io.pk;
+
+  for (long long g = warp_id; g < ngroups; g += warps_total) {
+    const long long row0 = g * (8 * MT);
+    double h[MT][NT][2], acc[MT][NT][2];
+    // ---- layer 0
+    double a0[MT];
+#pragma unroll
+    for (int m = 0; m < MT; m++) a0[m] = mlp_input(s, io, row0 + 8 * m + r, c);
+#pragma unroll
+    for (int jn = 0; jn < NT; jn++) {
+      const double2 b2 = *reinterpret_cast<const double2*>(pk + s.pFB + ((long long)(0 * NT + jn) * 32 + lane) * 2);
+      const double bf = pk[s.pF0 + jn * 32 + lane];
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        acc[m][jn][0] = b2.x;
+        acc[m][jn][1] = b2.y;
+        dmma(acc[m][jn][0], acc[m][jn][1], a0[m], bf);
+      }
+    }
+    for (int i = 0;; i++) {
+      // activation of layer i
+#pragma unroll
+      for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int jn = 0; jn < NT; jn++) {
+          h[m][jn][0] = tanh(acc[m][jn][0]);
+          h[m][jn][1] = tanh(acc[m][jn][1]);
+        }
+      if (io.act) {
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+          const long long row = row0 + 8 * m + r;
+          if (row < io.n) {
+#pragma unroll
+            for (int jn = 0; jn < NT; jn++)
+              st_cs_f64x2(io.act + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, h[m][jn][0], h[m][jn][1]);
+          }
+        }
+      }
+      if (i == s.depth - 1) break;
+      // ---- hidden layer i+1
+      const double* fb = pk + s.pFB + (long long)(i + 1) * NT * 64;
+      const double* fh = pk + s.pFH + (long long)i * KSP * NT * 32;
+#pragma unroll
+      for (int jn = 0; jn < NT; jn++) {
+        const double2 b2 = *reinterpret_cast<const double2*>(fb + (jn * 32 + lane) * 2);
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+          acc[m][jn][0] = b2.x;
+          acc[m][jn][1] = b2.y;
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < KSP; ks++) {
+        if (ks < s.KS) {
+#pragma unroll
+          for (int jn = 0; jn < NT; jn++) {
+            const double bf = fh[(ks * NT + jn) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < MT; m++) dmma(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
+          }
+        }
+      }
+    }
+    // ---- output layer
+    if (io.u) {
+      double o[MT][2];
+      const double2 ob = *reinterpret_cast<const double2*>(pk + s.pFOB + lane * 2);
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        o[m][0] = ob.x;
+        o[m][1] = ob.y;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KSP; ks++) {
+        if (ks < s.KS) {
+          const double bf = pk[s.pFO + ks * 32 + lane];
+#pragma unroll
+          for (int m = 0; m < MT; m++) dmma(o[m][0], o[m][1], h[m][ks >> 1][ks & 1], bf);
+        }
+      }
+      // lane (r,c) holds z[row r][2c+x]; u = a + b*z (fields.py:101 with a tabulated affine wrapper)
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const long long row = row0 + 8 * m + r;
+        if (row < io.n) {
+#pragma unroll
+          for (int x = 0; x < 2; x++) {
+            const int oi = 2 * c + x;
+            if (oi < s.n_out) {
+              const long long k = row * s.n_out + oi;
+              double z = o[m][x];
+              if (io.bc_b) z *= io.bc_b[k];
+              if (io.bc_a) z += io.bc_a[k];
+              io.u[k] = z;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward.  CTA = NT+1 warps.  Per CTA tile of 8*(NT+1) rows:
+//   each warp runs the delta chain of its own 8 rows (registers, DMMA with transposed fragments);
+//   d_i / h_i tiles go to shared memory; warp w < NT owns rows 8w..8w+7 (out slots) of every hidden
+//   dW_i and of dW_0 ... all in registers for the whole persistent loop; the last warp owns dW_out.
+// DH = depth-1 (number of hidden->hidden layers), compile time so accumulators index statically.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int DH>
+struct BwdSmem {
+  static constexpr int NW = NT + 1;
+  static constexpr int ROWS = 8 * NW;
+  static constexpr int S = 8 * NT + 4;   // stride mod 16 in {4, 12}: conflict-free fragment reads
+  static constexpr int SN = 12;          // narrow tiles (inputs / zbar)
+  double D[ROWS * S];
+  double H[ROWS * S];
+  double Zb[ROWS * SN];
+  double In[ROWS * SN];
+};
+
+template <int NT, int DH>
+__global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
+  using SM = BwdSmem<NT, DH>;
+  constexpr int NW = SM::NW, ROWS = SM::ROWS, S = SM::S, SN = SM::SN;
+  constexpr int KSP = 2 * NT;
+  constexpr int KR = ROWS / 4;  // k-steps over rows in the weight-gradient contraction
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 2, c = lane & 3;
+  const double* __restrict__ pk = io.pk;
+  const int ones_slot = feat_to_slot(s.width);
+
+  // weight-gradient accumulators (accumulator layout: lane(r,c): [out slot 8*jr + r][in slot 8*jc+2c+x])
+  double gH[DH > 0 ? DH : 1][NT][2];  // warp < NT : hidden layers 1..DH, row tile jr = warp
+  double g0[2];                       // warp < NT : layer 0 (out slots 8*warp.., in cols 2c+x of [inputs,1])
+  // warp == NT owns the output layer (out r, in slot 8*jc+2c+x) and keeps it in gH[0] (it has no hidden block)
+#define gO gH[0]
+#pragma unroll
+  for (int l = 0; l < (DH > 0 ? DH : 1); l++)
+#pragma unroll
+    for (int j = 0; j < NT; j++) gH[l][j][0] = gH[l][j][1] = 0.0;
+  g0[0] = g0[1] = 0.0;
+
+  const long long ntiles = (io.n + ROWS - 1) / ROWS;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * ROWS + warp * 8 + r;   // this lane's row
+    const int lrow = warp * 8 + r;                      // local row in the CTA tile
+    const bool live = row < io.n;
+
+    // ---- top: zbar = g_u * bc_b  -> A fragment (k = out index c) and Zb tile
+    double zA = 0.0;
+    if (live && c < s.n_out) {
+      const long long k = row * s.n_out + c;
+      zA = io.g_u[k];
+      if (io.bc_b) zA *= io.bc_b[k];
+    }
+    sm.Zb[lrow * SN + c] = zA;
+    sm.Zb[lrow * SN + 4 + c] = 0.0;
+    // inputs tile [x_hat, t_hat, 1, 0...]
+    {
+      double v0 = mlp_input(s, io, row, c);
+      double v1 = (4 + c == s.n_in) ? 1.0 : 0.0;
+      if (c == s.n_in) v0 = 1.0;  // n_in < 4
+      if (!live) { v0 = 0.0; v1 = 0.0; }
+      sm.In[lrow * SN + c] = v0;
+      sm.In[lrow * SN + 4 + c] = v1;
+    }
+    // h_depth (act[depth-1]) in accumulator layout
+    double hC[NT][2], dC[NT][2];
+    auto load_h = [&](int layer) {
+#pragma unroll
+      for (int jn = 0; jn < NT; jn++) {
+        double2 v = make_double2(0.0, 0.0);
+        if (live) v = ld_cs_f64x2(io.act + (((long long)layer * NT + jn) * io.rows_cap + row) * 8 + 2 * c);
+        hC[jn][0] = v.x;
+        hC[jn][1] = v.y;
+      }
+    };
+    auto stage = [&](bool with_ones) {
+      // D <- dC, H <- hC (+ the column of ones that yields the bias gradient)
+#pragma unroll
+      for (int jn = 0; jn < NT; jn++) {
+        *reinterpret_cast<double2*>(&sm.D[lrow * S + 8 * jn + 2 * c]) = make_double2(dC[jn][0], dC[jn][1]);
+        double h0 = hC[jn][0], h1 = hC[jn][1];
+        if (with_ones && live) {
+          if (8 * jn + 2 * c == ones_slot) h0 = 1.0;
+          if (8 * jn + 2 * c + 1 == ones_slot) h1 = 1.0;
+        }
+        *reinterpret_cast<double2*>(&sm.H[lrow * S + 8 * jn + 2 * c]) = make_double2(h0, h1);
+      }
+    };
+
+    load_h(s.depth - 1);
+    // d_{depth-1} = (zbar W_out) * (1 - h^2)
+#pragma unroll
+    for (int jn = 0; jn < NT; jn++) {
+      double a0 = 0.0, a1 = 0.0;
+      dmma(a0, a1, zA, pk[s.pBO + jn * 32 + lane]);
+      dC[jn][0] = a0 * (1.0 - hC[jn][0] * hC[jn][0]);
+      dC[jn][1] = a1 * (1.0 - hC[jn][1] * hC[jn][1]);
+    }
+    // stage h_depth for the output-layer weight gradient (D not needed yet but harmless)
+    stage(true);
+    __syncthreads();
+    if (warp == NT) {
+      // dW_out[o][slot] += sum_rows zbar[row][o] * h_depth[row][slot]
+#pragma unroll 2
+      for (int ks = 0; ks < KR; ks++) {
+        const double a = sm.Zb[(4 * ks + c) * SN + r];
+#pragma unroll
+        for (int jc = 0; jc < NT; jc++) dmma(gO[jc][0], gO[jc][1], a, sm.H[(4 * ks + c) * S + 8 * jc + r]);
+      }
+    }
+    // ---- hidden layers i = depth-1 .. 1 : dW_i = d_i^T h_i ; d_{i-1} = (d_i W_i) * (1 - h_i^2)
+#pragma unroll
+    for (int L = DH; L >= 1; L--) {
+      // here dC = d_L (delta at the output of layer L), need h_L = act[L-1]
+      __syncthreads();       // everyone done reading the previous H / D tiles
+      load_h(L - 1);
+      stage(true);           // D = d_L, H = h_L
+      __syncthreads();
+      if (warp < NT) {
+#pragma unroll 2
+        for (int ks = 0; ks < KR; ks++) {
+          const double a = sm.D[(4 * ks + c) * S + 8 * warp + r];
+#pragma unroll
+          for (int jc = 0; jc < NT; jc++)
+            dmma(gH[L - 1][jc][0], gH[L - 1][jc][1], a, sm.H[(4 * ks + c) * S + 8 * jc + r]);
+        }
+      }
+      // delta chain
+      double dn[NT][2];
+#pragma unroll
+      for (int jn = 0; jn < NT; jn++) dn[jn][0] = dn[jn][1] = 0.0;
+      const double* bh = pk + s.pBH + (long long)(L - 1) * KSP * NT * 32;
+#pragma unroll
+      for (int ks = 0; ks < KSP; ks++) {
+        if (ks < s.KS) {
+#pragma unroll
+          for (int jn = 0; jn < NT; jn++) dmma(dn[jn][0], dn[jn][1], dC[ks >> 1][ks & 1], bh[(ks * NT + jn) * 32 + lane]);
+        }
+      }
+#pragma unroll
+      for (int jn = 0; jn < NT; jn++) {
+        dC[jn][0] = dn[jn][0] * (1.0 - hC[jn][0] * hC[jn][0]);
+        dC[jn][1] = dn[jn][1] * (1.0 - hC[jn][1] * hC[jn][1]);
+      }
+    }
+    // ---- layer 0: dW_0 = d_0^T [inputs, 1]
+    __syncthreads();
+#pragma unroll
+    for (int jn = 0; jn < NT; jn++)
+      *reinterpret_cast<double2*>(&sm.D[lrow * S + 8 * jn + 2 * c]) = make_double2(dC[jn][0], dC[jn][1]);
+    __syncthreads();
+    if (warp < NT) {
+#pragma unroll 2
+      for (int ks = 0; ks < KR; ks++)
+        dmma(g0[0], g0[1], sm.D[(4 * ks + c) * S + 8 * warp + r], sm.In[(4 * ks + c) * SN + r]);
+    }
+    __syncthreads();
+  }
+
+  // ---- write per-CTA partials (padded slot layout):
+  //   part[cta] = [ L0: NT*8 x 8 | hidden l: (8NT x 8NT) each | out: 8 x 8NT ]
+  double* P = io.part + (long long)blockIdx.x * io.part_stride;
+  constexpr int WPd = 8 * NT;
+  if (warp < NT) {
+    P[(8 * warp + r) * 8 + 2 * c] = g0[0];
+    P[(8 * warp + r) * 8 + 2 * c + 1] = g0[1];
+#pragma unroll
+    for (int l = 0; l < DH; l++) {
+      double* Pl = P + WPd * 8 + (long long)l * WPd * WPd;
+#pragma unroll
+      for (int jc = 0; jc < NT; jc++) {
+        Pl[(8 * warp + r) * WPd + 8 * jc + 2 * c] = gH[l][jc][0];
+        Pl[(8 * warp + r) * WPd + 8 * jc + 2 * c + 1] = gH[l][jc][1];
+      }
+    }
+  } else {
+    double* Po = P + WPd * 8 + (long long)DH * WPd * WPd;
+#pragma unroll
+    for (int jc = 0; jc < NT; jc++) {
+      Po[r * WPd + 8 * jc + 2 * c] = gO[jc][0];
+      Po[r * WPd + 8 * jc + 2 * c + 1] = gO[jc][1];
+    }
+  }
+#undef gO
+}
+
+// Fixed-order sum over CTAs + un-padding into the flat equinox-order gradient.
+// One thread per real parameter.
+__global__ void k_reduce_wgrad(MlpShape s, const double* __restrict__ part, long long part_stride, int nparts,
+                               double* __restrict__ g) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= s.nweights) return;
+  const int WPd = 8 * s.NT, W = s.width, D = s.depth;
+  // locate the layer
+  int layer = 0;
+  bool is_bias = false;
+  long long local = 0;
+  for (int i = 0; i <= D; i++) {
+    const int fin = (i == 0) ? s.n_in : W, fout = (i == D) ? s.n_out : W;
+    if (p >= s.offW[i] && p < s.offW[i] + (long long)fin * fout) { layer = i; is_bias = false; local = p - s.offW[i]; break; }
+    if (s.offB[i] >= 0 && p >= s.offB[i] && p < s.offB[i] + fout) { layer = i; is_bias = true; local = p - s.offB[i]; break; }
+  }
+  const int fin = (layer == 0) ? s.n_in : W;
+  const int o = is_bias ? (int)local : (int)(local / fin);
+  const int k = is_bias ? -1 : (int)(local % fin);
+  long long off;
+  if (layer == 0) {
+    off = (long long)feat_to_slot(o) * 8 + (is_bias ? s.n_in : k);
+  } else if (layer < D) {
+    off = (long long)WPd * 8 + (long long)(layer - 1) * WPd * WPd + (long long)feat_to_slot(o) * WPd +
+          feat_to_slot(is_bias ? W : k);
+  } else {
+    off = (long long)WPd * 8 + (long long)(D - 1) * WPd * WPd + (long long)o * WPd + feat_to_slot(is_bias ? W : k);
+  }
+  double acc = 0.0;
+  for (int q = 0; q < nparts; q++) acc += part[(long long)q * part_stride + off];
+  g[p] = acc;
+}
+
+}  // namespace pcx

@@ -1,0 +1,438 @@
+// pcx_models.cuh -- per-quadrature-point constitutive math (device code).
+//
+// What pancax obtains by tracing `model.energy` through jax.jacfwd / jax.grad
+// (pancax/constitutive_models/mechanics/base.py:112-118, physics_kernels/base.py:356-361) is written
+// here in closed form: W(F), P = dW/dF and dW/d(property).  Every function is a template on the
+// scalar type so the SAME source evaluated on dual numbers (value + one tangent) yields the
+// material-tangent action dP = (d^2W/dF^2):dF and d(P:dF)/d(property) needed by the residual losses.
+#pragma once
+#include <math.h>
+#include "../../include/pcx_abi.h"
+
+namespace pcx {
+
+// ------------------------------------------------------------------ dual numbers (forward mode)
+struct Dual {
+  double v, d;
+  __host__ __device__ Dual() {}
+  __host__ __device__ Dual(double v_) : v(v_), d(0.0) {}
+  __host__ __device__ Dual(double v_, double d_) : v(v_), d(d_) {}
+};
+__host__ __device__ inline Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+__host__ __device__ inline Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+__host__ __device__ inline Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+__host__ __device__ inline Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, fma(a.v, b.d, a.d * b.v)); }
+__host__ __device__ inline Dual operator/(Dual a, Dual b) {
+  double q = a.v / b.v;
+  return Dual(q, (a.d - q * b.d) / b.v);
+}
+__host__ __device__ inline Dual operator+(Dual a, double b) { return Dual(a.v + b, a.d); }
+__host__ __device__ inline Dual operator+(double a, Dual b) { return Dual(a + b.v, b.d); }
+__host__ __device__ inline Dual operator-(Dual a, double b) { return Dual(a.v - b, a.d); }
+__host__ __device__ inline Dual operator-(double a, Dual b) { return Dual(a - b.v, -b.d); }
+__host__ __device__ inline Dual operator*(Dual a, double b) { return Dual(a.v * b, a.d * b); }
+__host__ __device__ inline Dual operator*(double a, Dual b) { return Dual(a * b.v, a * b.d); }
+__host__ __device__ inline Dual operator/(Dual a, double b) { return Dual(a.v / b, a.d / b); }
+__host__ __device__ inline Dual operator/(double a, Dual b) {
+  double q = a / b.v;
+  return Dual(q, -q * b.d / b.v);
+}
+__host__ __device__ inline Dual& operator+=(Dual& a, Dual b) { a.v += b.v; a.d += b.d; return a; }
+
+__host__ __device__ inline double value_of(double x) { return x; }
+__host__ __device__ inline double value_of(Dual x) { return x.v; }
+__host__ __device__ inline double tangent_of(double) { return 0.0; }
+__host__ __device__ inline double tangent_of(Dual x) { return x.d; }
+
+__host__ __device__ inline double s_log(double x) { return log(x); }
+__host__ __device__ inline Dual s_log(Dual x) { return Dual(log(x.v), x.d / x.v); }
+// x^p for a real exponent p (x > 0)
+__host__ __device__ inline double s_pow(double x, double p) { return pow(x, p); }
+__host__ __device__ inline Dual s_pow(Dual x, double p) {
+  double r = pow(x.v, p);
+  return Dual(r, p * r / x.v * x.d);
+}
+
+// ------------------------------------------------------------------ 3x3 helpers (row-major F[3*i+j])
+template <class T>
+__host__ __device__ inline void cofactor3(const T* F, T* C) {
+  C[0] = F[4] * F[8] - F[5] * F[7];
+  C[1] = F[5] * F[6] - F[3] * F[8];
+  C[2] = F[3] * F[7] - F[4] * F[6];
+  C[3] = F[2] * F[7] - F[1] * F[8];
+  C[4] = F[0] * F[8] - F[2] * F[6];
+  C[5] = F[1] * F[6] - F[0] * F[7];
+  C[6] = F[1] * F[5] - F[2] * F[4];
+  C[7] = F[2] * F[3] - F[0] * F[5];
+  C[8] = F[0] * F[4] - F[1] * F[3];
+}
+
+struct Props {
+  double p[PCX_MAX_PROPS];
+};
+
+// Volumetric part shared by NeoHookean and Gent: W_vol = 0.5 K (0.5 (J^2 - 1) - ln J)
+// (neohookean.py:31, gent.py:37).
+
+// ------------------------------------------------------------------ NeoHookean (neohookean.py:20-34)
+//   W = 0.5 K (0.5 (J^2-1) - ln J) + 0.5 G (I1bar - 3),  I1bar = J^(-2/3) tr(F F^T)
+//   P = [0.5 K (J - 1/J) - (G/3) I1bar / J] cof F + G J^(-2/3) F
+template <class T>
+__device__ inline void neohookean(const T* F, const Props& pr, T& W, T* P, T* dWdp, bool want_dp) {
+  const double K = pr.p[0], G = pr.p[1];
+  T cof[9];
+  cofactor3(F, cof);
+  T J = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
+  T I1 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2] + F[3] * F[3] + F[4] * F[4] + F[5] * F[5] +
+         F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+  T Jm23 = s_pow(J, -2.0 / 3.0);
+  T I1bar = Jm23 * I1;
+  T wK = 0.5 * (0.5 * (J * J - 1.0) - s_log(J));
+  T wG = 0.5 * (I1bar - 3.0);
+  W = K * wK + G * wG;
+  T a = 0.5 * K * (J - 1.0 / J) - (G / 3.0) * I1bar / J;
+  T b = G * Jm23;
+#pragma unroll
+  for (int i = 0; i < 9; i++) P[i] = a * cof[i] + b * F[i];
+  if (want_dp) {
+    dWdp[0] = wK;
+    dWdp[1] = wG;
+  }
+}
+
+// ------------------------------------------------------------------ Gent (gent.py:22-39)
+//   W_dev = -0.5 G Jm ln(1 - (I1bar-3)/Jm); I1bar is replaced by the constant Jm+3-0.001 when it
+//   exceeds it (lax.cond, gent.py:30-34): zero F-gradient in that branch, Jm-gradient kept.
+template <class T>
+__device__ inline void gent(const T* F, const Props& pr, T& W, T* P, T* dWdp, bool want_dp) {
+  const double K = pr.p[0], G = pr.p[1], Jm = pr.p[2];
+  T cof[9];
+  cofactor3(F, cof);
+  T J = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
+  T I1 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2] + F[3] * F[3] + F[4] * F[4] + F[5] * F[5] +
+         F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+  T Jm23 = s_pow(J, -2.0 / 3.0);
+  T I1bar = Jm23 * I1;
+  const bool clamped = value_of(I1bar) > Jm + 3.0 - 0.001;
+  T wK = 0.5 * (0.5 * (J * J - 1.0) - s_log(J));
+  T a = 0.5 * K * (J - 1.0 / J);
+  T Wdev, c1;
+  T dWdJm;
+  if (!clamped) {
+    T x = (I1bar - 3.0) / Jm;
+    T lg = s_log(1.0 - x);
+    Wdev = -0.5 * G * Jm * lg;
+    c1 = 0.5 * G / (1.0 - x);
+    dWdJm = -0.5 * G * (lg + x / (1.0 - x));
+  } else {
+    const double I1c = Jm + 3.0 - 0.001;
+    const double x = (I1c - 3.0) / Jm;
+    const double lg = log(1.0 - x);
+    Wdev = T(-0.5 * G * Jm * lg);
+    c1 = T(0.0);
+    // d/dJm of -0.5 G Jm ln(0.001/Jm) = -0.5 G (ln(0.001/Jm) - 1)
+    dWdJm = T(-0.5 * G * (lg - 1.0));
+  }
+  W = K * wK + Wdev;
+  T ca = a - c1 * (2.0 / 3.0) * I1bar / J;
+  T cb = 2.0 * c1 * Jm23;
+#pragma unroll
+  for (int i = 0; i < 9; i++) P[i] = ca * cof[i] + cb * F[i];
+  if (want_dp) {
+    dWdp[0] = wK;
+    dWdp[1] = Wdev / G;
+    dWdp[2] = dWdJm;
+  }
+}
+
+// ------------------------------------------------------------------ Swanson (swanson.py:28-65)
+//   props: K, A1, P1, B1, Q1, C1, R1, cutoff_strain
+template <class T>
+__device__ inline T swanson_term_dexp(T t, double tc, double A, double Pw) {
+  // d/dPw of A/(Pw+1) (t^(Pw+1) - tc^(Pw+1))
+  T tp = s_pow(t, Pw + 1.0);
+  double cp = pow(tc, Pw + 1.0);
+  double inv = 1.0 / (Pw + 1.0);
+  return A * ((tp * (s_log(t) * inv - inv * inv)) - cp * (log(tc) * inv - inv * inv));
+}
+
+template <class T>
+__device__ inline void swanson(const T* F, const Props& pr, T& W, T* P, T* dWdp, bool want_dp) {
+  const double K = pr.p[0], A1 = pr.p[1], P1 = pr.p[2], B1 = pr.p[3], Q1 = pr.p[4], C1 = pr.p[5],
+               R1 = pr.p[6], cs = pr.p[7];
+  const double tc = (1.0 / 3.0) * (3.0 + cs * cs) - 1.0;
+  T cof[9];
+  cofactor3(F, cof);
+  T J = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
+  // C = F^T F
+  T C[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
+  T I1 = C[0] + C[4] + C[8];
+  T trC2 = C[0] * C[0] + C[4] * C[4] + C[8] * C[8] + 2.0 * (C[1] * C[1] + C[2] * C[2] + C[5] * C[5]);
+  T I2 = 0.5 * (I1 * I1 - trC2);
+  T Jm23 = s_pow(J, -2.0 / 3.0);
+  T Jm43 = Jm23 * Jm23;
+  T I1bar = Jm23 * I1;
+  T I2bar = Jm43 * I2;
+  T t1 = (1.0 / 3.0) * I1bar - 1.0 + tc;
+  T t2 = (1.0 / 3.0) * I2bar - 1.0 + tc;
+  T lJ = s_log(J);
+  T wK = J * lJ - J + 1.0;
+  T t1P = s_pow(t1, P1), t1R = s_pow(t1, R1), t2Q = s_pow(t2, Q1);
+  T wA = 1.5 / (P1 + 1.0) * (t1P * t1 - pow(tc, P1 + 1.0));
+  T wB = 1.5 / (Q1 + 1.0) * (t2Q * t2 - pow(tc, Q1 + 1.0));
+  T wC = 1.5 / (R1 + 1.0) * (t1R * t1 - pow(tc, R1 + 1.0));
+  W = K * wK + A1 * wA + B1 * wB + C1 * wC;
+  T dJ = K * lJ;
+  T d1 = 0.5 * (A1 * t1P + C1 * t1R);
+  T d2 = 0.5 * B1 * t2Q;
+  // P = dJ cof + d1 (2 Jm23 F - (2/3) I1bar/J cof) + d2 (Jm43 (2 I1 F - 2 F C) - (4/3) I2bar/J cof)
+  T ccof = dJ - d1 * (2.0 / 3.0) * I1bar / J - d2 * (4.0 / 3.0) * I2bar / J;
+  T cF = 2.0 * d1 * Jm23 + 2.0 * d2 * Jm43 * I1;
+  T cFC = -2.0 * d2 * Jm43;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      T FC = F[3 * i] * C[j] + F[3 * i + 1] * C[3 + j] + F[3 * i + 2] * C[6 + j];
+      P[3 * i + j] = ccof * cof[3 * i + j] + cF * F[3 * i + j] + cFC * FC;
+    }
+  if (want_dp) {
+    dWdp[0] = wK;
+    dWdp[1] = wA;
+    dWdp[2] = 1.5 * swanson_term_dexp(t1, tc, A1, P1);
+    dWdp[3] = wB;
+    dWdp[4] = 1.5 * swanson_term_dexp(t2, tc, B1, Q1);
+    dWdp[5] = wC;
+    dWdp[6] = 1.5 * swanson_term_dexp(t1, tc, C1, R1);
+    dWdp[7] = T(0.0);
+  }
+}
+
+// ------------------------------------------------------------------ Hencky (hencky.py:10-18)
+// Closed-form eigen decomposition of a symmetric 3x3 tensor, following the algorithm of
+// pancax/math/tensor_math.py:76-295 step by step (trace shift, trigonometric root with a Pade
+// approximant of cos(acos(x)/3), pivoted QR for the first eigenvector, 2x2 Wilkinson step,
+// degenerate-case fallbacks, ascending sort) so that degenerate inputs (C = I at t = 0) take the
+// same branches as the reference.
+__device__ inline double cos_acos_third(double x) {  // tensor_math.py:307-334
+  double x2 = x * x, x4 = x2 * x2;
+  double numer = 0.866025403784438713 + 2.12714890259493060 * x +
+                 ((1.89202064815951569 + 0.739603278343401613 * x) * x2 +
+                  (0.121973926953064794 + x * (0.00655637626263929360 + 0.0000390884982780803443 * x)) * x4);
+  double denom = 1.0 + 2.26376989330935617 * x +
+                 ((1.80461009751278976 + 0.603976798217196003 * x) * x2 +
+                  (0.0783255761115461708 + 0.00268525944538021629 * x) * x4);
+  return numer / denom;
+}
+__device__ inline double sgn(double x) { return (x > 0.0) - (x < 0.0); }
+
+// A: symmetric 3x3 (row-major). lam[3] ascending, V column k = eigenvector k (V[3*i+k]), NOT normalised.
+__device__ inline void eigen_sym33_non_unit(const double* A, double* lam, double* V) {
+  double cxx = A[0], cyy = A[4], czz = A[8];
+  const double cxy = 0.5 * (A[1] + A[3]), cyz = 0.5 * (A[5] + A[7]), czx = 0.5 * (A[6] + A[2]);
+  const double c1 = (cxx + cyy + czz) / 3.0;
+  cxx -= c1; cyy -= c1; czz -= c1;
+  const double cxy2 = cxy * cxy, cyz2 = cyz * cyz, czx2 = czx * czx, cxxcyy = cxx * cyy;
+  const double c2 = cxxcyy + cyy * czz + czz * cxx - cxy2 - cyz2 - czx2;
+  const bool neg = c2 < 0.0;
+  const double threeOverA = neg ? -3.0 / c2 : 1.0;
+  const double sq = neg ? sqrt(threeOverA) : 1.0;
+  const double c3 = cxx * cyz2 + cyy * czx2 - 2.0 * cxy * cyz * czx + czz * (cxy2 - cxxcyy);
+  const double rr = -0.5 * c3 * threeOverA * sq;
+  const double arg = fmin(fabs(rr), 1.0);
+  double eval2 = neg ? (2.0 * cos_acos_third(arg) * sgn(rr)) / sq : 1.0;
+
+  double r0[3] = {cxx - eval2, cxy, czx};
+  double r1[3] = {cxy, cyy - eval2, cyz};
+  double r2[3] = {czx, cyz, czz - eval2};
+  const double k0 = r0[0] * r0[0] + cxy2 + czx2;
+  const double k1 = cxy2 + r1[1] * r1[1] + cyz2;
+  const double k2 = czx2 + cyz2 + r2[2] * r2[2];
+  const bool k0gk1 = k1 <= k0, k0gk2 = k2 <= k0, k1gk2 = k2 <= k1;
+  const bool k0L = k0gk1 && k0gk2;
+  const bool k1L = k1gk2 && !k0gk1;
+  const bool k2L = !(k0L || k1L);
+  double kr[3], row2[3], row3[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    kr[i] = (k0L ? r0[i] : 0.0) + (k1L ? r1[i] : 0.0) + (k2L ? r2[i] : 0.0);
+    row2[i] = k0L ? r1[i] : r0[i];
+    row3[i] = k2L ? r1[i] : r2[i];
+  }
+  const double kiki = 1.0 / ((k0L ? k0 : 0.0) + (k1L ? k1 : 0.0) + (k2L ? k2 : 0.0));
+  const double d1 = kiki * (kr[0] * row2[0] + kr[1] * row2[1] + kr[2] * row2[2]);
+  const double d2 = kiki * (kr[0] * row3[0] + kr[1] * row3[1] + kr[2] * row3[2]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    row2[i] -= d1 * kr[i];
+    row3[i] -= d2 * kr[i];
+  }
+  const double a0 = row2[0] * row2[0] + row2[1] * row2[1] + row2[2] * row2[2];
+  const double a1 = row3[0] * row3[0] + row3[1] * row3[1] + row3[2] * row3[2];
+  const bool a0le = a0 <= a1;
+  double ar[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) ar[i] = a0le ? row3[i] : row2[i];
+  const double aiai = 1.0 / (a0le ? a1 : a0);
+
+  double e2[3] = {kr[1] * ar[2] - kr[2] * ar[1], kr[2] * ar[0] - kr[0] * ar[2], kr[0] * ar[1] - kr[1] * ar[0]};
+
+  const double k11 = cxx * kr[0] + cxy * kr[1] + czx * kr[2];
+  const double k21 = cxy * kr[0] + cyy * kr[1] + cyz * kr[2];
+  const double k31 = czx * kr[0] + cyz * kr[1] + czz * kr[2];
+  const double a12 = cxx * ar[0] + cxy * ar[1] + czx * ar[2];
+  const double a22 = cxy * ar[0] + cyy * ar[1] + cyz * ar[2];
+  const double a32 = czx * ar[0] + cyz * ar[1] + czz * ar[2];
+  double rxx = (kr[0] * k11 + kr[1] * k21 + kr[2] * k31) * kiki;
+  const double kaxy = kr[0] * a12 + kr[1] * a22 + kr[2] * a32;
+  double ryy = (ar[0] * a12 + ar[1] * a22 + ar[2] * a32) * aiai;
+  const double rxy2 = kaxy * kaxy * aiai * kiki;
+
+  const double b = 0.5 * (rxx - ryy);
+  const double sqrtTerm = sqrt(b * b + rxy2) * sgn(b);
+  double eval0 = ryy + b - sqrtTerm;
+  double eval1 = rxx + ryy - eval0;
+  rxx -= eval0;
+  ryy -= eval0;
+  const double rxx2 = rxx * rxx, ryy2 = ryy * ryy;
+  const bool lt = rxx2 < ryy2;
+  const double fac1 = lt ? kaxy * aiai : rxx;
+  const double fac2 = lt ? ryy : kiki * kaxy;
+  double e0[3];
+  const bool both_zero = (rxx2 == 0.0) && (rxy2 == 0.0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) e0[i] = both_zero ? ar[i] : fac1 * ar[i] - fac2 * kr[i];
+  double e1[3] = {e2[1] * e0[2] - e2[2] * e0[1], e2[2] * e0[0] - e2[0] * e0[2], e2[0] * e0[1] - e2[1] * e0[0]};
+
+  eval0 += c1; eval1 += c1; eval2 += c1;
+  const bool ok = c2 < (c1 * c1) * (-1.0e-30);
+  if (!ok) {
+    eval0 = eval1 = eval2 = c1;
+    e0[0] = 1.0; e0[1] = 0.0; e0[2] = 0.0;
+    e1[0] = 0.0; e1[1] = 1.0; e1[2] = 0.0;
+    e2[0] = 0.0; e2[1] = 0.0; e2[2] = 1.0;
+  }
+  // stable ascending sort of (eval0, eval1, eval2) carrying the vectors (argsort, tensor_math.py:276)
+  double ev[3] = {eval0, eval1, eval2};
+  double* vec[3] = {e0, e1, e2};
+  int idx[3] = {0, 1, 2};
+  // insertion sort (stable)
+  if (ev[idx[1]] < ev[idx[0]]) { int t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
+  if (ev[idx[2]] < ev[idx[1]]) {
+    int t = idx[1]; idx[1] = idx[2]; idx[2] = t;
+    if (ev[idx[1]] < ev[idx[0]]) { t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    lam[k] = ev[idx[k]];
+    const double* s = vec[idx[k]];
+    V[k] = s[0]; V[3 + k] = s[1]; V[6 + k] = s[2];
+  }
+}
+
+__device__ inline void eigen_sym33_unit(const double* A, double* lam, double* V) {  // tensor_math.py:281-295
+  double cmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) cmax = fmax(cmax, fabs(A[3 * i]) + fabs(A[3 * i + 1]) + fabs(A[3 * i + 2]));
+  const double inv = cmax > 0.0 ? 1.0 / cmax : 1.0;
+  double S[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) S[i] = inv * A[i];
+  eigen_sym33_non_unit(S, lam, V);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double n = sqrt(V[k] * V[k] + V[3 + k] * V[3 + k] + V[6 + k] * V[6 + k]);
+    V[k] /= n; V[3 + k] /= n; V[6 + k] /= n;
+    lam[k] *= cmax;
+  }
+}
+
+__device__ inline double relative_log_difference(double l1, double l2) {  // tensor_math.py:517-551
+  const bool large = fabs(l1 - l2) > 0.05 * fmin(l1, l2);
+  if (large) return log(l1 / l2) / (l1 - l2);
+  const double frac = (l1 - l2) / (l1 + l2);
+  const double f2 = frac * frac, f4 = f2 * f2;
+  return (2.0 + (2.0 / 3.0) * f2 + (2.0 / 5.0) * f4 + (2.0 / 7.0) * f4 * f2 + (2.0 / 9.0) * f4 * f4) / (l1 + l2);
+}
+
+// W = 0.5 K tr(E)^2 + G E:E with E = 0.5 log(F^T F) (mtk_log_sqrt, tensor_math.py:337-340).
+// P = 2 F S, S = L(Ebar), Ebar = K tr(E) I + 2 G E, L = the (self-adjoint) derivative rule of
+// mtk_log_sqrt (tensor_math.py:343-424).  Value path only: the second derivative of the custom rule
+// is refused upstream (PCX_ERR_UNSUPPORTED) for residual losses.
+__device__ inline void hencky(const double* F, const Props& pr, double& W, double* P, double* dWdp, bool want_dp) {
+  const double K = pr.p[0], G = pr.p[1];
+  double C[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
+  double lam[3], V[9];
+  eigen_sym33_unit(C, lam, V);
+  double e[3] = {0.5 * log(lam[0]), 0.5 * log(lam[1]), 0.5 * log(lam[2])};
+  double E[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      E[3 * i + j] = V[3 * i] * e[0] * V[3 * j] + V[3 * i + 1] * e[1] * V[3 * j + 1] + V[3 * i + 2] * e[2] * V[3 * j + 2];
+  const double trE = E[0] + E[4] + E[8];
+  double EE = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) EE += E[i] * E[i];
+  W = 0.5 * K * trE * trE + G * EE;
+  // Ebar and its image under L
+  double Eb[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Eb[i] = 2.0 * G * E[i];
+  Eb[0] += K * trE; Eb[4] += K * trE; Eb[8] += K * trE;
+  double T1[9], hh[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) T1[3 * i + k] = Eb[3 * i] * V[k] + Eb[3 * i + 1] * V[3 + k] + Eb[3 * i + 2] * V[6 + k];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) hh[3 * a + k] = 0.5 * (V[a] * T1[k] + V[3 + a] * T1[3 + k] + V[6 + a] * T1[6 + k]);
+  double L[9];
+  L[0] = hh[0] / lam[0]; L[4] = hh[4] / lam[1]; L[8] = hh[8] / lam[2];
+  L[1] = L[3] = 0.5 * (hh[1] + hh[3]) * relative_log_difference(lam[0], lam[1]);
+  L[5] = L[7] = 0.5 * (hh[5] + hh[7]) * relative_log_difference(lam[1], lam[2]);
+  L[2] = L[6] = 0.5 * (hh[6] + hh[2]) * relative_log_difference(lam[2], lam[0]);
+  double T2[9], S[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) T2[3 * i + k] = V[3 * i] * L[k] + V[3 * i + 1] * L[3 + k] + V[3 * i + 2] * L[6 + k];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) S[3 * i + j] = T2[3 * i] * V[3 * j] + T2[3 * i + 1] * V[3 * j + 1] + T2[3 * i + 2] * V[3 * j + 2];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) P[3 * i + j] = 2.0 * (F[3 * i] * S[j] + F[3 * i + 1] * S[3 + j] + F[3 * i + 2] * S[6 + j]);
+  if (want_dp) {
+    dWdp[0] = 0.5 * trE * trE;
+    dWdp[1] = EE;
+  }
+}
+__device__ inline void hencky(const Dual*, const Props&, Dual& W, Dual* P, Dual*, bool) {
+  // never instantiated at run time (refused on the host); keeps templates compiling
+  W = Dual(0.0);
+  for (int i = 0; i < 9; i++) P[i] = Dual(0.0);
+}
+
+template <int MODEL, class T>
+__device__ inline void model_eval(const T* F, const Props& pr, T& W, T* P, T* dWdp, bool want_dp) {
+  if constexpr (MODEL == PCX_MODEL_NEOHOOKEAN) neohookean(F, pr, W, P, dWdp, want_dp);
+  else if constexpr (MODEL == PCX_MODEL_GENT) gent(F, pr, W, P, dWdp, want_dp);
+  else if constexpr (MODEL == PCX_MODEL_SWANSON) swanson(F, pr, W, P, dWdp, want_dp);
+  else hencky(F, pr, W, P, dWdp, want_dp);
+}
+
+}  // namespace pcx

@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs.  Tolerance: 1e-10 relative in fp64 (BASELINE.json north_star); indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import (make_case, make_engine, oracle_problem, run_engine_loss, run_oracle_loss)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    d = np.linalg.norm((a - b).ravel())
+    n = np.linalg.norm(b.ravel())
+    return d / n if n > 0 else d
+
+
+@pytest.mark.parametrize("elem,n,q", [("hex8", 5, 2), ("hex8", 4, 1), ("quad4", 9, 2), ("quad4", 6, 3),
+                                      ("quad4", 7, 1), ("tri3", 8, 2), ("tri3", 8, 1)])
+def test_element_geometry(cuda_device, elem, n, q):
+    from oracle import fem as ofem
+    from oracle.physics import element_geometry
+    from pancax_b200 import Engine
+    mesh = ofem.structured_mesh(elem, n, permute_seed=3)
+    rng = np.random.default_rng(0)
+    mesh["coords"] = mesh["coords"] + 0.02 * rng.standard_normal(mesh["coords"].shape)  # distort
+    eng = Engine(mesh["coords"], mesh["conns"], elem, q, 1, np.array([0.0, 1.0]))
+    gN, JxW, xq = eng.element_geometry()
+    pe = ofem.ParentElement(elem, q)
+    X = torch.as_tensor(mesh["coords"])[torch.as_tensor(mesh["conns"], dtype=torch.long)]
+    gN_o, JxW_o, _ = element_geometry(pe, X)
+    xq_o = torch.einsum("qa,eaj->eqj", torch.as_tensor(pe.N), X)
+    assert rel(gN.cpu().numpy(), gN_o.numpy()) < 1e-13
+    assert rel(JxW.cpu().numpy(), JxW_o.numpy()) < 1e-13
+    assert rel(xq.cpu().numpy(), xq_o.numpy()) < 1e-14
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["hex8_neohookean", "quad4_neohookean", "poisson_quad4", "tri3_gent"])
+def test_field_forward_backward(cuda_device, name):
+    from oracle import losses as ol
+    case = make_case(name, n=5, nt=3)
+    eng = make_engine(case)
+    prob = oracle_problem(case)
+    rng = np.random.default_rng(1)
+    for t_idx in (0, 2):
+        us = eng.field_forward(case.weights, t_idx).cpu().numpy()
+        us_o = ol.field_values(prob, case.weights, case.times[t_idx])
+        assert rel(us, us_o) < 1e-13, (name, t_idx)
+        # VJP against torch autograd
+        g = rng.standard_normal(us.shape)
+        gw = eng.field_backward(case.weights, t_idx, g).cpu().numpy()
+        w = torch.as_tensor(case.weights).clone().requires_grad_(True)
+        pr = torch.as_tensor(case.prop_raw)
+        fld, _, _ = ol._build(prob, w, pr)
+        u = fld(torch.as_tensor(case.mesh["coords"]), float(case.times[t_idx]))
+        (gw_o,) = torch.autograd.grad((u * torch.as_tensor(g)).sum(), w)
+        assert rel(gw, gw_o.numpy()) < 1e-12, (name, t_idx)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "hex8_hencky",
+                                  "quad4_neohookean", "quad4_gent", "quad4_swanson", "quad4_hencky",
+                                  "tri3_neohookean", "poisson_quad4", "poisson_tri3", "poisson_hex8"])
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_energy_force(cuda_device, name, deterministic):
+    from oracle import losses as ol
+    case = make_case(name, n=4, nt=2)
+    eng = make_engine(case, deterministic=deterministic)
+    prob = oracle_problem(case)
+    us = ol.field_values(prob, case.weights, 1.0)
+    Pi, f, _ = eng.energy_force(us, case.prop_raw if eng.n_train else None)
+    Pi_o, f_o = ol.energy_and_force(prob, us)
+    assert abs(float(Pi.cpu()[0]) - Pi_o) <= TOL * abs(Pi_o), name
+    assert rel(f.cpu().numpy(), f_o) < TOL, name
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "quad4_neohookean",
+                                  "quad4_gent", "quad4_swanson", "tri3_neohookean", "poisson_quad4"])
+def test_stiffness_action(cuda_device, name):
+    from oracle import losses as ol
+    case = make_case(name, n=4, nt=2)
+    eng = make_engine(case)
+    prob = oracle_problem(case)
+    us = ol.field_values(prob, case.weights, 1.0)
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal(us.shape)
+    Kv, _ = eng.stiffness_action(us, v)
+    Kv_o = ol.stiffness_action(prob, us, v)
+    assert rel(Kv.cpu().numpy(), Kv_o) < TOL, name
+    # symmetry of K: <w, K v> == <v, K w>
+    w2 = rng.standard_normal(us.shape)
+    Kw, _ = eng.stiffness_action(us, w2)
+    a = float((torch.as_tensor(w2) * Kv.cpu()).sum())
+    b = float((torch.as_tensor(v) * Kw.cpu()).sum())
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    eng.close()
+
+
+def test_hencky_tangent_refused(cuda_device):
+    from pancax_b200._lib import PcxError
+    case = make_case("hex8_hencky", n=3)
+    eng = make_engine(case)
+    us = np.zeros((eng.nn, 3))
+    with pytest.raises(PcxError):
+        eng.stiffness_action(us, us)
+    with pytest.raises(PcxError):
+        eng.loss_and_grad("energy_residual", case.weights)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "hex8_hencky",
+                                  "quad4_neohookean", "tri3_neohookean", "poisson_quad4"])
+def test_energy_loss_and_grad(cuda_device, name):
+    case = make_case(name, n=5, nt=3)
+    L, aux, gw, gp = run_engine_loss(case, "energy")
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy")
+    assert abs(L - Lo) <= TOL * abs(Lo), name
+    assert abs(aux[0] - auxo["energy"]) <= TOL * abs(auxo["energy"])
+    assert aux[3] == 0.0
+    assert rel(gw, gwo) < TOL, name
+
+
+@pytest.mark.parametrize("name", ["quad4_neohookean", "quad4_gent", "quad4_swanson", "hex8_neohookean",
+                                  "tri3_neohookean_bounded", "quad4_gent_bounded"])
+@pytest.mark.parametrize("kind", ["energy_residual", "energy_residual_reaction"])
+def test_residual_losses(cuda_device, name, kind):
+    case = make_case(name, n=5, nt=3)
+    case.times = np.linspace(0.25, 1.0, 3)   # F9: parity on steps with ||f|| > 0
+    L, aux, gw, gp = run_engine_loss(case, kind)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, kind)
+    assert abs(L - Lo) <= TOL * abs(Lo), (name, kind)
+    assert abs(aux[1] - auxo["residual"]) <= TOL * abs(auxo["residual"])
+    if kind == "energy_residual_reaction":
+        assert rel(aux[4:], auxo["reactions"]) < TOL
+        assert abs(aux[2] - auxo["global_data_loss"]) <= TOL * abs(auxo["global_data_loss"])
+    assert rel(gw, gwo) < TOL, (name, kind)
+    if gpo.size:
+        assert rel(gp, gpo) < TOL, (name, kind)
+
+
+def test_residual_loss_at_t0_is_finite(cuda_device):
+    """F9: at t = 0 the ramped wrapper gives u == 0, f == 0 exactly; the gradient must stay finite
+    (convention d||f||/df := 0) and agree with the oracle using the same convention."""
+    case = make_case("quad4_neohookean", n=5, nt=3)
+    L, aux, gw, gp = run_engine_loss(case, "energy_residual_reaction")
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy_residual_reaction")
+    assert np.all(np.isfinite(gw)) and np.isfinite(L)
+    assert abs(aux[4]) < 1e-12
+    assert abs(L - Lo) <= TOL * abs(Lo)
+    assert rel(gw, gwo) < TOL
+
+
+def test_time_chunking_matches(cuda_device, monkeypatch):
+    case = make_case("quad4_neohookean", n=5, nt=5)
+    case.times = np.linspace(0.2, 1.0, 5)
+    ref = run_engine_loss(case, "energy_residual_reaction")
+    monkeypatch.setenv("PCX_TCHUNK", "2")
+    out = run_engine_loss(case, "energy_residual_reaction")
+    assert abs(ref[0] - out[0]) <= 1e-13 * abs(ref[0])
+    assert rel(out[2], ref[2]) < 1e-12
+
+
+def test_full_field_data_loss(cuda_device):
+    from oracle import losses as ol
+    case = make_case("tri3_neohookean", n=6, nt=4)
+    eng = make_engine(case)
+    prob = oracle_problem(case)
+    rng = np.random.default_rng(5)
+    nb = 1024
+    pts = np.column_stack([rng.uniform(0, 1, (nb, 2)), rng.uniform(0, 1, nb)])
+    outs = 0.1 * rng.standard_normal((nb, 2))
+    from pancax_b200 import bvps
+    bc = bvps.UniaxialTensionLinearRamp(case.bc[1], case.bc[2], case.bc[3], 2)
+    a = np.empty((nb, 2)); b = np.empty((nb, 2))
+    for i in range(nb):   # per-row time
+        a[i] = bc(pts[i:i + 1, :2], pts[i, 2], np.zeros((1, 2)))[0]
+        b[i] = bc(pts[i:i + 1, :2], pts[i, 2], np.ones((1, 2)))[0] - a[i]
+    loss, gw = eng.field_data_loss_and_grad(case.weights, pts, outs, a, b, weight=10.0)
+    Lo, gwo = ol.full_field_data_loss_and_grad(prob, case.weights, pts, outs, weight=10.0)
+    assert abs(float(loss.cpu()[0]) - Lo) <= TOL * abs(Lo)
+    assert rel(gw.cpu().numpy(), gwo) < TOL
+    eng.close()
+
+
+def test_deterministic_bitwise_repeat(cuda_device):
+    case = make_case("hex8_neohookean", n=6, nt=2)
+    eng = make_engine(case, deterministic=True)
+    r1 = run_engine_loss(case, "energy", eng=eng)
+    r2 = run_engine_loss(case, "energy", eng=eng)
+    assert r1[0] == r2[0]
+    assert np.array_equal(r1[2], r2[2])
+    eng.close()
+
+
+@pytest.mark.parametrize("width,depth", [(10, 2), (20, 1), (30, 3), (50, 3), (50, 5), (55, 2), (60, 2)])
+def test_mlp_shapes(cuda_device, width, depth):
+    case = make_case("quad4_neohookean", n=4, nt=2, width=width, depth=depth)
+    L, aux, gw, gp = run_engine_loss(case, "energy")
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy")
+    assert abs(L - Lo) <= TOL * abs(Lo)
+    assert rel(gw, gwo) < TOL
