@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- quadrature-point loss+gradient evaluations per second (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one rank per GPU)
+  python bench.py --impl reference --gpus N ...             the CPU restatement of pancax's path
+
+A "step" is one evaluation of loss and d(loss)/d(theta) over every quadrature point and time step of
+the workload (what pancax's eqx.filter_value_and_grad(loss.filtered_loss) computes inside
+opt.step, pancax/optimizers.py:77-88).  One eval = one quadrature point at one time step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MLP_IN, MLP_OUT, WIDTH, DEPTH = 4, 3, 50, 4
+K_BULK, G_SHEAR = 1000.0, 1.0
+
+
+def algorithmic_flops_per_row_bwd():
+    # MLP backward (no input gradient for layer 0) = 4 P_w - 2 in0 width
+    pw = MLP_IN * WIDTH + (DEPTH - 1) * WIDTH * WIDTH + WIDTH * MLP_OUT
+    return 4 * pw - 2 * MLP_IN * WIDTH
+
+
+def algorithmic_flops_per_row_fwd():
+    pw = MLP_IN * WIDTH + (DEPTH - 1) * WIDTH * WIDTH + WIDTH * MLP_OUT
+    return 2 * pw
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(n, nt, rank, world, device):
+    """Unit-cube slab [0,1]^2 x [rank, rank+1] of n^3 Hex8 elements per rank (weak scaling: the bar
+    grows along z with the GPU count), 3D NeoHookean, uniaxial-tension Dirichlet wrapper."""
+    import pancax_b200 as px
+    from pancax_b200 import parallel
+    mesh = px.create_structured_mesh("hex8", (n, n, n), lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, float(rank)))
+    times = np.linspace(0.0, 1.0, nt)
+    domain = px.VariationalDomain(mesh, times, q_order=2)
+    physics = px.SolidMechanics(px.NeoHookean(bulk_modulus=K_BULK, shear_modulus=G_SHEAR), px.ThreeDimensional())
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)]
+    problem = px.ForwardProblem(domain, physics, dirichlet_bcs=bcs)
+    params = px.Parameters(problem, key=0, n_layers=DEPTH, n_neurons=WIDTH, device=device,
+                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 3))
+    lo, hi = parallel.global_bounds(mesh.coords)
+    params.fields.x_mins, params.fields.x_maxs = lo, hi
+    return problem, params
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import pancax_b200 as px
+    from pancax_b200 import parallel
+    from pancax_b200.loss_functions import get_engine
+    rank, world, local_rank = parallel.init_distributed()
+    if world != args.gpus:
+        if rank == 0:
+            print(f"[bench] note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
+    device = torch.device("cuda", local_rank)
+    n, nt = args.n, args.nt
+    problem, params = build_problem(n, nt, rank, world, device)
+    loss_fn = px.EnergyLoss()
+    eng = get_engine(problem, params)
+    evals_per_rank = eng.ne * eng.nq * nt
+    w = params.fields.networks.weights
+    res = parallel.PackedResult(4 + nt, eng.n_weights, eng.n_train, device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        eng.loss_and_grad("energy", w, out=res.as_out())
+        res.allreduce()
+
+    # ---------------- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count
+    eng.profile_enable(True)
+    eng.profile_collect()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = eng.profile_collect()
+    eng.profile_enable(False)
+    launches = eng.launch_count - launches0
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.cpu()[0])
+    value = evals_per_rank * world * args.steps / (ms * 1e-3)
+
+    # ---------------- end to end through the public API with HOST buffers
+    host_w = torch.empty_like(w, device="cpu").pin_memory()
+    host_w.copy_(w)
+    host_out = torch.empty(1 + eng.n_weights, dtype=torch.float64).pin_memory()
+    opt_res = parallel.PackedResult(0, eng.n_weights, 0, device)
+
+    def step_e2e():
+        params.fields.networks.weights.copy_(host_w, non_blocking=True)          # H2D: the step's inputs
+        (loss, aux), grads = loss_fn.value_and_grad(params, problem)              # the call a user makes
+        opt_res.loss.copy_(loss.reshape(1)); opt_res.gw.copy_(grads.fields)
+        opt_res.allreduce()
+        host_out.copy_(opt_res.buf[:1 + eng.n_weights], non_blocking=True)        # D2H: loss + gradient
+        torch.cuda.current_stream().synchronize()                                 # the user reads them
+        return float(host_out[0])
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 0.0)
+    t_ms = torch.tensor([ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t_ms.cpu()[0])
+    e2e_value = evals_per_rank * world * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- roofline of the dominant kernel (mlp_backward), live numbers
+    from pancax_b200 import _lib
+    import ctypes as C
+    pk = C.c_double()
+    _lib.check(_lib.load().pcx_measure_dmma_peak(C.byref(pk), 5))
+    bwd_ms, bwd_n = prof["mlp_backward"]
+    rows_per_launch = eng.nn * min(nt, int(os.environ.get("PCX_TCHUNK", nt)))
+    # launches may be split in time chunks: use measured launches per step
+    rows_total = eng.nn * nt * args.steps
+    achieved = algorithmic_flops_per_row_bwd() * rows_total / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("mlp_backward_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "k_mlp_backward (FP64 DMMA)", "achieved": achieved, "peak": pk.value,
+                "unit": "TFLOP/s", "frac": (achieved / pk.value) if achieved else None, "traffic": traffic,
+                "peak_source": "fp64 mma.sync.m8n8k4 chain measured live on this GPU by pcx_measure_dmma_peak "
+                               "(MEASURED_PEAKS.json has no FP64 figure)",
+                "avg_launch_ms": bwd_ms / bwd_n if bwd_n else None, "launches": bwd_n,
+                "algorithmic_flop_per_row": algorithmic_flops_per_row_bwd(), "rows_per_step": eng.nn * nt,
+                "step_share": {k: round(v[0] / ms, 4) for k, v in prof.items() if v[1]}}
+    # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_n, nt, max_seconds=25.0)
+    out = {
+        "metric": "quad-pt loss+grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3: 3D NeoHookean Hex8 {n}^3 per GPU ({eng.ne * eng.nq} qp x nt={nt}), EnergyLoss, "
+                               f"MLP {MLP_IN}->{WIDTH}x{DEPTH}->{MLP_OUT} fp64, weights U(+-1/sqrt(fan_in)) seed 0",
+                   "elements_per_gpu": eng.ne, "nodes_per_gpu": eng.nn, "qp_per_gpu": eng.ne * eng.nq, "nt": nt,
+                   "parallelism": f"qp-sharded dp{world} (z slabs), one allreduce of loss+grads per step",
+                   "cache": "per-step working set (activations 3.4 GB per time step) is far larger than the 126 MB L2",
+                   "deterministic_assembly": True},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(host_w.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8),
+                "api": "EnergyLoss().value_and_grad(params, problem) with pinned-host weights in, loss+grad out"},
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _oracle_case(n, nt):
+    from tests.cases import make_case
+    return make_case("hex8_neohookean", n=n, nt=nt, width=WIDTH, depth=DEPTH, permute=False)
+
+
+def cpu_baseline(n, nt, max_seconds=25.0, threads=None):
+    """The CPU restatement of pancax's path (oracle/, torch fp64, all host threads) timed on a bounded
+    sample of the SAME workload (smaller mesh, same physics / network / loss)."""
+    from tests.cases import run_oracle_loss
+    if threads:
+        torch.set_num_threads(threads)
+    case = _oracle_case(n, nt)
+    evals = case.mesh["conns"].shape[0] * 8 * nt
+    run_oracle_loss(case, "energy", energy_weight=1.0)      # warm-up
+    ts = []
+    t_start = time.perf_counter()
+    while len(ts) < 5 and (time.perf_counter() - t_start) < max_seconds:
+        t0 = time.perf_counter()
+        run_oracle_loss(case, "energy", energy_weight=1.0)
+        ts.append(time.perf_counter() - t0)
+    med = float(np.median(ts))
+    return {"value": evals / med, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"Hex8 {n}^3 ({evals} evals per step), same physics/MLP/loss, median of {len(ts)} steps, "
+                      f"{med * 1e3:.1f} ms per step; CPU restatement (oracle/), not pancax/JAX: jax is not "
+                      "installable in this image", "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: pancax's own CPU implementation is not runnable here (no jax / equinox wheels,
+    no network), so this arm times the oracle port on all host threads, on the same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.cases import run_oracle_loss
+    n, nt = args.cpu_n, args.nt
+    case = _oracle_case(n, nt)
+    evals = case.mesh["conns"].shape[0] * 8 * nt
+    for _ in range(max(1, min(args.warmup, 3))):
+        run_oracle_loss(case, "energy", energy_weight=1.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_oracle_loss(case, "energy", energy_weight=1.0)
+    dt = time.perf_counter() - t0
+    value = evals * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = one loss+grad over Hex8 {n}^3 ({evals} evals), a bounded sample of the C3 workload; "
+              "CPU restatement (oracle/, torch fp64), not pancax/JAX")
+    out = {"impl": "reference", "metric": "quad-pt loss+grad evals/sec", "value": value, "unit": "evals/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"C3 sample: 3D NeoHookean Hex8 {n}^3, EnergyLoss, MLP {MLP_IN}->{WIDTH}x{DEPTH}->"
+                                  f"{MLP_OUT} fp64, nt={nt}"},
+           "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample,
+                            "host_cpus": os.cpu_count()},
+           "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="Hex8 elements per direction per GPU (C3: 128)")
+    ap.add_argument("--nt", type=int, default=2, help="time steps (C3: 2 or 11)")
+    ap.add_argument("--cpu-n", type=int, default=32, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; pancax_b200 has no CPU path (use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

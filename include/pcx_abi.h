@@ -198,7 +198,8 @@ int pcx_residual_reaction(pcx_handle* h, const double* f, double* out, void* str
 
 /* fused fast path: loss, aux and d loss / d (weights, prop_raw) for the built-in weak-form losses --
  * eqx.filter_value_and_grad(loss.filtered_loss), pancax/optimizers.py:77-88.
- *   loss: device scalar; aux: device [PCX_AUX_FIXED+nt]; g_weights [num_weights]; g_props [n_trainable] or NULL. */
+ *   loss: device scalar; aux: device [PCX_AUX_FIXED+nt]; g_weights [num_weights] or NULL (value and aux
+ *   only: what calling the loss without grad does); g_props [n_trainable] or NULL. */
 int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* loss, const double* weights,
                       const double* prop_raw, double* loss_out, double* aux, double* g_weights,
                       double* g_props, void* stream);
@@ -211,6 +212,26 @@ int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const dou
 
 /* number of kernels this library has launched on the handle so far (for bench.py "gpu_launches") */
 int64_t pcx_launch_count(const pcx_handle* h);
+
+/* Adam update of one flat leaf on the device -- optax.chain(scale_by_adam(), scale_by_schedule(..),
+ * scale(-1)) as composed in pancax/optimizers.py:155-173.  `count` is the 1-based update number (bias
+ * correction), `lr` the schedule value for this update.  params/mu/nu are updated in place. */
+int pcx_adam_step(double* params, const double* grads, double* mu, double* nu, int64_t n, int64_t count,
+                  double lr, double b1, double b2, double eps, void* stream);
+
+/* measurement helpers (no reference counterpart): per-kernel-class device time from CUDA events
+ * recorded on the launching stream, and the live FP64 tensor-pipe (DMMA) peak of the device. */
+#define PCX_PROF_PACK            0
+#define PCX_PROF_MLP_FORWARD     1
+#define PCX_PROF_ELEMENT_FORCE   2
+#define PCX_PROF_ASSEMBLE        3
+#define PCX_PROF_ELEMENT_TANGENT 4
+#define PCX_PROF_MLP_BACKWARD    5
+#define PCX_PROF_REDUCE_WGRAD    6
+#define PCX_PROF_NCLASS          8
+int pcx_profile_enable(pcx_handle* h, int on);
+int pcx_profile_collect(pcx_handle* h, double* ms_by_class, int64_t* launches_by_class);
+int pcx_measure_dmma_peak(double* tflops, int reps);
 
 #ifdef __cplusplus
 }

@@ -10,3 +10,19 @@ from . import _lib  # noqa: F401
 from .engine import Engine, tabulate_bc, mlp_num_weights  # noqa: F401
 
 __version__ = "0.1.0"
+
+# pancax's public names for the hot path (same constructors / argument meaning as the reference)
+from .bcs import DirichletBC  # noqa: F401,E402
+from .bvps import BiaxialLinearRamp, SimpleShearLinearRamp, UniaxialTensionLinearRamp  # noqa: F401,E402
+from .constitutive_models import (BoundedProperty, FixedProperty, Gent, Hencky, NeoHookean,  # noqa: F401,E402
+                                  Swanson)
+from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E402
+from .domains import VariationalDomain  # noqa: F401,E402
+from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, write_exodus_mesh  # noqa: F401,E402
+from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, EnergyLoss,  # noqa: F401,E402
+                             EnergyResidualAndReactionLoss, FullFieldDataLoss)
+from .networks import MLP, Field, Parameters  # noqa: F401,E402
+from .optimizers import Adam  # noqa: F401,E402
+from .physics_kernels import PlaneStrain, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
+from .problems import ForwardProblem, InverseProblem  # noqa: F401,E402
+from .trainer import Trainer  # noqa: F401,E402

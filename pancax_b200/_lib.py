@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpancax_b200.so")
 
 PCX_MAX_PROPS = 8
 PCX_AUX_FIXED = 4
+PROF_CLASSES = ["pack_weights", "mlp_forward", "element_force", "assemble", "element_tangent",
+                "mlp_backward", "reduce_wgrad", "other"]
 
 ELEM = {"hex8": 0, "quad4": 1, "tri3": 2}
 PHYS_POISSON, PHYS_SOLID = 0, 1
@@ -78,7 +80,8 @@ SYMBOLS = [
     "pcx_nnpe", "pcx_nd", "pcx_element_geometry", "pcx_field_forward", "pcx_field_backward",
     "pcx_points_forward", "pcx_points_backward", "pcx_energy_force", "pcx_stiffness_action",
     "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
-    "pcx_launch_count",
+    "pcx_launch_count", "pcx_adam_step", "pcx_profile_enable", "pcx_profile_collect",
+    "pcx_measure_dmma_peak",
 ]
 
 
@@ -115,6 +118,10 @@ def load():
     lib.pcx_residual_reaction.argtypes = [vp, vp, vp, vp]
     lib.pcx_loss_and_grad.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp]
     lib.pcx_field_data_loss_and_grad.argtypes = [vp, vp, vp, vp, vp, vp, i64, dbl, vp, vp, vp]
+    lib.pcx_adam_step.argtypes = [vp, vp, vp, vp, i64, i64, dbl, dbl, dbl, dbl, vp]
+    lib.pcx_profile_enable.argtypes = [vp, C.c_int]
+    lib.pcx_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.pcx_measure_dmma_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
     for name in SYMBOLS:
         if name not in ("pcx_last_error", "pcx_num_weights", "pcx_num_trainable_props",
                         "pcx_num_qp", "pcx_launch_count", "pcx_nq", "pcx_nnpe", "pcx_nd"):

@@ -1,0 +1,90 @@
+"""pancax/constitutive_models: property containers of the hyperelastic models on the B200 path.
+The energies themselves are evaluated in csrc/pcx_models.cuh."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, fields
+from typing import Union
+
+import numpy as np
+
+
+class BoundedProperty:
+    """pancax/constitutive_models/properties.py:10-38: trainable raw value ``prop_val`` with
+    p = prop_min + (prop_max - prop_min) * sigmoid(prop_val).  ``key`` may be a numpy Generator /
+    int seed (the initial value is drawn U(prop_min, prop_max) like properties.py:97-103) or a
+    float: the initial *physical* value."""
+
+    def __init__(self, prop_min: float, prop_max: float, key=None):
+        self.prop_min, self.prop_max = float(prop_min), float(prop_max)
+        if prop_min == prop_max:
+            self.prop_val = np.zeros(1)
+            return
+        if isinstance(key, float):
+            p_actual = key
+        else:
+            rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(key)
+            p_actual = rng.uniform(prop_min, prop_max)
+        y = (p_actual - prop_min) / (prop_max - prop_min)
+        self.prop_val = np.array([math.log(y / (1.0 - y))])
+
+    def __call__(self):
+        s = 1.0 / (1.0 + math.exp(-float(self.prop_val[0])))
+        return self.prop_min + (self.prop_max - self.prop_min) * s
+
+    def __repr__(self):
+        return str(self.__call__())
+
+
+FixedProperty = float
+Property = Union[BoundedProperty, FixedProperty]
+
+
+class HyperelasticModel:
+    name = None
+
+    def properties(self):
+        return [f.name for f in fields(self)]
+
+    @property
+    def num_state_variables(self):
+        return 0
+
+
+@dataclass
+class NeoHookean(HyperelasticModel):
+    """hyperelasticity/neohookean.py:6-34"""
+    bulk_modulus: Property
+    shear_modulus: Property
+    name = "neohookean"
+
+
+@dataclass
+class Gent(HyperelasticModel):
+    """hyperelasticity/gent.py:7-39"""
+    bulk_modulus: Property
+    shear_modulus: Property
+    Jm_parameter: Property
+    name = "gent"
+
+
+@dataclass
+class Swanson(HyperelasticModel):
+    """hyperelasticity/swanson.py:7-65"""
+    bulk_modulus: Property
+    A1: Property
+    P1: Property
+    B1: Property
+    Q1: Property
+    C1: Property
+    R1: Property
+    cutoff_strain: float
+    name = "swanson"
+
+
+@dataclass
+class Hencky(HyperelasticModel):
+    """hyperelasticity/hencky.py:6-18"""
+    bulk_modulus: Property
+    shear_modulus: Property
+    name = "hencky"

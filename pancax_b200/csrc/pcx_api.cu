@@ -75,6 +75,21 @@ struct pcx_handle {
   int32_t* adj_idx = nullptr;
   long long launches = 0;
   int sm_count = 148;
+  bool prof_on = false;
+  struct ProfEv { int cat; cudaEvent_t e0, e1; };
+  std::vector<ProfEv> prof_events;
+};
+
+// optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py
+// to report the dominant kernel's average launch duration from inside the timed region.
+struct ProfScope {
+  pcx_handle* h; int cat; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(pcx_handle* h_, int cat_, cudaStream_t st_) : h(h_), cat(cat_), st(st_) {
+    if (h->prof_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+  }
+  ~ProfScope() {
+    if (e0) { cudaEventRecord(e1, st); h->prof_events.push_back({cat, e0, e1}); }
+  }
 };
 
 // device scalar block layout (per handle), all sized by nt
@@ -288,6 +303,7 @@ static int launch_element_m(int model, bool tangent, dim3 grid, cudaStream_t st,
 }
 
 static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, const ElemArgs& a) {
+  ProfScope ps(h, tangent ? PCX_PROF_ELEMENT_TANGENT : PCX_PROF_ELEMENT_FORCE, st);
   dim3 grid(h->nblk_el, T);
   int rc = -1;
   if (h->phys.physics == PCX_PHYS_POISSON) {
@@ -331,6 +347,7 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
 }
 
 static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  ProfScope ps(h, PCX_PROF_MLP_FORWARD, st);
   const long long groups = (io.n + 15) / 16;
   long long blocks = (groups + 7) / 8;
   const long long maxb = (long long)h->sm_count * 2;
@@ -354,6 +371,7 @@ static int launch_mlp_bwd(pcx_handle* h, cudaStream_t st, const MlpIO& io, int* 
   int grid = (int)(ntiles < h->bwd_grid ? ntiles : h->bwd_grid);
   if (grid < 1) grid = 1;
   *grid_out = grid;
+  ProfScope ps(h, PCX_PROF_MLP_BACKWARD, st);
   const int DH = h->ms.depth - 1;
   switch (h->ms.NT) {
     case 2: return launch_mlp_bwd_nt<2>(h, DH, grid, st, io);
@@ -365,6 +383,7 @@ static int launch_mlp_bwd(pcx_handle* h, cudaStream_t st, const MlpIO& io, int* 
 }
 
 static int pack_weights(pcx_handle* h, const double* w, cudaStream_t st) {
+  ProfScope ps(h, PCX_PROF_PACK, st);
   const int thr = 256;
   const int blocks = (int)((h->ms.npacked + thr - 1) / thr);
   k_pack_weights<<<blocks, thr, 0, st>>>(h->ms, w, h->pk);
@@ -373,6 +392,7 @@ static int pack_weights(pcx_handle* h, const double* w, cudaStream_t st) {
 }
 
 static int reduce_wgrad(pcx_handle* h, int nparts, double* g, cudaStream_t st) {
+  ProfScope ps(h, PCX_PROF_REDUCE_WGRAD, st);
   const int thr = 128;
   const int blocks = (int)((h->ms.nweights + thr - 1) / thr);
   k_reduce_wgrad<<<blocks, thr, 0, st>>>(h->ms, h->part, h->part_stride, nparts, g);
@@ -624,6 +644,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
     const long long n = (long long)T * ndofs;
     const int thr = 256;
     const int blocks = (int)((n + thr - 1) / thr);
+    ProfScope ps(h, PCX_PROF_ASSEMBLE, st);
     if (h->deterministic) {
       k_assemble<<<blocks, thr, 0, st>>>(h->nn, h->ndof, T, h->ne * h->nnpe, h->adj_ptr, h->adj_idx, h->fe, alpha, add, beta, out);
       LAUNCH_CHECK(h);
@@ -843,7 +864,8 @@ extern "C" int pcx_residual_reaction(pcx_handle* h, const double* f, double* out
 extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
                                  double* loss_out, double* aux, double* g_weights, double* g_props, void* stream) {
   NEED_READY(h);
-  if (!L || !weights || !loss_out || !aux || !g_weights) return fail(PCX_ERR_INVALID, "pcx_loss_and_grad: null argument");
+  if (!L || !weights || !loss_out || !aux) return fail(PCX_ERR_INVALID, "pcx_loss_and_grad: null argument");
+  const bool want_grad = g_weights != nullptr;   // NULL: value + aux only (loss.__call__)
   const int kind = L->kind;
   if (kind < PCX_LOSS_ENERGY || kind > PCX_LOSS_ENERGY_RESIDUAL_REACTION) return fail(PCX_ERR_INVALID, "unknown loss kind %d", kind);
   const bool resid = kind != PCX_LOSS_ENERGY;
@@ -864,7 +886,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
   if ((rc = set_props(h, prop_raw, st))) return rc;
   if ((rc = pack_weights(h, weights, st))) return rc;
-  const bool want_dp = g_props != nullptr && h->ntrain > 0;
+  const bool want_dp = want_grad && g_props != nullptr && h->ntrain > 0;
   const long long ndofs = h->nn * h->ndof;
   bool first = true;
   for (int t0 = 0; t0 < h->nt; t0 += h->T) {
@@ -875,7 +897,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
     if ((rc = launch_mlp_fwd(h, st, io))) return rc;
     // (1)+(3)+(5) energy, force; ubar = we * f for the energy loss
     if (!resid) {
-      if ((rc = sweep(h, false, T, h->us, nullptr, h->ubar, we, nullptr, 0.0, true, want_dp, true, st))) return rc;
+      if ((rc = sweep(h, false, T, h->us, nullptr, h->ubar, we, nullptr, 0.0, true, want_dp, want_grad, st))) return rc;
     } else {
       if ((rc = sweep(h, false, T, h->us, nullptr, h->f, 1.0, nullptr, 0.0, true, want_dp, true, st))) return rc;
     }
@@ -890,6 +912,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
                                        kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? h->gout_dev : nullptr,
                                        h->scal + SC_R(h), h->scal + SC_REACT(h), h->scal + SC_C1(h), h->scal + SC_C2(h));
       LAUNCH_CHECK(h);
+      if (!want_grad) continue;
       CUDA_TRY(cudaMemsetAsync(h->v, 0, (size_t)T * ndofs * sizeof(double), st));
       {
         dim3 g0((unsigned)((h->n_unknown + 255) / 256), T);
@@ -910,6 +933,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
         if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T,
                               h->scal + SC_DFV(h) + (long long)t0 * PCX_MAX_PROPS, PCX_MAX_PROPS, st))) return rc;
     }
+    if (!want_grad) continue;
     // (4) adjoint through the field
     io.u = nullptr;
     io.g_u = h->ubar;
@@ -927,5 +951,101 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr);
   LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: optimizer
+// optax.scale_by_adam (b1, b2, eps, eps_root = 0) followed by scale(-lr): pancax/optimizers.py:155-173
+__global__ void k_adam(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ mu, double* __restrict__ nu,
+                       long long n, double lr, double b1, double b2, double eps, double bc1, double bc2) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double gi = g[i];
+  const double m = b1 * mu[i] + (1.0 - b1) * gi;
+  const double v = b2 * nu[i] + (1.0 - b2) * gi * gi;
+  mu[i] = m;
+  nu[i] = v;
+  const double mhat = m / bc1, vhat = v / bc2;
+  p[i] -= lr * (mhat / (sqrt(vhat) + eps));
+}
+
+extern "C" int pcx_adam_step(double* params, const double* grads, double* mu, double* nu, int64_t n, int64_t count,
+                             double lr, double b1, double b2, double eps, void* stream) {
+  if (n <= 0) return PCX_OK;
+  if (!params || !grads || !mu || !nu || count < 1) return fail(PCX_ERR_INVALID, "pcx_adam_step: bad argument");
+  const double bc1 = 1.0 - pow(b1, (double)count), bc2 = 1.0 - pow(b2, (double)count);
+  const int thr = 256;
+  k_adam<<<(int)((n + thr - 1) / thr), thr, 0, (cudaStream_t)stream>>>(params, grads, mu, nu, n, lr, b1, b2, eps, bc1, bc2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PCX_ERR_CUDA, "k_adam launch failed: %s", cudaGetErrorString(e));
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: profiling helpers
+extern "C" int pcx_profile_enable(pcx_handle* h, int on) {
+  if (!h) return fail(PCX_ERR_INVALID, "null handle");
+  h->prof_on = on != 0;
+  return PCX_OK;
+}
+
+extern "C" int pcx_profile_collect(pcx_handle* h, double* ms_by_class, int64_t* launches_by_class) {
+  if (!h || !ms_by_class || !launches_by_class) return fail(PCX_ERR_INVALID, "null argument");
+  for (int i = 0; i < PCX_PROF_NCLASS; i++) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+  for (auto& ev : h->prof_events) {
+    CUDA_TRY(cudaEventSynchronize(ev.e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    ms_by_class[ev.cat] += ms;
+    launches_by_class[ev.cat] += 1;
+    cudaEventDestroy(ev.e0);
+    cudaEventDestroy(ev.e1);
+  }
+  h->prof_events.clear();
+  return PCX_OK;
+}
+
+// FP64 tensor-pipe peak of THIS device, measured live (MEASURED_PEAKS.json has no FP64 figure):
+// independent chains of mma.sync.m8n8k4.f64, best of `reps`; returns TFLOP/s in *tflops.
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int pcx_measure_dmma_peak(double* tflops, int reps) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  double* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, 64));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int grid = prop.multiProcessorCount * 4, iters = 8192;
+  k_dmma_peak<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+  CUDA_TRY(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < (reps < 1 ? 1 : reps); r++) {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  *tflops = (double)grid * 8 /*warps*/ * iters * 8 /*mma per iter*/ * 512.0 / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
   return PCX_OK;
 }

@@ -1,0 +1,43 @@
+"""pancax/domains.py: VariationalDomain(mesh_file, times, p_order=1, q_order=2) (:132-156)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .fem import DofManager, Mesh, read_exodus_mesh
+
+
+class SimulationTimesNotUniqueException(Exception):
+    pass
+
+
+class SimulationTimesNotStrictlyIncreasingException(Exception):
+    pass
+
+
+class VariationalDomain:
+    def __init__(self, mesh_file, times, p_order: int = 1, q_order: int = 2):
+        """``mesh_file``: path of an Exodus file, or an in-memory ``Mesh`` (synthetic meshes)."""
+        if isinstance(mesh_file, Mesh):
+            mesh, self.mesh_file = mesh_file, None
+        else:
+            mesh, self.mesh_file = read_exodus_mesh(mesh_file), mesh_file
+        if p_order != 1:
+            raise NotImplementedError("pancax_b200 handles first-order elements (Hex8/Quad4/Tri3)")
+        times = np.asarray(times, dtype=np.float64)
+        # domains.py:50-57
+        if len(times) != len(set(times.tolist())):
+            raise SimulationTimesNotUniqueException()
+        for i in range(len(times) - 1):
+            if times[i] >= times[i + 1]:
+                raise SimulationTimesNotStrictlyIncreasingException()
+        self.mesh = mesh
+        self.coords = mesh.coords
+        self.conns = mesh.conns
+        self.times = times
+        self.q_order = int(q_order)
+        self.dof_manager = None
+
+    def update_dof_manager(self, dirichlet_bcs, n_dofs):
+        """domains.py:64-71"""
+        self.dof_manager = DofManager(self.mesh, n_dofs, dirichlet_bcs)
+        return self

@@ -247,7 +247,7 @@ class Engine:
         return out
 
     def loss_and_grad(self, kind, weights, prop_raw=None, energy_weight=1.0, residual_weight=1.0,
-                      reaction_weight=1.0, global_outputs=None, out=None):
+                      reaction_weight=1.0, global_outputs=None, out=None, want_grad=True):
         """Returns device tensors (loss[1], aux[4+nt], g_weights, g_props)."""
         w, pr = self._dev(weights), self._dev(prop_raw)
         ld = LossDesc()
@@ -263,7 +263,7 @@ class Engine:
         if out is None:
             loss = self._empty(1)
             aux = self._empty(PCX_AUX_FIXED + self.nt)
-            gw = self._empty(self.n_weights)
+            gw = self._empty(self.n_weights) if want_grad else None
             gp = self._empty(max(self.n_train, 1))
         else:
             loss, aux, gw, gp = out
@@ -282,6 +282,16 @@ class Engine:
         check(self.lib.pcx_field_data_loss_and_grad(self.h, _ptr(w), _ptr(p), _ptr(a), _ptr(b), _ptr(y),
                                                     n, float(weight), _ptr(loss), _ptr(gw), _stream()))
         return loss, gw
+
+    def profile_enable(self, on=True):
+        check(self.lib.pcx_profile_enable(self.h, 1 if on else 0))
+
+    def profile_collect(self):
+        """{class: (total ms, launches)} since the last collect (synchronises)."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        check(self.lib.pcx_profile_collect(self.h, ms, cnt))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROF_CLASSES)}
 
     def close(self):
         if getattr(self, "h", None):

@@ -1,0 +1,279 @@
+"""pancax/loss_functions: the weak-form losses and the full-field data loss, evaluated by the
+CUDA library.  ``loss(params, problem, *args) -> (loss, aux)`` as in the reference;
+``loss.value_and_grad(params, problem, *args) -> ((loss, aux), grads)`` is what
+``eqx.filter_value_and_grad(loss.filtered_loss, has_aux=True)`` returns in pancax/optimizers.py:79-88.
+Values are device tensors (no host synchronisation inside)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .constitutive_models import BoundedProperty
+from .engine import Engine, tabulate_bc
+from .physics_kernels import Poisson, SolidMechanics
+
+
+class Grads:
+    """Gradient 'pytree': flat MLP weight gradient + trainable-property gradient."""
+
+    def __init__(self, fields, props):
+        self.fields, self.props = fields, props
+
+    def __add__(self, other):
+        return Grads(self.fields + other.fields, self.props + other.props)
+
+
+def _wrap_bc(bc_func, ndof):
+    """Accept batched wrappers (x (N,nd), t, z (N,ndof)) -- pancax_b200.bvps -- and, for small
+    meshes, per-point wrappers written for pancax (x (nd,), t, z (ndof,))."""
+    def batched(x, t, z):
+        try:
+            out = np.asarray(bc_func(x, t, z), dtype=np.float64)
+            if out.shape == z.shape:
+                return out
+        except Exception:
+            pass
+        out = np.empty_like(z)
+        tt = np.broadcast_to(np.asarray(t, dtype=np.float64), (x.shape[0],))
+        for n in range(x.shape[0]):
+            out[n] = np.asarray(bc_func(_AtArray(x[n]), float(tt[n]), _AtArray(z[n])), dtype=np.float64)
+        return out
+    return batched
+
+
+class _AtArray(np.ndarray):
+    """numpy array with jax's functional ``.at[idx].set(v)`` so per-point wrappers written for
+    pancax (bvps/*.py use ``u_out.at[0].set(...)``) can be tabulated on the host."""
+    def __new__(cls, a):
+        return np.asarray(a, dtype=np.float64).view(cls)
+
+    class _At:
+        def __init__(self, a):
+            self.a = a
+
+        def __getitem__(self, idx):
+            a = self.a
+
+            class _S:
+                def set(self_inner, v):
+                    b = a.copy().view(_AtArray)
+                    b[idx] = v
+                    return b
+            return _S()
+
+    @property
+    def at(self):
+        return _AtArray._At(self)
+
+
+def get_engine(problem, params, deterministic: bool = True) -> Engine:
+    """One Engine (pcx_handle) per (problem, field shape); built on first use, like the first
+    traced call of a jitted step."""
+    fld = params.fields
+    net = fld.networks
+    key = (net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers, net.use_final_bias,
+           id(fld.dirichlet_bc_func), deterministic)
+    eng = problem._engines.get(key)
+    if eng is not None:
+        return eng
+    dom = problem.domain
+    gd = getattr(problem, "global_data", None)
+    eng = Engine(dom.coords, dom.conns, dom.mesh.elem_type, dom.q_order, problem.n_dofs, dom.times,
+                 unknown_idx=None if dom.dof_manager is None else dom.dof_manager.unknownIndices,
+                 reaction_nodes=None if gd is None else gd.reaction_nodes,
+                 reaction_dof=0 if gd is None else gd.reaction_dof, deterministic=deterministic,
+                 device=net.weights.device)
+    phys = problem.physics
+    if isinstance(phys, Poisson):
+        _, _, xq = eng.element_geometry(want_grad_N=False, want_JxW=False)
+        eng.set_physics("poisson", source_q=np.asarray(phys.f(xq.cpu().numpy()), dtype=np.float64))
+    elif isinstance(phys, SolidMechanics):
+        model = phys.constitutive_model
+        props = []
+        for name in model.properties():
+            p = getattr(model, name)
+            props.append((p.prop_min, p.prop_max) if isinstance(p, BoundedProperty) else float(p))
+        eng.set_physics("solid", model.name, phys.formulation.name, props)
+    else:
+        raise NotImplementedError(f"physics {type(phys)} is not on the B200 hot path")
+    a = b = None
+    if fld.dirichlet_bc_func is not None:
+        a, b = tabulate_bc(_wrap_bc(fld.dirichlet_bc_func, problem.n_dofs), dom.coords, dom.times,
+                           problem.n_dofs)
+    eng.set_field(net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers, net.use_final_bias,
+                  bc_a=a, bc_b=b, x_min=fld.x_mins, x_max=fld.x_maxs, t_min=fld.t_min, t_max=fld.t_max,
+                  normalize_time=fld.normalize_time)
+    problem._engines[key] = eng
+    return eng
+
+
+class BaseLossFunction:
+    def filtered_loss(self, diff_params, static_params, *args, **kwargs):
+        # base_loss_function.py:23-25; params are not partitioned here: the trainable subset is
+        # selected by the optimizer's filter
+        return self.__call__(diff_params, *args, **kwargs)
+
+    def value_and_grad(self, params, problem, *args):
+        raise NotImplementedError
+
+
+class PhysicsLossFunction(BaseLossFunction):
+    kind: str = None
+    deterministic: bool = True
+
+    def _weights(self):
+        return dict(energy_weight=1.0, residual_weight=1.0, reaction_weight=1.0)
+
+    def _run(self, params, problem, want_grad):
+        if getattr(self, "is_path_dependent", False):
+            raise NotImplementedError("path-dependent losses (state variables) are not on the B200 path")
+        eng = get_engine(problem, params, self.deterministic)
+        gd = getattr(problem, "global_data", None)
+        gout = None
+        if self.kind == "energy_residual_reaction":
+            if gd is None:
+                raise ValueError("EnergyResidualAndReactionLoss needs problem.global_data")
+            gout = gd.outputs
+        loss, aux, gw, gp = eng.loss_and_grad(
+            self.kind, params.fields.networks.weights,
+            params.prop_raw if eng.n_train else None, global_outputs=gout, want_grad=want_grad,
+            **self._weights())
+        return loss, aux, gw, gp
+
+    def _aux(self, aux):
+        raise NotImplementedError
+
+    def __call__(self, params, problem, *args):
+        loss, aux, _, _ = self._run(params, problem, False)
+        return loss[0], self._aux(aux)
+
+    def value_and_grad(self, params, problem, *args):
+        loss, aux, gw, gp = self._run(params, problem, True)
+        return (loss[0], self._aux(aux)), Grads(gw, gp)
+
+
+class EnergyLoss(PhysicsLossFunction):
+    """weak_form_loss_functions.py:8-88: L = w * sum_t Pi_t, aux energy."""
+    kind = "energy"
+
+    def __init__(self, is_path_dependent: Optional[bool] = False, use_fori_loop: Optional[bool] = False,
+                 weight: Optional[float] = 1.0):
+        self.is_path_dependent, self.use_fori_loop, self.weight = is_path_dependent, use_fori_loop, weight
+
+    def _weights(self):
+        return dict(energy_weight=self.weight)
+
+    def _aux(self, aux):
+        return dict(energy=aux[0])
+
+
+class EnergyAndResidualLoss(PhysicsLossFunction):
+    """weak_form_loss_functions.py:115-212.  The reference's ``__call__`` drops its return value
+    (:145-149); here it returns what ``path_independent_call`` (:194-205) computes:
+    L = w_e sum_t Pi_t + w_r mean_t R_t."""
+    kind = "energy_residual"
+
+    def __init__(self, energy_weight: Optional[float] = 1.0, is_path_dependent: Optional[bool] = False,
+                 residual_weight: Optional[float] = 1.0, use_fori_loop: Optional[bool] = False):
+        self.energy_weight, self.residual_weight = energy_weight, residual_weight
+        self.is_path_dependent, self.use_fori_loop = is_path_dependent, use_fori_loop
+
+    def _weights(self):
+        return dict(energy_weight=self.energy_weight, residual_weight=self.residual_weight)
+
+    def _aux(self, aux):
+        return dict(energy=aux[0], residual=aux[1])
+
+    def path_independent_call(self, params, problem):
+        return self.__call__(params, problem)
+
+
+class EnergyResidualAndReactionLoss(PhysicsLossFunction):
+    """weak_form_loss_functions.py:215-308: L = w_e sum Pi_t + w_r sum R_t / nt
+    + w_g mean_t (reaction_t - data_t)^2; aux energy, residual, global_data_loss, reactions(nt)."""
+    kind = "energy_residual_reaction"
+
+    def __init__(self, energy_weight: Optional[float] = 1.0, is_path_dependent: Optional[bool] = False,
+                 residual_weight: Optional[float] = 1.0, reaction_weight: Optional[float] = 1.0,
+                 use_fori_loop: Optional[bool] = False):
+        self.energy_weight, self.residual_weight = energy_weight, residual_weight
+        self.reaction_weight = reaction_weight
+        self.is_path_dependent, self.use_fori_loop = is_path_dependent, use_fori_loop
+
+    def _weights(self):
+        return dict(energy_weight=self.energy_weight, residual_weight=self.residual_weight,
+                    reaction_weight=self.reaction_weight)
+
+    def _aux(self, aux):
+        return dict(energy=aux[0], residual=aux[1], global_data_loss=aux[2], reactions=aux[4:])
+
+
+class FullFieldDataLoss(BaseLossFunction):
+    """data_loss_functions.py:7-24: w * mean((u(x_i, t_i) - u_i)^2) on a batch (inputs = [x..., t])."""
+
+    def __init__(self, weight: Optional[float] = 1.0):
+        self.weight = weight
+
+    def _run(self, params, problem, inputs, outputs):
+        eng = get_engine(problem, params)
+        inputs = np.asarray(inputs, dtype=np.float64)
+        nd = problem.n_dims
+        a = b = None
+        bc = params.fields.dirichlet_bc_func
+        if bc is not None:
+            g = _wrap_bc(bc, problem.n_dofs)
+            xs, ts = inputs[:, :nd], inputs[:, nd]
+            z0 = np.zeros((inputs.shape[0], problem.n_dofs))
+            a = g(xs, ts, z0)
+            b = g(xs, ts, z0 + 1.0) - a
+        return eng.field_data_loss_and_grad(params.fields.networks.weights, inputs, outputs, a, b,
+                                            weight=self.weight)
+
+    def __call__(self, params, problem, inputs, outputs):
+        loss, _ = self._run(params, problem, inputs, outputs)
+        return loss[0], {"field_data_loss": loss[0] / self.weight if self.weight else loss[0]}
+
+    def value_and_grad(self, params, problem, inputs, outputs):
+        loss, gw = self._run(params, problem, inputs, outputs)
+        aux = {"field_data_loss": loss[0] / self.weight if self.weight else loss[0]}
+        return (loss[0], aux), Grads(gw, torch.zeros_like(params.prop_raw))
+
+
+class CombineLossFunctions(BaseLossFunction):
+    """loss_functions/utils.py:4-27.  Data losses inside the combination receive the extra
+    ``(inputs, outputs)`` arguments; physics losses do not (example_v2.py:106-109)."""
+
+    def __init__(self, *funcs, with_props=False):
+        self.funcs = funcs
+        self.with_props = with_props
+
+    def _args_for(self, f, args):
+        return args if isinstance(f, FullFieldDataLoss) else ()
+
+    def __call__(self, params, domain, *args):
+        loss, aux = 0.0, dict()
+        for f in self.funcs:
+            tl, ta = f(params, domain, *self._args_for(f, args))
+            loss = loss + tl
+            aux.update(ta)
+        if self.with_props:
+            aux.update({"props": params.properties()})
+        return loss, aux
+
+    def value_and_grad(self, params, domain, *args):
+        loss, aux, grads = 0.0, dict(), None
+        for f in self.funcs:
+            (tl, ta), g = f.value_and_grad(params, domain, *self._args_for(f, args))
+            loss = loss + tl
+            aux.update(ta)
+            grads = g if grads is None else grads + g
+        if self.with_props:
+            aux.update({"props": params.properties()})
+        return (loss, aux), grads
+
+
+class UserDefinedLossFunction(BaseLossFunction):
+    def __init__(self, func):
+        raise NotImplementedError("user-defined Python losses cannot run on the B200 path (no fallback)")

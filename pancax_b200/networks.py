@@ -1,0 +1,169 @@
+"""pancax/networks: MLP (mlp.py:49-85), Field (fields.py:10-101), Parameters (parameters.py:62-176).
+
+Weights live in ONE flat float64 tensor in equinox leaf order [W0, b0, W1, b1, ..., Wout(, bout)]
+(the layout the C ABI consumes; equinox.nn.Linear stores weight (out, in), bias (out,)), with
+per-layer views for inspection and checkpoint compatibility."""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from .constitutive_models import BoundedProperty
+
+
+def _default_device():
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+        else torch.device("cpu")
+
+
+def _rng(key):
+    if isinstance(key, np.random.Generator):
+        return key
+    return np.random.default_rng(key)
+
+
+class MLP:
+    """Same constructor arguments as pancax.networks.MLP (mlp.py:52-63).  ``activation`` must be
+    tanh (the only one the kernels implement); ``key`` is a numpy seed / Generator.  Initialisation
+    follows equinox.nn.Linear: U(-1/sqrt(in), 1/sqrt(in)) for weights and biases."""
+
+    def __init__(self, n_inputs: int, n_outputs: int, n_neurons: int, n_layers: int,
+                 activation: Callable = "tanh", key=0, use_final_bias: Optional[bool] = False,
+                 ensure_positivity: Optional[bool] = False, device=None):
+        name = getattr(activation, "__name__", activation)
+        if name != "tanh":
+            raise NotImplementedError("pancax_b200 implements the tanh MLP only (no fallback)")
+        if ensure_positivity:
+            raise NotImplementedError("ensure_positivity (softplus head) is not on the B200 path")
+        self.n_inputs, self.n_outputs = int(n_inputs), int(n_outputs)
+        self.n_neurons, self.n_layers = int(n_neurons), int(n_layers)
+        self.use_final_bias = bool(use_final_bias)
+        rng = _rng(key)
+        sizes = [self.n_inputs] + [self.n_neurons] * self.n_layers + [self.n_outputs]
+        chunks, self._slices = [], []
+        o = 0
+        for i in range(len(sizes) - 1):
+            fi, fo = sizes[i], sizes[i + 1]
+            lim = 1.0 / math.sqrt(fi)
+            W = rng.uniform(-lim, lim, size=(fo, fi))
+            chunks.append(W.ravel())
+            sl_w = (o, o + fi * fo, (fo, fi))
+            o += fi * fo
+            last = i == len(sizes) - 2
+            if not last or self.use_final_bias:
+                chunks.append(rng.uniform(-lim, lim, size=(fo,)))
+                sl_b = (o, o + fo, (fo,))
+                o += fo
+            else:
+                sl_b = None
+            self._slices.append((sl_w, sl_b))
+        self.weights = torch.from_numpy(np.concatenate(chunks)).to(device or _default_device())
+
+    @property
+    def num_weights(self):
+        return self.weights.numel()
+
+    def layers(self):
+        """[(W, b|None)] views into the flat tensor."""
+        out = []
+        for sw, sb in self._slices:
+            W = self.weights[sw[0]:sw[1]].view(*sw[2])
+            b = None if sb is None else self.weights[sb[0]:sb[1]]
+            out.append((W, b))
+        return out
+
+    def set_weights(self, flat):
+        self.weights.copy_(torch.as_tensor(np.asarray(flat), dtype=torch.float64))
+
+
+class Field:
+    """fields.py:10-76: normalisation constants from the problem, one MLP (nd+1 -> ndof) and the
+    Dirichlet wrapper."""
+
+    def __init__(self, problem, key, ensure_positivity=False, seperate_networks=False, n_layers: int = 3,
+                 n_neurons: int = 50, activation="tanh", dirichlet_bc_func: Optional[Callable] = None,
+                 network_type=MLP, device=None):
+        if seperate_networks:
+            raise NotImplementedError("seperate_networks=True is not on the B200 path")
+        if network_type is not MLP:
+            raise NotImplementedError("only networks.MLP is on the B200 path")
+        self.dirichlet_bc_func = dirichlet_bc_func      # None = identity (fields.py:33)
+        self.networks = MLP(problem.n_dims + 1, problem.n_dofs, n_neurons, n_layers, activation, key,
+                            ensure_positivity=ensure_positivity, device=device)
+        self.seperate_networks = False
+        self.t_min, self.t_max = float(np.min(problem.times)), float(np.max(problem.times))
+        self.x_mins = np.min(problem.coords, axis=0)
+        self.x_maxs = np.max(problem.coords, axis=0)
+        self.normalize_time = not np.allclose(self.t_min, self.t_max)   # fields.py:73-76
+
+
+class Parameters:
+    """parameters.py:62-110: (fields, physics, state).  Trainable BoundedProperty raw values are
+    gathered in one small device tensor ``prop_raw`` in property order."""
+
+    def __init__(self, problem, key=0, dirichlet_bc_func: Optional[Callable] = None, network_type=MLP,
+                 seperate_networks: Optional[bool] = False, n_layers: int = 3, n_neurons: int = 50,
+                 device=None):
+        if isinstance(key, np.ndarray) and key.ndim == 2:
+            raise NotImplementedError("ensembles (2-D keys) are not on the B200 path")
+        self.is_ensemble, self.n_ensemble = False, 1
+        self.fields = Field(problem, key, dirichlet_bc_func=dirichlet_bc_func, network_type=network_type,
+                            seperate_networks=seperate_networks, n_layers=n_layers, n_neurons=n_neurons,
+                            device=device)
+        self.physics = problem.physics
+        self.state = None
+        dev = self.fields.networks.weights.device
+        raw = []
+        model = getattr(self.physics, "constitutive_model", None)
+        if model is not None:
+            for name in model.properties():
+                p = getattr(model, name)
+                if isinstance(p, BoundedProperty):
+                    raw.append(float(p.prop_val[0]))
+        self.prop_raw = torch.tensor(raw, dtype=torch.float64, device=dev)
+
+    def __iter__(self):
+        return iter((self.fields, self.physics, self.state))
+
+    def properties(self):
+        """Current physical property values (trainable ones read back from the device)."""
+        out = {}
+        model = getattr(self.physics, "constitutive_model", None)
+        if model is None:
+            return out
+        raw = self.prop_raw.detach().cpu().numpy()
+        k = 0
+        for name in model.properties():
+            p = getattr(model, name)
+            if isinstance(p, BoundedProperty):
+                s = 1.0 / (1.0 + math.exp(-raw[k]))
+                out[name] = p.prop_min + (p.prop_max - p.prop_min) * s
+                k += 1
+            else:
+                out[name] = float(p)
+        return out
+
+    # parameters.py:158-176: what is trainable by default = everything but the normalisation
+    def freeze_physics_normalization_filter(self):
+        return dict(fields=True, props=True)
+
+    def freeze_physics_filter(self):
+        return dict(fields=True, props=False)
+
+    def freeze_fields_filter(self):
+        return dict(fields=False, props=True)
+
+    def serialise(self, base_name: str, epoch: int):
+        """networks/base.py:80-96 equivalent: {base}_{epoch:07d}.npz with the flat leaves."""
+        np.savez(f"{base_name}_{str(epoch).zfill(7)}.npz",
+                 weights=self.fields.networks.weights.detach().cpu().numpy(),
+                 prop_raw=self.prop_raw.detach().cpu().numpy())
+
+    def deserialise(self, f_name: str):
+        d = np.load(f_name)
+        self.fields.networks.set_weights(d["weights"])
+        self.prop_raw.copy_(torch.as_tensor(d["prop_raw"]))
+        return self

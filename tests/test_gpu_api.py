@@ -1,0 +1,216 @@
+"""GPU: (a) the CUDA path against vectors produced by the reference's own source (tests/golden),
+(b) the pancax-named host API (Problem / Parameters / losses / Adam / Trainer) end to end against the
+oracle on the same inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-10
+
+SW = [10.0, 0.93074321, -0.07673672, 0.0, -0.5, 0.10448312, 1.71691036, 0.01]
+PROPS = {"neohookean": ("neohookean", [0.833, 0.3846]), "neohookean_stiff": ("neohookean", [1000.0, 1.0]),
+         "gent": ("gent", [0.833, 0.3846, 3.0]), "swanson": ("swanson", SW), "hencky": ("hencky", [0.833, 0.3846])}
+
+
+@pytest.mark.parametrize("elem,mname", [("hex8", "neohookean_stiff"), ("hex8", "gent"), ("hex8", "swanson"),
+                                        ("hex8", "hencky"), ("quad4", "neohookean_stiff"), ("quad4", "gent"),
+                                        ("quad4", "swanson"), ("quad4", "hencky"), ("tri3", "neohookean")])
+def test_cuda_potential_energy_matches_reference_source(cuda_device, elem, mname):
+    """Pi computed by the CUDA sweep on the reference's fixture meshes == Pi computed by the
+    reference's own potential_energy (physics_kernels/base.py:349-354) through oracle/refshim."""
+    from pancax_b200 import Engine
+    g, fsg = np.load(os.path.join(G, "potential_energy.npz")), np.load(os.path.join(G, "function_space.npz"))
+    ndof = 3 if elem == "hex8" else 2
+    eng = Engine(fsg[f"{elem}_coords"], fsg[f"{elem}_conns"], elem, 2, ndof, np.array([0.0, 1.0]))
+    model, props = PROPS[mname]
+    eng.set_physics("solid", model, "three_dimensional" if elem == "hex8" else "plane_strain", props)
+    eng.set_field(ndof + 1, ndof, 8, 1)
+    Pi, _, _ = eng.energy_force(g[f"{elem}_us"], want_force=False)
+    ref = float(g[f"{elem}_{mname}_Pi"])
+    assert abs(float(Pi.cpu()[0]) - ref) <= 1e-11 * abs(ref)
+    eng.close()
+
+
+def test_cuda_geometry_matches_reference_source(cuda_device):
+    from pancax_b200 import Engine
+    fsg = np.load(os.path.join(G, "function_space.npz"))
+    for elem in ("hex8", "quad4", "tri3"):
+        eng = Engine(fsg[f"{elem}_coords"], fsg[f"{elem}_conns"], elem, 2, 1, np.array([0.0, 1.0]))
+        gN, JxW, _ = eng.element_geometry()
+        sel = fsg[f"{elem}_sel"]
+        assert np.allclose(gN.cpu().numpy()[sel], fsg[f"{elem}_gradN"], rtol=1e-12, atol=1e-13)
+        assert np.allclose(JxW.cpu().numpy()[sel], fsg[f"{elem}_JxW"], rtol=1e-13)
+        assert abs(float(JxW.sum()) - float(fsg[f"{elem}_volume"])) < 1e-12
+        eng.close()
+
+
+def _build(elem="quad4", n=6, nt=3, bounded=False, inverse=False, t0=0.25):
+    import pancax_b200 as px
+    m = px.create_structured_mesh(elem, n, permute_seed=5)
+    times = np.linspace(t0, 1.0, nt)
+    d = px.VariationalDomain(m, times, q_order=2)
+    nd = m.num_dimensions
+    G_ = px.BoundedProperty(0.01, 5.0, 0.9) if bounded else 1.0
+    K_ = 10.0 if bounded else 1000.0
+    phys = px.SolidMechanics(px.NeoHookean(bulk_modulus=K_, shear_modulus=G_),
+                             px.PlaneStrain() if nd == 2 else px.ThreeDimensional())
+    top, bot = ("nset_1", "nset_3") if nd == 2 else ("nset_5", "nset_3")
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in (top, bot) for c in range(nd)]
+    if inverse:
+        gd = px.GlobalData.from_arrays(times, 0.3 * times, m.nodeSets[top], 1)
+        prob = px.InverseProblem(d, phys, None, gd, dirichlet_bcs=bcs)
+    else:
+        prob = px.ForwardProblem(d, phys, dirichlet_bcs=bcs)
+    params = px.Parameters(prob, key=3, n_layers=3, n_neurons=50,
+                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", nd))
+    return prob, params
+
+
+def _oracle_problem(prob, params):
+    from oracle import bvps as obvps
+    from oracle import losses as ol
+    net = params.fields.networks
+    model = prob.physics.constitutive_model
+    props = []
+    import pancax_b200 as px
+    for name in model.properties():
+        p = getattr(model, name)
+        if isinstance(p, px.BoundedProperty):
+            props.append(ol.PropSpec(name, float(p.prop_val[0]), True, p.prop_min, p.prop_max))
+        else:
+            props.append(ol.PropSpec(name, float(p)))
+    gd = getattr(prob, "global_data", None)
+    nd = prob.n_dims
+    return ol.OracleProblem(
+        coords=prob.coords, conns=prob.conns, elem=prob.mesh.elem_type, q_order=2, times=prob.times, kind="solid",
+        ndof=prob.n_dofs, mlp=ol.MLPSpec(net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers),
+        model=model.name, formulation=prob.physics.formulation.name, props=props,
+        bc_func=obvps.UniaxialTensionLinearRamp(0.5, 1.0, "y", nd),
+        unknown_idx=prob.dof_manager.unknownIndices,
+        reaction_nodes=None if gd is None else gd.reaction_nodes, reaction_dof=0 if gd is None else gd.reaction_dof,
+        global_outputs=None if gd is None else gd.outputs)
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+def test_energy_loss_through_the_public_api(cuda_device):
+    import pancax_b200 as px
+    from oracle import losses as ol
+    prob, params = _build("hex8", n=4, nt=2, t0=0.0)
+    loss_fn = px.EnergyLoss(weight=2.5)
+    val, aux = loss_fn(params, prob)                       # value only
+    (val2, aux2), grads = loss_fn.value_and_grad(params, prob)
+    w = params.fields.networks.weights.cpu().numpy()
+    Lo, auxo, gwo, _ = ol.loss_and_grad(_oracle_problem(prob, params), dict(kind="energy", energy_weight=2.5), w)
+    assert abs(float(val) - Lo) <= TOL * abs(Lo) and float(val) == float(val2)
+    assert abs(float(aux["energy"]) - float(auxo["energy"])) <= TOL * abs(float(auxo["energy"]))
+    assert rel(grads.fields.cpu().numpy(), gwo) < TOL
+
+
+def test_inverse_problem_combined_loss_and_adam(cuda_device):
+    """C4-style: EnergyResidualAndReactionLoss + FullFieldDataLoss combined, trainable shear modulus,
+    three Adam steps; parameters track the oracle + restated optax Adam."""
+    import pancax_b200 as px
+    from oracle import losses as ol
+    from oracle.optim import AdamState, adam_step
+    prob, params = _build("quad4", n=6, nt=3, bounded=True, inverse=True)
+    rng = np.random.default_rng(0)
+    nb = 256
+    inputs = np.column_stack([rng.uniform(0, 1, (nb, 2)), rng.choice(prob.times, nb)])
+    outputs = 0.05 * rng.standard_normal((nb, 2))
+    loss_fn = px.CombineLossFunctions(
+        px.EnergyResidualAndReactionLoss(energy_weight=1.0, residual_weight=25.0, reaction_weight=2.5),
+        px.FullFieldDataLoss(weight=10.0), with_props=True)
+    opt = px.Adam(loss_fn, learning_rate=1e-3, has_aux=True, transition_steps=2)
+    st = opt.init(params)
+    op = _oracle_problem(prob, params)
+    w = params.fields.networks.weights.cpu().numpy().copy()
+    pr = params.prop_raw.cpu().numpy().copy()
+    sw, sp = AdamState(w.size), AdamState(pr.size)
+    for it in range(3):
+        params, st, (loss, aux) = opt.step(params, st, prob, inputs, outputs)
+        L1, a1, gw1, gp1 = ol.loss_and_grad(op, dict(kind="energy_residual_reaction", energy_weight=1.0,
+                                                     residual_weight=25.0, reaction_weight=2.5), w, pr)
+        L2, gw2 = ol.full_field_data_loss_and_grad(op, w, inputs, outputs, weight=10.0)
+        assert abs(float(loss) - (L1 + L2)) <= TOL * abs(L1 + L2), it
+        assert rel(aux["reactions"].cpu().numpy(), a1["reactions"]) < TOL
+        assert "props" in aux and abs(aux["props"]["bulk_modulus"] - 10.0) < 1e-15
+        w = adam_step(w, gw1 + gw2, sw, 1e-3, transition_steps=2)
+        pr = adam_step(pr, gp1, sp, 1e-3, transition_steps=2)
+        assert rel(params.fields.networks.weights.cpu().numpy(), w) < 1e-9, it
+        assert rel(params.prop_raw.cpu().numpy(), pr) < 1e-9, it
+    assert st.epoch == 3
+
+
+def test_trainer_reduces_energy_and_checkpoints(cuda_device, tmp_path):
+    import pancax_b200 as px
+    prob, params = _build("quad4", n=8, nt=2, t0=0.0)
+    opt = px.Adam(px.EnergyLoss(), learning_rate=1e-3, has_aux=True)
+    tr = px.Trainer(prob, opt, log_every=5, serialise_every=10, workdir=str(tmp_path))
+    l0 = float(px.EnergyLoss()(params, prob)[0])
+    params = tr.train(params, 30)
+    l1 = float(px.EnergyLoss()(params, prob)[0])
+    assert l1 < l0
+    assert os.path.exists(tmp_path / "history" / "history.csv")
+    ck = sorted(os.listdir(tmp_path / "checkpoint"))
+    assert len(ck) == 3
+    w = params.fields.networks.weights.clone()
+    params.fields.networks.weights.zero_()
+    params.deserialise(str(tmp_path / "checkpoint" / ck[-1]))
+    assert float(params.fields.networks.weights.abs().sum()) > 0 and not torch.equal(w, params.fields.networks.weights)
+
+
+def test_poisson_example_through_the_api(cuda_device):
+    """C1: the reference's Poisson example (examples/forward_problems/poisson/variational_example.py)."""
+    import math
+    import pancax_b200 as px
+    from oracle import bvps as obvps
+    from oracle import losses as ol
+    fsg = np.load(os.path.join(G, "function_space.npz"))
+    nodesets = {k[len("quad4_ns_"):]: fsg[k] for k in fsg.files if k.startswith("quad4_ns_")}
+    mesh = px.Mesh(fsg["quad4_coords"], fsg["quad4_conns"], "quad4", nodesets)
+    times = np.linspace(0.0, 1.0, 2)
+    domain = px.VariationalDomain(mesh, times)
+    physics = px.Poisson(lambda x: 2 * math.pi ** 2 * np.sin(2.0 * math.pi * x[..., 0]) * np.sin(2.0 * math.pi * x[..., 1]))
+
+    def bc_func(x, t, z):           # per-point, exactly as in the example
+        x, y = x[0], x[1]
+        return x * (1. - x) * y * (1. - y) * z
+    bcs = [px.DirichletBC(nset_name=f"nset_{i}", component=0) for i in (1, 2, 3, 4)]
+    problem = px.ForwardProblem(domain, physics, [], bcs, [])
+    params = px.Parameters(problem, key=100, dirichlet_bc_func=bc_func)
+    assert params.fields.networks.num_weights == 5350
+    (loss, aux), grads = px.EnergyLoss().value_and_grad(params, problem)
+    op = ol.OracleProblem(coords=mesh.coords, conns=mesh.conns, elem="quad4", q_order=2, times=times, kind="poisson",
+                          ndof=1, mlp=ol.MLPSpec(3, 1, 50, 3), bc_func=obvps.poisson_example_bc,
+                          source=obvps.poisson_example_source)
+    Lo, _, gwo, _ = ol.loss_and_grad(op, dict(kind="energy", energy_weight=1.0),
+                                     params.fields.networks.weights.cpu().numpy())
+    assert abs(float(loss) - Lo) <= TOL * abs(Lo)
+    assert rel(grads.fields.cpu().numpy(), gwo) < TOL
+
+
+def test_adam_kernel_matches_restated_optax(cuda_device):
+    from oracle.optim import AdamState, adam_step
+    from pancax_b200 import _lib
+    from pancax_b200.engine import _ptr, _stream
+    rng = np.random.default_rng(0)
+    n = 10007
+    p = rng.standard_normal(n)
+    st = AdamState(n)
+    dp = torch.as_tensor(p).cuda()
+    mu, nu = torch.zeros_like(dp), torch.zeros_like(dp)
+    lib = _lib.load()
+    for k in range(1, 6):
+        g = rng.standard_normal(n)
+        lr = 1e-2 * 0.99 ** ((k - 1) / 500)
+        p = adam_step(p, g, st, 1e-2)
+        _lib.check(lib.pcx_adam_step(_ptr(dp), _ptr(torch.as_tensor(g).cuda()), _ptr(mu), _ptr(nu), n, k, lr,
+                                     0.9, 0.999, 1e-8, _stream()))
+    assert rel(dp.cpu().numpy(), p) < 1e-14

@@ -1,0 +1,202 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pcx_abi.h declares (no compute
+calls), and the host-side mirror of the reference interface behaves like the reference's."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from pancax_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pcx_abi.h")).read()
+    declared = sorted(set(re.findall(r"\b(pcx_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in pcx_abi.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared
+    assert lib.pcx_abi_version() == 1
+    assert lib.pcx_last_error() is not None
+
+
+def test_null_handle_is_an_error_not_a_crash():
+    from pancax_b200 import _lib
+    lib = _lib.load()
+    assert lib.pcx_num_weights(None) == -1
+    assert lib.pcx_create(None, None) != 0
+    assert b"null" in lib.pcx_last_error()
+
+
+def test_engine_refuses_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pancax_b200 import Engine
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Engine(np.zeros((4, 2)), np.zeros((1, 4), dtype=np.int32), "quad4", 2, 2, np.array([0.0, 1.0]))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pancax_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+                assert "/root/reference" not in src
+
+
+# ------------------------------------------------------------------ fem
+def test_read_reference_fixture_arrays_and_roundtrip(tmp_path):
+    import pancax_b200 as px
+    g = np.load(os.path.join(G, "function_space.npz"))
+    for elem in ("hex8", "quad4", "tri3"):
+        nodesets = {k[len(elem) + 4:]: g[k] for k in g.files if k.startswith(f"{elem}_ns_")}
+        m = px.Mesh(g[f"{elem}_coords"], g[f"{elem}_conns"], elem, nodesets)
+        p = str(tmp_path / f"{elem}.g")
+        px.write_exodus_mesh(p, m)
+        m2 = px.read_exodus_mesh(p)
+        assert m2.elem_type == elem
+        assert np.array_equal(m2.coords, m.coords) and np.array_equal(m2.conns, m.conns)
+        assert sorted(m2.nodeSets) == sorted(m.nodeSets)
+        for k in m.nodeSets:
+            assert np.array_equal(m2.nodeSets[k], m.nodeSets[k])
+        assert m2.conns.dtype == np.int32 and m2.conns.min() == 0   # connect1 - 1, read_exodus_mesh.py:90-93
+
+
+def test_structured_mesh():
+    import pancax_b200 as px
+    m = px.create_structured_mesh("hex8", (3, 4, 5), lengths=(1.0, 2.0, 3.0), origin=(0.0, 0.0, 1.0))
+    assert m.num_elements == 60 and m.num_nodes == 4 * 5 * 6
+    assert np.allclose(m.coords.min(0), [0, 0, 1]) and np.allclose(m.coords.max(0), [1, 2, 4])
+    assert np.allclose(m.coords[m.nodeSets["nset_5"], 1], 2.0) and np.allclose(m.coords[m.nodeSets["nset_1"], 2], 4.0)
+    mp = px.create_structured_mesh("quad4", 6, permute_seed=3)
+    assert np.allclose(mp.coords[mp.nodeSets["nset_1"], 1], 1.0)
+    # element areas are unchanged by the permutation
+    X = mp.coords[mp.conns]
+    area = 0.5 * np.abs((X[:, 2, 0] - X[:, 0, 0]) * (X[:, 3, 1] - X[:, 1, 1]) - (X[:, 3, 0] - X[:, 1, 0]) * (X[:, 2, 1] - X[:, 0, 1]))
+    assert np.allclose(area, 1.0 / 36.0)
+    with pytest.raises(ValueError):
+        px.Mesh(np.zeros((3, 2)), np.zeros((1, 4), dtype=np.int32), "hex8")
+
+
+def test_domain_time_checks():
+    import pancax_b200 as px
+    from pancax_b200.domains import (SimulationTimesNotStrictlyIncreasingException,
+                                     SimulationTimesNotUniqueException)
+    m = px.create_structured_mesh("quad4", 2)
+    with pytest.raises(SimulationTimesNotUniqueException):
+        px.VariationalDomain(m, np.array([0.0, 0.5, 0.5]))
+    with pytest.raises(SimulationTimesNotStrictlyIncreasingException):
+        px.VariationalDomain(m, np.array([0.0, 0.7, 0.5]))
+    d = px.VariationalDomain(m, np.linspace(0, 1, 3))
+    assert d.q_order == 2 and d.conns.shape == (4, 4)
+
+
+def _problem(elem="quad4", n=3, nt=3):
+    import pancax_b200 as px
+    m = px.create_structured_mesh(elem, n)
+    d = px.VariationalDomain(m, np.linspace(0, 1, nt))
+    nd = m.num_dimensions
+    if nd == 2:
+        phys = px.SolidMechanics(px.NeoHookean(bulk_modulus=1000.0, shear_modulus=px.BoundedProperty(0.01, 5.0, 0)),
+                                 px.PlaneStrain())
+    else:
+        phys = px.SolidMechanics(px.NeoHookean(bulk_modulus=1000.0, shear_modulus=1.0), px.ThreeDimensional())
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_1", "nset_3") for c in range(nd)]
+    return px.ForwardProblem(d, phys, dirichlet_bcs=bcs)
+
+
+def test_problem_and_parameters_shapes():
+    import pancax_b200 as px
+    prob = _problem("quad4")
+    assert prob.n_dims == 2 and prob.n_dofs == 2
+    assert prob.dof_manager.get_unknown_size() == 2 * 16 - 2 * 8
+    params = px.Parameters(prob, key=0, device="cpu")
+    net = params.fields.networks
+    # test/networks/test_mlp.py, test_fields.py: shapes; default n_layers=3, n_neurons=50 (fields.py:28-29)
+    assert (net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers) == (3, 2, 50, 3)
+    assert net.num_weights == 3 * 50 + 50 + 2 * (50 * 50 + 50) + 50 * 2 == 5400
+    assert px.mlp_num_weights(4, 3, 50, 4) == 8050 and px.mlp_num_weights(3, 1, 50, 3) == 5350
+    layers = net.layers()
+    assert layers[0][0].shape == (50, 3) and layers[-1][0].shape == (2, 50) and layers[-1][1] is None
+    assert float(layers[0][0].abs().max()) <= 1 / np.sqrt(3)
+    assert params.prop_raw.numel() == 1
+    assert params.fields.normalize_time is True
+    assert set(params.properties()) == {"bulk_modulus", "shear_modulus"}
+    p3 = _problem("hex8", 2)
+    assert px.Parameters(p3, key=0, n_layers=4, device="cpu").fields.networks.num_weights == 8050
+    # a static problem (all times equal is impossible: unique) -> single time disables normalisation
+    m = px.create_structured_mesh("quad4", 2)
+    d1 = px.VariationalDomain(m, np.array([0.0]))
+    prob1 = px.ForwardProblem(d1, px.Poisson(lambda x: x[..., 0]), dirichlet_bcs=[])
+    assert px.Parameters(prob1, key=0, device="cpu").fields.normalize_time is False
+
+
+def test_incompatible_problem_pieces_raise():
+    import pancax_b200 as px
+    from pancax_b200.problems import DomainPhysicsCompatabilityError
+    m = px.create_structured_mesh("quad4", 2)
+    d = px.VariationalDomain(m, np.linspace(0, 1, 2))
+    with pytest.raises(DomainPhysicsCompatabilityError):
+        px.ForwardProblem(d, object())
+    with pytest.raises(NotImplementedError):
+        from pancax_b200.physics_kernels import PlaneStress
+        PlaneStress()
+    with pytest.raises(NotImplementedError):
+        px.MLP(3, 2, 50, 3, activation="relu", device="cpu")
+
+
+def test_tabulate_bc_and_refusal_of_non_affine_wrappers():
+    import pancax_b200 as px
+    from pancax_b200.loss_functions import _wrap_bc
+    m = px.create_structured_mesh("quad4", 3)
+    times = np.linspace(0, 1, 3)
+    f = px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 2)
+    a, b = px.tabulate_bc(f, m.coords, times, 2)
+    z = np.random.default_rng(0).standard_normal((m.num_nodes, 2))
+    assert np.allclose(a[2] + b[2] * z, f(m.coords, 1.0, z))
+    assert np.all(a[0] == 0) and np.all(b[0] == 0)          # ramp: u(x, 0) == 0 exactly
+    with pytest.raises(NotImplementedError):
+        px.tabulate_bc(lambda x, t, z: z ** 2, m.coords, times, 2)
+    with pytest.raises(NotImplementedError):
+        px.tabulate_bc(lambda x, t, z: z[:, ::-1], m.coords, times, 2)   # not diagonal
+
+    # a per-point wrapper written for pancax (jax-style .at[].set) is tabulated through the adapter
+    def per_point(xs, t, nn):
+        y = xs[1]
+        u_out = nn
+        u_out = u_out.at[0].set(y * (y - 1.0) * t * nn[0])
+        u_out = u_out.at[1].set(y * t * 1.0 + y * (y - 1.0) * t * nn[1])
+        return u_out
+    a2, b2 = px.tabulate_bc(_wrap_bc(per_point, 2), m.coords, times, 2)
+    assert np.allclose(a2, a) and np.allclose(b2, b)
+
+
+def test_partition_mesh_closure_and_coverage():
+    import pancax_b200 as px
+    from pancax_b200.parallel import partition_mesh
+    m = px.create_structured_mesh("hex8", 4, permute_seed=1)
+    seen = np.zeros(m.num_elements, dtype=int)
+    total_nodes = 0
+    for r in range(3):
+        sub, l2g = partition_mesh(m, r, 3)
+        lo, hi = (m.num_elements * r) // 3, (m.num_elements * (r + 1)) // 3
+        seen[lo:hi] += 1
+        assert np.array_equal(l2g[sub.conns], m.conns[lo:hi])          # bit-exact connectivity
+        assert np.array_equal(sub.coords, m.coords[l2g])
+        for k, v in sub.nodeSets.items():
+            assert set(l2g[v]) <= set(m.nodeSets[k])
+        total_nodes += sub.num_nodes
+    assert np.all(seen == 1) and total_nodes >= m.num_nodes
+
+
+def test_adam_restatement_first_step_is_lr_sign():
+    from oracle.optim import AdamState, adam_step
+    g = np.array([0.5, -2.0, 1e-3])
+    p = adam_step(np.zeros(3), g, AdamState(3), 1e-3)
+    assert np.allclose(p, -1e-3 * np.sign(g), rtol=1e-6)     # |mhat|/sqrt(vhat) = 1 on the first update

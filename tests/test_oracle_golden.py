@@ -1,0 +1,314 @@
+"""CPU: pins the oracle (oracle/) and the host-side mirrors against vectors produced by the
+reference's OWN source (tests/golden/*.npz, generator oracle/gen_golden.py), and replays the
+closed-form known-answer tests of the reference's test-suite."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bvps as obvps
+from oracle import fem as ofem
+from oracle import models as om
+from oracle.physics import Physics, element_geometry, potential_energy
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def T(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64)
+
+
+# ------------------------------------------------------------------ parent tables / quadrature
+@pytest.mark.parametrize("elem,q", [("hex8", 1), ("hex8", 2), ("quad4", 1), ("quad4", 2), ("quad4", 3),
+                                    ("tri3", 1), ("tri3", 2)])
+def test_tables_match_reference(elem, q):
+    g = load("tables.npz")
+    pe = ofem.ParentElement(elem, q)
+    assert np.array_equal(pe.xi, g[f"{elem}_q{q}_xi"])
+    assert np.array_equal(pe.w, g[f"{elem}_q{q}_w"])
+    assert np.allclose(pe.N, g[f"{elem}_q{q}_N"], rtol=0, atol=4e-16)
+    assert np.allclose(pe.dN, g[f"{elem}_q{q}_dN"], rtol=0, atol=4e-16)
+
+
+def test_quadrature_errors_like_reference():
+    # test/fem/test_quadrature_rules.py:145-168: ValueError on hex degree 3 / quad degree 4
+    g = load("tables.npz")
+    with pytest.raises(ValueError) as e:
+        ofem.quadrature_rule("hex8", 3)
+    assert str(e.value) == str(g["hex8_q3_error"])
+    with pytest.raises(ValueError) as e:
+        ofem.quadrature_rule("quad4", 4)
+    assert str(e.value) == str(g["quad4_q4_error"])
+
+
+@pytest.mark.parametrize("elem", ["hex8", "quad4", "tri3"])
+def test_shape_function_identities(elem):
+    # test/fem/elements/test_elements.py:286-319
+    g = load("tables.npz")
+    nodes = g[f"{elem}_nodes"]
+    N, dN = ofem.shape_tables(elem, nodes)
+    assert np.allclose(N, np.eye(nodes.shape[0]), atol=1e-14)          # Kronecker delta at nodes
+    for q in (1, 2):
+        pe = ofem.ParentElement(elem, q)
+        assert np.allclose(pe.N.sum(1), 1.0, atol=1e-14)               # partition of unity
+        assert np.allclose(pe.dN.sum(1), 0.0, atol=1e-14)              # gradients sum to zero
+        assert np.all(pe.w > 0)
+
+
+def test_rule_sizes():
+    # test/fem/test_quadrature_rules.py:135-141
+    assert len(ofem.quadrature_rule("hex8", 1)[1]) == 1
+    assert len(ofem.quadrature_rule("hex8", 2)[1]) == 8
+    assert len(ofem.quadrature_rule("quad4", 2)[1]) == 4
+
+
+# ------------------------------------------------------------------ function space
+@pytest.mark.parametrize("elem", ["hex8", "quad4", "tri3"])
+def test_function_space_matches_reference(elem):
+    g = load("function_space.npz")
+    coords, conns, sel = g[f"{elem}_coords"], g[f"{elem}_conns"], g[f"{elem}_sel"]
+    pe = ofem.ParentElement(elem, 2)
+    X = T(coords)[torch.as_tensor(conns[sel], dtype=torch.long)]
+    gN, JxW, _ = element_geometry(pe, X)
+    assert np.allclose(gN.numpy(), g[f"{elem}_gradN"], rtol=1e-12, atol=1e-13)
+    assert np.allclose(JxW.numpy(), g[f"{elem}_JxW"], rtol=1e-13, atol=0)
+    Xall = T(coords)[torch.as_tensor(conns, dtype=torch.long)]
+    vol = float(element_geometry(pe, Xall)[1].sum())
+    assert abs(vol - float(g[f"{elem}_volume"])) < 1e-12
+
+
+def test_linear_field_gradient_reproduced():
+    # test/fem/test_function_space.py:104-137: a linear field has an exact constant gradient
+    g = load("function_space.npz")
+    for elem, nd in (("hex8", 3), ("quad4", 2), ("tri3", 2)):
+        coords, conns = g[f"{elem}_coords"], g[f"{elem}_conns"]
+        A = np.arange(1, nd * nd + 1, dtype=np.float64).reshape(nd, nd) / 7.0
+        u = coords @ A.T
+        pe = ofem.ParentElement(elem, 2)
+        idx = torch.as_tensor(conns, dtype=torch.long)
+        gN, _, _ = element_geometry(pe, T(coords)[idx])
+        grad_u = torch.einsum("eai,eqaj->eqij", T(u)[idx], gN).numpy()
+        assert np.allclose(grad_u, A, atol=1e-12)
+
+
+def test_unknown_indices_match_reference_dof_manager():
+    g = load("function_space.npz")
+    nodesets = {k[len("hex8_ns_"):]: g[k] for k in g.files if k.startswith("hex8_ns_")}
+    bcs = [(s, c) for s in ("nset_3", "nset_5") for c in range(3)]
+    ui = ofem.unknown_indices(g["hex8_coords"].shape[0], 3, nodesets, bcs)
+    assert np.array_equal(ui, g["hex8_unknownIndices"])
+    # the product's DofManager mirror
+    import types
+    from pancax_b200.bcs import DirichletBC
+    from pancax_b200.fem import DofManager
+    mesh = types.SimpleNamespace(num_nodes=g["hex8_coords"].shape[0], nodeSets=nodesets)
+    dm = DofManager(mesh, 3, [DirichletBC(component=c, nset_name=s) for s, c in bcs])
+    assert np.array_equal(dm.unknownIndices, g["hex8_unknownIndices"])
+    assert dm.get_bc_size() + dm.get_unknown_size() == 3 * mesh.num_nodes
+
+
+# ------------------------------------------------------------------ constitutive models
+SW = dict(bulk_modulus=10.0, A1=0.93074321, P1=-0.07673672, B1=0.0, Q1=-0.5, C1=0.10448312, R1=1.71691036,
+          cutoff_strain=0.01)
+PROPS = {
+    "neohookean": ("neohookean", dict(bulk_modulus=0.833, shear_modulus=0.3846)),
+    "neohookean_stiff": ("neohookean", dict(bulk_modulus=1000.0, shear_modulus=1.0)),
+    "gent": ("gent", dict(bulk_modulus=0.833, shear_modulus=0.3846, Jm_parameter=3.0)),
+    "swanson": ("swanson", SW),
+    "swanson_b": ("swanson", dict(SW, B1=0.21, Q1=0.5)),
+    "hencky": ("hencky", dict(bulk_modulus=0.833, shear_modulus=0.3846)),
+}
+
+
+@pytest.mark.parametrize("name", list(PROPS))
+def test_energy_and_stress_match_reference(name):
+    g = load("constitutive.npz")
+    model, props = PROPS[name]
+    H = T(g["grad_u"])
+    W = om.energy(model, H, props).numpy()
+    assert np.allclose(W, g[f"{name}_W"], rtol=1e-12, atol=1e-14), np.abs(W - g[f"{name}_W"]).max()
+    P = om.pk1_stress(model, H, props).numpy()
+    exact = str(g[f"{name}_P_method"]) == "complex-step"
+    tol = 1e-11 if exact else 2e-7
+    scale = np.abs(g[f"{name}_P"]).max()
+    assert np.abs(P - g[f"{name}_P"]).max() <= tol * max(scale, 1.0), name
+    assert np.allclose(om.jacobian(H).numpy(), g[f"{name}_J"], rtol=1e-13)
+    assert np.allclose(om.I1_bar(H).numpy(), g[f"{name}_I1bar"], rtol=1e-13)
+    if name == "swanson":
+        assert np.allclose(om.I2_bar(H).numpy(), g["swanson_I2bar"], rtol=1e-13)
+
+
+def test_bounded_property():
+    g = load("constitutive.npz")
+    v = om.bounded_property(0.01, 5.0, T(g["bounded_raw"])).numpy()
+    assert np.allclose(v, g["bounded_val"], rtol=1e-15)
+    from pancax_b200.constitutive_models import BoundedProperty
+    bp = BoundedProperty(0.01, 5.0, 0)
+    for r, val in zip(g["bounded_raw"], g["bounded_val"]):
+        bp.prop_val = np.array([r])
+        assert abs(bp() - val) < 1e-15
+
+
+def _simple_shear(gm):
+    F = np.tile(np.eye(3), (len(gm), 1, 1)); F[:, 0, 1] = gm
+    return F
+
+
+def _uniaxial(lm):
+    F = np.tile(np.eye(3), (len(lm), 1, 1)); F[:, 0, 0] = lm
+    return F
+
+
+def _cauchy(model, props, F):
+    H = T(F - np.eye(3))
+    P = om.pk1_stress(model, H, props).numpy()
+    J = np.linalg.det(F)
+    return np.einsum("nij,nkj->nik", P, F) / J[:, None, None]     # (1/J) P F^T, mechanics/base.py:11-17
+
+
+def test_neohookean_closed_forms():
+    # test/constitutive_models/test_neohookean.py:27-130
+    K, Gs = 0.833, 0.3846
+    props = dict(bulk_modulus=K, shear_modulus=Gs)
+    gm = np.linspace(0.0, 1.0, 100)
+    F = _simple_shear(gm)
+    s = _cauchy("neohookean", props, F)
+    assert np.allclose(s[:, 0, 0], 2.0 / 3.0 * Gs * gm ** 2)
+    assert np.allclose(s[:, 1, 1], -1.0 / 3.0 * Gs * gm ** 2)
+    assert np.allclose(s[:, 2, 2], -1.0 / 3.0 * Gs * gm ** 2)
+    assert np.allclose(s[:, 0, 1], Gs * gm) and np.allclose(s[:, 1, 0], Gs * gm)
+    assert np.allclose(s[:, 1, 2], 0.0) and np.allclose(s[:, 2, 0], 0.0)
+    lm = np.linspace(1.0, 4.0, 100)
+    F = _uniaxial(lm)
+    s = _cauchy("neohookean", props, F)
+    s11 = 0.5 * K * (lm - 1.0 / lm) + 2.0 / 3.0 * Gs * (lm ** 2 - 1.0) * lm ** (-5.0 / 3.0)
+    s22 = 0.5 * K * (lm - 1.0 / lm) - 1.0 / 3.0 * Gs * (lm ** 2 - 1.0) * lm ** (-5.0 / 3.0)
+    assert np.allclose(s[:, 0, 0], s11) and np.allclose(s[:, 1, 1], s22) and np.allclose(s[:, 2, 2], s22)
+    J = lm
+    I1b = J ** (-2.0 / 3.0) * (lm ** 2 + 2.0)
+    psi = om.energy("neohookean", T(F - np.eye(3)), props).numpy()
+    assert np.allclose(psi, 0.5 * K * (0.5 * (J ** 2 - 1) - np.log(J)) + 0.5 * Gs * (I1b - 3.0))
+
+
+def test_gent_closed_forms():
+    # test/constitutive_models/test_gent.py:29-138 (Jm = 3)
+    K, Gs, Jm = 0.833, 0.3846, 3.0
+    props = dict(bulk_modulus=K, shear_modulus=Gs, Jm_parameter=Jm)
+    gm = np.linspace(0.0, 1.0, 100)
+    s = _cauchy("gent", props, _simple_shear(gm))
+    assert np.allclose(s[:, 0, 0], 2.0 / 3.0 * Gs * Jm * gm ** 2 / (Jm - gm ** 2))
+    assert np.allclose(s[:, 1, 1], -1.0 / 3.0 * Gs * Jm * gm ** 2 / (Jm - gm ** 2))
+    assert np.allclose(s[:, 0, 1], Gs * Jm * gm / (Jm - gm ** 2))
+
+
+def test_swanson_closed_forms():
+    # test/constitutive_models/test_swanson.py:45-165 (atol 1e-3: the cutoff-strain regularisation)
+    K, A1, P1, C1, R1 = SW["bulk_modulus"], SW["A1"], SW["P1"], SW["C1"], SW["R1"]
+    gm = np.linspace(0.05, 1.0, 100)
+    F = _simple_shear(gm)
+    s = _cauchy("swanson", SW, F)
+    J = np.linalg.det(F)
+    Bb = J[:, None, None] ** (-2.0 / 3.0) * np.einsum("nij,nkj->nik", F, F)
+    I1b = np.trace(Bb, axis1=1, axis2=2)
+    dU = 0.5 * A1 * (I1b / 3.0 - 1.0) ** P1 + 0.5 * C1 * (I1b / 3.0 - 1.0) ** R1
+    dev = Bb - I1b[:, None, None] / 3.0 * np.eye(3)
+    san = (2.0 / J)[:, None, None] * dU[:, None, None] * dev + (K * np.log(J))[:, None, None] * np.eye(3)
+    assert np.allclose(s[:, 0, 0], san[:, 0, 0], atol=1e-3)
+    assert np.allclose(s[:, 1, 1], san[:, 1, 1], atol=1e-3)
+    assert np.allclose(s[:, 0, 1], san[:, 0, 1], atol=1e-3)
+    psi = om.energy("swanson", T(F - np.eye(3)), SW).numpy()
+    psi_an = (K * (J * np.log(J) - J + 1.0) + 1.5 * A1 / (P1 + 1.0) * (I1b / 3.0 - 1.0) ** (P1 + 1.0)
+              + 1.5 * C1 / (R1 + 1.0) * (I1b / 3.0 - 1.0) ** (R1 + 1.0))
+    assert np.allclose(psi, psi_an, atol=1e-3)
+
+
+def test_jacobian_of_diagonal():
+    # test/constitutive_models/test_base_constitutive_model.py:5-13
+    H = T(np.diag([4.0, 2.0, 1.0]) - np.eye(3))
+    assert abs(float(om.jacobian(H)) - 8.0) < 1e-14
+
+
+def test_formulations():
+    # test/physics_kernels/test_solid_mechanics.py:37-53,133-148
+    H2 = torch.arange(1.0, 5.0, dtype=torch.float64).reshape(2, 2)
+    H3 = om.tensor_2D_to_3D(H2)
+    assert torch.equal(H3[:2, :2], H2) and float(H3[2].abs().sum() + H3[:, 2].abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------ tensor math (Hencky)
+def test_eigen_and_log_sqrt_match_reference():
+    g = load("tensor_math.npz")
+    C = T(g["C"])
+    lam, V = om.eigen_sym33_unit(C)
+    assert np.allclose(lam.numpy(), g["evals"], rtol=1e-12, atol=1e-15)
+    assert np.allclose(V.numpy(), g["evecs"], rtol=0, atol=1e-10)
+    assert np.allclose(om.mtk_log_sqrt_value(C).numpy(), g["log_sqrt"], rtol=0, atol=1e-12)
+    jv = om.mtk_log_sqrt_jvp(C, T(g["H"])).numpy()
+    assert np.allclose(jv, g["log_sqrt_jvp"], rtol=1e-10, atol=1e-12 * np.abs(g["log_sqrt_jvp"]).max())
+    assert np.allclose(om.cos_of_acos_divided_by_3(T(g["cos3_x"])).numpy(), g["cos3"], rtol=1e-15)
+    assert np.allclose(om.relative_log_difference(T(g["rld_l1"]), T(g["rld_l2"])).numpy(), g["rld"], rtol=1e-13)
+
+
+def test_log_sqrt_against_scipy():
+    # test/math/test_tensor_math.py: log_sqrt of an SPD tensor == 0.5 logm
+    from scipy.linalg import logm
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((3, 3))
+    C = A.T @ A + 0.5 * np.eye(3)
+    assert np.allclose(om.mtk_log_sqrt_value(T(C)).numpy(), 0.5 * logm(C).real, atol=1e-12)
+
+
+# ------------------------------------------------------------------ potential energy on the reference's fixtures
+@pytest.mark.parametrize("elem,mname", [("hex8", "neohookean_stiff"), ("hex8", "gent"), ("hex8", "swanson"),
+                                        ("hex8", "hencky"), ("quad4", "neohookean_stiff"), ("quad4", "gent"),
+                                        ("quad4", "swanson"), ("quad4", "hencky"), ("tri3", "neohookean")])
+def test_potential_energy_matches_reference(elem, mname):
+    g, fsg = load("potential_energy.npz"), load("function_space.npz")
+    model, props = PROPS[mname]
+    form = "three_dimensional" if elem == "hex8" else "plane_strain"
+    phys = Physics("solid", 3 if elem == "hex8" else 2, model, props, form)
+    pe = ofem.ParentElement(elem, 2)
+    pi = potential_energy(phys, pe, T(fsg[f"{elem}_coords"]),
+                          torch.as_tensor(fsg[f"{elem}_conns"], dtype=torch.long), T(g[f"{elem}_us"]))
+    ref = float(g[f"{elem}_{mname}_Pi"])
+    assert abs(float(pi) - ref) <= 1e-12 * abs(ref), (float(pi), ref)
+
+
+def test_poisson_energy_matches_reference():
+    g, fsg = load("potential_energy.npz"), load("function_space.npz")
+    phys = Physics("poisson", 1, source=obvps.poisson_example_source)
+    pe = ofem.ParentElement("quad4", 2)
+    pi = potential_energy(phys, pe, T(fsg["quad4_coords"]), torch.as_tensor(fsg["quad4_conns"], dtype=torch.long),
+                          T(g["quad4_poisson_us"]))
+    ref = float(g["quad4_poisson_Pi"])
+    assert abs(float(pi) - ref) <= 1e-12 * abs(ref)
+
+
+# ------------------------------------------------------------------ Dirichlet wrappers
+def test_bvps_match_reference():
+    from pancax_b200 import bvps as pbvps
+    g = load("bvps.npz")
+    t = float(g["t"])
+    for mod, conv in ((obvps, T), (pbvps, np.asarray)):
+        def run(f, pts, z):
+            out = f(conv(pts), t, conv(z))
+            return out.numpy() if hasattr(out, "numpy") else out
+        for d in ("x", "y"):
+            assert np.allclose(run(mod.UniaxialTensionLinearRamp(0.8, 1.5, d, 2), g["pts2"], g["z2"]),
+                               g[f"uniaxial2_{d}"], rtol=1e-14, atol=1e-16)
+        for d in ("x", "y", "z"):
+            assert np.allclose(run(mod.UniaxialTensionLinearRamp(0.8, 1.5, d, 3), g["pts3"], g["z3"]),
+                               g[f"uniaxial3_{d}"], rtol=1e-14, atol=1e-16)
+        assert np.allclose(run(mod.SimpleShearLinearRamp(0.8, 1.5, "xy"), g["pts2"], g["z2"]), g["simple_shear"],
+                           rtol=1e-14, atol=1e-16)
+        assert np.allclose(run(mod.BiaxialLinearRamp(0.8, 0.3, 1.5, 1.2), g["pts2"], g["z2"]), g["biaxial"],
+                           rtol=1e-14, atol=1e-16)
+    with pytest.raises(ValueError):
+        pbvps.UniaxialTensionLinearRamp(1.0, 1.0, "z", 2)
+    with pytest.raises(ValueError):
+        pbvps.UniaxialTensionLinearRamp(1.0, 1.0, "x", 4)
