@@ -75,6 +75,7 @@ struct pcx_handle {
   int32_t* adj_idx = nullptr;
   long long launches = 0;
   int sm_count = 148;
+  int fwd_variant = 12;   // (MT, min CTAs/SM) of the forward kernel; PCX_FWD_VARIANT overrides (tuning)
   bool prof_on = false;
   struct ProfEv { int cat; cudaEvent_t e0, e1; };
   std::vector<ProfEv> prof_events;
@@ -320,48 +321,74 @@ static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, c
   return PCX_OK;
 }
 
+template <int NT, int DH, bool WSMEM>
+static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
+  const size_t smem = sizeof(BwdSmem<NT, DH, WSMEM>);
+  if (smem > 227 * 1024)
+    return fail(PCX_ERR_UNSUPPORTED, "MLP %d x %d needs %zu bytes of shared memory in the adjoint kernel", h->ms.width,
+                h->ms.depth, smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, DH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_mlp_backward<NT, DH, WSMEM><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+template <int NT, int DH>
+static int launch_mlp_bwd_d(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
+  // weight fragments in shared memory when they fit next to the tiles, else through L1
+  if constexpr (sizeof(BwdSmem<NT, DH, true>) <= 227 * 1024) return launch_mlp_bwd_v<NT, DH, true>(h, grid, st, io);
+  else return launch_mlp_bwd_v<NT, DH, false>(h, grid, st, io);
+}
+
 template <int NT>
 static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, const MlpIO& io) {
-#define PCX_BWD_CASE(dh)                                                                                     \
-  case dh: {                                                                                                 \
-    const size_t smem = sizeof(BwdSmem<NT, dh>);                                                            \
-    static bool attr_set = false;                                                                            \
-    if (!attr_set) {                                                                                         \
-      CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, dh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set = true;                                                                                       \
-    }                                                                                                        \
-    k_mlp_backward<NT, dh><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);                                   \
-    break;                                                                                                   \
-  }
   switch (DH) {
-    PCX_BWD_CASE(0)
-    PCX_BWD_CASE(1)
-    PCX_BWD_CASE(2)
-    PCX_BWD_CASE(3)
-    PCX_BWD_CASE(4)
+    case 0: return launch_mlp_bwd_d<NT, 0>(h, grid, st, io);
+    case 1: return launch_mlp_bwd_d<NT, 1>(h, grid, st, io);
+    case 2: return launch_mlp_bwd_d<NT, 2>(h, grid, st, io);
+    case 3: return launch_mlp_bwd_d<NT, 3>(h, grid, st, io);
+    case 4: return launch_mlp_bwd_d<NT, 4>(h, grid, st, io);
     default: return fail(PCX_ERR_UNSUPPORTED, "MLP depth %d not supported (1..5 hidden layers)", DH + 1);
   }
-#undef PCX_BWD_CASE
+}
+
+template <int NT, int MT, int MINB>
+static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
+  const long long groups = (io.n + 8 * MT - 1) / (8 * MT);
+  long long blocks = (groups + 7) / 8;
+  const long long maxb = (long long)h->sm_count * MINB;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  k_mlp_forward<NT, MT, MINB><<<(int)blocks, 256, smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
 
 static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   ProfScope ps(h, PCX_PROF_MLP_FORWARD, st);
-  const long long groups = (io.n + 15) / 16;
-  long long blocks = (groups + 7) / 8;
-  const long long maxb = (long long)h->sm_count * 2;
-  if (blocks > maxb) blocks = maxb;
-  if (blocks < 1) blocks = 1;
   switch (h->ms.NT) {
-    case 2: k_mlp_forward<2, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
-    case 4: k_mlp_forward<4, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
-    case 7: k_mlp_forward<7, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
-    case 8: k_mlp_forward<8, 2><<<(int)blocks, 256, 0, st>>>(h->ms, io); break;
+    case 2: return launch_mlp_fwd_v<2, 2, 2>(h, st, io);
+    case 4: return launch_mlp_fwd_v<4, 2, 2>(h, st, io);
+    case 7:
+      switch (h->fwd_variant) {
+        case 12: return launch_mlp_fwd_v<7, 1, 2>(h, st, io);
+        case 21: return launch_mlp_fwd_v<7, 2, 1>(h, st, io);
+        default: return launch_mlp_fwd_v<7, 2, 2>(h, st, io);
+      }
+    case 8: return launch_mlp_fwd_v<8, 1, 2>(h, st, io);
     default: return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
   }
-  LAUNCH_CHECK(h);
-  return PCX_OK;
 }
 
 static int bwd_rows_per_cta(const pcx_handle* h) { return 8 * (h->ms.NT + 1); }
@@ -471,6 +498,7 @@ extern "C" int pcx_create(pcx_handle** out, const pcx_mesh_desc* m) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
   if (prop.major < 10) { delete h; return fail(PCX_ERR_UNSUPPORTED, "libpancax_b200 requires an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor); }
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("PCX_FWD_VARIANT")) h->fwd_variant = atoi(e);
   h->elem_type = m->elem_type; h->q_order = m->q_order;
   h->nd = h->tab.nd; h->nnpe = h->tab.nnpe; h->nq = h->tab.nq;
   h->ndof = m->ndof; h->ne = m->ne; h->nn = m->nn; h->nt = m->nt;
