@@ -321,7 +321,7 @@ static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, c
   return PCX_OK;
 }
 
-template <int NT, int DH, bool WSMEM>
+template <int NT, int KODD, int DH, bool WSMEM>
 static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
   const size_t smem = sizeof(BwdSmem<NT, DH, WSMEM>);
   if (smem > 227 * 1024)
@@ -329,10 +329,10 @@ static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpI
                 h->ms.depth, smem);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, DH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  k_mlp_backward<NT, DH, WSMEM><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
+  k_mlp_backward<NT, KODD, DH, WSMEM><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
@@ -340,8 +340,11 @@ static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpI
 template <int NT, int DH>
 static int launch_mlp_bwd_d(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
   // weight fragments in shared memory when they fit next to the tiles, else through L1
-  if constexpr (sizeof(BwdSmem<NT, DH, true>) <= 227 * 1024) return launch_mlp_bwd_v<NT, DH, true>(h, grid, st, io);
-  else return launch_mlp_bwd_v<NT, DH, false>(h, grid, st, io);
+  const bool kodd = h->ms.KS <= 2 * NT - 1;   // k-steps beyond ceil(width/4) multiply packed zeros
+  if constexpr (sizeof(BwdSmem<NT, DH, true>) <= 227 * 1024)
+    return kodd ? launch_mlp_bwd_v<NT, 1, DH, true>(h, grid, st, io) : launch_mlp_bwd_v<NT, 0, DH, true>(h, grid, st, io);
+  else
+    return kodd ? launch_mlp_bwd_v<NT, 1, DH, false>(h, grid, st, io) : launch_mlp_bwd_v<NT, 0, DH, false>(h, grid, st, io);
 }
 
 template <int NT>
@@ -356,12 +359,12 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
   }
 }
 
-template <int NT, int MT, int MINB>
+template <int NT, int KODD, int MT, int MINB>
 static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
@@ -370,23 +373,28 @@ static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   const long long maxb = (long long)h->sm_count * MINB;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
-  k_mlp_forward<NT, MT, MINB><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+  k_mlp_forward<NT, KODD, MT, MINB><<<(int)blocks, 256, smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
+}
+
+template <int NT, int MT, int MINB>
+static int launch_mlp_fwd_k(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  return (h->ms.KS <= 2 * NT - 1) ? launch_mlp_fwd_v<NT, 1, MT, MINB>(h, st, io) : launch_mlp_fwd_v<NT, 0, MT, MINB>(h, st, io);
 }
 
 static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   ProfScope ps(h, PCX_PROF_MLP_FORWARD, st);
   switch (h->ms.NT) {
-    case 2: return launch_mlp_fwd_v<2, 2, 2>(h, st, io);
-    case 4: return launch_mlp_fwd_v<4, 2, 2>(h, st, io);
+    case 2: return launch_mlp_fwd_k<2, 2, 2>(h, st, io);
+    case 4: return launch_mlp_fwd_k<4, 2, 2>(h, st, io);
     case 7:
       switch (h->fwd_variant) {
-        case 12: return launch_mlp_fwd_v<7, 1, 2>(h, st, io);
-        case 21: return launch_mlp_fwd_v<7, 2, 1>(h, st, io);
-        default: return launch_mlp_fwd_v<7, 2, 2>(h, st, io);
+        case 22: return launch_mlp_fwd_k<7, 2, 2>(h, st, io);
+        case 21: return launch_mlp_fwd_k<7, 2, 1>(h, st, io);
+        default: return launch_mlp_fwd_k<7, 1, 2>(h, st, io);
       }
-    case 8: return launch_mlp_fwd_v<8, 1, 2>(h, st, io);
+    case 8: return launch_mlp_fwd_k<8, 1, 2>(h, st, io);
     default: return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
   }
 }

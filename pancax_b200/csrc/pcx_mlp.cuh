@@ -263,7 +263,7 @@ __device__ __forceinline__ double tanh_bf(double x) {
 // fragments [F0 | FB | FH | FO | FOB] are staged ONCE per CTA into shared memory with a bulk
 // (TMA) copy and read conflict-free (lane-contiguous); activations are streamed to HBM (.cs).
 // ---------------------------------------------------------------------------------------------
-template <int NT, int MT, int MINB>
+template <int NT, int KODD, int MT, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
   const int lane = threadIdx.x & 31;
   const int r = lane >> 2, c = lane & 3;
   constexpr int KSP = 2 * NT;
+  constexpr int KS = 2 * NT - KODD;   // compile-time k-step count: no per-step branch, loads pipeline freely
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
   const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long ngroups = (io.n + 8 * MT - 1) / (8 * MT);
@@ -334,14 +335,12 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
         }
       }
 #pragma unroll
-      for (int ks = 0; ks < KSP; ks++) {
-        if (ks < s.KS) {
+      for (int ks = 0; ks < KS; ks++) {
 #pragma unroll
-          for (int jn = 0; jn < NT; jn++) {
-            const double bf = fh[(ks * NT + jn) * 32 + lane];
+        for (int jn = 0; jn < NT; jn++) {
+          const double bf = fh[(ks * NT + jn) * 32 + lane];
 #pragma unroll
-            for (int m = 0; m < MT; m++) dmma(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
-          }
+          for (int m = 0; m < MT; m++) dmma(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
         }
       }
     }
@@ -355,12 +354,10 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
         o[m][1] = ob.y;
       }
 #pragma unroll
-      for (int ks = 0; ks < KSP; ks++) {
-        if (ks < s.KS) {
-          const double bf = pk[s.pFO + ks * 32 + lane];
+      for (int ks = 0; ks < KS; ks++) {
+        const double bf = pk[s.pFO + ks * 32 + lane];
 #pragma unroll
-          for (int m = 0; m < MT; m++) dmma(o[m][0], o[m][1], h[m][ks >> 1][ks & 1], bf);
-        }
+        for (int m = 0; m < MT; m++) dmma(o[m][0], o[m][1], h[m][ks >> 1][ks & 1], bf);
       }
       // lane (r,c) holds z[row r][2c+x]; u = a + b*z (fields.py:101 with a tabulated affine wrapper)
 #pragma unroll
@@ -418,11 +415,12 @@ struct BwdSmem {
   uint64_t bar;
 };
 
-template <int NT, int DH, bool WSMEM>
+template <int NT, int KODD, int DH, bool WSMEM>
 __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   using SM = BwdSmem<NT, DH, WSMEM>;
   constexpr int ROWS = SM::ROWS, S = SM::S, SN = SM::SN;
   constexpr int KSP = 2 * NT;
+  constexpr int KS = 2 * NT - KODD;
   constexpr int KR = ROWS / 4;  // k-steps over rows in the weight-gradient contraction
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -543,11 +541,9 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
       for (int jn = 0; jn < NT; jn++) dn[jn][0] = dn[jn][1] = 0.0;
       const double* bh = wBH + (long long)(L - 1) * KSP * NT * 32;
 #pragma unroll
-      for (int ks = 0; ks < KSP; ks++) {
-        if (ks < s.KS) {
+      for (int ks = 0; ks < KS; ks++) {
 #pragma unroll
-          for (int jn = 0; jn < NT; jn++) dmma(dn[jn][0], dn[jn][1], dC[ks >> 1][ks & 1], bh[(ks * NT + jn) * 32 + lane]);
-        }
+        for (int jn = 0; jn < NT; jn++) dmma(dn[jn][0], dn[jn][1], dC[ks >> 1][ks & 1], bh[(ks * NT + jn) * 32 + lane]);
       }
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) {
