@@ -44,8 +44,8 @@ def _prop_names(model):
     return olosses.models.MODELS[model][1]
 
 
-def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=2) -> Case:
-    times = np.linspace(0.0, 1.0, nt)
+def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=2, t0=0.0) -> Case:
+    times = np.linspace(t0, 1.0, nt)
     if name.startswith("hex8_"):
         model = name.split("_", 1)[1]
         mesh = ofem.structured_mesh("hex8", n, permute_seed=7 if permute else None)
