@@ -32,8 +32,13 @@ numerically.  Therefore:
     (``oracle/refshim``; generator ``oracle/gen_golden.py``; vectors in
     ``tests/golden/``), and the closed-form curves of the reference's
     ``test/constitutive_models`` tests are replayed as known-answer tests;
-  * end to end (loss + d loss / d theta through jax.grad, equinox's MLP) it is
-    **parity unpinned**: there is no JAX here to produce those vectors.  Gradients
-    are instead cross-checked three ways (torch autograd, hand adjoint in the CUDA
-    path, central differences).
+  * end to end (loss, aux, d loss / d theta, d loss / d prop_val) it is pinned too:
+    ``oracle/refshim_torch.py`` backs the same namespaces with torch and maps every
+    ``jax.grad`` / ``value_and_grad`` on the path to ``torch.autograd.grad``, so the
+    reference's OWN loss functions, physics kernels, Field, function space and
+    constitutive models are executed end to end (``oracle/gen_golden_ad.py`` ->
+    ``tests/golden/loss_grad.npz``) and the oracle matches them to 1e-10
+    (``tests/test_loss_grad_golden.py``).  Still restated, not executed:
+    ``equinox.nn.MLP``/``Linear`` and optax's Adam (un-vendored third-party); not pinned
+    against a running jax (none exists here).
 """
