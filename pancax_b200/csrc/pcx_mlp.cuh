@@ -189,6 +189,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes multiple of 16, 16 B aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -413,6 +416,7 @@ struct BwdSmem {
   double Zb[ROWS * SN];
   double In[2][ROWS * SN];
   uint64_t bar;
+  uint64_t sync;   // split-phase CTA barrier (arrive early, wait late): count = blockDim.x
 };
 
 template <int NT, int KODD, int DH, bool WSMEM>
@@ -461,36 +465,51 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     cp_async_commit();
   };
 
+  // Split-phase CTA barrier: every thread ARRIVEs as soon as its own rows of the D / H tiles are
+  // published and WAITs only right before it reads other warps' rows (the weight-gradient
+  // contraction).  The delta chain of the layer -- which needs nothing from other warps -- runs
+  // between the two, so the skew between warps (and the DRAM latency of the slowest prefetch) is
+  // absorbed by a whole layer of DMMA work instead of stalling at a __syncthreads().
+  if (threadIdx.x == 0) mbar_init(&sm.sync, blockDim.x);
+  __syncthreads();
+  uint32_t sphase = 0;
+#define SYNC_ARRIVE() mbar_arrive(&sm.sync)
+#define SYNC_WAIT() do { mbar_wait(&sm.sync, sphase); sphase ^= 1; } while (0)
+
+  // per-tile top inputs (cotangent column and normalised inputs), loaded one tile ahead
+  auto load_top = [&](long long tile, double& zA, double& v0, double& v1) {
+    const long long row = tile * ROWS + lrow;
+    const bool live = tile < ntiles && row < io.n;
+    zA = 0.0;
+    if (live && c < s.n_out) {
+      const long long k = row * s.n_out + c;
+      zA = io.g_u[k];
+      if (io.bc_b) zA *= io.bc_b[k];
+    }
+    v0 = live ? mlp_input(s, io, row, c) : 0.0;
+    v1 = (4 + c == s.n_in) ? 1.0 : 0.0;
+    if (c == s.n_in) v0 = 1.0;  // n_in < 4
+    if (!live) { v0 = 0.0; v1 = 0.0; }
+  };
+
   int hb = 0, db = 0;
   prefetch_h(blockIdx.x, s.depth - 1, hb);
+  double zA, in0, in1;
+  load_top(blockIdx.x, zA, in0, in1);
   int parity = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     const long long row = tile * ROWS + lrow;
     const bool live = row < io.n;
 
     // ---- top: zbar = g_u * bc_b  -> A fragment (k = out index c) and Zb tile; inputs tile
-    double zA = 0.0;
-    if (live && c < s.n_out) {
-      const long long k = row * s.n_out + c;
-      zA = io.g_u[k];
-      if (io.bc_b) zA *= io.bc_b[k];
-    }
     sm.Zb[lrow * SN + c] = zA;
     sm.Zb[lrow * SN + 4 + c] = 0.0;
-    {
-      double v0 = mlp_input(s, io, row, c);
-      double v1 = (4 + c == s.n_in) ? 1.0 : 0.0;
-      if (c == s.n_in) v0 = 1.0;  // n_in < 4
-      if (!live) { v0 = 0.0; v1 = 0.0; }
-      sm.In[parity][lrow * SN + c] = v0;
-      sm.In[parity][lrow * SN + 4 + c] = v1;
-    }
+    sm.In[parity][lrow * SN + c] = in0;
+    sm.In[parity][lrow * SN + 4 + c] = in1;
     cp_async_wait_all();
     if (live && c == ((ones_slot & 7) >> 1)) sm.H[hb][lrow * S + (ones_slot ^ gl)] = 1.0;
-    __syncthreads();   // H[hb] = h_depth (+ones), Zb, In visible
-    // prefetch the next h: layer DH-1 of this tile, or (depth == 1) the next tile's top layer
-    if (DH > 0) prefetch_h(tile, DH - 1, hb ^ 1);
-    else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
+    __syncwarp();      // the ones patch is read back by the other lanes of this row below
+    SYNC_ARRIVE();     // own rows of H[hb] = h_depth (+ones), Zb, In published
 
     // d_{depth-1} = (zbar W_out) * (1 - h^2), h read back from the own row of the tile
     double dC[NT][2];
@@ -503,6 +522,10 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
       dC[jn][0] = p0 ? 0.0 : a0 * (1.0 - hv.x * hv.x);
       dC[jn][1] = p1 ? 0.0 : a1 * (1.0 - hv.y * hv.y);
     }
+    SYNC_WAIT();       // everybody is done with the previous tile: H[hb^1] is free, Zb / H[hb] complete
+    // prefetch the next h: layer DH-1 of this tile, or (depth == 1) the next tile's top layer
+    if (DH > 0) prefetch_h(tile, DH - 1, hb ^ 1);
+    else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
     if (warp == NT) {
       // dW_out[o][slot] += sum_rows zbar[row][o] * h_depth[row][slot]
 #pragma unroll 2
@@ -512,30 +535,18 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
         for (int jc = 0; jc < NT; jc++) dmma(gO[jc][0], gO[jc][1], a, sm.H[hb][(4 * ks + c) * S + ((8 * jc + r) ^ gc)]);
       }
     }
-    // ---- hidden layers L = DH .. 1 : dW_L = d_L^T h_L ; d_{L-1} = (d_L W_L) * (1 - h_L^2)
+    // ---- hidden layers L = DH .. 1 : d_{L-1} = (d_L W_L) * (1 - h_L^2) ; dW_L = d_L^T h_L
 #pragma unroll
     for (int L = DH; L >= 1; L--) {
-      // dC = d_L.  Publish it, wait for h_L (prefetched into H[hb^1]).
+      // dC = d_L.  Publish it together with the own rows of h_L (prefetched into H[hb^1]).
 #pragma unroll
       for (int jn = 0; jn < NT; jn++)
         *reinterpret_cast<double2*>(&sm.D[db][lrow * S + ((8 * jn + 2 * c) ^ gl)]) = make_double2(dC[jn][0], dC[jn][1]);
       cp_async_wait_all();
       hb ^= 1;
       if (live && c == ((ones_slot & 7) >> 1)) sm.H[hb][lrow * S + (ones_slot ^ gl)] = 1.0;
-      __syncthreads();
-      // prefetch h for the next layer (or the next tile's top layer) into the buffer just released
-      if (L > 1) prefetch_h(tile, L - 2, hb ^ 1);
-      else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
-      if (warp < NT) {
-#pragma unroll 2
-        for (int ks = 0; ks < KR; ks++) {
-          const double a = sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)];
-#pragma unroll
-          for (int jc = 0; jc < NT; jc++)
-            dmma(gH[L - 1][jc][0], gH[L - 1][jc][1], a, sm.H[hb][(4 * ks + c) * S + ((8 * jc + r) ^ gc)]);
-        }
-      }
-      // delta chain
+      SYNC_ARRIVE();
+      // delta chain (own rows only)
       double dn[NT][2];
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) dn[jn][0] = dn[jn][1] = 0.0;
@@ -552,13 +563,28 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
         dC[jn][0] = p0 ? 0.0 : dn[jn][0] * (1.0 - hv.x * hv.x);
         dC[jn][1] = p1 ? 0.0 : dn[jn][1] * (1.0 - hv.y * hv.y);
       }
+      SYNC_WAIT();     // all rows of D[db] = d_L and H[hb] = h_L are in; H[hb^1] is free
+      // prefetch h for the next layer (or the next tile's top layer) into the buffer just released
+      if (L > 1) prefetch_h(tile, L - 2, hb ^ 1);
+      else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
+      if (warp < NT) {
+#pragma unroll 2
+        for (int ks = 0; ks < KR; ks++) {
+          const double a = sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)];
+#pragma unroll
+          for (int jc = 0; jc < NT; jc++)
+            dmma(gH[L - 1][jc][0], gH[L - 1][jc][1], a, sm.H[hb][(4 * ks + c) * S + ((8 * jc + r) ^ gc)]);
+        }
+      }
       db ^= 1;
     }
     // ---- layer 0: dW_0 = d_0^T [inputs, 1]
 #pragma unroll
     for (int jn = 0; jn < NT; jn++)
       *reinterpret_cast<double2*>(&sm.D[db][lrow * S + ((8 * jn + 2 * c) ^ gl)]) = make_double2(dC[jn][0], dC[jn][1]);
-    __syncthreads();
+    SYNC_ARRIVE();
+    load_top(tile + gridDim.x, zA, in0, in1);   // next tile's global loads fly during the wait + dW_0
+    SYNC_WAIT();
     if (warp < NT) {
 #pragma unroll 2
       for (int ks = 0; ks < KR; ks++)
@@ -568,6 +594,8 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     // the next tile's top-layer h is already in flight into H[hb^1]
     hb ^= 1;
   }
+#undef SYNC_ARRIVE
+#undef SYNC_WAIT
   cp_async_wait_all();
 
   // ---- write per-CTA partials (padded slot layout):
