@@ -361,7 +361,7 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
 
 template <int NT, int KODD, int MT, int MINB>
 static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
-  const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0) * sizeof(double);
+  const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + EXP2_TAB_N) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
