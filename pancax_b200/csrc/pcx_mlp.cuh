@@ -517,26 +517,44 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
 #define SYNC_ARRIVE() mbar_arrive(&sm.sync)
 #define SYNC_WAIT() do { mbar_wait(&sm.sync, sphase); sphase ^= 1; } while (0)
 
-  // per-tile top inputs (cotangent column and normalised inputs), loaded one tile ahead
-  auto load_top = [&](long long tile, double& zA, double& v0, double& v1) {
+  // per-tile top inputs (cotangent column and normalised inputs): the raw global loads are issued
+  // a whole tile ahead (4 registers in flight), the arithmetic happens when the tile starts
+  struct TopRaw { double g, b, x, t; };
+  auto issue_top = [&](long long tile) {
+    TopRaw q = {0.0, 1.0, 0.0, 0.0};
+    const long long row = tile * ROWS + lrow;
+    if (tile < ntiles && row < io.n) {
+      if (c < s.n_out) {
+        const long long k = row * s.n_out + c;
+        q.g = io.g_u[k];
+        if (io.bc_b) q.b = io.bc_b[k];
+      }
+      const long long xr = io.nn_mod > 0 ? row % io.nn_mod : row;
+      if (c < s.nd) q.x = io.x[xr * io.x_stride + c];
+      else if (c == s.nd) q.t = io.nn_mod > 0 ? io.times[row / io.nn_mod] : (io.trow ? io.trow[row * io.x_stride] : io.t);
+    }
+    return q;
+  };
+  auto finish_top = [&](long long tile, const TopRaw& q, double& zA, double& v0, double& v1) {
     const long long row = tile * ROWS + lrow;
     const bool live = tile < ntiles && row < io.n;
-    zA = 0.0;
-    if (live && c < s.n_out) {
-      const long long k = row * s.n_out + c;
-      zA = io.g_u[k];
-      if (io.bc_b) zA *= io.bc_b[k];
-    }
-    v0 = live ? mlp_input(s, io, row, c) : 0.0;
+    zA = q.g * q.b;
+    // fields.py:80-88: inputs = hstack(x_norm, t_norm)  (same arithmetic as mlp_input)
+    v0 = 0.0;
+    if (c < s.nd) v0 = (q.x - s.x_min[c]) / s.x_scale[c];
+    else if (c == s.nd) v0 = s.normalize_time ? (q.t - s.t_min) / s.t_scale : q.t;
     v1 = (4 + c == s.n_in) ? 1.0 : 0.0;
     if (c == s.n_in) v0 = 1.0;  // n_in < 4
-    if (!live) { v0 = 0.0; v1 = 0.0; }
+    if (!live) { zA = 0.0; v0 = 0.0; v1 = 0.0; }
   };
 
   int hb = 0, db = 0;
   prefetch_h(blockIdx.x, s.depth - 1, hb);
   double zA, in0, in1;
-  load_top(blockIdx.x, zA, in0, in1);
+  {
+    const TopRaw q0 = issue_top(blockIdx.x);
+    finish_top(blockIdx.x, q0, zA, in0, in1);
+  }
   int parity = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     const long long row = tile * ROWS + lrow;
@@ -551,6 +569,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     if (live && c == ((ones_slot & 7) >> 1)) sm.H[hb][lrow * S + (ones_slot ^ gl)] = 1.0;
     __syncwarp();      // the ones patch is read back by the other lanes of this row below
     SYNC_ARRIVE();     // own rows of H[hb] = h_depth (+ones), Zb, In published
+    const TopRaw qn = issue_top(tile + gridDim.x);   // next tile's global loads fly during this whole tile
 
     // d_{depth-1} = (zbar W_out) * (1 - h^2), h read back from the own row of the tile
     double dC[NT][2];
@@ -624,7 +643,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     for (int jn = 0; jn < NT; jn++)
       *reinterpret_cast<double2*>(&sm.D[db][lrow * S + ((8 * jn + 2 * c) ^ gl)]) = make_double2(dC[jn][0], dC[jn][1]);
     SYNC_ARRIVE();
-    load_top(tile + gridDim.x, zA, in0, in1);   // next tile's global loads fly during the wait + dW_0
+    finish_top(tile + gridDim.x, qn, zA, in0, in1);
     SYNC_WAIT();
     if (warp < NT) {
 #pragma unroll 2
