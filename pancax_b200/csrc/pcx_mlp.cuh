@@ -325,13 +325,30 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
   // slots of the last tile whose features are all padding need no tanh (their pre-activation is 0)
   const int last_real_x1 = (8 * (NT - 1) + 4 < s.width);   // reg x=1 of tile NT-1 holds features 8(NT-1)+4+c
 
+  // inputs of the next row group are loaded one iteration ahead; the Dirichlet tables of this group
+  // at the top of the iteration (consumed after the whole layer chain): no exposed DRAM latency
+  double a0n[MT];
+#pragma unroll
+  for (int m = 0; m < MT; m++) a0n[m] = mlp_input(s, io, warp_id * (8 * MT) + 8 * m + r, c);
   for (long long g = warp_id; g < ngroups; g += warps_total) {
     const long long row0 = g * (8 * MT);
     double h[MT][NT][2], acc[MT][NT][2];
     // ---- layer 0
     double a0[MT];
+    double bcA[MT][2], bcB[MT][2];
 #pragma unroll
-    for (int m = 0; m < MT; m++) a0[m] = mlp_input(s, io, row0 + 8 * m + r, c);
+    for (int m = 0; m < MT; m++) {
+      a0[m] = a0n[m];
+      a0n[m] = mlp_input(s, io, (g + warps_total) * (8 * MT) + 8 * m + r, c);   // rows >= n give 0
+      const long long row = row0 + 8 * m + r;
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        const int oi = 2 * c + x;
+        const bool ok = io.u && row < io.n && oi < s.n_out;
+        bcA[m][x] = (ok && io.bc_a) ? io.bc_a[row * s.n_out + oi] : 0.0;
+        bcB[m][x] = (ok && io.bc_b) ? io.bc_b[row * s.n_out + oi] : 1.0;
+      }
+    }
 #pragma unroll
     for (int jn = 0; jn < NT; jn++) {
       const double2 b2 = *reinterpret_cast<const double2*>(pk + s.pFB + ((long long)(0 * NT + jn) * 32 + lane) * 2);
@@ -414,8 +431,8 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
             if (oi < s.n_out) {
               const long long k = row * s.n_out + oi;
               double z = o[m][x];
-              if (io.bc_b) z *= io.bc_b[k];
-              if (io.bc_a) z += io.bc_a[k];
+              if (io.bc_b) z *= bcB[m][x];
+              if (io.bc_a) z += bcA[m][x];
               io.u[k] = z;
             }
           }
