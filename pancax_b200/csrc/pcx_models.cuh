@@ -53,6 +53,13 @@ __host__ __device__ inline Dual s_pow(Dual x, double p) {
   return Dual(r, p * r / x.v * x.d);
 }
 
+// x^(-2/3) (x > 0): rcbrt is ~4x cheaper than pow on the FP64 pipe and as accurate (1 ulp)
+__device__ inline double s_pow_m23(double x) { const double r = rcbrt(x); return r * r; }
+__device__ inline Dual s_pow_m23(Dual x) {
+  const double r = rcbrt(x.v), r2 = r * r;
+  return Dual(r2, (-2.0 / 3.0) * r2 / x.v * x.d);
+}
+
 // ------------------------------------------------------------------ 3x3 helpers (row-major F[3*i+j])
 template <class T>
 __host__ __device__ inline void cofactor3(const T* F, T* C) {
@@ -85,12 +92,13 @@ __device__ inline void neohookean(const T* F, const Props& pr, T& W, T* P, T* dW
   T J = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
   T I1 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2] + F[3] * F[3] + F[4] * F[4] + F[5] * F[5] +
          F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
-  T Jm23 = s_pow(J, -2.0 / 3.0);
+  T Jm23 = s_pow_m23(J);
   T I1bar = Jm23 * I1;
   T wK = 0.5 * (0.5 * (J * J - 1.0) - s_log(J));
   T wG = 0.5 * (I1bar - 3.0);
   W = K * wK + G * wG;
-  T a = 0.5 * K * (J - 1.0 / J) - (G / 3.0) * I1bar / J;
+  T Jinv = 1.0 / J;
+  T a = 0.5 * K * (J - Jinv) - (G / 3.0) * I1bar * Jinv;
   T b = G * Jm23;
 #pragma unroll
   for (int i = 0; i < 9; i++) P[i] = a * cof[i] + b * F[i];
@@ -111,11 +119,12 @@ __device__ inline void gent(const T* F, const Props& pr, T& W, T* P, T* dWdp, bo
   T J = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
   T I1 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2] + F[3] * F[3] + F[4] * F[4] + F[5] * F[5] +
          F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
-  T Jm23 = s_pow(J, -2.0 / 3.0);
+  T Jm23 = s_pow_m23(J);
   T I1bar = Jm23 * I1;
   const bool clamped = value_of(I1bar) > Jm + 3.0 - 0.001;
   T wK = 0.5 * (0.5 * (J * J - 1.0) - s_log(J));
-  T a = 0.5 * K * (J - 1.0 / J);
+  T Jinv = 1.0 / J;
+  T a = 0.5 * K * (J - Jinv);
   T Wdev, c1;
   T dWdJm;
   if (!clamped) {
@@ -134,7 +143,7 @@ __device__ inline void gent(const T* F, const Props& pr, T& W, T* P, T* dWdp, bo
     dWdJm = T(-0.5 * G * (lg - 1.0));
   }
   W = K * wK + Wdev;
-  T ca = a - c1 * (2.0 / 3.0) * I1bar / J;
+  T ca = a - c1 * (2.0 / 3.0) * I1bar * Jinv;
   T cb = 2.0 * c1 * Jm23;
 #pragma unroll
   for (int i = 0; i < 9; i++) P[i] = ca * cof[i] + cb * F[i];
@@ -173,7 +182,7 @@ __device__ inline void swanson(const T* F, const Props& pr, T& W, T* P, T* dWdp,
   T I1 = C[0] + C[4] + C[8];
   T trC2 = C[0] * C[0] + C[4] * C[4] + C[8] * C[8] + 2.0 * (C[1] * C[1] + C[2] * C[2] + C[5] * C[5]);
   T I2 = 0.5 * (I1 * I1 - trC2);
-  T Jm23 = s_pow(J, -2.0 / 3.0);
+  T Jm23 = s_pow_m23(J);
   T Jm43 = Jm23 * Jm23;
   T I1bar = Jm23 * I1;
   T I2bar = Jm43 * I2;
@@ -190,7 +199,8 @@ __device__ inline void swanson(const T* F, const Props& pr, T& W, T* P, T* dWdp,
   T d1 = 0.5 * (A1 * t1P + C1 * t1R);
   T d2 = 0.5 * B1 * t2Q;
   // P = dJ cof + d1 (2 Jm23 F - (2/3) I1bar/J cof) + d2 (Jm43 (2 I1 F - 2 F C) - (4/3) I2bar/J cof)
-  T ccof = dJ - d1 * (2.0 / 3.0) * I1bar / J - d2 * (4.0 / 3.0) * I2bar / J;
+  T Jinv = 1.0 / J;
+  T ccof = dJ - d1 * (2.0 / 3.0) * I1bar * Jinv - d2 * (4.0 / 3.0) * I2bar * Jinv;
   T cF = 2.0 * d1 * Jm23 + 2.0 * d2 * Jm43 * I1;
   T cFC = -2.0 * d2 * Jm43;
 #pragma unroll
