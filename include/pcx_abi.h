@@ -204,6 +204,29 @@ int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* loss, const double* we
                       const double* prop_raw, double* loss_out, double* aux, double* g_weights,
                       double* g_props, void* stream);
 
+/* Sharded residual / reaction losses (one shard of the elements per GPU): pcx_loss_and_grad cut at the two
+ * points where shards must talk to each other (reference semantics are still
+ * weak_form_loss_functions.py:194-205,278-300 on the WHOLE mesh).
+ *   pcx_set_ownership: entries [0, n_unknown_owned) of unknown_idx and [0, n_reaction_owned) of
+ *     reaction_nodes belong to this shard (they enter the norm / reaction sums exactly once over all
+ *     shards); the remaining entries are closure copies owned elsewhere (they still carry v).
+ *   pcx_loss_begin : field forward + energy/force sweep over the shard's elements; f_partial
+ *     [nt*nn*ndof] (caller's device buffer) = the shard's partial internal force.
+ *   -- caller: f_full = f_partial with the rows of shared nodes summed over shards (may be in place).
+ *   pcx_loss_mid   : rr_partial [nt*2] (device) = (sum of f_full^2 over OWNED unknown dofs, sum of f_full
+ *     over OWNED reaction nodes) per time step.
+ *   -- caller: rr_total = sum over shards of rr_partial (may be in place).
+ *   pcx_loss_finish: v, tangent action, adjoint.  Outputs are the shard's PARTIAL loss / aux / gradients:
+ *     their SUM over shards is the value pcx_loss_and_grad returns on the whole mesh, provided
+ *     replicated_scale = 1 / n_shards (it weights the terms all shards compute identically). */
+int pcx_set_ownership(pcx_handle* h, int64_t n_unknown_owned, int64_t n_reaction_owned);
+int pcx_loss_begin(pcx_handle* h, const pcx_loss_desc* loss, const double* weights, const double* prop_raw,
+                   double* f_partial, void* stream);
+int pcx_loss_mid(pcx_handle* h, const double* f_full, double* rr_partial, void* stream);
+int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* loss, const double* f_full, const double* rr_total,
+                    double replicated_scale, double* loss_out, double* aux, double* g_weights, double* g_props,
+                    void* stream);
+
 /* FullFieldDataLoss value + weight gradient on one batch -- data_loss_functions.py:13-24.
  *   loss: device scalar = weight * mean((u - outputs)^2). */
 int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const double* pts,

@@ -42,6 +42,8 @@ struct pcx_handle {
   // mesh
   int elem_type = 0, q_order = 0, nd = 0, nnpe = 0, ndof = 0, nq = 0, nt = 0, reaction_dof = 0, deterministic = 1;
   long long ne = 0, nn = 0, n_unknown = 0, n_reaction = 0;
+  long long n_unknown_owned = 0, n_reaction_owned = 0;   // sharded meshes: leading entries owned by this shard
+  int phase = 0;                // phased (sharded) loss: 0 idle, 1 after begin, 2 after mid
   const double* coords = nullptr;
   const int32_t* conns = nullptr;
   const long long* unknown_idx = nullptr;
@@ -228,7 +230,9 @@ __global__ void k_finish(int kind, int nt, double we, double wr, double wg, cons
                          const double* __restrict__ sc_R, const double* __restrict__ sc_re, const double* __restrict__ gout,
                          const double* __restrict__ dpi, const double* __restrict__ dfv, const double* __restrict__ props_dev,
                          pcx_physics_desc d, const int* __restrict__ flags, double* __restrict__ loss, double* __restrict__ aux,
-                         double* __restrict__ g_props) {
+                         double* __restrict__ g_props, double rep) {
+  // rep: weight of the terms every shard computes identically (R, reaction loss, reactions): 1 for a
+  // whole mesh, 1/n_shards for a shard, so that SUM over shards of (loss, aux) is the global value
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double e = 0.0, R = 0.0, gl = 0.0;
   for (int t = 0; t < nt; t++) e += sc_pi[t];
@@ -236,19 +240,19 @@ __global__ void k_finish(int kind, int nt, double we, double wr, double wg, cons
   if (kind != PCX_LOSS_ENERGY) {
     for (int t = 0; t < nt; t++) R += sc_R[t];
     R /= nt;  // mean (EnergyAndResidual :203) == sum/nt (EnergyResidualAndReaction :289)
-    L += wr * R;
+    L += rep * wr * R;
   }
   if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) {
     for (int t = 0; t < nt; t++) { const double dd = sc_re[t] - gout[t]; gl += dd * dd; }
     gl /= nt;
-    L += wg * gl;
+    L += rep * wg * gl;
   }
   *loss = L;
   aux[PCX_AUX_ENERGY] = e;
-  aux[PCX_AUX_RESIDUAL] = R;
-  aux[PCX_AUX_GLOBAL_DATA] = gl;
+  aux[PCX_AUX_RESIDUAL] = rep * R;
+  aux[PCX_AUX_GLOBAL_DATA] = rep * gl;
   aux[PCX_AUX_FLAGS] = (double)(*flags);
-  for (int t = 0; t < nt; t++) aux[PCX_AUX_FIXED + t] = (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) ? sc_re[t] : 0.0;
+  for (int t = 0; t < nt; t++) aux[PCX_AUX_FIXED + t] = (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) ? rep * sc_re[t] : 0.0;
   if (g_props) {
     int k = 0;
     for (int i = 0; i < d.nprops; i++) {
@@ -512,6 +516,8 @@ extern "C" int pcx_create(pcx_handle** out, const pcx_mesh_desc* m) {
   h->ndof = m->ndof; h->ne = m->ne; h->nn = m->nn; h->nt = m->nt;
   h->n_unknown = m->unknown_idx ? m->n_unknown : 0;
   h->n_reaction = m->reaction_nodes ? m->n_reaction : 0;
+  h->n_unknown_owned = h->n_unknown;
+  h->n_reaction_owned = h->n_reaction;
   h->reaction_dof = m->reaction_dof;
   h->deterministic = m->deterministic ? 1 : 0;
   h->coords = m->coords; h->conns = m->conns;
@@ -878,8 +884,8 @@ extern "C" int pcx_stiffness_action(pcx_handle* h, const double* prop_raw, const
 
 static int resid_react(pcx_handle* h, int T, const double* f, double* out_rr /* [T][2] raw (R^2, react) */, cudaStream_t st) {
   dim3 grid(256, T);
-  k_resid_react_partials<<<grid, 256, 0, st>>>(f, h->nn * h->ndof, h->unknown_idx, h->n_unknown, h->reaction_nodes,
-                                               h->n_reaction, h->ndof, h->reaction_dof, h->rpart);
+  k_resid_react_partials<<<grid, 256, 0, st>>>(f, h->nn * h->ndof, h->unknown_idx, h->n_unknown_owned, h->reaction_nodes,
+                                               h->n_reaction_owned, h->ndof, h->reaction_dof, h->rpart);
   LAUNCH_CHECK(h);
   return reduce_rows(h, h->rpart, 256, 2, 2, T, out_rr, 2, st);
 }
@@ -985,7 +991,122 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   }
   k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
-                             want_dp ? g_props : nullptr);
+                             want_dp ? g_props : nullptr, 1.0);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: phased loss for shards
+// residual / reaction losses on an element-sharded mesh need the ASSEMBLED internal force on
+// the nodes shared between shards before the norm, and the global norm / reactions before v.  The three
+// phases below are pcx_loss_and_grad cut at exactly those two points; the caller (one process per GPU)
+// does the two small exchanges in between (NCCL allreduce of the shared-node rows, then of nt*2 scalars).
+extern "C" int pcx_set_ownership(pcx_handle* h, int64_t n_unknown_owned, int64_t n_reaction_owned) {
+  if (!h) return fail(PCX_ERR_INVALID, "null handle");
+  if (n_unknown_owned < 0 || n_unknown_owned > h->n_unknown || n_reaction_owned < 0 || n_reaction_owned > h->n_reaction)
+    return fail(PCX_ERR_INVALID, "owned counts must lie in [0, n_unknown] / [0, n_reaction]");
+  h->n_unknown_owned = n_unknown_owned;
+  h->n_reaction_owned = n_reaction_owned;
+  return PCX_OK;
+}
+
+static int check_phased(pcx_handle* h, const pcx_loss_desc* L) {
+  if (!L) return fail(PCX_ERR_INVALID, "null loss descriptor");
+  if (L->kind != PCX_LOSS_ENERGY_RESIDUAL && L->kind != PCX_LOSS_ENERGY_RESIDUAL_REACTION)
+    return fail(PCX_ERR_INVALID, "the phased API is for the residual losses (EnergyLoss shards need no exchange)");
+  int rc = check_tangent_supported(h);
+  if (rc) return rc;
+  if (!h->unknown_idx) return fail(PCX_ERR_STATE, "residual losses need unknown_idx in pcx_mesh_desc");
+  if (L->kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION && !L->global_outputs)
+    return fail(PCX_ERR_STATE, "reaction loss needs global_outputs");
+  if (h->T < h->nt)
+    return fail(PCX_ERR_UNSUPPORTED, "phased loss needs all %d time steps in one batch (workspace holds %d): raise PCX_WORKSPACE_GB",
+                h->nt, h->T);
+  return PCX_OK;
+}
+
+extern "C" int pcx_loss_begin(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
+                              double* f_partial, void* stream) {
+  NEED_READY(h);
+  int rc = check_phased(h, L);
+  if (rc) return rc;
+  if (!weights || !f_partial) return fail(PCX_ERR_INVALID, "pcx_loss_begin: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = h->nt;
+  if (L->kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION)
+    CUDA_TRY(cudaMemcpyAsync(h->gout_dev, L->global_outputs, h->nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+  if ((rc = set_props(h, prop_raw, st))) return rc;
+  if ((rc = pack_weights(h, weights, st))) return rc;
+  const bool want_dp = h->ntrain > 0;
+  MlpIO io = node_io(h, 0, T);
+  io.u = h->us;
+  if ((rc = launch_mlp_fwd(h, st, io))) return rc;
+  if ((rc = sweep(h, false, T, h->us, nullptr, h->f, 1.0, nullptr, 0.0, true, want_dp, true, st))) return rc;
+  if ((rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, T, h->scal + SC_PI(h), 1, st))) return rc;
+  if (want_dp)
+    if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T, h->scal + SC_DPI(h), PCX_MAX_PROPS, st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(f_partial, h->f, (size_t)T * h->nn * h->ndof * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  h->phase = 1;
+  return PCX_OK;
+}
+
+extern "C" int pcx_loss_mid(pcx_handle* h, const double* f_full, double* rr_partial, void* stream) {
+  NEED_READY(h);
+  if (h->phase != 1) return fail(PCX_ERR_STATE, "pcx_loss_mid must follow pcx_loss_begin");
+  if (!f_full || !rr_partial) return fail(PCX_ERR_INVALID, "pcx_loss_mid: null argument");
+  int rc = resid_react(h, h->nt, f_full, rr_partial, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->phase = 2;
+  return PCX_OK;
+}
+
+extern "C" int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* L, const double* f_full, const double* rr_total,
+                               double replicated_scale, double* loss_out, double* aux, double* g_weights, double* g_props,
+                               void* stream) {
+  NEED_READY(h);
+  if (h->phase != 2) return fail(PCX_ERR_STATE, "pcx_loss_finish must follow pcx_loss_mid");
+  int rc = check_phased(h, L);
+  if (rc) return rc;
+  if (!f_full || !rr_total || !loss_out || !aux || !g_weights) return fail(PCX_ERR_INVALID, "pcx_loss_finish: null argument");
+  h->phase = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = h->nt, kind = L->kind;
+  const double we = L->energy_weight, wr = L->residual_weight;
+  const double wg = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->reaction_weight : 0.0;
+  const bool want_dp = g_props != nullptr && h->ntrain > 0;
+  const long long ndofs = h->nn * h->ndof;
+  k_resid_coeffs<<<1, 64, 0, st>>>(0, T, h->nt, wr, wg, rr_total, kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? h->gout_dev : nullptr,
+                                   h->scal + SC_R(h), h->scal + SC_REACT(h), h->scal + SC_C1(h), h->scal + SC_C2(h));
+  LAUNCH_CHECK(h);
+  CUDA_TRY(cudaMemsetAsync(h->v, 0, (size_t)T * ndofs * sizeof(double), st));
+  // v lives on EVERY unknown dof / reaction node of the shard's closure (owned or not): K v over the
+  // shard's elements needs it at all of their nodes
+  if (h->n_unknown > 0) {
+    dim3 g0((unsigned)((h->n_unknown + 255) / 256), T);
+    k_make_v<<<g0, 256, 0, st>>>(0, h->nn, h->ndof, f_full, h->unknown_idx, h->n_unknown, h->reaction_nodes, h->n_reaction,
+                                 h->reaction_dof, h->scal + SC_C1(h), h->scal + SC_C2(h), h->v, 0);
+    LAUNCH_CHECK(h);
+  }
+  if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION && h->n_reaction > 0) {
+    dim3 g1((unsigned)((h->n_reaction + 255) / 256), T);
+    k_make_v<<<g1, 256, 0, st>>>(0, h->nn, h->ndof, f_full, h->unknown_idx, h->n_unknown, h->reaction_nodes, h->n_reaction,
+                                 h->reaction_dof, h->scal + SC_C1(h), h->scal + SC_C2(h), h->v, 1);
+    LAUNCH_CHECK(h);
+  }
+  // ubar = we * f_partial + K v over the shard's own elements: partial cotangents add up across shards
+  if ((rc = sweep(h, true, T, h->us, h->v, h->ubar, 1.0, h->f, we, false, want_dp, true, st))) return rc;
+  if (want_dp)
+    if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T, h->scal + SC_DFV(h), PCX_MAX_PROPS, st))) return rc;
+  MlpIO io = node_io(h, 0, T);
+  io.u = nullptr;
+  io.g_u = h->ubar;
+  int grid = 0;
+  if ((rc = launch_mlp_bwd(h, st, io, &grid))) return rc;
+  if ((rc = reduce_wgrad(h, grid, g_weights, st))) return rc;
+  k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
+                             h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
+                             want_dp ? g_props : nullptr, replicated_scale);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }

@@ -273,6 +273,63 @@ class Engine:
         #  so `go` may be released here)
         return loss, aux, gw, gp[: self.n_train]
 
+    # ---- sharded residual / reaction losses: pcx_loss_and_grad cut at the two exchange points
+    def set_ownership(self, n_unknown_owned, n_reaction_owned):
+        check(self.lib.pcx_set_ownership(self.h, int(n_unknown_owned), int(n_reaction_owned)))
+
+    def _loss_desc(self, kind, energy_weight, residual_weight, reaction_weight, global_outputs):
+        ld = LossDesc()
+        ld.kind = LOSS[kind]
+        ld.energy_weight, ld.residual_weight, ld.reaction_weight = \
+            float(energy_weight), float(residual_weight), float(reaction_weight)
+        go = None
+        if global_outputs is not None:
+            go = np.ascontiguousarray(global_outputs, dtype=np.float64)
+            if go.shape[0] != self.nt:
+                raise ValueError("global_outputs must have nt entries")
+            ld.global_outputs = go.ctypes.data_as(C.POINTER(C.c_double))
+        return ld, go
+
+    def loss_begin(self, kind, weights, prop_raw=None, energy_weight=1.0, residual_weight=1.0,
+                   reaction_weight=1.0, global_outputs=None):
+        """Phase 1: field forward + force sweep.  Returns this shard's partial f [nt, nn, ndof]."""
+        w, pr = self._dev(weights), self._dev(prop_raw)
+        self._ld, self._go = self._loss_desc(kind, energy_weight, residual_weight, reaction_weight, global_outputs)
+        if not hasattr(self, "_f_full"):
+            self._f_full = self._empty(self.nt, self.nn, self.ndof)
+            self._rr = self._empty(self.nt, 2)
+        check(self.lib.pcx_loss_begin(self.h, C.byref(self._ld), _ptr(w), _ptr(pr), _ptr(self._f_full), _stream()))
+        return self._f_full
+
+    def loss_mid(self):
+        """Phase 2 (after the shared rows of f were summed over shards, in place): partial
+        (sum f^2 over owned unknown dofs, reaction over owned nodes) [nt, 2]."""
+        check(self.lib.pcx_loss_mid(self.h, _ptr(self._f_full), _ptr(self._rr), _stream()))
+        return self._rr
+
+    def loss_finish(self, n_shards, out=None):
+        """Phase 3 (after rr was summed over shards, in place): PARTIAL (loss, aux, g_weights, g_props)."""
+        if out is None:
+            loss = self._empty(1)
+            aux = self._empty(PCX_AUX_FIXED + self.nt)
+            gw = self._empty(self.n_weights)
+            gp = self._empty(max(self.n_train, 1))
+        else:
+            loss, aux, gw, gp = out
+        check(self.lib.pcx_loss_finish(self.h, C.byref(self._ld), _ptr(self._f_full), _ptr(self._rr),
+                                       1.0 / n_shards, _ptr(loss), _ptr(aux), _ptr(gw),
+                                       _ptr(gp) if self.n_train > 0 else None, _stream()))
+        return loss, aux, gw, gp[: self.n_train]
+
+    def sharded_loss_and_grad(self, kind, weights, prop_raw, exchange, out=None, **kw):
+        """One shard's part of a residual / reaction loss.  ``exchange.sum_shared(f)`` adds, in place,
+        the other shards' rows of the shared nodes; ``exchange.sum_scalars(rr)`` sums rr over shards in
+        place; ``exchange.n_shards`` is the shard count.  The sum over shards of the returned
+        (loss, aux, g_weights, g_props) is the whole-mesh result of ``loss_and_grad``."""
+        exchange.sum_shared(self.loss_begin(kind, weights, prop_raw, **kw))
+        exchange.sum_scalars(self.loss_mid())
+        return self.loss_finish(exchange.n_shards, out=out)
+
     def field_data_loss_and_grad(self, weights, pts, outputs, a=None, b=None, weight=1.0):
         w, p, y, a, b = (self._dev(weights), self._dev(pts), self._dev(outputs), self._dev(a),
                          self._dev(b))

@@ -80,11 +80,17 @@ def get_engine(problem, params, deterministic: bool = True) -> Engine:
         return eng
     dom = problem.domain
     gd = getattr(problem, "global_data", None)
+    unk = None if dom.dof_manager is None else dom.dof_manager.unknownIndices
+    rn = None if gd is None else gd.reaction_nodes
+    shard = getattr(problem, "shard", None)
+    if shard is not None:     # entries owned by this shard first (pcx_set_ownership)
+        unk, n_uo, rn, n_ro = shard.plan.order_owned_first(unk, rn, problem.n_dofs)
     eng = Engine(dom.coords, dom.conns, dom.mesh.elem_type, dom.q_order, problem.n_dofs, dom.times,
-                 unknown_idx=None if dom.dof_manager is None else dom.dof_manager.unknownIndices,
-                 reaction_nodes=None if gd is None else gd.reaction_nodes,
+                 unknown_idx=unk, reaction_nodes=rn,
                  reaction_dof=0 if gd is None else gd.reaction_dof, deterministic=deterministic,
                  device=net.weights.device)
+    if shard is not None:
+        eng.set_ownership(n_uo, n_ro)
     phys = problem.physics
     if isinstance(phys, Poisson):
         _, _, xq = eng.element_geometry(want_grad_N=False, want_JxW=False)
@@ -136,6 +142,13 @@ class PhysicsLossFunction(BaseLossFunction):
             if gd is None:
                 raise ValueError("EnergyResidualAndReactionLoss needs problem.global_data")
             gout = gd.outputs
+        shard = getattr(problem, "shard", None)
+        if shard is not None and shard.plan.n_shards > 1 and self.kind != "energy":
+            # one element shard per rank: phased ABI, two small exchanges in between; the returned
+            # values are PARTIAL -- sum them over ranks (parallel.PackedResult.allreduce) like EnergyLoss
+            return eng.sharded_loss_and_grad(
+                self.kind, params.fields.networks.weights, params.prop_raw if eng.n_train else None,
+                shard.exchange, global_outputs=gout, **self._weights())
         loss, aux, gw, gp = eng.loss_and_grad(
             self.kind, params.fields.networks.weights,
             params.prop_raw if eng.n_train else None, global_outputs=gout, want_grad=want_grad,

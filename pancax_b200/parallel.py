@@ -5,8 +5,10 @@ ranks, ONE collective per step: allreduce(sum) of [loss | aux | weight grads | p
 EnergyLoss needs no halo exchange: u at a node is a pure function of (x, t, theta), so every rank
 evaluates the field on the closure nodes of its own elements, accumulates the partial internal force
 f_r of its own elements only and back-propagates it; the VJP is linear in the cotangent, hence
-sum_r grads_r is exact.  Residual / reaction losses need the assembled f on interface nodes before
-the norm and are refused on more than one rank for now."""
+sum_r grads_r is exact.  Residual / reaction losses need the assembled f on the nodes shared between
+shards before the norm, and the global norm / reactions before v: two more small allreduces
+(shared-node rows of f, then nt*2 scalars) between the phases of the C ABI's phased loss
+(pcx_loss_begin / _mid / _finish); see ShardPlan / ShardExchange."""
 from __future__ import annotations
 
 import os
@@ -87,3 +89,137 @@ class PackedResult:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
         return self
+
+
+# ------------------------------------------------------------------------------------------------
+# residual / reaction losses on shards: who shares which node, who owns it
+# ------------------------------------------------------------------------------------------------
+class ShardPlan:
+    """Static exchange plan of ONE shard, derived from every shard's local->global node map.
+
+    shared_local : local indices of this shard's nodes that also live on another shard
+    shared_slot  : their slot in the (sorted) global list of shared nodes
+    n_shared     : length of that global list
+    owned        : bool mask over local nodes; a shared node is owned by the lowest shard holding it
+    """
+
+    def __init__(self, shared_local, shared_slot, n_shared, owned, n_shards, index):
+        self.shared_local, self.shared_slot = shared_local, shared_slot
+        self.n_shared, self.owned, self.n_shards, self.index = n_shared, owned, n_shards, index
+
+    def order_owned_first(self, unknown_idx, reaction_nodes, ndof):
+        """Reorder dof / node lists so the entries owned by this shard come first (what
+        pcx_set_ownership expects).  Returns (unknown_idx, n_unknown_owned, reaction_nodes, n_reaction_owned)."""
+        out = []
+        for arr, div in ((unknown_idx, ndof), (reaction_nodes, 1)):
+            if arr is None:
+                out += [None, 0]
+                continue
+            arr = np.asarray(arr)
+            own = self.owned[arr // div]
+            out += [np.concatenate([arr[own], arr[~own]]), int(own.sum())]
+        return tuple(out)
+
+
+def make_shard_plans(l2g_all):
+    """Plans for all shards from their local->global node maps (list of int arrays)."""
+    n = len(l2g_all)
+    ids, counts = np.unique(np.concatenate([np.asarray(a, dtype=np.int64) for a in l2g_all]), return_counts=True)
+    shared_ids = ids[counts > 1]
+    locs, slots = [], []
+    for l2g in l2g_all:
+        l2g = np.asarray(l2g, dtype=np.int64)
+        if shared_ids.size:
+            pos = np.clip(np.searchsorted(shared_ids, l2g), 0, shared_ids.size - 1)
+            hit = shared_ids[pos] == l2g
+        else:
+            pos, hit = np.zeros(l2g.shape, dtype=np.int64), np.zeros(l2g.shape, dtype=bool)
+        loc = np.nonzero(hit)[0]
+        locs.append(loc)
+        slots.append(pos[loc])
+    owner = np.full(shared_ids.size, -1, dtype=np.int64)
+    for r in reversed(range(n)):
+        owner[slots[r]] = r
+    plans = []
+    for r, l2g in enumerate(l2g_all):
+        owned = np.ones(len(l2g), dtype=bool)
+        owned[locs[r]] = owner[slots[r]] == r
+        plans.append(ShardPlan(locs[r], slots[r], int(shared_ids.size), owned, n, r))
+    return plans
+
+
+def make_shard_plan(local_to_global):
+    """This rank's plan; the node maps of all ranks are gathered once at set-up."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return make_shard_plans([local_to_global])[0]
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, np.asarray(local_to_global, dtype=np.int64))
+    return make_shard_plans(gathered)[dist.get_rank()]
+
+
+class ShardExchange:
+    """The two exchanges of the phased loss over torch.distributed (NCCL on GPUs, gloo in the CPU
+    tests): pack the shared-node rows, ONE allreduce, unpack; then ONE allreduce of nt*2 scalars.
+    Both run on the current stream without host synchronisation."""
+
+    def __init__(self, plan: ShardPlan, device):
+        self.plan, self.n_shards = plan, plan.n_shards
+        self.loc = torch.as_tensor(plan.shared_local, dtype=torch.long, device=device)
+        self.slot = torch.as_tensor(plan.shared_slot, dtype=torch.long, device=device)
+        self._buf = None
+
+    def sum_shared(self, f):
+        if self.n_shards == 1 or self.plan.n_shared == 0:
+            return f
+        nt, _, ndof = f.shape
+        if self._buf is None or self._buf.shape != (nt, self.plan.n_shared, ndof):
+            self._buf = torch.empty(nt, self.plan.n_shared, ndof, dtype=f.dtype, device=f.device)
+        self._buf.zero_()
+        self._buf[:, self.slot] = f[:, self.loc]
+        dist.all_reduce(self._buf, op=dist.ReduceOp.SUM)
+        f[:, self.loc] = self._buf[:, self.slot]
+        return f
+
+    def sum_scalars(self, rr):
+        if self.n_shards > 1:
+            dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+        return rr
+
+
+class ShardInfo:
+    def __init__(self, plan, exchange):
+        self.plan, self.exchange = plan, exchange
+
+
+def shard_problem(problem, local_to_global, device=None):
+    """Declare ``problem`` (built on this rank's element shard, nodes numbered locally) to be one shard
+    of a larger mesh: ``local_to_global`` maps its nodes to mesh-wide node ids.  Residual / reaction
+    losses evaluated on it then go through the phased ABI with the two exchanges; EnergyLoss needs
+    nothing.  Collective: every rank must call it."""
+    plan = make_shard_plan(local_to_global)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+    problem.shard = ShardInfo(plan, ShardExchange(plan, device))
+    problem._engines = {}
+    return problem
+
+
+def run_shards_in_process(engines, plans, kind, weights, prop_raw=None, **kw):
+    """All shards driven in lock-step from ONE process (tests; one GPU): the same three phases and two
+    exchanges as the distributed path, the sums done with plain tensor adds.  Returns the summed
+    (loss, aux, g_weights, g_props)."""
+    n = len(engines)
+    fs = [e.loss_begin(kind, weights, prop_raw, **kw) for e in engines]
+    dev = fs[0].device
+    tot = torch.zeros(fs[0].shape[0], plans[0].n_shared, fs[0].shape[2], dtype=fs[0].dtype, device=dev)
+    idx = [(torch.as_tensor(p.shared_local, device=dev), torch.as_tensor(p.shared_slot, device=dev)) for p in plans]
+    for f, (loc, slot) in zip(fs, idx):
+        tot[:, slot] += f[:, loc]
+    for f, (loc, slot) in zip(fs, idx):
+        f[:, loc] = tot[:, slot]
+    rrs = [e.loss_mid() for e in engines]
+    rr = torch.stack(rrs).sum(0)
+    for r in rrs:
+        r.copy_(rr)
+    outs = [e.loss_finish(n) for e in engines]
+    return tuple(sum(o[i] for o in outs) for i in range(4))

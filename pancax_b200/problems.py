@@ -28,6 +28,7 @@ class ForwardProblem:
         self.dirichlet_bcs = dirichlet_bcs
         self.neumann_bcs = []
         self.is_delta_pinn = False
+        self.shard = None          # parallel.shard_problem(): this problem is one element shard of a larger mesh
         self._engines = {}
 
     conns = property(lambda self: self.domain.conns)

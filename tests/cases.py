@@ -190,3 +190,44 @@ def run_engine_loss(case, kind, weights=None, deterministic=True, eng=None, **kw
     if own:
         eng.close()
     return out
+
+
+def make_shard_engines(case, n_shards, deterministic=True, scramble=False):
+    """The same problem cut into ``n_shards`` contiguous element ranges (each with the closure nodes of
+    its elements, renumbered locally) -> (engines, plans).  ``scramble`` permutes the element order first
+    so that shards interleave in space (many shared nodes, nodes shared by more than two shards)."""
+    from pancax_b200 import Engine, parallel, tabulate_bc
+    coords, conns = case.mesh["coords"], case.mesh["conns"]
+    if scramble:
+        conns = conns[np.random.default_rng(5).permutation(conns.shape[0])]
+    ne = conns.shape[0]
+    subs = []
+    for r in range(n_shards):
+        lo, hi = (ne * r) // n_shards, (ne * (r + 1)) // n_shards
+        nodes, inv = np.unique(conns[lo:hi], return_inverse=True)
+        subs.append((nodes, inv.reshape(-1, conns.shape[1]).astype(np.int32)))
+    plans = parallel.make_shard_plans([s[0] for s in subs])
+    engines = []
+    bc = engine_bc(case)
+    for (nodes, lconns), plan in zip(subs, plans):
+        g2l = -np.ones(coords.shape[0], dtype=np.int64)
+        g2l[nodes] = np.arange(nodes.size)
+        unk = rn = None
+        if case.unknown_idx is not None:
+            gn, comp = case.unknown_idx // case.ndof, case.unknown_idx % case.ndof
+            keep = g2l[gn] >= 0
+            unk = g2l[gn[keep]] * case.ndof + comp[keep]
+        if case.reaction_nodes is not None:
+            loc = g2l[case.reaction_nodes]
+            rn = loc[loc >= 0]
+        unk, n_uo, rn, n_ro = plan.order_owned_first(unk, rn, case.ndof)
+        eng = Engine(coords[nodes], lconns, case.mesh["elem"], case.q_order, case.ndof, case.times,
+                     unknown_idx=unk, reaction_nodes=rn, reaction_dof=case.reaction_dof,
+                     deterministic=deterministic)
+        eng.set_ownership(n_uo, n_ro)
+        props = [(p[0], p[1]) if isinstance(p, tuple) else p for p in case.props]
+        eng.set_physics("solid", case.model, case.formulation, props)
+        a, b = tabulate_bc(bc, coords[nodes], case.times, case.ndof)
+        eng.set_field(*case.mlp, bc_a=a, bc_b=b, x_min=coords.min(0), x_max=coords.max(0))   # GLOBAL bounds
+        engines.append(eng)
+    return engines, plans

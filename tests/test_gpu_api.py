@@ -214,3 +214,24 @@ def test_adam_kernel_matches_restated_optax(cuda_device):
         _lib.check(lib.pcx_adam_step(_ptr(dp), _ptr(torch.as_tensor(g).cuda()), _ptr(mu), _ptr(nu), n, k, lr,
                                      0.9, 0.999, 1e-8, _stream()))
     assert rel(dp.cpu().numpy(), p) < 1e-14
+
+
+def test_sharded_residual_loss_on_all_visible_gpus(cuda_device):
+    """SURVEY 8e on real devices: one element shard per GPU, NCCL, through the host mirror
+    (tests/mgpu_residual_check.py).  Needs >= 2 GPUs; with one GPU the same phased path is covered by
+    test_gpu_parity.py::test_sharded_residual_losses_sum_to_whole_mesh."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(ng, 8)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(root, "tests", "mgpu_residual_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]

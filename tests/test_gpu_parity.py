@@ -203,3 +203,43 @@ def test_mlp_shapes(cuda_device, width, depth):
     Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy")
     assert abs(L - Lo) <= TOL * abs(Lo)
     assert rel(gw, gwo) < TOL
+
+
+@pytest.mark.parametrize("name,n,shards,scramble", [("quad4_neohookean", 8, 2, False), ("quad4_gent_bounded", 7, 3, True),
+                                                     ("hex8_neohookean", 4, 2, False), ("hex8_swanson", 3, 4, True),
+                                                     ("tri3_neohookean_bounded", 6, 3, True)])
+@pytest.mark.parametrize("kind", ["energy_residual", "energy_residual_reaction"])
+def test_sharded_residual_losses_sum_to_whole_mesh(cuda_device, name, n, shards, scramble, kind):
+    """residual / reaction losses on element shards (phased ABI + two exchanges) == the fused
+    whole-mesh call, including nodes shared by more than two shards and trainable properties."""
+    from pancax_b200 import parallel
+    from tests.cases import LOSS_WEIGHTS, make_shard_engines
+    case = make_case(name, n=n, nt=3, width=20, depth=2, t0=0.2)
+    L, aux, gw, gp = run_engine_loss(case, kind)
+    engines, plans = make_shard_engines(case, shards, scramble=scramble)
+    assert any(p.n_shared > 0 for p in plans)
+    Ls, auxs, gws, gps = parallel.run_shards_in_process(
+        engines, plans, kind, case.weights, case.prop_raw if engines[0].n_train else None,
+        global_outputs=case.global_outputs, **LOSS_WEIGHTS)
+    assert abs(float(Ls.cpu()[0]) - L) <= 1e-11 * abs(L)
+    a2 = auxs.cpu().numpy()
+    assert rel(a2[:2], aux[:2]) < 1e-11
+    if kind == "energy_residual_reaction":
+        assert rel(a2[2], aux[2]) < 1e-10 and rel(a2[4:], aux[4:]) < 1e-11
+    assert rel(gws.cpu().numpy(), gw) < 1e-10
+    if gp.size:
+        assert rel(gps.cpu().numpy(), gp) < 1e-10
+    for e in engines:
+        e.close()
+
+
+def test_phased_api_call_order_is_enforced(cuda_device):
+    from pancax_b200._lib import PcxError
+    case = make_case("quad4_neohookean", n=4, nt=2, width=12, depth=2)
+    eng = make_engine(case)
+    eng.loss_begin("energy_residual", case.weights)
+    with pytest.raises(PcxError):
+        eng.loss_finish(1)            # mid missing
+    with pytest.raises(PcxError):
+        eng.loss_begin("energy", case.weights)   # the phased API is for the residual losses only
+    eng.close()
