@@ -1,0 +1,145 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle cannot run these
+sizes): C3 = Hex8 128^3 (16.8 M qp) NeoHookean / EnergyLoss, C2 = Quad4 512^2 (1.05 M qp) plane-strain
+NeoHookean / EnergyResidualAndReactionLoss with nt = 11.
+
+  * sum JxW = volume; patch test (affine u: Pi = W(F) vol, f = 0 on interior nodes);
+  * symmetry of the tangent action <w, K v> = <v, K w>;
+  * directional derivative of the loss by central differences vs <grad, direction>;
+  * the sum over element shards equals the whole mesh; deterministic mode is bit-reproducible."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _neohookean_W(F, K, G):
+    J = np.linalg.det(F)
+    I1bar = J ** (-2.0 / 3.0) * np.trace(F @ F.T)
+    return 0.5 * K * (0.5 * (J * J - 1.0) - np.log(J)) + 0.5 * G * (I1bar - 3.0)
+
+
+@pytest.fixture(scope="module")
+def c3(cuda_device):
+    import pancax_b200 as px
+    from pancax_b200 import Engine, tabulate_bc
+    mesh = px.create_structured_mesh("hex8", 128)
+    times = np.linspace(0.0, 1.0, 2)
+    eng = Engine(mesh.coords, mesh.conns, "hex8", 2, 3, times)
+    eng.set_physics("solid", "neohookean", "three_dimensional", [1000.0, 1.0])
+    a, b = tabulate_bc(px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 3), mesh.coords, times, 3)
+    eng.set_field(4, 3, 50, 4, bc_a=a, bc_b=b)
+    from oracle.field import flatten_mlp, init_mlp
+    w = flatten_mlp(init_mlp(4, 3, 50, 4, seed=0))
+    yield mesh, eng, w
+    eng.close()
+
+
+def test_c3_volume_and_patch_test(c3):
+    mesh, eng, _ = c3
+    _, JxW, _ = eng.element_geometry(want_grad_N=False, want_xq=False)
+    assert JxW.shape == (128 ** 3, 8)
+    assert abs(float(JxW.sum()) - 1.0) < 1e-12 and float(JxW.min()) > 0.0
+    A = np.array([[0.03, 0.01, -0.02], [0.00, 0.05, 0.01], [0.02, -0.01, -0.04]])
+    us = mesh.coords @ A.T
+    Pi, f, _ = eng.energy_force(us)
+    W = _neohookean_W(np.eye(3) + A, 1000.0, 1.0)
+    assert abs(float(Pi.cpu()[0]) - W) <= 1e-11 * abs(W)
+    f = f.cpu().numpy()
+    interior = np.all((mesh.coords > 1e-9) & (mesh.coords < 1 - 1e-9), axis=1)
+    assert interior.sum() == 127 ** 3
+    assert np.abs(f[interior]).max() <= 1e-12 * np.abs(f).max()
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).sum()      # global equilibrium of a closed body
+
+
+def test_c3_loss_gradient_directional_derivative_and_repeatability(c3):
+    _, eng, w = c3
+    L0, aux0, g0, _ = eng.loss_and_grad("energy", w)
+    L1, aux1, g1, _ = eng.loss_and_grad("energy", w)
+    assert torch.equal(L0, L1) and torch.equal(g0, g1)                # deterministic assembly + fixed-order sums
+    assert float(aux0[3]) == 0.0                                      # no det(F) <= 0 / NaN flag
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal(w.shape)
+    d /= np.linalg.norm(d)
+    h = 1e-5
+    Lp = float(eng.loss_and_grad("energy", w + h * d, want_grad=False)[0].cpu()[0])
+    Lm = float(eng.loss_and_grad("energy", w - h * d, want_grad=False)[0].cpu()[0])
+    fd = (Lp - Lm) / (2 * h)
+    an = float(g0.cpu().numpy() @ d)
+    assert abs(fd - an) <= 2e-7 * max(abs(an), np.linalg.norm(g0.cpu().numpy()) * 1e-3), (fd, an)
+
+
+def test_c3_two_shards_sum_to_whole(c3):
+    import pancax_b200 as px
+    from pancax_b200 import Engine, tabulate_bc
+    mesh, eng, w = c3
+    L, _, g, _ = eng.loss_and_grad("energy", w)
+    ne = mesh.conns.shape[0]
+    Ls, gs = 0.0, 0.0
+    for r in range(2):
+        nodes, inv = np.unique(mesh.conns[ne * r // 2: ne * (r + 1) // 2], return_inverse=True)
+        sub = Engine(mesh.coords[nodes], inv.reshape(-1, 8).astype(np.int32), "hex8", 2, 3, eng.times)
+        sub.set_physics("solid", "neohookean", "three_dimensional", [1000.0, 1.0])
+        a, b = tabulate_bc(px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 3), mesh.coords[nodes], eng.times, 3)
+        sub.set_field(4, 3, 50, 4, bc_a=a, bc_b=b, x_min=mesh.coords.min(0), x_max=mesh.coords.max(0))
+        Lr, _, gr, _ = sub.loss_and_grad("energy", w)
+        Ls, gs = Ls + float(Lr.cpu()[0]), gs + gr.cpu().numpy()
+        sub.close()
+    assert abs(Ls - float(L.cpu()[0])) <= 1e-12 * abs(Ls)
+    assert np.linalg.norm(gs - g.cpu().numpy()) <= 1e-11 * np.linalg.norm(gs)
+
+
+@pytest.fixture(scope="module")
+def c2(cuda_device):
+    import pancax_b200 as px
+    from pancax_b200 import Engine, tabulate_bc
+    from pancax_b200.fem import DofManager
+    mesh = px.create_structured_mesh("quad4", 512)
+    times = np.linspace(0.0, 1.0, 11)
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_1", "nset_3") for c in range(2)]
+    dm = DofManager(mesh, 2, bcs)
+    eng = Engine(mesh.coords, mesh.conns, "quad4", 2, 2, times, unknown_idx=dm.unknownIndices,
+                 reaction_nodes=mesh.nodeSets["nset_1"], reaction_dof=1)
+    eng.set_physics("solid", "neohookean", "plane_strain", [1000.0, 1.0])
+    a, b = tabulate_bc(px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 2), mesh.coords, times, 2)
+    eng.set_field(3, 2, 50, 3, bc_a=a, bc_b=b)
+    from oracle.field import flatten_mlp, init_mlp
+    w = flatten_mlp(init_mlp(3, 2, 50, 3, seed=0))
+    yield mesh, eng, w
+    eng.close()
+
+
+def test_c2_tangent_is_symmetric_and_consistent_with_force(c2):
+    mesh, eng, w = c2
+    us = eng.field_forward(w, 7)
+    rng = np.random.default_rng(1)
+    v = torch.as_tensor(rng.standard_normal(us.shape), device=us.device)
+    z = torch.as_tensor(rng.standard_normal(us.shape), device=us.device)
+    Kv, _ = eng.stiffness_action(us, v)
+    Kz, _ = eng.stiffness_action(us, z)
+    s1, s2 = float((z * Kv).sum()), float((v * Kz).sum())
+    assert abs(s1 - s2) <= 1e-10 * max(abs(s1), abs(s2))
+    h = 1e-6
+    _, fp, _ = eng.energy_force(us + h * v)
+    _, fm, _ = eng.energy_force(us - h * v)
+    fd = (fp - fm) / (2 * h)
+    assert float((fd - Kv).norm() / Kv.norm()) < 1e-6
+
+
+def test_c2_reaction_loss_gradient_directional_derivative(c2):
+    mesh, eng, w = c2
+    gout = np.linspace(0.0, 0.05, 11)
+    kw = dict(energy_weight=1.0, residual_weight=250.0, reaction_weight=250.0, global_outputs=gout)
+    L0, aux0, g0, _ = eng.loss_and_grad("energy_residual_reaction", w, **kw)
+    L1, _, g1, _ = eng.loss_and_grad("energy_residual_reaction", w, **kw)
+    assert torch.equal(L0, L1) and torch.equal(g0, g1)
+    assert float(aux0[3]) == 0.0 and aux0.shape[0] == 4 + 11
+    rng = np.random.default_rng(4)
+    d = rng.standard_normal(w.shape)
+    d /= np.linalg.norm(d)
+    h = 1e-6
+    Lp = float(eng.loss_and_grad("energy_residual_reaction", w + h * d, want_grad=False, **kw)[0].cpu()[0])
+    Lm = float(eng.loss_and_grad("energy_residual_reaction", w - h * d, want_grad=False, **kw)[0].cpu()[0])
+    fd = (Lp - Lm) / (2 * h)
+    an = float(g0.cpu().numpy() @ d)
+    assert abs(fd - an) <= 1e-6 * max(abs(an), np.linalg.norm(g0.cpu().numpy()) * 1e-3), (fd, an)
