@@ -153,6 +153,13 @@ int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* phys);
 int pcx_set_field(pcx_handle* h, const pcx_field_desc* field);
 int pcx_destroy(pcx_handle* h);
 
+/* options.  PCX_OPT_CULL_NULL_STEPS (default 1): a time step whose Dirichlet table b is identically zero
+ * (every shipped load ramp at t = 0, pancax/bvps/*.py) has u = a exactly and a zero cotangent on the network
+ * output, so the MLP forward / adjoint are skipped for it.  Results are identical to evaluating every row;
+ * 0 evaluates every row like the reference does. */
+#define PCX_OPT_CULL_NULL_STEPS 1
+int pcx_set_option(pcx_handle* h, int32_t option, int64_t value);
+
 /* sizes the caller needs to allocate outputs */
 int64_t pcx_num_weights(const pcx_handle* h);     /* flat MLP parameter count          */
 int64_t pcx_num_trainable_props(const pcx_handle* h);

@@ -80,7 +80,7 @@ SYMBOLS = [
     "pcx_nnpe", "pcx_nd", "pcx_element_geometry", "pcx_field_forward", "pcx_field_backward",
     "pcx_points_forward", "pcx_points_backward", "pcx_energy_force", "pcx_stiffness_action",
     "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
-    "pcx_set_ownership", "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish",
+    "pcx_set_option", "pcx_set_ownership", "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish",
     "pcx_launch_count", "pcx_adam_step", "pcx_profile_enable", "pcx_profile_collect",
     "pcx_measure_dmma_peak",
 ]
@@ -118,6 +118,7 @@ def load():
     lib.pcx_stiffness_action.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pcx_residual_reaction.argtypes = [vp, vp, vp, vp]
     lib.pcx_loss_and_grad.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp]
+    lib.pcx_set_option.argtypes = [vp, i32, i64]
     lib.pcx_set_ownership.argtypes = [vp, i64, i64]
     lib.pcx_loss_begin.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp]
     lib.pcx_loss_mid.argtypes = [vp, vp, vp, vp]

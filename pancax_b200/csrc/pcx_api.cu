@@ -44,6 +44,8 @@ struct pcx_handle {
   long long ne = 0, nn = 0, n_unknown = 0, n_reaction = 0;
   long long n_unknown_owned = 0, n_reaction_owned = 0;   // sharded meshes: leading entries owned by this shard
   int phase = 0;                // phased (sharded) loss: 0 idle, 1 after begin, 2 after mid
+  std::vector<char> step_null;  // time steps whose Dirichlet table b is identically 0: u = a, zero cotangent
+  int cull_null_steps = 1;      // skip the MLP on those steps (exact); PCX_OPT_CULL_NULL_STEPS / env PCX_CULL_NULL_STEPS
   const double* coords = nullptr;
   const int32_t* conns = nullptr;
   const long long* unknown_idx = nullptr;
@@ -572,6 +574,36 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
   return PCX_OK;
 }
 
+// per time step: does the tabulated Dirichlet wrapper annihilate the network output (b == 0 everywhere)?
+__global__ void __launch_bounds__(256) k_step_nonzero(const double* __restrict__ b, long long n_per_step, int* __restrict__ out) {
+  const double* p = b + (long long)blockIdx.x * n_per_step;
+  int nz = 0;
+  for (long long i = threadIdx.x; i < n_per_step; i += blockDim.x) nz |= (p[i] != 0.0);
+  if (__syncthreads_or(nz) && threadIdx.x == 0) out[blockIdx.x] = 1;
+}
+
+static int find_null_steps(pcx_handle* h) {
+  h->step_null.assign(h->nt, 0);
+  if (!h->bc_b) return PCX_OK;
+  int* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, h->nt * sizeof(int)));
+  CUDA_TRY(cudaMemset(d, 0, h->nt * sizeof(int)));
+  k_step_nonzero<<<h->nt, 256>>>(h->bc_b, h->nn * h->ndof, d);
+  std::vector<int> host(h->nt);
+  CUDA_TRY(cudaMemcpy(host.data(), d, h->nt * sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  for (int t = 0; t < h->nt; t++) h->step_null[t] = host[t] ? 0 : 1;
+  return PCX_OK;
+}
+
+extern "C" int pcx_set_option(pcx_handle* h, int32_t option, int64_t value) {
+  if (!h) return fail(PCX_ERR_INVALID, "null handle");
+  switch (option) {
+    case PCX_OPT_CULL_NULL_STEPS: h->cull_null_steps = value != 0; return PCX_OK;
+    default: return fail(PCX_ERR_INVALID, "unknown option %d", option);
+  }
+}
+
 extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
   if (!h || !f) return fail(PCX_ERR_INVALID, "pcx_set_field: null argument");
   if (f->n_in != h->nd + 1) return fail(PCX_ERR_INVALID, "field n_in must be nd+1 = %d (fields.py:88), got %d", h->nd + 1, f->n_in);
@@ -606,6 +638,9 @@ extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
   s.t_min = f->t_min; s.t_scale = f->t_max - f->t_min; s.normalize_time = f->normalize_time;
   h->bc_a = f->bc_a; h->bc_b = f->bc_b;
   h->have_field = true;
+  if (const char* e = getenv("PCX_CULL_NULL_STEPS")) h->cull_null_steps = atoi(e) != 0;
+  int rc = find_null_steps(h);
+  if (rc) return rc;
   if (h->have_phys) return alloc_ws(h);
   return PCX_OK;
 }
@@ -658,6 +693,64 @@ static MlpIO node_io(pcx_handle* h, int t0, int T) {
   io.bc_b = h->bc_b ? h->bc_b + (long long)t0 * h->nn * h->ndof : nullptr;
   io.act = h->act; io.rows_cap = h->rows_cap; io.pk = h->pk; io.part = h->part; io.part_stride = h->part_stride;
   return io;
+}
+
+// Field at the nodes for time steps [t0, t0+T) -> us [T][nn][ndof] (activations kept for the adjoint) and its
+// adjoint.  A time step whose Dirichlet table b is identically zero (every shipped ramp at t = 0) has
+// u = a exactly and a zero cotangent on the network output: with cull_null_steps the MLP is not run on it.
+// The results are identical; only the work differs.
+static bool step_is_null(const pcx_handle* h, int t) { return h->cull_null_steps && !h->step_null.empty() && h->step_null[t]; }
+
+static int field_forward_steps(pcx_handle* h, int t0, int T, double* us, bool keep_act, cudaStream_t st) {
+  const long long per = h->nn * h->ndof;
+  int t = t0;
+  while (t < t0 + T) {
+    if (step_is_null(h, t)) {
+      if (h->bc_a)
+        CUDA_TRY(cudaMemcpyAsync(us + (long long)(t - t0) * per, h->bc_a + (long long)t * per, per * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+      else
+        CUDA_TRY(cudaMemsetAsync(us + (long long)(t - t0) * per, 0, per * sizeof(double), st));
+      t++;
+      continue;
+    }
+    int te = t;
+    while (te < t0 + T && !step_is_null(h, te)) te++;
+    MlpIO io = node_io(h, t, te - t);
+    io.u = us + (long long)(t - t0) * per;
+    io.act = keep_act ? h->act + (long long)(t - t0) * h->nn * 8 : nullptr;
+    int rc = launch_mlp_fwd(h, st, io);
+    if (rc) return rc;
+    t = te;
+  }
+  return PCX_OK;
+}
+
+// g_weights (+)= adjoint of the field over steps [t0, t0+T) for the cotangent ubar [T][nn][ndof]; `first` tracks
+// whether g_weights has been written yet (the first launch overwrites, later ones accumulate)
+static int field_backward_steps(pcx_handle* h, int t0, int T, const double* ubar, double* g_weights, bool& first, cudaStream_t st) {
+  const long long per = h->nn * h->ndof;
+  int t = t0;
+  while (t < t0 + T) {
+    if (step_is_null(h, t)) { t++; continue; }
+    int te = t;
+    while (te < t0 + T && !step_is_null(h, te)) te++;
+    MlpIO io = node_io(h, t, te - t);
+    io.u = nullptr;
+    io.act = h->act + (long long)(t - t0) * h->nn * 8;
+    io.g_u = ubar + (long long)(t - t0) * per;
+    int grid = 0, rc;
+    if ((rc = launch_mlp_bwd(h, st, io, &grid))) return rc;
+    if ((rc = reduce_wgrad(h, grid, first ? g_weights : h->gtmp, st))) return rc;
+    if (!first) {
+      const int thr = 256;
+      k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);
+      LAUNCH_CHECK(h);
+    }
+    first = false;
+    t = te;
+  }
+  return PCX_OK;
 }
 
 // energy (+force) sweep over T time steps of `us` -> f (assembled, scaled by alpha, + beta*add)
@@ -727,9 +820,7 @@ extern "C" int pcx_field_forward(pcx_handle* h, const double* weights, int32_t t
   cudaStream_t st = (cudaStream_t)stream;
   int rc = pack_weights(h, weights, st);
   if (rc) return rc;
-  MlpIO io = node_io(h, t_idx, 1);
-  io.u = us;
-  return launch_mlp_fwd(h, st, io);
+  return field_forward_steps(h, t_idx, 1, us, false, st);
 }
 
 extern "C" int pcx_field_backward(pcx_handle* h, const double* weights, int32_t t_idx, const double* g_us,
@@ -739,6 +830,10 @@ extern "C" int pcx_field_backward(pcx_handle* h, const double* weights, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = pack_weights(h, weights, st);
   if (rc) return rc;
+  if (step_is_null(h, t_idx)) {   // u does not depend on the network at this step
+    CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
+    return PCX_OK;
+  }
   MlpIO io = node_io(h, t_idx, 1);
   io.u = nullptr;  // recompute activations only
   rc = launch_mlp_fwd(h, st, io);
@@ -934,9 +1029,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   for (int t0 = 0; t0 < h->nt; t0 += h->T) {
     const int T = (h->nt - t0 < h->T) ? h->nt - t0 : h->T;
     // (2) field at the nodes for T time steps
-    MlpIO io = node_io(h, t0, T);
-    io.u = h->us;
-    if ((rc = launch_mlp_fwd(h, st, io))) return rc;
+    if ((rc = field_forward_steps(h, t0, T, h->us, want_grad, st))) return rc;
     // (1)+(3)+(5) energy, force; ubar = we * f for the energy loss
     if (!resid) {
       if ((rc = sweep(h, false, T, h->us, nullptr, h->ubar, we, nullptr, 0.0, true, want_dp, want_grad, st))) return rc;
@@ -977,18 +1070,9 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
     }
     if (!want_grad) continue;
     // (4) adjoint through the field
-    io.u = nullptr;
-    io.g_u = h->ubar;
-    int grid = 0;
-    if ((rc = launch_mlp_bwd(h, st, io, &grid))) return rc;
-    if ((rc = reduce_wgrad(h, grid, first ? g_weights : h->gtmp, st))) return rc;
-    if (!first) {
-      const int thr = 256;
-      k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);
-      LAUNCH_CHECK(h);
-    }
-    first = false;
+    if ((rc = field_backward_steps(h, t0, T, h->ubar, g_weights, first, st))) return rc;
   }
+  if (want_grad && first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr, 1.0);
@@ -1039,9 +1123,7 @@ extern "C" int pcx_loss_begin(pcx_handle* h, const pcx_loss_desc* L, const doubl
   if ((rc = set_props(h, prop_raw, st))) return rc;
   if ((rc = pack_weights(h, weights, st))) return rc;
   const bool want_dp = h->ntrain > 0;
-  MlpIO io = node_io(h, 0, T);
-  io.u = h->us;
-  if ((rc = launch_mlp_fwd(h, st, io))) return rc;
+  if ((rc = field_forward_steps(h, 0, T, h->us, true, st))) return rc;
   if ((rc = sweep(h, false, T, h->us, nullptr, h->f, 1.0, nullptr, 0.0, true, want_dp, true, st))) return rc;
   if ((rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, T, h->scal + SC_PI(h), 1, st))) return rc;
   if (want_dp)
@@ -1098,12 +1180,9 @@ extern "C" int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* L, const doub
   if ((rc = sweep(h, true, T, h->us, h->v, h->ubar, 1.0, h->f, we, false, want_dp, true, st))) return rc;
   if (want_dp)
     if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T, h->scal + SC_DFV(h), PCX_MAX_PROPS, st))) return rc;
-  MlpIO io = node_io(h, 0, T);
-  io.u = nullptr;
-  io.g_u = h->ubar;
-  int grid = 0;
-  if ((rc = launch_mlp_bwd(h, st, io, &grid))) return rc;
-  if ((rc = reduce_wgrad(h, grid, g_weights, st))) return rc;
+  bool first = true;
+  if ((rc = field_backward_steps(h, 0, T, h->ubar, g_weights, first, st))) return rc;
+  if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr, replicated_scale);

@@ -164,6 +164,8 @@ class Engine:
         if normalize_time is None:   # fields.py:73-76
             normalize_time = not np.isclose(fd.t_min, fd.t_max, rtol=1e-5, atol=1e-8)
         fd.normalize_time = 1 if normalize_time else 0
+        self._bc_b_host_zero = None if bc_b is None else \
+            ~np.any(np.asarray(bc_b).reshape(self.nt, -1) != 0.0, axis=1)
         for name, tab in (("bc_a", bc_a), ("bc_b", bc_b)):
             if tab is not None:
                 t = torch.as_tensor(np.ascontiguousarray(tab, dtype=np.float64)).to(self.device)
@@ -272,6 +274,16 @@ class Engine:
         # (cudaMemcpyAsync from pageable host memory returns once the source has been staged,
         #  so `go` may be released here)
         return loss, aux, gw, gp[: self.n_train]
+
+    def null_steps(self):
+        """Which time steps have an identically-zero Dirichlet table b (u = a there)."""
+        if self._bc_b_host_zero is None:
+            return np.zeros(self.nt, dtype=bool)
+        return self._bc_b_host_zero
+
+    def set_option(self, name, value):
+        """``cull_null_steps``: skip the MLP on time steps whose Dirichlet table b is identically zero (exact)."""
+        check(self.lib.pcx_set_option(self.h, {"cull_null_steps": 1}[name], int(value)))
 
     # ---- sharded residual / reaction losses: pcx_loss_and_grad cut at the two exchange points
     def set_ownership(self, n_unknown_owned, n_reaction_owned):

@@ -243,3 +243,27 @@ def test_phased_api_call_order_is_enforced(cuda_device):
     with pytest.raises(PcxError):
         eng.loss_begin("energy", case.weights)   # the phased API is for the residual losses only
     eng.close()
+
+
+@pytest.mark.parametrize("name,kind", [("hex8_neohookean", "energy"), ("quad4_neohookean_bounded", "energy_residual_reaction"),
+                                       ("tri3_gent", "energy_residual")])
+def test_null_step_culling_is_exact(cuda_device, name, kind):
+    """t = 0 of a load ramp has b == 0: u = a and the cotangent on the network output vanishes, so the MLP is
+    skipped there (PCX_OPT_CULL_NULL_STEPS).  Same loss / aux / gradients as evaluating every row."""
+    case = make_case(name, n=5, nt=4, width=20, depth=2)     # times 0, 1/3, 2/3, 1: step 0 is null
+    eng = make_engine(case)
+    assert list(eng.null_steps()) == [True, False, False, False]
+    outs = []
+    for cull in (1, 0):
+        eng.set_option("cull_null_steps", cull)
+        outs.append(run_engine_loss(case, kind, eng=eng))
+        us0 = eng.field_forward(case.weights, 0).cpu().numpy()
+        assert np.array_equal(us0, np.zeros_like(us0))
+        g0 = eng.field_backward(case.weights, 0, np.ones_like(us0)).cpu().numpy()
+        assert np.abs(g0).max() == 0.0
+    (L1, a1, g1, p1), (L0, a0, g0, p0) = outs
+    assert abs(L1 - L0) <= 1e-13 * abs(L0) and rel(a1, a0) < 1e-13
+    assert rel(g1, g0) < 1e-12
+    if p0.size:
+        assert rel(p1, p0) < 1e-12
+    eng.close()
