@@ -576,10 +576,11 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
 
 // per time step: does the tabulated Dirichlet wrapper annihilate the network output (b == 0 everywhere)?
 __global__ void __launch_bounds__(256) k_step_nonzero(const double* __restrict__ b, long long n_per_step, int* __restrict__ out) {
-  const double* p = b + (long long)blockIdx.x * n_per_step;
+  const double* p = b + (long long)blockIdx.y * n_per_step;
   int nz = 0;
-  for (long long i = threadIdx.x; i < n_per_step; i += blockDim.x) nz |= (p[i] != 0.0);
-  if (__syncthreads_or(nz) && threadIdx.x == 0) out[blockIdx.x] = 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_per_step; i += (long long)gridDim.x * blockDim.x)
+    nz |= (p[i] != 0.0);
+  if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(out + blockIdx.y, 1);
 }
 
 static int find_null_steps(pcx_handle* h) {
@@ -588,7 +589,7 @@ static int find_null_steps(pcx_handle* h) {
   int* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, h->nt * sizeof(int)));
   CUDA_TRY(cudaMemset(d, 0, h->nt * sizeof(int)));
-  k_step_nonzero<<<h->nt, 256>>>(h->bc_b, h->nn * h->ndof, d);
+  k_step_nonzero<<<dim3(296, h->nt), 256>>>(h->bc_b, h->nn * h->ndof, d);
   std::vector<int> host(h->nt);
   CUDA_TRY(cudaMemcpy(host.data(), d, h->nt * sizeof(int), cudaMemcpyDeviceToHost));
   cudaFree(d);
