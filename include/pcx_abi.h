@@ -194,6 +194,14 @@ int pcx_points_backward(pcx_handle* h, const double* weights, const double* pts,
 int pcx_energy_force(pcx_handle* h, const double* prop_raw, const double* us, double* Pi,
                      double* f, double* g_props, void* stream);
 
+/* post-processing fields at the quadrature points (what pancax's element_pp wrappers evaluate for the Exodus
+ * output: pancax/physics_kernels/base.py:24-158, solid_mechanics.py:115-170):
+ *   F [ne*nq*9] deformation gradient (3x3 row-major; plane strain embedded, mechanics/base.py:19-21),
+ *   I1_bar [ne*nq] (mechanics/base.py:50-63), P [ne*nq*9] first Piola-Kirchhoff stress = d energy / d grad_u
+ *   (mechanics/base.py:112-118).  Any output may be NULL. */
+int pcx_element_fields(pcx_handle* h, const double* prop_raw, const double* us, double* F, double* I1_bar,
+                       double* P, void* stream);
+
 /* tangent-stiffness action Kv = d/d(eps) f(us + eps v): the second-order term the reference gets
  * by differentiating through value_and_grad in base.py:363-385.  g_props = d<f,v>/d prop_raw or NULL. */
 int pcx_stiffness_action(pcx_handle* h, const double* prop_raw, const double* us, const double* v,

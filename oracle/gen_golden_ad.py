@@ -177,6 +177,12 @@ def main():
             out[f"{tag}__us_last"] = us.numpy()
             out[f"{tag}__Pi_last"] = np.array(float(pi))
             out[f"{tag}__f_last"] = f.detach().numpy()
+            # element variables of the post-processor (physics_kernels/base.py:24-158 element_pp wrappers
+            # registered in solid_mechanics.py:115-170): F, I1_bar, pk1_stress at the quadrature points
+            pp = physics.update_var_name_to_method().var_name_to_method
+            for key, name in (("deformation_gradient", "F"), ("I1_bar", "I1bar"), ("pk1_stress", "P")):
+                val = pp[key]["method"](params, problem.domain, t, us, 60.0, state, 1.0)
+                out[f"{tag}__pp_{name}"] = val.detach().numpy()
 
     # FullFieldDataLoss (data_loss_functions.py:13-24) on a seeded batch
     case = make_case("quad4_neohookean", n=5, nt=3, width=50, depth=3)

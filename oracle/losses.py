@@ -111,6 +111,17 @@ def energy_and_force(problem, us, prop_raw=None):
     return float(pi), f.detach().numpy()
 
 
+def element_fields(problem, us, prop_raw=None):
+    """(F, I1_bar, P) at the quadrature points as numpy arrays -- oracle/physics.element_fields."""
+    from .physics import element_fields as _ef
+    w, pr = _leaves(problem, np.zeros(_nparams(problem.mlp)), prop_raw)
+    _, phys, pe = _build(problem, w, pr)
+    coords = torch.as_tensor(problem.coords, dtype=F64)
+    conns = torch.as_tensor(problem.conns, dtype=torch.long)
+    F, I1b, P = _ef(phys, pe, coords, conns, torch.as_tensor(us, dtype=F64))
+    return F.detach().numpy(), I1b.detach().numpy(), P.detach().numpy()
+
+
 def stiffness_action(problem, us, v, prop_raw=None):
     """K v = d/d(eps) f(us + eps v) by double backward (K symmetric => grad of <f, v>)."""
     w, pr = _leaves(problem, np.zeros(_nparams(problem.mlp)), prop_raw)

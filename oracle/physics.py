@@ -103,3 +103,20 @@ def residual_norm(f, unknown_idx):
 def reaction_force(f, reaction_nodes, reaction_dof):
     """sum f[reaction_nodes, reaction_dof].  base.py:382-384."""
     return f[reaction_nodes, reaction_dof].sum()
+
+
+def element_fields(physics: Physics, pe: ParentElement, coords, conns, us):
+    """Post-processing fields at the quadrature points: (F (ne,nq,3,3), I1_bar (ne,nq), P (ne,nq,3,3)).
+
+    Restates what the element_pp wrappers evaluate (pancax/physics_kernels/base.py:24-158 with the
+    methods registered in solid_mechanics.py:115-170): the formulation embeds grad_u in 3x3
+    (modify_field_gradient), then deformation_gradient / I1_bar (kinematic methods,
+    mechanics/base.py:19-21,50-63) and pk1_stress = jacfwd(energy) w.r.t. the 3x3 gradient
+    (constitutive method, mechanics/base.py:112-118)."""
+    X_el, U_el = coords[conns], us[conns]
+    _, _, grad_u, _ = element_interpolants(pe, X_el, U_el)
+    H = models.tensor_2D_to_3D(grad_u) if physics.formulation == "plane_strain" else grad_u
+    F = models.deformation_gradient(H)
+    I1b = models.I1_bar(H)
+    P = models.pk1_stress(physics.model, H, physics.props)
+    return F, I1b, P

@@ -260,6 +260,30 @@ def grad(fun, argnums=0, has_aux=False):
     return g
 
 
+def jacfwd(fun, argnums=0, has_aux=False):
+    """Jacobian w.r.t. one argument for every output of ``fun`` (tuple outputs give a tuple of
+    Jacobians, as jax does); built from reverse-mode rows -- same values as forward mode."""
+    def jf(*args):
+        args = list(args)
+        x = _fresh(args[argnums])
+        args[argnums] = x
+        out = fun(*args)
+
+        def jac(o):
+            o = _t(o)
+            if o.numel() == 0 or not o.requires_grad:
+                return torch.zeros(tuple(o.shape) + tuple(x.shape), dtype=F64)
+            rows = []
+            for k in range(o.numel()):
+                (g,) = torch.autograd.grad(o.reshape(-1)[k], x, create_graph=True, allow_unused=True)
+                rows.append(torch.zeros_like(x) if g is None else g)
+            return torch.stack(rows).reshape(tuple(o.shape) + tuple(x.shape))
+        if isinstance(out, tuple):
+            return tuple(jac(o) for o in out)
+        return jac(out)
+    return jf
+
+
 class custom_jvp:
     """Differentiates through the REGISTERED rule: VJP(ct) = sum_k <rule(e_k), ct> e_k (first order)."""
 
@@ -461,7 +485,9 @@ def install():
         def f(*a, **k):
             raise NotImplementedError(f"jax.{name} is not provided by the torch stand-in")
         return f
-    for nm in ("jacfwd", "jacrev", "hessian", "jvp"):
+    jax.jacfwd = jacfwd
+    jax.jacrev = jacfwd
+    for nm in ("hessian", "jvp"):
         setattr(jax, nm, lambda f, *a, _n=nm, **k: _na(_n))
     jsp = types.ModuleType("jax.scipy")
     jsp.linalg = types.ModuleType("jax.scipy.linalg")

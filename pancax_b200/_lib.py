@@ -79,7 +79,7 @@ SYMBOLS = [
     "pcx_destroy", "pcx_num_weights", "pcx_num_trainable_props", "pcx_num_qp", "pcx_nq",
     "pcx_nnpe", "pcx_nd", "pcx_element_geometry", "pcx_field_forward", "pcx_field_backward",
     "pcx_points_forward", "pcx_points_backward", "pcx_energy_force", "pcx_stiffness_action",
-    "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
+    "pcx_element_fields", "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
     "pcx_set_option", "pcx_set_ownership", "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish",
     "pcx_launch_count", "pcx_adam_step", "pcx_profile_enable", "pcx_profile_collect",
     "pcx_measure_dmma_peak",
@@ -116,6 +116,7 @@ def load():
     lib.pcx_points_backward.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     lib.pcx_energy_force.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pcx_stiffness_action.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.pcx_element_fields.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pcx_residual_reaction.argtypes = [vp, vp, vp, vp]
     lib.pcx_loss_and_grad.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp]
     lib.pcx_set_option.argtypes = [vp, i32, i64]

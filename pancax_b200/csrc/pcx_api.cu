@@ -958,6 +958,39 @@ extern "C" int pcx_energy_force(pcx_handle* h, const double* prop_raw, const dou
   return PCX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ ABI: post-processing fields
+template <int NNPE, int ND, int NDOF>
+static int launch_pp_m(pcx_handle* h, const double* us, double* F, double* I1, double* P, cudaStream_t st) {
+  const int epb = 64;
+  const int grid = (int)((h->ne + epb - 1) / epb);
+  const size_t smem = (size_t)epb * NNPE * sizeof(int32_t);
+#define PCX_PP(M) k_element_pp<NNPE, ND, NDOF, M><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, us, h->props_dev, \
+                                                                           h->phys.nprops, F, I1, P, epb)
+  switch (h->phys.model) {
+    case PCX_MODEL_NEOHOOKEAN: PCX_PP(PCX_MODEL_NEOHOOKEAN); break;
+    case PCX_MODEL_GENT: PCX_PP(PCX_MODEL_GENT); break;
+    case PCX_MODEL_SWANSON: PCX_PP(PCX_MODEL_SWANSON); break;
+    case PCX_MODEL_HENCKY: PCX_PP(PCX_MODEL_HENCKY); break;
+    default: return fail(PCX_ERR_INVALID, "unknown constitutive model %d", h->phys.model);
+  }
+#undef PCX_PP
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+extern "C" int pcx_element_fields(pcx_handle* h, const double* prop_raw, const double* us, double* F, double* I1_bar,
+                                  double* P, void* stream) {
+  NEED_READY(h);
+  if (h->phys.physics != PCX_PHYS_SOLID) return fail(PCX_ERR_UNSUPPORTED, "element fields exist for SolidMechanics only");
+  if (!us) return fail(PCX_ERR_INVALID, "pcx_element_fields: us is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = set_props(h, prop_raw, st);
+  if (rc) return rc;
+  if (h->elem_type == PCX_ELEM_HEX8) return launch_pp_m<8, 3, 3>(h, us, F, I1_bar, P, st);
+  if (h->elem_type == PCX_ELEM_QUAD4) return launch_pp_m<4, 2, 2>(h, us, F, I1_bar, P, st);
+  return launch_pp_m<3, 2, 2>(h, us, F, I1_bar, P, st);
+}
+
 extern "C" int pcx_stiffness_action(pcx_handle* h, const double* prop_raw, const double* us, const double* v,
                                     double* Kv, double* g_props, void* stream) {
   NEED_READY(h);

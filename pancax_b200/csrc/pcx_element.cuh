@@ -374,6 +374,111 @@ __global__ void __launch_bounds__(256) k_geometry(const __grid_constant__ Parent
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Post-processing fields at the quadrature points: what pancax's element_pp wrappers
+// evaluate for the Exodus output -- deformation_gradient (kinematic method), I1_bar (kinematic), pk1_stress
+// (constitutive method = jacfwd(energy) w.r.t. the 3x3 gradient): pancax/physics_kernels/base.py:24-158,
+// solid_mechanics.py:115-170, constitutive_models/mechanics/base.py:19-21,50-63,112-118.
+// One thread per (element, qp), connectivity rows staged through shared memory; HBM-bound
+// (19 doubles = 152 B written per point).  F, P: [ne][nq][3][3] row-major; I1bar: [ne][nq].
+// ----------------------------------------------------------------------------------------------
+template <int NNPE, int ND, int NDOF, int MODEL>
+__global__ void __launch_bounds__(256) k_element_pp(const __grid_constant__ ParentTab tab, long long ne,
+                                                    const double* __restrict__ coords, const int32_t* __restrict__ conns,
+                                                    const double* __restrict__ us, const double* __restrict__ props_dev,
+                                                    int nprops, double* __restrict__ Fout, double* __restrict__ I1out,
+                                                    double* __restrict__ Pout, int epb) {
+  extern __shared__ int32_t s_conn[];  // [epb][NNPE]
+  __shared__ double s_tile[8 * 32 * 9];
+  __shared__ double s_dN[TAB_MAX_NQ * 25];   // parent gradients, row stride 25: lanes with different q hit different banks
+  for (int i = threadIdx.x; i < TAB_MAX_NQ * TAB_MAX_NNPE * 3; i += blockDim.x) s_dN[(i / 24) * 25 + i % 24] = tab.dN[i];
+  const long long e0 = (long long)blockIdx.x * epb;
+  const int nloc = (int)min((long long)epb, ne - e0);
+  for (int i = threadIdx.x; i < nloc * NNPE; i += blockDim.x) s_conn[i] = __ldg(conns + e0 * NNPE + i);
+  Props props;
+#pragma unroll
+  for (int k = 0; k < PCX_MAX_PROPS; k++) props.p[k] = (k < nprops) ? __ldg(props_dev + k) : 0.0;
+  __syncthreads();
+  const int nq = tab.nq;
+  const int npts = nloc * nq;
+  for (int tb = (threadIdx.x & ~31); tb < npts; tb += blockDim.x) {   // warp-uniform trip count
+    const int t = tb + (threadIdx.x & 31);
+    const bool livept = t < npts;
+    const int tt = livept ? t : npts - 1;                              // dead lanes recompute the last point
+    const int el = tt / nq, q = tt - el * nq;
+    const double* dN = s_dN + q * 25;
+    double J[ND * ND], Ji[ND * ND], Gu[NDOF][ND];
+#pragma unroll
+    for (int k = 0; k < ND * ND; k++) J[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+      for (int k = 0; k < ND; k++) Gu[i][k] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NNPE; a++) {
+      const long long n = s_conn[el * NNPE + a];
+      double X[ND], U[NDOF];
+#pragma unroll
+      for (int j = 0; j < ND; j++) X[j] = __ldg(coords + n * ND + j);
+#pragma unroll
+      for (int i = 0; i < NDOF; i++) U[i] = __ldg(us + n * NDOF + i);
+#pragma unroll
+      for (int k = 0; k < ND; k++) {
+#pragma unroll
+        for (int j = 0; j < ND; j++) J[k * ND + j] = fma(dN[a * 3 + k], X[j], J[k * ND + j]);
+#pragma unroll
+        for (int i = 0; i < NDOF; i++) Gu[i][k] = fma(U[i], dN[a * 3 + k], Gu[i][k]);
+      }
+    }
+    inv_det<ND>(J, Ji);
+    // F = I + [grad_u embedded in 3x3] (plane strain: tensor_math.py:64-65)
+    double F[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+#pragma unroll
+    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < ND; k++) s = fma(Gu[i][k], Ji[j * ND + k], s);
+        F[3 * i + j] += s;
+      }
+    const long long qi = e0 * nq + t;
+    if (I1out) {
+      // mechanics/base.py:50-63: J^(-2/3) tr(F F^T)
+      double cof[9];
+      cofactor3(F, cof);
+      const double Jd = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
+      double I1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; i++) I1 = fma(F[i], F[i], I1);
+      if (livept) I1out[qi] = s_pow_m23(Jd) * I1;
+    }
+    double P[9];
+    if (Pout) {
+      double W, dp[PCX_MAX_PROPS];
+      model_eval<MODEL, double>(F, props, W, P, dp, false);
+    }
+    // 3x3 outputs: a lane's 9 doubles are 72 B apart from its neighbour's, so a direct store touches 32
+    // sectors per instruction.  Transpose through a per-warp shared tile (stride 9: conflict-free) and
+    // write the warp's 32 x 9 doubles as 9 fully coalesced 256 B rows.  Points of a warp are consecutive
+    // (t = threadIdx.x + k * blockDim.x), hence contiguous in the output.
+    const int lane = threadIdx.x & 31;
+    double* tile = s_tile + (threadIdx.x >> 5) * (32 * 9);
+    const long long q0 = qi - lane;                       // first point of this warp's batch
+    const int nvalid = min(32, npts - tb);                // live lanes of the batch
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+      double* dst = pass == 0 ? Fout : Pout;
+      if (!dst) continue;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 9; i++) tile[lane * 9 + i] = pass == 0 ? F[i] : P[i];
+      __syncwarp();
+      for (int i = lane; i < nvalid * 9; i += 32) dst[q0 * 9 + i] = tile[i];
+    }
+  }
+}
+
 // node-centric fixed-order assembly for T time steps:
 //   out[ts][n][i] = alpha * sum_{k in adj(n)} fe[ts][adj_idx[k]][i] (+ beta*add[ts][n][i])
 __global__ void k_assemble(long long nn, int ndof, int T, long long nent, const long long* __restrict__ adj_ptr,

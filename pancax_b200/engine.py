@@ -242,6 +242,16 @@ class Engine:
         check(self.lib.pcx_stiffness_action(self.h, _ptr(pr), _ptr(u), _ptr(vv), _ptr(Kv), _ptr(gp), _stream()))
         return Kv, (gp[: self.n_train] if gp is not None else None)
 
+    def element_fields(self, us, prop_raw=None, want_F=True, want_I1bar=True, want_P=True):
+        """Per-quadrature-point deformation gradient (ne, nq, 3, 3), I1_bar (ne, nq) and PK1 stress
+        (ne, nq, 3, 3): the element variables pancax's post-processor writes."""
+        u, pr = self._dev(us), self._dev(prop_raw)
+        F = self._empty(self.ne, self.nq, 3, 3) if want_F else None
+        I1 = self._empty(self.ne, self.nq) if want_I1bar else None
+        P = self._empty(self.ne, self.nq, 3, 3) if want_P else None
+        check(self.lib.pcx_element_fields(self.h, _ptr(pr), _ptr(u), _ptr(F), _ptr(I1), _ptr(P), _stream()))
+        return F, I1, P
+
     def residual_reaction(self, f):
         f = self._dev(f)
         out = self._empty(2)

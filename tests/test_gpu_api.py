@@ -235,3 +235,42 @@ def test_sharded_residual_loss_on_all_visible_gpus(cuda_device):
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"]
+
+
+def test_post_processor_writes_reference_layout(cuda_device, tmp_path):
+    """SURVEY 8f N2: PostProcessor.init / write_outputs (post_processor.py:141-354) through the CUDA library;
+    the values in the file equal the oracle's fields, the variable names / order are the reference's."""
+    import pancax_b200 as px
+    from oracle import losses as ol
+    from pancax_b200.post_processor import read_exodus_results
+    from tests.cases import make_case, oracle_problem
+    case = make_case("quad4_neohookean", n=4, nt=3, width=20, depth=2, permute=False)
+    mesh = px.Mesh(case.mesh["coords"], case.mesh["conns"], "quad4", case.mesh["nodesets"])
+    domain = px.VariationalDomain(mesh, case.times, q_order=2)
+    physics = px.SolidMechanics(px.NeoHookean(bulk_modulus=1000.0, shear_modulus=1.0), px.PlaneStrain())
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_1", "nset_3") for c in range(2)]
+    problem = px.ForwardProblem(domain, physics, dirichlet_bcs=bcs)
+    params = px.Parameters(problem, key=0, n_layers=2, n_neurons=20,
+                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 2))
+    params.fields.networks.set_weights(case.weights)
+    pp = px.PostProcessor(None)
+    with pytest.raises(ValueError):
+        pp.init(params, problem, str(tmp_path / "x.e"), ["not_a_variable"], [])
+    out = str(tmp_path / "out.e")
+    pp.init(params, problem, out, ["field_values", "internal_force"], ["deformation_gradient", "I1_bar", "pk1_stress"])
+    pp.write_outputs(params, problem)
+    pp.close()
+    times, nod, el = read_exodus_results(out)
+    assert np.array_equal(times, case.times)
+    assert list(nod) == ["displ_x", "displ_y", "internal_force_x", "internal_force_y"]
+    assert list(el)[:5] == ["F_xx_1", "F_xx_2", "F_xx_3", "F_xx_4", "F_xy_1"] and len(el) == (9 + 1 + 9) * 4
+    prob = oracle_problem(case)
+    for n, t in enumerate(case.times):
+        us = ol.field_values(prob, case.weights, t)
+        assert np.abs(nod["displ_y"][n] - us[:, 1]).max() <= 1e-13 * max(1.0, np.abs(us).max())
+        _, f = ol.energy_and_force(prob, us)
+        assert np.linalg.norm(nod["internal_force_x"][n] - f[:, 0]) <= 1e-10 * np.linalg.norm(f) + 1e-13
+        F, I1b, P = ol.element_fields(prob, us)
+        assert np.abs(el["F_yy_3"][n] - F[:, 2, 1, 1]).max() <= 1e-13
+        assert np.abs(el["I1_bar_2"][n] - I1b[:, 1]).max() <= 1e-12 * np.abs(I1b).max()
+        assert np.linalg.norm(el["P_zz_4"][n] - P[:, 3, 2, 2]) <= 1e-10 * np.linalg.norm(P) + 1e-13

@@ -200,3 +200,28 @@ def test_adam_restatement_first_step_is_lr_sign():
     g = np.array([0.5, -2.0, 1e-3])
     p = adam_step(np.zeros(3), g, AdamState(3), 1e-3)
     assert np.allclose(p, -1e-3 * np.sign(g), rtol=1e-6)     # |mhat|/sqrt(vhat) = 1 on the first update
+
+
+def test_exodus_results_writer_roundtrip(tmp_path):
+    """post_processor.py:156-354 layout: nodal vals_nod_var{k}, element vals_elem_var{k}eb1, names, times."""
+    import pancax_b200 as px
+    from pancax_b200.post_processor import output_names, read_exodus_results, write_exodus_results
+    mesh = px.create_structured_mesh("quad4", 3)
+    times = np.linspace(0.0, 1.0, 4)
+    rng = np.random.default_rng(0)
+    nod = {"displ_x": rng.standard_normal((4, 16)), "displ_y": rng.standard_normal((4, 16))}
+    el = {f"{c}_{q + 1}": rng.standard_normal((4, 9)) for c in output_names("F", "full_tensor")[:2] for q in range(4)}
+    path = str(tmp_path / "out.e")
+    write_exodus_results(path, mesh, times, nod, el)
+    t2, nod2, el2 = read_exodus_results(path)
+    assert np.array_equal(t2, times)
+    assert list(nod2) == list(nod) and list(el2) == list(el)       # F_xx_1..F_xx_4, F_xy_1.. (components outer)
+    for k in nod:
+        assert np.array_equal(nod2[k], nod[k])
+    for k in el:
+        assert np.array_equal(el2[k], el[k])
+    m2 = px.read_exodus_mesh(path)                                  # still a valid mesh file
+    assert np.array_equal(m2.conns, mesh.conns) and np.allclose(m2.coords, mesh.coords)
+    assert output_names("I1_bar", "scalar") == ("I1_bar",)
+    with pytest.raises(ValueError):
+        output_names("x", "vector")

@@ -124,3 +124,38 @@ def test_cuda_matches_reference_full_field_data_loss(cuda_device):
     assert abs(float(L.cpu()[0]) - float(G["ffd_quad4_n5_nt3_w50_d3__loss"])) <= TOL * abs(float(L.cpu()[0]))
     assert rel(gw.cpu().numpy(), G["ffd_quad4_n5_nt3_w50_d3__gw"]) < TOL
     eng.close()
+
+
+# ---- post-processing element variables: deformation_gradient, I1_bar, pk1_stress as the
+# reference's element_pp wrappers return them (physics_kernels/base.py:24-158, solid_mechanics.py:115-170)
+PP_CASES = [c[:6] for c in CASES if not c[0].startswith("poisson")]
+
+
+@pytest.mark.parametrize("name,n,nt,width,depth,q", PP_CASES)
+def test_oracle_matches_reference_element_fields(name, n, nt, width, depth, q):
+    from oracle import losses as ol
+    from tests.cases import oracle_problem
+    case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q, t0=T0.get(name, 0.0))
+    tag = f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}"
+    F, I1b, P = ol.element_fields(oracle_problem(case), G[f"{tag}__us_last"], case.prop_raw)
+    assert rel(F, G[f"{tag}__pp_F"]) < 1e-13
+    assert rel(I1b, G[f"{tag}__pp_I1bar"]) < 1e-12
+    assert rel(P, G[f"{tag}__pp_P"]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,nt,width,depth,q", PP_CASES)
+def test_cuda_matches_reference_element_fields(cuda_device, name, n, nt, width, depth, q):
+    from tests.cases import make_engine
+    case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q, t0=T0.get(name, 0.0))
+    tag = f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}"
+    eng = make_engine(case)
+    F, I1b, P = eng.element_fields(G[f"{tag}__us_last"], case.prop_raw if eng.n_train else None)
+    assert rel(F.cpu().numpy(), G[f"{tag}__pp_F"]) < 1e-13
+    assert rel(I1b.cpu().numpy(), G[f"{tag}__pp_I1bar"]) < 1e-12
+    assert rel(P.cpu().numpy(), G[f"{tag}__pp_P"]) < TOL
+    # outputs are optional
+    F2, I2, P2 = eng.element_fields(G[f"{tag}__us_last"], case.prop_raw if eng.n_train else None,
+                                    want_F=False, want_P=False)
+    assert F2 is None and P2 is None and np.array_equal(I2.cpu().numpy(), I1b.cpu().numpy())
+    eng.close()
