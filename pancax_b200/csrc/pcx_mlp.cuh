@@ -499,10 +499,15 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
   const double* __restrict__ wBH = wBO + NT * 32;
 
   // weight-gradient accumulators (accumulator layout: lane(r,c): [out slot 8*jr + r][in slot 8*jc+2c+x])
-  double gH[DH > 0 ? DH : 1][NT][2];  // warp < NT : hidden layers 1..DH, row tile jr = warp
+  // Work split of the weight-gradient contraction (balanced to within 5 %: 320 DMMAs per tile for warps
+  // 0..NT-1, 336 for warp NT, so no tensor pipe of the four SM sub-partitions idles):
+  //   warp w < NT : hidden layers: out-slot block w x in-slot tiles 0..NT-2 (gH[l][jc]); output layer:
+  //                 in-slot tile w (gO); layer 0: out-slot block w (g0)
+  //   warp NT     : hidden layers: in-slot tile NT-1 of EVERY out-slot block (gH[l][jr])
+  double gH[DH > 0 ? DH : 1][NT][2];
   double g0[2];                       // warp < NT : layer 0 (out slots 8*warp.., in cols 2c+x of [inputs,1])
-  // warp == NT owns the output layer (out r, in slot 8*jc+2c+x) and keeps it in gH[0] (it has no hidden block)
-#define gO gH[0]
+  double gO[2];                       // warp < NT : output layer (out r, in slots 8*warp + 2c + x)
+  gO[0] = gO[1] = 0.0;
 #pragma unroll
   for (int l = 0; l < (DH > 0 ? DH : 1); l++)
 #pragma unroll
@@ -603,14 +608,11 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     // prefetch the next h: layer DH-1 of this tile, or (depth == 1) the next tile's top layer
     if (DH > 0) prefetch_h(tile, DH - 1, hb ^ 1);
     else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
-    if (warp == NT) {
-      // dW_out[o][slot] += sum_rows zbar[row][o] * h_depth[row][slot]
-#pragma unroll 2
-      for (int ks = 0; ks < KR; ks++) {
-        const double a = sm.Zb[(4 * ks + c) * SN + r];
-#pragma unroll
-        for (int jc = 0; jc < NT; jc++) dmma(gO[jc][0], gO[jc][1], a, sm.H[hb][(4 * ks + c) * S + ((8 * jc + r) ^ gc)]);
-      }
+    if (warp < NT) {
+      // dW_out[o][slot] += sum_rows zbar[row][o] * h_depth[row][slot], in-slot tile `warp`
+#pragma unroll 4
+      for (int ks = 0; ks < KR; ks++)
+        dmma(gO[0], gO[1], sm.Zb[(4 * ks + c) * SN + r], sm.H[hb][(4 * ks + c) * S + ((8 * warp + r) ^ gc)]);
     }
     // ---- hidden layers L = DH .. 1 : d_{L-1} = (d_L W_L) * (1 - h_L^2) ; dW_L = d_L^T h_L
 #pragma unroll
@@ -649,8 +651,16 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
         for (int ks = 0; ks < KR; ks++) {
           const double a = sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)];
 #pragma unroll
-          for (int jc = 0; jc < NT; jc++)
+          for (int jc = 0; jc < NT - 1; jc++)
             dmma(gH[L - 1][jc][0], gH[L - 1][jc][1], a, sm.H[hb][(4 * ks + c) * S + ((8 * jc + r) ^ gc)]);
+        }
+      } else {
+#pragma unroll 2
+        for (int ks = 0; ks < KR; ks++) {
+          const double b = sm.H[hb][(4 * ks + c) * S + ((8 * (NT - 1) + r) ^ gc)];
+#pragma unroll
+          for (int jr = 0; jr < NT; jr++)
+            dmma(gH[L - 1][jr][0], gH[L - 1][jr][1], sm.D[db][(4 * ks + c) * S + ((8 * jr + r) ^ gc)], b);
         }
       }
       db ^= 1;
@@ -679,6 +689,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
   //   part[cta] = [ L0: NT*8 x 8 | hidden l: (8NT x 8NT) each | out: 8 x 8NT ]
   double* P = io.part + (long long)blockIdx.x * io.part_stride;
   constexpr int WPd = 8 * NT;
+  double* Po = P + WPd * 8 + (long long)DH * WPd * WPd;
   if (warp < NT) {
     P[(8 * warp + r) * 8 + 2 * c] = g0[0];
     P[(8 * warp + r) * 8 + 2 * c + 1] = g0[1];
@@ -686,20 +697,24 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     for (int l = 0; l < DH; l++) {
       double* Pl = P + WPd * 8 + (long long)l * WPd * WPd;
 #pragma unroll
-      for (int jc = 0; jc < NT; jc++) {
+      for (int jc = 0; jc < NT - 1; jc++) {
         Pl[(8 * warp + r) * WPd + 8 * jc + 2 * c] = gH[l][jc][0];
         Pl[(8 * warp + r) * WPd + 8 * jc + 2 * c + 1] = gH[l][jc][1];
       }
     }
+    Po[r * WPd + 8 * warp + 2 * c] = gO[0];
+    Po[r * WPd + 8 * warp + 2 * c + 1] = gO[1];
   } else {
-    double* Po = P + WPd * 8 + (long long)DH * WPd * WPd;
 #pragma unroll
-    for (int jc = 0; jc < NT; jc++) {
-      Po[r * WPd + 8 * jc + 2 * c] = gO[jc][0];
-      Po[r * WPd + 8 * jc + 2 * c + 1] = gO[jc][1];
+    for (int l = 0; l < DH; l++) {
+      double* Pl = P + WPd * 8 + (long long)l * WPd * WPd;
+#pragma unroll
+      for (int jr = 0; jr < NT; jr++) {
+        Pl[(8 * jr + r) * WPd + 8 * (NT - 1) + 2 * c] = gH[l][jr][0];
+        Pl[(8 * jr + r) * WPd + 8 * (NT - 1) + 2 * c + 1] = gH[l][jr][1];
+      }
     }
   }
-#undef gO
 }
 
 // Fixed-order sum over CTAs + un-padding into the flat equinox-order gradient.
