@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
       if (L > 1) prefetch_h(tile, L - 2, hb ^ 1);
       else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
       if (warp < NT) {
-#pragma unroll 2
+#pragma unroll 4
         for (int ks = 0; ks < KR; ks++) {
           const double a = sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)];
 #pragma unroll
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
             dmma(gH[L - 1][jc][0], gH[L - 1][jc][1], a, sm.H[hb][(4 * ks + c) * S + ((8 * jc + r) ^ gc)]);
         }
       } else {
-#pragma unroll 2
+#pragma unroll 4
         for (int ks = 0; ks < KR; ks++) {
           const double b = sm.H[hb][(4 * ks + c) * S + ((8 * (NT - 1) + r) ^ gc)];
 #pragma unroll
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     finish_top(tile + gridDim.x, qn, zA, in0, in1);
     SYNC_WAIT();
     if (warp < NT) {
-#pragma unroll 2
+#pragma unroll 4
       for (int ks = 0; ks < KR; ks++)
         dmma(g0[0], g0[1], sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)], sm.In[parity][(4 * ks + c) * SN + r]);
     }
