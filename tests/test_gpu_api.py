@@ -274,3 +274,37 @@ def test_post_processor_writes_reference_layout(cuda_device, tmp_path):
         assert np.abs(el["F_yy_3"][n] - F[:, 2, 1, 1]).max() <= 1e-13
         assert np.abs(el["I1_bar_2"][n] - I1b[:, 1]).max() <= 1e-12 * np.abs(I1b).max()
         assert np.linalg.norm(el["P_zz_4"][n] - P[:, 3, 2, 2]) <= 1e-10 * np.linalg.norm(P) + 1e-13
+
+
+def test_loss_and_grad_is_cuda_graph_capturable(cuda_device):
+    """The C ABI never allocates, synchronises or reads back inside a compute call, so a whole loss+gradient
+    step can be captured in a CUDA graph by the caller (launch-bound small meshes; tools/bench_small.py)."""
+    import torch
+    from tests.cases import make_case, make_engine
+    case = make_case("quad4_neohookean", n=6, nt=3, width=20, depth=2)
+    eng = make_engine(case)
+    w = torch.as_tensor(case.weights, device=eng.device)
+    out = tuple(torch.empty(k, dtype=torch.float64, device=eng.device) for k in (1, 4 + 3, eng.n_weights, 1))
+    kw = dict(global_outputs=case.global_outputs, energy_weight=1.3, residual_weight=0.7, reaction_weight=2.1)
+    eng.loss_and_grad("energy_residual_reaction", w, out=out, **kw)
+    ref = [o.clone() for o in out]
+    g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.loss_and_grad("energy_residual_reaction", w, out=out, **kw)
+        with torch.cuda.graph(g, stream=s):
+            eng.loss_and_grad("energy_residual_reaction", w, out=out, **kw)
+    torch.cuda.current_stream().wait_stream(s)
+    for o in out:
+        o.zero_()
+    w2 = w * 1.01
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(out, ref))
+    # new weights through the same graph: the captured pointers are the caller's buffers
+    w.copy_(w2)
+    g.replay()
+    torch.cuda.synchronize()
+    L2, _, g2, _ = eng.loss_and_grad("energy_residual_reaction", w2, **kw)
+    assert torch.equal(out[0], L2) and torch.equal(out[2], g2)
+    eng.close()
