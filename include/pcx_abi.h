@@ -257,6 +257,15 @@ int64_t pcx_launch_count(const pcx_handle* h);
 int pcx_adam_step(double* params, const double* grads, double* mu, double* nu, int64_t n, int64_t count,
                   double lr, double b1, double b2, double eps, void* stream);
 
+/* The same update with the update counter and the exponential-decay schedule evaluated on the device
+ * (lr_k = lr0 * decay_rate^(k / transition_steps), optax.exponential_decay as used in
+ * pancax/optimizers.py:155-163): no argument depends on host state, so loss + gradient + update can be
+ * captured once in a CUDA graph and replayed.  state: device f64[1] = updates done so far; `advance` != 0 on
+ * the last leaf of a step increments it. */
+int pcx_adam_step_sched(double* params, const double* grads, double* mu, double* nu, int64_t n, double* state,
+                        int32_t advance, double lr0, double decay_rate, double transition_steps, double b1,
+                        double b2, double eps, void* stream);
+
 /* measurement helpers (no reference counterpart): per-kernel-class device time from CUDA events
  * recorded on the launching stream, and the live FP64 tensor-pipe (DMMA) peak of the device. */
 #define PCX_PROF_PACK            0

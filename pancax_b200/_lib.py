@@ -81,7 +81,7 @@ SYMBOLS = [
     "pcx_points_forward", "pcx_points_backward", "pcx_energy_force", "pcx_stiffness_action",
     "pcx_element_fields", "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
     "pcx_set_option", "pcx_set_ownership", "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish",
-    "pcx_launch_count", "pcx_adam_step", "pcx_profile_enable", "pcx_profile_collect",
+    "pcx_launch_count", "pcx_adam_step", "pcx_adam_step_sched", "pcx_profile_enable", "pcx_profile_collect",
     "pcx_measure_dmma_peak",
 ]
 
@@ -126,6 +126,7 @@ def load():
     lib.pcx_loss_finish.argtypes = [vp, C.POINTER(LossDesc), vp, vp, dbl, vp, vp, vp, vp, vp]
     lib.pcx_field_data_loss_and_grad.argtypes = [vp, vp, vp, vp, vp, vp, i64, dbl, vp, vp, vp]
     lib.pcx_adam_step.argtypes = [vp, vp, vp, vp, i64, i64, dbl, dbl, dbl, dbl, vp]
+    lib.pcx_adam_step_sched.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp]
     lib.pcx_profile_enable.argtypes = [vp, C.c_int]
     lib.pcx_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.pcx_measure_dmma_peak.argtypes = [C.POINTER(C.c_double), C.c_int]

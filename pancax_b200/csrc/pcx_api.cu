@@ -1251,6 +1251,45 @@ extern "C" int pcx_adam_step(double* params, const double* grads, double* mu, do
   return PCX_OK;
 }
 
+// Same update with the step counter and the learning-rate schedule on the DEVICE, so that a whole training
+// step (loss + gradient + update) can be captured once in a CUDA graph and replayed: nothing in the call
+// depends on host state.  state[0] = number of updates done so far (as a double; incremented by the call
+// that is flagged `advance`, i.e. the last leaf of the step).
+//   lr_k = lr0 * decay_rate^(k / transition_steps)   (optax.exponential_decay, non-staircase)
+__global__ void k_adam_sched(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ mu,
+                             double* __restrict__ nu, long long n, double* __restrict__ state, double lr0, double decay_rate,
+                             double transition_steps, double b1, double b2, double eps) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const double k = state[0];                       // updates done before this one
+  const double lr = lr0 * pow(decay_rate, k / transition_steps);
+  const double bc1 = 1.0 - pow(b1, k + 1.0), bc2 = 1.0 - pow(b2, k + 1.0);
+  if (i >= n) return;
+  const double gi = g[i];
+  const double m = b1 * mu[i] + (1.0 - b1) * gi;
+  const double v = b2 * nu[i] + (1.0 - b2) * gi * gi;
+  mu[i] = m;
+  nu[i] = v;
+  p[i] -= lr * ((m / bc1) / (sqrt(v / bc2) + eps));
+}
+__global__ void k_advance(double* state) { if (threadIdx.x == 0 && blockIdx.x == 0) state[0] += 1.0; }
+
+extern "C" int pcx_adam_step_sched(double* params, const double* grads, double* mu, double* nu, int64_t n, double* state,
+                                   int32_t advance, double lr0, double decay_rate, double transition_steps, double b1,
+                                   double b2, double eps, void* stream) {
+  if (!state) return fail(PCX_ERR_INVALID, "pcx_adam_step_sched: null state");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    if (!params || !grads || !mu || !nu) return fail(PCX_ERR_INVALID, "pcx_adam_step_sched: null argument");
+    const int thr = 256;
+    k_adam_sched<<<(int)((n + thr - 1) / thr), thr, 0, st>>>(params, grads, mu, nu, n, state, lr0, decay_rate, transition_steps,
+                                                            b1, b2, eps);
+  }
+  if (advance) k_advance<<<1, 32, 0, st>>>(state);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PCX_ERR_CUDA, "k_adam_sched launch failed: %s", cudaGetErrorString(e));
+  return PCX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ ABI: profiling helpers
 extern "C" int pcx_profile_enable(pcx_handle* h, int on) {
   if (!h) return fail(PCX_ERR_INVALID, "null handle");

@@ -268,9 +268,7 @@ class Engine:
             float(energy_weight), float(residual_weight), float(reaction_weight)
         go = None
         if global_outputs is not None:
-            go = np.ascontiguousarray(global_outputs, dtype=np.float64)
-            if go.shape[0] != self.nt:
-                raise ValueError("global_outputs must have nt entries")
+            go = self._host_outputs(global_outputs)
             ld.global_outputs = go.ctypes.data_as(C.POINTER(C.c_double))
         if out is None:
             loss = self._empty(1)
@@ -291,6 +289,19 @@ class Engine:
             return np.zeros(self.nt, dtype=bool)
         return self._bc_b_host_zero
 
+    def _host_outputs(self, global_outputs):
+        """Host copy of problem.global_data.outputs that lives as long as the engine: the library copies it
+        to the device inside the call, and a captured CUDA graph re-reads the same host address on replay."""
+        go = np.ascontiguousarray(global_outputs, dtype=np.float64)
+        if go.shape[0] != self.nt:
+            raise ValueError("global_outputs must have nt entries")
+        cur = getattr(self, "_go_host", None)
+        if cur is None:
+            self._go_host = cur = go.copy()
+        elif not np.array_equal(cur, go):
+            cur[:] = go
+        return cur
+
     def set_option(self, name, value):
         """``cull_null_steps``: skip the MLP on time steps whose Dirichlet table b is identically zero (exact)."""
         check(self.lib.pcx_set_option(self.h, {"cull_null_steps": 1}[name], int(value)))
@@ -306,9 +317,7 @@ class Engine:
             float(energy_weight), float(residual_weight), float(reaction_weight)
         go = None
         if global_outputs is not None:
-            go = np.ascontiguousarray(global_outputs, dtype=np.float64)
-            if go.shape[0] != self.nt:
-                raise ValueError("global_outputs must have nt entries")
+            go = self._host_outputs(global_outputs)
             ld.global_outputs = go.ctypes.data_as(C.POINTER(C.c_double))
         return ld, go
 

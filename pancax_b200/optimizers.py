@@ -37,7 +37,8 @@ class Adam:
             filter_spec = params.freeze_physics_normalization_filter()
         w, p = params.fields.networks.weights, params.prop_raw
         opt_state = dict(mu_w=torch.zeros_like(w), nu_w=torch.zeros_like(w),
-                         mu_p=torch.zeros_like(p), nu_p=torch.zeros_like(p), count=0)
+                         mu_p=torch.zeros_like(p), nu_p=torch.zeros_like(p), count=0,
+                         count_dev=torch.zeros(1, dtype=torch.float64, device=w.device))
         return OptimizerState(opt_state, 0, filter_spec, False)
 
     def _schedule(self, count):
@@ -67,3 +68,51 @@ class Adam:
                                     st["count"], lr, self.b1, self.b2, self.eps, _stream()))
         state.epoch += 1
         return params, state, ((loss, aux) if self.has_aux else loss)
+
+
+    # ------------------------------------------------------------------ device-resident training step
+    def device_step(self, params, state: OptimizerState, problem, *args):
+        """Same update as ``step`` with the update counter and the learning-rate schedule on the device
+        (pcx_adam_step_sched): nothing depends on host state, so the call can be captured in a CUDA graph.
+        Gradient clipping is not available on this path."""
+        if self.clip_gradients:
+            raise NotImplementedError("clip_gradients is not available on the device-resident step")
+        (loss, aux), grads = self.loss_function.value_and_grad(params, problem, *args)
+        st = state.opt_state
+        lib = _lib.load()
+        spec = state.filter_spec
+        w, p = params.fields.networks.weights, params.prop_raw
+        do_w = spec.get("fields", True)
+        do_p = spec.get("props", True) and p.numel() > 0
+        sched = (self.learning_rate, self.decay_rate, float(self.transition_steps), self.b1, self.b2, self.eps)
+        if do_w:
+            check(lib.pcx_adam_step_sched(_ptr(w), _ptr(grads.fields), _ptr(st["mu_w"]), _ptr(st["nu_w"]), w.numel(),
+                                          _ptr(st["count_dev"]), 0 if do_p else 1, *sched, _stream()))
+        if do_p:
+            check(lib.pcx_adam_step_sched(_ptr(p), _ptr(grads.props), _ptr(st["mu_p"]), _ptr(st["nu_p"]), p.numel(),
+                                          _ptr(st["count_dev"]), 1, *sched, _stream()))
+        if not (do_w or do_p):
+            check(lib.pcx_adam_step_sched(None, None, None, None, 0, _ptr(st["count_dev"]), 1, *sched, _stream()))
+        return (loss, aux)
+
+    def capture(self, params, state: OptimizerState, problem, *args):
+        """Capture ONE training step (loss + gradient + Adam update) in a CUDA graph.  Returns
+        (graph, (loss, aux)): every ``graph.replay()`` advances the parameters by one step and refreshes the
+        static ``loss`` / ``aux`` device tensors.  For launch-bound (small) problems."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        snap = [t.clone() for t in (params.fields.networks.weights, params.prop_raw, state.opt_state["mu_w"],
+                                    state.opt_state["nu_w"], state.opt_state["mu_p"], state.opt_state["nu_p"],
+                                    state.opt_state["count_dev"])]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            self.device_step(params, state, problem, *args)          # warm-up (builds the engine, allocates)
+            s.synchronize()
+            for t, v in zip((params.fields.networks.weights, params.prop_raw, state.opt_state["mu_w"],
+                             state.opt_state["nu_w"], state.opt_state["mu_p"], state.opt_state["nu_p"],
+                             state.opt_state["count_dev"]), snap):
+                t.copy_(v)                                            # undo the warm-up step
+            with torch.cuda.graph(g, stream=s):
+                out = self.device_step(params, state, problem, *args)
+        torch.cuda.current_stream().wait_stream(s)
+        return g, out

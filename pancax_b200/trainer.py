@@ -54,8 +54,21 @@ class Trainer:
         self.epoch += 1
         return params, opt_st
 
-    def train(self, params, n_epochs, *args):
+    def train(self, params, n_epochs, *args, cuda_graph: bool = False):
+        """``cuda_graph=True``: the whole step (loss + gradient + Adam update, schedule and counter on the
+        device) is captured once and replayed ``n_epochs`` times -- for launch-bound small problems; the
+        loss history is still written every ``log_every`` epochs."""
         opt_st = self.init(params)
+        if not cuda_graph:
+            for _ in range(n_epochs):
+                params, opt_st = self.step(params, opt_st, *args)
+            return params
+        graph, loss = self.opt.capture(params, opt_st, self.problem, *args)
         for _ in range(n_epochs):
-            params, opt_st = self.step(params, opt_st, *args)
+            graph.replay()
+            opt_st.epoch += 1
+            opt_st.opt_state["count"] += 1
+            self._write_history(loss)
+            self.serialise(params)
+            self.epoch += 1
         return params

@@ -308,3 +308,32 @@ def test_loss_and_grad_is_cuda_graph_capturable(cuda_device):
     L2, _, g2, _ = eng.loss_and_grad("energy_residual_reaction", w2, **kw)
     assert torch.equal(out[0], L2) and torch.equal(out[2], g2)
     eng.close()
+
+
+def test_graph_replayed_training_matches_eager_training(cuda_device, tmp_path):
+    """Trainer.train as a pure device loop.  One captured step (loss + gradient + Adam with the
+    schedule / counter on the device, pcx_adam_step_sched) replayed N times == N eager opt.step calls."""
+    import torch
+    import pancax_b200 as px
+    finals = []
+    for use_graph in (False, True):
+        mesh = px.create_structured_mesh("quad4", 6)
+        times = np.linspace(0.0, 1.0, 3)
+        domain = px.VariationalDomain(mesh, times, q_order=2)
+        model = px.NeoHookean(bulk_modulus=10.0, shear_modulus=px.BoundedProperty(0.01, 5.0, 1.0))
+        physics = px.SolidMechanics(model, px.PlaneStrain())
+        bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_1", "nset_3") for c in range(2)]
+        gd = px.GlobalData.from_arrays(times, np.linspace(0.0, 0.1, 3), mesh.nodeSets["nset_1"], 1)
+        problem = px.InverseProblem(domain, physics, None, gd, dirichlet_bcs=bcs)
+        params = px.Parameters(problem, key=0, n_layers=2, n_neurons=20,
+                               dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.3, 1.0, "y", 2))
+        opt = px.Adam(px.EnergyResidualAndReactionLoss(1.0, False, 2.0, 3.0), learning_rate=1e-3, has_aux=True,
+                      transition_steps=7, decay_rate=0.9)
+        tr = px.Trainer(problem, opt, workdir=str(tmp_path / ("g" if use_graph else "e")), log_every=5,
+                        serialise_every=10 ** 9)
+        params = tr.train(params, 25, cuda_graph=use_graph)
+        torch.cuda.synchronize()
+        finals.append((params.fields.networks.weights.cpu().numpy().copy(), params.prop_raw.cpu().numpy().copy()))
+    (we, pe), (wg, pg) = finals
+    assert np.linalg.norm(wg - we) <= 1e-12 * np.linalg.norm(we)
+    assert np.abs(pg - pe).max() <= 1e-12 * max(1.0, np.abs(pe).max())
