@@ -29,14 +29,14 @@ K_BULK, G_SHEAR = 1000.0, 1.0
 
 
 def algorithmic_flops_per_row_bwd():
-    # MLP backward (no input gradient for layer 0) = 4 P_w - 2 in0 width
-    pw = MLP_IN * WIDTH + (DEPTH - 1) * WIDTH * WIDTH + WIDTH * MLP_OUT
-    return 4 * pw - 2 * MLP_IN * WIDTH
+    # pancax_b200/roofline.py (SURVEY 8d formulas): 4 P_w - 2 in0 width
+    from pancax_b200 import roofline
+    return roofline.mlp_backward_flops_per_row(MLP_IN, MLP_OUT, WIDTH, DEPTH)
 
 
 def algorithmic_flops_per_row_fwd():
-    pw = MLP_IN * WIDTH + (DEPTH - 1) * WIDTH * WIDTH + WIDTH * MLP_OUT
-    return 2 * pw
+    from pancax_b200 import roofline
+    return roofline.mlp_forward_flops_per_row(MLP_IN, MLP_OUT, WIDTH, DEPTH)
 
 
 class ClockSampler:
@@ -242,6 +242,7 @@ def run_ours(args):
                                "(MEASURED_PEAKS.json has no FP64 figure)",
                 "avg_launch_ms": bwd_ms / bwd_n if bwd_n else None, "launches": bwd_n,
                 "algorithmic_flop_per_row": algorithmic_flops_per_row_bwd(), "rows_per_step": eng.nn * nt,
+                "formulas": "pancax_b200/roofline.py",
                 "step_share": {k: round(v[0] / ms, 4) for k, v in prof.items() if v[1]}}
     # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
     cpu = None

@@ -333,11 +333,8 @@ static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpI
   if (smem > 227 * 1024)
     return fail(PCX_ERR_UNSUPPORTED, "MLP %d x %d needs %zu bytes of shared memory in the adjoint kernel", h->ms.width,
                 h->ms.depth, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per device and cheap: set it on every launch (a process may drive several devices)
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_mlp_backward<NT, KODD, DH, WSMEM><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
@@ -368,11 +365,7 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
 template <int NT, int KODD, int MT, int MINB>
 static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + EXP2_TAB_N) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
   const long long groups = (io.n + 8 * MT - 1) / (8 * MT);
   long long blocks = (groups + 7) / 8;

@@ -225,3 +225,17 @@ def test_exodus_results_writer_roundtrip(tmp_path):
     assert output_names("I1_bar", "scalar") == ("I1_bar",)
     with pytest.raises(ValueError):
         output_names("x", "vector")
+
+
+def test_roofline_formulas_match_the_survey_numbers():
+    """algorithmic work per unit as formulas of the shape (used by bench.py)."""
+    from pancax_b200 import roofline as r
+    assert r.mlp_pw(4, 3, 50, 4) == 7850 and r.mlp_pw(3, 1, 50, 3) == 5200
+    assert r.mlp_forward_flops_per_row(4, 3, 50, 4) == 15700
+    assert r.mlp_backward_flops_per_row(4, 3, 50, 4) == 31000
+    assert r.activation_bytes_per_row(50, 4) == 1792
+    assert r.mlp_padded_dmma_per_tile(50, 4) == dict(NT=7, KS=13, forward_per_8_rows=293, adjoint_per_64_rows=4816)
+    assert 700 <= r.element_flops_per_qp("hex8", 3) <= 900 and 1200 <= r.element_flops_per_qp("hex8", 3, True) <= 1400
+    assert abs(r.element_bytes_per_qp("hex8", 3, 8) - 16.0) < 1e-12
+    total = r.step_flops_per_qp_eval("hex8", 4, 3, 50, 4, 2146689 / 16777216)
+    assert 6500 <= total <= 7100          # "~6.8 kflop per qp-eval" for EnergyLoss on Hex8 128^3
