@@ -197,6 +197,46 @@ def main():
     out["ffd_quad4_n5_nt3_w50_d3__loss"], out["ffd_quad4_n5_nt3_w50_d3__gw"] = np.array(float(loss)), gw
     print("FullFieldDataLoss", float(loss), np.linalg.norm(gw))
 
+    # ---------------------------------------------------------------- strong form
+    # Poisson: StrongFormResidualLoss.__call__ (strong_form_loss_functions.py:15-27) -> physics.strong_form_residual
+    # (poisson.py:26-29) -> field_laplacians = trace(jax.hessian(field_values)) (base.py:213-226), with the
+    # collocation example's Dirichlet wrapper x(1-x)y(1-y)z (examples/.../poisson/collocation_example.py:11-13).
+    from pancax.loss_functions.strong_form_loss_functions import StrongFormResidualLoss
+    from pancax.physics_kernels.heat_equation import HeatEquation
+    sfo = {}
+    case = make_case("poisson_quad4", n=4, nt=2, width=20, depth=3)
+    params, problem, leaves, raws = build(case)
+    dom = types.SimpleNamespace(coords=problem.coords, times=problem.times)
+    loss, aux = StrongFormResidualLoss(weight=2.5)(params, dom)
+    gw, _ = flat_grad(loss, leaves, [])
+    fld, physics, _ = params
+    res = torch.stack([torch.stack([physics.strong_form_residual(fld, x, t) for x in problem.coords])
+                       for t in problem.times])                       # (nt, nn, 1)
+    sfo["poisson_quad4_n4_nt2_w20_d3__loss"], sfo["poisson_quad4_n4_nt2_w20_d3__gw"] = np.array(float(loss)), gw
+    sfo["poisson_quad4_n4_nt2_w20_d3__residuals"] = res.detach().numpy()
+    # the jet itself at the nodes, last time step: base.py:205-229
+    tl = problem.times[-1]
+    sfo["poisson_quad4_n4_nt2_w20_d3__u"] = torch.stack([physics.field_values(fld, x, tl) for x in problem.coords]).detach().numpy()
+    sfo["poisson_quad4_n4_nt2_w20_d3__grad_u"] = torch.stack([physics.field_gradients(fld, x, tl) for x in problem.coords]).detach().numpy()
+    sfo["poisson_quad4_n4_nt2_w20_d3__lap_u"] = torch.stack([physics.field_laplacians(fld, x, tl) for x in problem.coords]).detach().numpy()
+    sfo["poisson_quad4_n4_nt2_w20_d3__u_t"] = torch.stack([physics.field_time_derivatives(fld, x, tl) for x in problem.coords]).detach().numpy()
+    print("strong-form Poisson", float(loss), np.linalg.norm(gw))
+    # Heat: HeatEquation.strong_form_residual (heat_equation.py:11-17) evaluated per point with params =
+    # (field, (rho, c, k)); StrongFormResidualLoss passes params.fields only, so the reference's own loss cannot
+    # reach this residual -- the mean of squares below is assembled here, the residuals are the reference's.
+    params, problem, leaves, raws = build(case)
+    fld, _, _ = params
+    heat = HeatEquation()
+    rck = (1.7, 0.9, 0.35)
+    res = torch.stack([torch.stack([heat.strong_form_residual((fld, rck), x, t) for x in problem.coords])
+                       for t in problem.times])
+    loss = 1.5 * torch.stack([torch.square(res[n]).mean() for n in range(res.shape[0])]).mean()
+    gw, _ = flat_grad(loss, leaves, [])
+    sfo["heat_quad4_n4_nt2_w20_d3__loss"], sfo["heat_quad4_n4_nt2_w20_d3__gw"] = np.array(float(loss)), gw
+    sfo["heat_quad4_n4_nt2_w20_d3__residuals"] = res.detach().numpy()
+    print("strong-form heat", float(loss), np.linalg.norm(gw))
+    np.savez_compressed(os.path.join(OUT, "strong_form.npz"), **sfo)
+
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, "loss_grad.npz")
     np.savez_compressed(path, **out)

@@ -126,6 +126,7 @@ def _make_jnp():
         if not hasattr(torch, nm):
             continue
         setattr(jnp, nm, (lambda f: (lambda x, *a, **k: f(_t(x), *a, **_axis_kw(k))))(getattr(torch, nm)))
+    jnp.trace = lambda x, offset=0, axis1=0, axis2=1: torch.diagonal(_t(x), offset=offset, dim1=axis1, dim2=axis2).sum(-1)
     jnp.array = lambda x, dtype=None: _t(x)
     jnp.asarray = jnp.array
     jnp.zeros = lambda shape, dtype=None: torch.zeros(shape, dtype=F64)
@@ -487,7 +488,8 @@ def install():
         return f
     jax.jacfwd = jacfwd
     jax.jacrev = jacfwd
-    for nm in ("hessian", "jvp"):
+    jax.hessian = lambda f, argnums=0, has_aux=False: jacfwd(jacfwd(f, argnums=argnums), argnums=argnums)
+    for nm in ("jvp",):
         setattr(jax, nm, lambda f, *a, _n=nm, **k: _na(_n))
     jsp = types.ModuleType("jax.scipy")
     jsp.linalg = types.ModuleType("jax.scipy.linalg")
