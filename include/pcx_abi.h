@@ -248,6 +248,27 @@ int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const dou
                                  const double* a, const double* b, const double* outputs, int64_t n,
                                  double weight, double* loss_out, double* g_weights, void* stream);
 
+/* Strong-form / collocation path: the jet of the Field at arbitrary points -- what pancax derives
+ * with nested jacfwd / hessian (pancax/physics_kernels/base.py:205-229: field_values, field_gradients,
+ * field_laplacians = trace of field_hessians, field_time_derivatives) -- evaluated in ONE fused pass per point
+ * (forward-mode coordinate tangents through the MLP on the FP64 tensor pipe).
+ *   pts [n*(nd+1)] rows (x..., t); tab [n*ndof*2*(nd+3)] or NULL: the Dirichlet wrapper u = a + b z (fields.py:101)
+ *   and its derivatives at the points, per (point, dof): (a, d_j a.., lap a, a_t, b, d_j b.., lap b, b_t); NULL = identity.
+ *   Outputs (any may be NULL): u [n*ndof], grad_u [n*ndof*nd], lap_u [n*ndof], u_t [n*ndof]. */
+int pcx_points_jet(pcx_handle* h, const double* weights, const double* pts, const double* tab, int64_t n,
+                   double* u, double* grad_u, double* lap_u, double* u_t, void* stream);
+
+/* Strong-form residual loss and its weight gradient on a batch of collocation points:
+ *   r = c_t u_t - c_lap lap(u) - src - target,   loss = weight * mean over (points, dofs) of r^2
+ * Poisson (poisson.py:26-29): c_t = 0, c_lap = 1, src = f(x); heat (heat_equation.py:11-17): c_t = rho c, c_lap = k;
+ * StrongFormResidualLoss (strong_form_loss_functions.py:8-27) when every time step carries the same points;
+ * `target` is the collocation example's `outputs` (NULL = 0).  src / target [n*ndof] or NULL.
+ *   loss_out: device scalar; resid_out [n*ndof] (r before the target is subtracted) or NULL; g_weights
+ *   [pcx_num_weights] or NULL (value only). */
+int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weights, const double* pts, const double* tab,
+                                  const double* src, const double* target, int64_t n, double c_t, double c_lap,
+                                  double weight, double* loss_out, double* resid_out, double* g_weights, void* stream);
+
 /* number of kernels this library has launched on the handle so far (for bench.py "gpu_launches") */
 int64_t pcx_launch_count(const pcx_handle* h);
 

@@ -11,6 +11,7 @@
 
 #include "../../include/pcx_abi.h"
 #include "pcx_element.cuh"
+#include "pcx_jet.cuh"
 #include "pcx_mlp.cuh"
 
 using namespace pcx;
@@ -44,6 +45,9 @@ struct pcx_handle {
   long long ne = 0, nn = 0, n_unknown = 0, n_reaction = 0;
   long long n_unknown_owned = 0, n_reaction_owned = 0;   // sharded meshes: leading entries owned by this shard
   int phase = 0;                // phased (sharded) loss: 0 idle, 1 after begin, 2 after mid
+  // strong-form (jet) workspace, allocated on first use
+  double *jet_post = nullptr, *jet_pre = nullptr, *jet_adj = nullptr, *jet_zjet = nullptr, *jet_obar = nullptr, *jet_lpart = nullptr;
+  long long jet_rows_cap = 0, jet_lpart_n = 0;
   std::vector<char> step_null;  // time steps whose Dirichlet table b is identically 0: u = a, zero cotangent
   int cull_null_steps = 1;      // skip the MLP on those steps (exact); PCX_OPT_CULL_NULL_STEPS / env PCX_CULL_NULL_STEPS
   const double* coords = nullptr;
@@ -435,6 +439,7 @@ static int reduce_wgrad(pcx_handle* h, int nparts, double* g, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ workspace
+static void jet_free(pcx_handle* h);
 static void free_ws(pcx_handle* h) {
   double** ptrs[] = {&h->pk, &h->act, &h->part, &h->us, &h->fe, &h->f, &h->v, &h->ubar, &h->epart, &h->ppart,
                      &h->rpart, &h->scal, &h->props_dev, &h->times_dev, &h->gout_dev, &h->gtmp};
@@ -642,6 +647,7 @@ extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
 extern "C" int pcx_destroy(pcx_handle* h) {
   if (!h) return PCX_OK;
   free_ws(h);
+  jet_free(h);
   if (h->adj_ptr) cudaFree(h->adj_ptr);
   if (h->adj_idx) cudaFree(h->adj_idx);
   delete h;
@@ -1215,6 +1221,193 @@ extern "C" int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* L, const doub
                              want_dp ? g_props : nullptr, replicated_scale);
   LAUNCH_CHECK(h);
   return PCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: strong-form / collocation path
+static void jet_free(pcx_handle* h) {
+  double** ptrs[] = {&h->jet_post, &h->jet_pre, &h->jet_adj, &h->jet_zjet, &h->jet_obar, &h->jet_lpart};
+  for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  h->jet_rows_cap = 0; h->jet_lpart_n = 0;
+}
+
+static int jet_alloc(pcx_handle* h, long long n) {
+  const int S = h->nd + 3;
+  const long long per_row = ((long long)(2 * h->ms.depth + 1) * S * h->ms.NT * 8 + 2LL * S * h->ndof) * sizeof(double);
+  long long budget = 8LL << 30;
+  if (const char* e = getenv("PCX_JET_WORKSPACE_GB")) budget = (long long)(atof(e) * (1LL << 30));
+  long long cap = budget / per_row;
+  if (cap < 64) cap = 64;
+  long long want = n < cap ? n : cap;
+  want = (want + 63) / 64 * 64;
+  if (want <= h->jet_rows_cap) return PCX_OK;
+  jet_free(h);
+  const long long PL = (long long)h->ms.NT * want * 8;
+  CUDA_TRY(cudaMalloc(&h->jet_post, (size_t)h->ms.depth * S * PL * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->jet_pre, (size_t)h->ms.depth * S * PL * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->jet_adj, (size_t)S * PL * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->jet_zjet, (size_t)want * S * h->ndof * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->jet_obar, (size_t)want * S * h->ndof * sizeof(double)));
+  h->jet_rows_cap = want;
+  return PCX_OK;
+}
+
+template <int NT>
+static int jet_launch_nt(pcx_handle* h, int what, const JetIO& io, const JetWgradArgs* wa, int mode, cudaStream_t st) {
+  const bool kodd = h->ms.KS <= 2 * NT - 1;
+  const long long groups = (io.n + 7) / 8;
+  long long blocks = (groups + 7) / 8;
+  if (blocks > h->sm_count) blocks = h->sm_count;
+  if (blocks < 1) blocks = 1;
+  if (what == 0) {
+    const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + EXP2_TAB_N) * sizeof(double);
+    if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
+    if (kodd) {
+      CUDA_TRY(cudaFuncSetAttribute(k_jet_forward<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      k_jet_forward<NT, 1><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(k_jet_forward<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      k_jet_forward<NT, 0><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+    }
+  } else if (what == 1) {
+    const size_t smem = (size_t)(h->ms.npacked - h->ms.pBO) * sizeof(double);
+    if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
+    if (kodd) {
+      CUDA_TRY(cudaFuncSetAttribute(k_jet_backward<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      k_jet_backward<NT, 1><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(k_jet_backward<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      k_jet_backward<NT, 0><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+    }
+  } else {
+    const size_t smem = (size_t)4 * 8 * (NT + 1) * 64 * sizeof(double);
+    const int grid = h->bwd_grid;
+#define PCX_WG(M)                                                                                                       \
+  do {                                                                                                                  \
+    CUDA_TRY(cudaFuncSetAttribute(k_jet_wgrad<NT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    k_jet_wgrad<NT, M><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, *wa);                                                   \
+  } while (0)
+    if (mode == 0) PCX_WG(0); else if (mode == 1) PCX_WG(1); else PCX_WG(2);
+#undef PCX_WG
+  }
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
+static int jet_launch(pcx_handle* h, int what, const JetIO& io, const JetWgradArgs* wa, int mode, cudaStream_t st) {
+  switch (h->ms.NT) {
+    case 2: return jet_launch_nt<2>(h, what, io, wa, mode, st);
+    case 4: return jet_launch_nt<4>(h, what, io, wa, mode, st);
+    case 7: return jet_launch_nt<7>(h, what, io, wa, mode, st);
+    case 8: return jet_launch_nt<8>(h, what, io, wa, mode, st);
+  }
+  return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
+}
+
+static JetIO jet_io(pcx_handle* h, const double* pts, long long n) {
+  JetIO io;
+  memset(&io, 0, sizeof(io));
+  io.pts = pts; io.n = n; io.rows_cap = h->jet_rows_cap;
+  io.post = h->jet_post; io.pre = h->jet_pre; io.adj = h->jet_adj; io.zjet = h->jet_zjet; io.obar = h->jet_obar;
+  io.pk = h->pk; io.S = h->nd + 3; io.nd = h->nd;
+  return io;
+}
+
+static JetPointArgs jet_point_args(pcx_handle* h, long long n, const double* tab, long long o) {
+  JetPointArgs a;
+  memset(&a, 0, sizeof(a));
+  a.zjet = h->jet_zjet; a.n = n; a.S = h->nd + 3; a.nd = h->nd; a.n_out = h->ndof;
+  a.tab = tab ? tab + o * h->ndof * 2 * (h->nd + 3) : nullptr;
+  return a;
+}
+
+extern "C" int pcx_points_jet(pcx_handle* h, const double* weights, const double* pts, const double* tab, int64_t n,
+                              double* u, double* grad_u, double* lap_u, double* u_t, void* stream) {
+  NEED_READY(h);
+  if (!weights || !pts || n <= 0) return fail(PCX_ERR_INVALID, "pcx_points_jet: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = jet_alloc(h, n);
+  if (rc) return rc;
+  if ((rc = pack_weights(h, weights, st))) return rc;
+  for (long long o = 0; o < n; o += h->jet_rows_cap) {
+    const long long m = (n - o < h->jet_rows_cap) ? n - o : h->jet_rows_cap;
+    JetIO io = jet_io(h, pts + o * (h->nd + 1), m);
+    if ((rc = jet_launch(h, 0, io, nullptr, 0, st))) return rc;
+    JetPointArgs a = jet_point_args(h, m, tab, o);
+    a.c_t = 0.0; a.c_lap = 0.0; a.scale = 0.0;
+    a.u = u ? u + o * h->ndof : nullptr;
+    a.grad_u = grad_u ? grad_u + o * h->ndof * h->nd : nullptr;
+    a.lap_u = lap_u ? lap_u + o * h->ndof : nullptr;
+    a.u_t = u_t ? u_t + o * h->ndof : nullptr;
+    k_jet_point<<<256, 256, 0, st>>>(a);
+    LAUNCH_CHECK(h);
+  }
+  return PCX_OK;
+}
+
+extern "C" int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weights, const double* pts, const double* tab,
+                                             const double* src, const double* target, int64_t n, double c_t, double c_lap,
+                                             double weight, double* loss_out, double* resid_out, double* g_weights,
+                                             void* stream) {
+  NEED_READY(h);
+  if (!weights || !pts || !loss_out || n <= 0) return fail(PCX_ERR_INVALID, "pcx_strong_form_loss_and_grad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = jet_alloc(h, n);
+  if (rc) return rc;
+  const long long nchunks = (n + h->jet_rows_cap - 1) / h->jet_rows_cap;
+  const int pgrid = 256;
+  if (h->jet_lpart_n < nchunks * pgrid) {
+    if (h->jet_lpart) cudaFree(h->jet_lpart);
+    h->jet_lpart = nullptr;
+    CUDA_TRY(cudaMalloc(&h->jet_lpart, (size_t)nchunks * pgrid * sizeof(double)));
+    h->jet_lpart_n = nchunks * pgrid;
+  }
+  if ((rc = pack_weights(h, weights, st))) return rc;
+  const int S = h->nd + 3, NT = h->ms.NT, WPd = 8 * NT, DH = h->ms.depth - 1;
+  const long long PL = (long long)NT * h->jet_rows_cap * 8;
+  const double scale = weight / ((double)n * h->ndof);       // weight * mean over (points, dofs)
+  bool first = true;
+  long long chunk = 0;
+  for (long long o = 0; o < n; o += h->jet_rows_cap, chunk++) {
+    const long long m = (n - o < h->jet_rows_cap) ? n - o : h->jet_rows_cap;
+    const double* p = pts + o * (h->nd + 1);
+    JetIO io = jet_io(h, p, m);
+    if ((rc = jet_launch(h, 0, io, nullptr, 0, st))) return rc;
+    JetPointArgs a = jet_point_args(h, m, tab, o);
+    a.c_t = c_t; a.c_lap = c_lap; a.scale = scale;
+    a.src = src ? src + o * h->ndof : nullptr;
+    a.target = target ? target + o * h->ndof : nullptr;
+    a.resid = resid_out ? resid_out + o * h->ndof : nullptr;
+    a.obar = g_weights ? h->jet_obar : nullptr;
+    a.part = h->jet_lpart + chunk * pgrid;
+    k_jet_point<<<pgrid, 256, 0, st>>>(a);
+    LAUNCH_CHECK(h);
+    if (!g_weights) continue;
+    if ((rc = jet_launch(h, 1, io, nullptr, 0, st))) return rc;
+    JetWgradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.n = m; wa.rows_cap = h->jet_rows_cap; wa.S = S; wa.nd = h->nd; wa.n_out = h->ndof; wa.n_in = h->ms.n_in;
+    wa.ones_slot = feat_to_slot(h->ms.width); wa.part = h->part; wa.part_stride = h->part_stride; wa.pts = p;
+    // layer 0
+    wa.Z = h->jet_pre; wa.P = nullptr; wa.sec_off = 0;
+    if ((rc = jet_launch(h, 2, io, &wa, 2, st))) return rc;
+    for (int l = 1; l <= DH; l++) {
+      wa.Z = h->jet_pre + (long long)l * S * PL;
+      wa.P = h->jet_post + (long long)(l - 1) * S * PL;
+      wa.sec_off = (long long)WPd * 8 + (long long)(l - 1) * WPd * WPd;
+      if ((rc = jet_launch(h, 2, io, &wa, 0, st))) return rc;
+    }
+    wa.Z = h->jet_obar; wa.P = h->jet_post + (long long)DH * S * PL;
+    wa.sec_off = (long long)WPd * 8 + (long long)DH * WPd * WPd;
+    if ((rc = jet_launch(h, 2, io, &wa, 1, st))) return rc;
+    if ((rc = reduce_wgrad(h, h->bwd_grid, first ? g_weights : h->gtmp, st))) return rc;
+    if (!first) {
+      const int thr = 256;
+      k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);
+      LAUNCH_CHECK(h);
+    }
+    first = false;
+  }
+  return reduce_rows(h, h->jet_lpart, nchunks * pgrid, 1, 1, 1, loss_out, 1, st);
 }
 
 // ------------------------------------------------------------------------------------------ ABI: optimizer

@@ -252,6 +252,33 @@ class Engine:
         check(self.lib.pcx_element_fields(self.h, _ptr(pr), _ptr(u), _ptr(F), _ptr(I1), _ptr(P), _stream()))
         return F, I1, P
 
+    # ---- strong-form / collocation path
+    def points_jet(self, weights, pts, tab=None, want=("u", "grad_u", "lap_u", "u_t")):
+        """(u (n,ndof), grad_u (n,ndof,nd), lap_u (n,ndof), u_t (n,ndof)) of the Field at points
+        pts (n, nd+1) = (x..., t); ``tab`` (n, ndof, 2*(nd+3)) = Dirichlet wrapper tables or None."""
+        w, p, tb = self._dev(weights), self._dev(pts), self._dev(tab)
+        n = p.shape[0]
+        u = self._empty(n, self.ndof) if "u" in want else None
+        gu = self._empty(n, self.ndof, self.nd) if "grad_u" in want else None
+        lu = self._empty(n, self.ndof) if "lap_u" in want else None
+        ut = self._empty(n, self.ndof) if "u_t" in want else None
+        check(self.lib.pcx_points_jet(self.h, _ptr(w), _ptr(p), _ptr(tb), n, _ptr(u), _ptr(gu), _ptr(lu), _ptr(ut),
+                                      _stream()))
+        return u, gu, lu, ut
+
+    def strong_form_loss_and_grad(self, weights, pts, c_t, c_lap, weight=1.0, tab=None, src=None, target=None,
+                                  want_grad=True, want_resid=False):
+        """weight * mean((c_t u_t - c_lap lap u - src - target)^2) over the batch and its weight gradient."""
+        w, p, tb, sr, tg = (self._dev(weights), self._dev(pts), self._dev(tab), self._dev(src), self._dev(target))
+        n = p.shape[0]
+        loss = self._empty(1)
+        res = self._empty(n, self.ndof) if want_resid else None
+        gw = self._empty(self.n_weights) if want_grad else None
+        check(self.lib.pcx_strong_form_loss_and_grad(self.h, _ptr(w), _ptr(p), _ptr(tb), _ptr(sr), _ptr(tg), n,
+                                                     float(c_t), float(c_lap), float(weight), _ptr(loss), _ptr(res),
+                                                     _ptr(gw), _stream()))
+        return loss, res, gw
+
     def residual_reaction(self, f):
         f = self._dev(f)
         out = self._empty(2)

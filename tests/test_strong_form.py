@@ -60,3 +60,95 @@ def test_oracle_strong_form_loss_matches_reference(kind):
     assert rel(r.reshape(len(case.times), -1, 1), G[k + "residuals"]) < 1e-11
     assert abs(L - float(G[k + "loss"])) <= TOL * abs(L)
     assert rel(gw, G[k + "gw"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------ CUDA path
+def poisson_wrapper_tables(x, ndof=1):
+    """(n, ndof, 2*(nd+3)) tables of u = x(1-x)y(1-y) z (collocation_example.py:11-13):
+    (a, d_j a, lap a, a_t | b, d_j b, lap b, b_t)."""
+    X, Y = x[:, 0], x[:, 1]
+    tab = np.zeros((x.shape[0], ndof, 2 * (2 + 3)))
+    b = X * (1 - X) * Y * (1 - Y)
+    tab[:, 0, 5] = b
+    tab[:, 0, 6] = (1 - 2 * X) * Y * (1 - Y)
+    tab[:, 0, 7] = X * (1 - X) * (1 - 2 * Y)
+    tab[:, 0, 8] = -2 * Y * (1 - Y) - 2 * X * (1 - X)
+    return tab
+
+
+def _engine(case):
+    from tests.cases import make_engine
+    return make_engine(case)
+
+
+@pytest.mark.gpu
+def test_cuda_jet_matches_reference(cuda_device):
+    case = _case()
+    eng = _engine(case)
+    x = case.mesh["coords"]
+    pts = np.column_stack([x, np.full(x.shape[0], case.times[-1])])
+    u, gu, lap, ut = eng.points_jet(case.weights, pts, poisson_wrapper_tables(x))
+    k = "poisson_quad4_n4_nt2_w20_d3__"
+    assert rel(u.cpu().numpy(), G[k + "u"]) < 1e-13
+    assert rel(gu.cpu().numpy(), G[k + "grad_u"]) < 1e-12
+    assert rel(lap.cpu().numpy(), G[k + "lap_u"]) < 1e-11
+    assert rel(ut.cpu().numpy(), G[k + "u_t"]) < 1e-12
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["poisson", "heat"])
+def test_cuda_strong_form_loss_matches_reference(cuda_device, kind):
+    from tests.cases import poisson_source_np
+    case = _case()
+    eng = _engine(case)
+    x, t = _points(case)
+    pts = np.column_stack([x, t])
+    tab = poisson_wrapper_tables(x)
+    k = f"{kind}_quad4_n4_nt2_w20_d3__"
+    if kind == "poisson":
+        L, r, gw = eng.strong_form_loss_and_grad(case.weights, pts, 0.0, 1.0, 2.5, tab=tab,
+                                                 src=poisson_source_np(x)[:, None], want_resid=True)
+    else:
+        L, r, gw = eng.strong_form_loss_and_grad(case.weights, pts, RCK[0] * RCK[1], RCK[2], 1.5, tab=tab, want_resid=True)
+    assert rel(r.cpu().numpy().reshape(len(case.times), -1, 1), G[k + "residuals"]) < 1e-11
+    assert abs(float(L.cpu()[0]) - float(G[k + "loss"])) <= TOL * abs(float(G[k + "loss"]))
+    assert rel(gw.cpu().numpy(), G[k + "gw"]) < TOL
+    # value only
+    L2, _, g2 = eng.strong_form_loss_and_grad(case.weights, pts, 0.0, 1.0, 2.5, tab=tab, want_grad=False)
+    assert g2 is None
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,width,depth,npts", [("hex8_neohookean", 3, 50, 4, 333), ("quad4_neohookean", 5, 30, 2, 64),
+                                                     ("hex8_neohookean", 2, 12, 1, 7), ("quad4_neohookean", 4, 55, 3, 1000)])
+def test_cuda_jet_and_heat_loss_match_oracle_on_other_shapes(cuda_device, name, n, width, depth, npts, monkeypatch):
+    """nd = 2 / 3, several dofs, ragged batches, identity wrapper, target term; chunked when the jet workspace is small."""
+    from oracle import strong_form as sf
+    from oracle.losses import _build, _leaves
+    from pancax_b200 import Engine
+    case = make_case(name, n=n, nt=3, width=width, depth=depth)
+    nd, ndof = case.mesh["coords"].shape[1], case.ndof
+    if npts == 1000:
+        monkeypatch.setenv("PCX_JET_WORKSPACE_GB", "0.004")        # forces several chunks
+    eng = Engine(case.mesh["coords"], case.mesh["conns"], case.mesh["elem"], 2, ndof, case.times)
+    eng.set_physics("solid", "neohookean", case.formulation, [1000.0, 1.0])
+    eng.set_field(*case.mlp)
+    rng = np.random.default_rng(2)
+    x = rng.uniform(0.0, 1.0, (npts, nd))
+    t = rng.uniform(0.0, 1.0, npts)
+    pts = np.column_stack([x, t])
+    prob = __import__("tests.cases", fromlist=["oracle_problem"]).oracle_problem(case)
+    prob.bc_func = None
+    u, gu, lap, ut = eng.points_jet(case.weights, pts)
+    uo, guo, lapo, uto = sf.jet_numpy(prob, case.weights, x, t)
+    assert rel(u.cpu().numpy(), uo) < 1e-13 and rel(gu.cpu().numpy(), guo) < 1e-12
+    assert rel(lap.cpu().numpy(), lapo) < 1e-11 and rel(ut.cpu().numpy(), uto) < 1e-12
+    target = 0.1 * rng.standard_normal((npts, ndof))
+    L, r, gw = eng.strong_form_loss_and_grad(case.weights, pts, 0.7, 0.3, 1.9, target=target, want_resid=True)
+    Lo, ro, gwo = sf.loss_and_grad(prob, case.weights, "heat", (0.7, 1.0, 0.3), x, t, 1.9, target=target)
+    assert rel(r.cpu().numpy() - target, ro) < 1e-11
+    assert abs(float(L.cpu()[0]) - Lo) <= TOL * abs(Lo)
+    assert rel(gw.cpu().numpy(), gwo) < TOL
+    eng.close()
