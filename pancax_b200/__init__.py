@@ -17,13 +17,13 @@ from .bvps import BiaxialLinearRamp, SimpleShearLinearRamp, UniaxialTensionLinea
 from .constitutive_models import (BoundedProperty, FixedProperty, Gent, Hencky, NeoHookean,  # noqa: F401,E402
                                   Swanson)
 from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E402
-from .domains import VariationalDomain  # noqa: F401,E402
+from .domains import CollocationDomain, VariationalDomain  # noqa: F401,E402
 from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, write_exodus_mesh  # noqa: F401,E402
 from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, EnergyLoss,  # noqa: F401,E402
-                             EnergyResidualAndReactionLoss, FullFieldDataLoss)
+                             EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss)
 from .networks import MLP, Field, Parameters  # noqa: F401,E402
 from .optimizers import Adam  # noqa: F401,E402
-from .physics_kernels import PlaneStrain, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
+from .physics_kernels import HeatEquation, PlaneStrain, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
 from .post_processor import ExodusPostProcessor, PostProcessor  # noqa: F401,E402
 from .problems import ForwardProblem, InverseProblem  # noqa: F401,E402
 from .trainer import Trainer  # noqa: F401,E402

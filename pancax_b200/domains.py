@@ -41,3 +41,31 @@ class VariationalDomain:
         """domains.py:64-71"""
         self.dof_manager = DofManager(self.mesh, n_dofs, dirichlet_bcs)
         return self
+
+
+class CollocationDomain:
+    """pancax/domains.py:72-81: the mesh nodes are the collocation points of the strong-form losses."""
+
+    def __init__(self, mesh_file, times, p_order: int = 1):
+        if isinstance(mesh_file, Mesh):
+            mesh, self.mesh_file = mesh_file, None
+        else:
+            mesh, self.mesh_file = read_exodus_mesh(mesh_file), mesh_file
+        times = np.asarray(times, dtype=np.float64)
+        if len(times) != len(set(times.tolist())):
+            raise SimulationTimesNotUniqueException()
+        for i in range(len(times) - 1):
+            if times[i] >= times[i + 1]:
+                raise SimulationTimesNotStrictlyIncreasingException()
+        self.mesh, self.coords, self.conns, self.times = mesh, mesh.coords, mesh.conns, times
+        self.q_order = 1
+        self.dof_manager = None
+
+    def update_dof_manager(self, dirichlet_bcs, n_dofs):
+        self.dof_manager = DofManager(self.mesh, n_dofs, dirichlet_bcs)
+        return self
+
+    def collocation_points(self):
+        """All (x..., t) rows, time-major: what CollocationDataLoader assembles (domains.py:96-110)."""
+        nn = self.coords.shape[0]
+        return np.column_stack([np.tile(self.coords, (len(self.times), 1)), np.repeat(self.times, nn)])

@@ -12,7 +12,7 @@ import torch
 
 from .constitutive_models import BoundedProperty
 from .engine import Engine, tabulate_bc
-from .physics_kernels import Poisson, SolidMechanics
+from .physics_kernels import BaseStrongFormPhysics, HeatEquation, Poisson, SolidMechanics
 
 
 class Grads:
@@ -92,7 +92,9 @@ def get_engine(problem, params, deterministic: bool = True) -> Engine:
     if shard is not None:
         eng.set_ownership(n_uo, n_ro)
     phys = problem.physics
-    if isinstance(phys, Poisson):
+    if isinstance(phys, HeatEquation):
+        eng.set_physics("poisson")          # strong form only: no energy functional, the engine just needs a physics
+    elif isinstance(phys, Poisson):
         _, _, xq = eng.element_geometry(want_grad_N=False, want_JxW=False)
         eng.set_physics("poisson", source_q=np.asarray(phys.f(xq.cpu().numpy()), dtype=np.float64))
     elif isinstance(phys, SolidMechanics):
@@ -251,6 +253,51 @@ class FullFieldDataLoss(BaseLossFunction):
     def value_and_grad(self, params, problem, inputs, outputs):
         loss, gw = self._run(params, problem, inputs, outputs)
         aux = {"field_data_loss": loss[0] / self.weight if self.weight else loss[0]}
+        return (loss[0], aux), Grads(gw, torch.zeros_like(params.prop_raw))
+
+
+class StrongFormResidualLoss(BaseLossFunction):
+    """strong_form_loss_functions.py:8-27: weight * mean_t mean_nodes residual^2 with the physics' strong-form
+    residual at the mesh nodes (collocation points); aux ``residual``.  The jet of the field (value, coordinate
+    tangents, Laplacian, time derivative) and its adjoint are fused CUDA kernels (pcx_strong_form_loss_and_grad).
+    ``__call__(params, problem, inputs, outputs)`` evaluates mean((residual - outputs)^2) on a batch of (x..., t)
+    rows instead: the user loss of examples/forward_problems/poisson/collocation_example.py:36-41."""
+
+    def __init__(self, weight: Optional[float] = 1.0):
+        self.weight = weight
+
+    def _run(self, params, problem, inputs, outputs, want_grad):
+        from .jets import tabulate_bc_jet
+        phys = problem.physics
+        if not isinstance(phys, BaseStrongFormPhysics):
+            raise TypeError(f"{type(phys)} has no strong form on the B200 path")
+        eng = get_engine(problem, params)
+
+        def tables(pts):
+            tab = tabulate_bc_jet(params.fields.dirichlet_bc_func, pts, problem.n_dofs)
+            src = phys.strong_form_source(pts[:, :problem.n_dims])
+            if src is not None:
+                src = np.asarray(src, dtype=np.float64).reshape(pts.shape[0], problem.n_dofs)
+            return eng._dev(pts), eng._dev(tab), eng._dev(src)
+        if inputs is None:          # every (time step, node): static, tabulated once per problem
+            cache = problem._engines.setdefault("_strong_form_static", {})
+            if id(params.fields.dirichlet_bc_func) not in cache:
+                cache[id(params.fields.dirichlet_bc_func)] = tables(problem.domain.collocation_points())
+            pts, tab, src = cache[id(params.fields.dirichlet_bc_func)]
+        else:
+            pts, tab, src = tables(np.ascontiguousarray(inputs, dtype=np.float64))
+        c_t, c_lap = phys.strong_form_coefficients()
+        loss, _, gw = eng.strong_form_loss_and_grad(params.fields.networks.weights, pts, c_t, c_lap, self.weight,
+                                                    tab=tab, src=src, target=outputs, want_grad=want_grad)
+        return loss, gw
+
+    def __call__(self, params, problem, inputs=None, outputs=None):
+        loss, _ = self._run(params, problem, inputs, outputs, False)
+        return loss[0], dict(residual=loss[0] / self.weight if self.weight else loss[0])
+
+    def value_and_grad(self, params, problem, inputs=None, outputs=None):
+        loss, gw = self._run(params, problem, inputs, outputs, True)
+        aux = dict(residual=loss[0] / self.weight if self.weight else loss[0])
         return (loss[0], aux), Grads(gw, torch.zeros_like(params.prop_raw))
 
 

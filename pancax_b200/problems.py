@@ -3,8 +3,8 @@ from __future__ import annotations
 
 from typing import Callable, List, Optional
 
-from .domains import VariationalDomain
-from .physics_kernels import BaseEnergyFormPhysics
+from .domains import CollocationDomain, VariationalDomain
+from .physics_kernels import BaseEnergyFormPhysics, BaseStrongFormPhysics
 
 
 class DomainPhysicsCompatabilityError(Exception):
@@ -14,7 +14,9 @@ class DomainPhysicsCompatabilityError(Exception):
 class ForwardProblem:
     def __init__(self, domain, physics, ics: Optional[List[Callable]] = None,
                  dirichlet_bcs: Optional[list] = None, neumann_bcs: Optional[list] = None) -> None:
-        if not isinstance(domain, VariationalDomain) or not isinstance(physics, BaseEnergyFormPhysics):
+        ok = (isinstance(domain, VariationalDomain) and isinstance(physics, BaseEnergyFormPhysics)) or \
+            (isinstance(domain, CollocationDomain) and isinstance(physics, BaseStrongFormPhysics))   # problems.py:52-66
+        if not ok:
             raise DomainPhysicsCompatabilityError(
                 f"Incompatable domain and physics.\nGot domain of type = {type(domain)}\n"
                 f"Got physics of type = {type(physics)}")

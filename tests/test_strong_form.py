@@ -152,3 +152,80 @@ def test_cuda_jet_and_heat_loss_match_oracle_on_other_shapes(cuda_device, name, 
     assert abs(float(L.cpu()[0]) - Lo) <= TOL * abs(Lo)
     assert rel(gw.cpu().numpy(), gwo) < TOL
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------ host mirror
+def test_jet_tabulation_of_dirichlet_wrappers():
+    """pancax_b200/jets.py: second-order forward mode on the host gives (a, grad a, lap a, a_t, b, ...) of a
+    Python wrapper written per point (x[0]) like the reference's, incl. .at[].set and numpy ufuncs."""
+    from pancax_b200.jets import tabulate_bc_jet
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 1, (11, 3))
+    X, Y, T = pts[:, 0], pts[:, 1], pts[:, 2]
+    tab = tabulate_bc_jet(lambda x, t, z: x[0] * (1. - x[0]) * x[1] * (1. - x[1]) * z, pts, 1)
+    assert np.abs(tab - poisson_wrapper_tables(pts[:, :2])).max() < 1e-15
+
+    def uniaxial(x, t, z):              # pancax/bvps/uniaxial_tension.py, 2D, direction y
+        u = z
+        u = u.at[0].set(x[1] * (x[1] - 1.0) * t * z[0] / 1.0 ** 2)
+        u = u.at[1].set(x[1] * t * 0.5 / 1.0 + x[1] * (x[1] - 1.0) * t * z[1] / 1.0 ** 2)
+        return u
+    tab = tabulate_bc_jet(uniaxial, pts, 2)
+    assert np.array_equal(tab[:, 1, 0], Y * T * 0.5) and np.array_equal(tab[:, 1, 4], Y * 0.5)      # a, a_t
+    assert np.array_equal(tab[:, 0, 5], Y * (Y - 1.0) * T) and np.array_equal(tab[:, 0, 8], 2.0 * T)  # b, lap b
+    tab = tabulate_bc_jet(lambda x, t, z: np.sin(x[0]) * np.exp(-t) * z + np.cos(x[1]), pts, 1)
+    assert np.abs(tab[:, 0, 3] + np.cos(Y)).max() < 1e-15 and np.abs(tab[:, 0, 9] + np.sin(X) * np.exp(-T)).max() < 1e-15
+    with pytest.raises(NotImplementedError):
+        tabulate_bc_jet(lambda x, t, z: z * z, pts, 1)
+    assert tabulate_bc_jet(None, pts, 1) is None
+
+
+def test_collocation_domain_points_and_problem_checks():
+    import pancax_b200 as px
+    mesh = px.create_structured_mesh("quad4", 3)
+    dom = px.CollocationDomain(mesh, np.linspace(0.0, 1.0, 3))
+    pts = dom.collocation_points()
+    assert pts.shape == (3 * 16, 3) and np.array_equal(pts[16:32, 2], np.full(16, 0.5))
+    assert np.array_equal(pts[32:, :2], mesh.coords)
+    px.ForwardProblem(dom, px.HeatEquation(1.0, 2.0, 3.0))
+    px.ForwardProblem(dom, px.Poisson(lambda x: x[..., 0]))
+    with pytest.raises(px.problems.DomainPhysicsCompatabilityError):
+        px.ForwardProblem(px.VariationalDomain(mesh, np.linspace(0, 1, 2)), px.HeatEquation())
+    assert px.HeatEquation(2.0, 3.0, 5.0).strong_form_coefficients() == (6.0, 5.0)
+
+
+@pytest.mark.gpu
+def test_strong_form_loss_through_the_public_api(cuda_device):
+    """CollocationDomain + Poisson + StrongFormResidualLoss (strong_form_loss_functions.py:8-27) == the vectors the
+    reference's own classes produced; then Adam drives the residual down (heat equation)."""
+    import pancax_b200 as px
+    from tests.cases import poisson_source_np
+    case = _case()
+    mesh = px.Mesh(case.mesh["coords"], case.mesh["conns"], "quad4", case.mesh["nodesets"])
+    dom = px.CollocationDomain(mesh, case.times)
+    problem = px.ForwardProblem(dom, px.Poisson(poisson_source_np))
+    params = px.Parameters(problem, key=0, n_layers=3, n_neurons=20,
+                           dirichlet_bc_func=lambda x, t, z: x[0] * (1. - x[0]) * x[1] * (1. - x[1]) * z)
+    params.fields.networks.set_weights(case.weights)
+    lf = px.StrongFormResidualLoss(weight=2.5)
+    (L, aux), g = lf.value_and_grad(params, problem)
+    k = "poisson_quad4_n4_nt2_w20_d3__"
+    assert abs(float(L) - float(G[k + "loss"])) <= TOL * abs(float(G[k + "loss"]))
+    assert rel(g.fields.cpu().numpy(), G[k + "gw"]) < TOL
+    L2, aux2 = lf(params, problem)
+    assert abs(float(L2) - float(L)) <= 1e-14 * abs(float(L)) and abs(float(aux2["residual"]) * 2.5 - float(L)) < 1e-12 * abs(float(L))
+    # batch form of the collocation example: mean((residual - outputs)^2)
+    pts = dom.collocation_points()[5:25]
+    (Lb, _), _ = lf.value_and_grad(params, problem, pts, np.zeros((20, 1)))
+    assert np.isfinite(float(Lb))
+    # training on the heat equation lowers the residual
+    problem = px.ForwardProblem(px.CollocationDomain(mesh, np.linspace(0.0, 1.0, 4)), px.HeatEquation(1.0, 1.0, 0.1))
+    params = px.Parameters(problem, key=1, n_layers=2, n_neurons=16,
+                           dirichlet_bc_func=lambda x, t, z: np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]) * np.exp(-t) + t * z)
+    opt = px.Adam(px.StrongFormResidualLoss(), learning_rate=2e-3)
+    st = opt.init(params)
+    l0 = None
+    for it in range(200):
+        params, st, loss = opt.step(params, st, problem)
+        l0 = float(loss) if l0 is None else l0
+    assert float(loss) < 0.5 * l0
