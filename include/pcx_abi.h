@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PCX_ABI_VERSION 1
+#define PCX_ABI_VERSION 2
 
 /* error codes */
 #define PCX_OK               0
@@ -132,6 +132,10 @@ typedef struct {
   double  residual_weight;
   double  reaction_weight;
   const double* global_outputs; /* HOST f64 [nt] (problem.global_data.outputs) or NULL          */
+  int32_t first_step;         /* 0: path-independent call (vmap over all times); 1: the path-dependent call of a
+                                 model without state variables (weak_form_loss_functions.py:48-72,242-276): the
+                                 loop starts at time step 1 ("time step 0 is the initial condition"), residual and
+                                 reaction terms are still divided by nt                                  */
 } pcx_loss_desc;
 
 /* aux layout written by pcx_loss_and_grad (device f64 [PCX_AUX_FIXED + nt]):

@@ -197,6 +197,23 @@ def main():
     out["ffd_quad4_n5_nt3_w50_d3__loss"], out["ffd_quad4_n5_nt3_w50_d3__gw"] = np.array(float(loss)), gw
     print("FullFieldDataLoss", float(loss), np.linalg.norm(gw))
 
+    # ---------------------------------------------------------------- path-dependent calls (stateless models)
+    # weak_form_loss_functions.py:48-72 (EnergyLoss.path_dependent_call) and :242-276
+    # (EnergyResidualAndReactionLoss.path_dependent_call): the scan starts at time step 1.
+    case = make_case("quad4_neohookean", n=5, nt=4, width=20, depth=2, t0=0.1)
+    for kind, lf in (("energy", EnergyLoss(is_path_dependent=True, weight=LOSS_WEIGHTS["energy_weight"])),
+                     ("energy_residual_reaction", EnergyResidualAndReactionLoss(
+                         energy_weight=LOSS_WEIGHTS["energy_weight"], is_path_dependent=True,
+                         residual_weight=LOSS_WEIGHTS["residual_weight"], reaction_weight=LOSS_WEIGHTS["reaction_weight"]))):
+        params, problem, leaves, raws = build(case)
+        loss, aux = lf(params, problem)
+        gw, _ = flat_grad(loss, leaves, raws)
+        out[f"pathdep_quad4_neohookean_n5_nt4_w20_d2__{kind}__loss"] = np.array(float(loss))
+        out[f"pathdep_quad4_neohookean_n5_nt4_w20_d2__{kind}__gw"] = gw
+        for k, v in aux.items():
+            out[f"pathdep_quad4_neohookean_n5_nt4_w20_d2__{kind}__aux_{k}"] = np.asarray(v.detach().numpy() if isinstance(v, torch.Tensor) else v)
+        print("path-dependent", kind, float(loss), np.linalg.norm(gw))
+
     # ---------------------------------------------------------------- strong form
     # Poisson: StrongFormResidualLoss.__call__ (strong_form_loss_functions.py:15-27) -> physics.strong_form_residual
     # (poisson.py:26-29) -> field_laplacians = trace(jax.hessian(field_values)) (base.py:213-226), with the

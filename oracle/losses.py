@@ -158,7 +158,10 @@ def loss_value(problem: OracleProblem, loss: dict, w, pr):
     wg = loss.get("reaction_weight", 1.0)
     nt = len(problem.times)
     pis, Rs, reacts = [], [], []
-    for t in problem.times:
+    # loss["first_step"] = 1: the path-dependent call of a stateless model (weak_form:48-72,242-276): the scan
+    # starts at time step 1; residual / reaction terms are still divided by len(times)
+    first = int(loss.get("first_step", 0))
+    for t in problem.times[first:]:
         us = fld(coords, float(t))                           # weak_form:42,208,304
         if kind == "energy":
             pis.append(potential_energy(phys, pe, coords, conns, us))   # :43-45
@@ -183,8 +186,8 @@ def loss_value(problem: OracleProblem, loss: dict, w, pr):
         # :289-300
         R = torch.stack(Rs).sum() / nt
         reactions = torch.stack(reacts)
-        outs = torch.as_tensor(problem.global_outputs, dtype=F64)
-        reaction_loss = torch.square(reactions - outs).mean()
+        outs = torch.as_tensor(problem.global_outputs, dtype=F64)[first:]
+        reaction_loss = torch.square(reactions - outs).sum() / nt
         val = we * energy + wr * R + wg * reaction_loss
         return val, dict(energy=energy.detach(), residual=R.detach(),
                          global_data_loss=reaction_loss.detach(),

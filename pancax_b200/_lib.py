@@ -62,6 +62,7 @@ class LossDesc(C.Structure):
         ("energy_weight", C.c_double), ("residual_weight", C.c_double),
         ("reaction_weight", C.c_double),
         ("global_outputs", C.POINTER(C.c_double)),
+        ("first_step", C.c_int32),
     ]
 
 

@@ -236,7 +236,7 @@ __global__ void k_finish(int kind, int nt, double we, double wr, double wg, cons
                          const double* __restrict__ sc_R, const double* __restrict__ sc_re, const double* __restrict__ gout,
                          const double* __restrict__ dpi, const double* __restrict__ dfv, const double* __restrict__ props_dev,
                          pcx_physics_desc d, const int* __restrict__ flags, double* __restrict__ loss, double* __restrict__ aux,
-                         double* __restrict__ g_props, double rep) {
+                         double* __restrict__ g_props, double rep, int t_first = 0) {
   // rep: weight of the terms every shard computes identically (R, reaction loss, reactions): 1 for a
   // whole mesh, 1/n_shards for a shard, so that SUM over shards of (loss, aux) is the global value
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -249,7 +249,7 @@ __global__ void k_finish(int kind, int nt, double we, double wr, double wg, cons
     L += rep * wr * R;
   }
   if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION) {
-    for (int t = 0; t < nt; t++) { const double dd = sc_re[t] - gout[t]; gl += dd * dd; }
+    for (int t = t_first; t < nt; t++) { const double dd = sc_re[t] - gout[t]; gl += dd * dd; }
     gl /= nt;
     L += rep * wg * gl;
   }
@@ -1059,7 +1059,10 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   const bool want_dp = want_grad && g_props != nullptr && h->ntrain > 0;
   const long long ndofs = h->nn * h->ndof;
   bool first = true;
-  for (int t0 = 0; t0 < h->nt; t0 += h->T) {
+  const int t_first = L->first_step;
+  if (t_first < 0 || t_first >= h->nt) return fail(PCX_ERR_INVALID, "first_step %d out of range (nt = %d)", t_first, h->nt);
+  if (t_first > 0) CUDA_TRY(cudaMemsetAsync(h->scal, 0, SC_SIZE(h) * sizeof(double), st));   // skipped steps contribute 0
+  for (int t0 = t_first; t0 < h->nt; t0 += h->T) {
     const int T = (h->nt - t0 < h->T) ? h->nt - t0 : h->T;
     // (2) field at the nodes for T time steps
     if ((rc = field_forward_steps(h, t0, T, h->us, want_grad, st))) return rc;
@@ -1108,7 +1111,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   if (want_grad && first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
-                             want_dp ? g_props : nullptr, 1.0);
+                             want_dp ? g_props : nullptr, 1.0, t_first);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
@@ -1136,6 +1139,7 @@ static int check_phased(pcx_handle* h, const pcx_loss_desc* L) {
   if (!h->unknown_idx) return fail(PCX_ERR_STATE, "residual losses need unknown_idx in pcx_mesh_desc");
   if (L->kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION && !L->global_outputs)
     return fail(PCX_ERR_STATE, "reaction loss needs global_outputs");
+  if (L->first_step != 0) return fail(PCX_ERR_UNSUPPORTED, "the phased (sharded) loss supports first_step = 0 only");
   if (h->T < h->nt)
     return fail(PCX_ERR_UNSUPPORTED, "phased loss needs all %d time steps in one batch (workspace holds %d): raise PCX_WORKSPACE_GB",
                 h->nt, h->T);

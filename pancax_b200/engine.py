@@ -286,11 +286,13 @@ class Engine:
         return out
 
     def loss_and_grad(self, kind, weights, prop_raw=None, energy_weight=1.0, residual_weight=1.0,
-                      reaction_weight=1.0, global_outputs=None, out=None, want_grad=True):
-        """Returns device tensors (loss[1], aux[4+nt], g_weights, g_props)."""
+                      reaction_weight=1.0, global_outputs=None, out=None, want_grad=True, first_step=0):
+        """Returns device tensors (loss[1], aux[4+nt], g_weights, g_props).  ``first_step=1``: the
+        path-dependent call of a model without state variables (the time loop starts at step 1)."""
         w, pr = self._dev(weights), self._dev(prop_raw)
         ld = LossDesc()
         ld.kind = LOSS[kind]
+        ld.first_step = int(first_step)
         ld.energy_weight, ld.residual_weight, ld.reaction_weight = \
             float(energy_weight), float(residual_weight), float(reaction_weight)
         go = None

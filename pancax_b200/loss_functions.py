@@ -135,8 +135,17 @@ class PhysicsLossFunction(BaseLossFunction):
         return dict(energy_weight=1.0, residual_weight=1.0, reaction_weight=1.0)
 
     def _run(self, params, problem, want_grad):
+        first_step = 0
         if getattr(self, "is_path_dependent", False):
-            raise NotImplementedError("path-dependent losses (state variables) are not on the B200 path")
+            # weak_form_loss_functions.py:48-72,242-276: the scan starts at time step 1.  Without state variables
+            # (every hyperelastic model here) that is the only difference from the path-independent call.
+            model = getattr(problem.physics, "constitutive_model", None)
+            if model is not None and model.num_state_variables != 0:
+                raise NotImplementedError("models with state variables are not on the B200 path")
+            if self.kind == "energy_residual":
+                raise AssertionError("EnergyAndResidualLoss: path-dependent call is disabled in the reference too "
+                                     "(weak_form_loss_functions.py:145-147)")
+            first_step = 1
         eng = get_engine(problem, params, self.deterministic)
         gd = getattr(problem, "global_data", None)
         gout = None
@@ -148,13 +157,15 @@ class PhysicsLossFunction(BaseLossFunction):
         if shard is not None and shard.plan.n_shards > 1 and self.kind != "energy":
             # one element shard per rank: phased ABI, two small exchanges in between; the returned
             # values are PARTIAL -- sum them over ranks (parallel.PackedResult.allreduce) like EnergyLoss
+            if first_step:
+                raise NotImplementedError("path-dependent residual losses on shards")
             return eng.sharded_loss_and_grad(
                 self.kind, params.fields.networks.weights, params.prop_raw if eng.n_train else None,
                 shard.exchange, global_outputs=gout, **self._weights())
         loss, aux, gw, gp = eng.loss_and_grad(
             self.kind, params.fields.networks.weights,
             params.prop_raw if eng.n_train else None, global_outputs=gout, want_grad=want_grad,
-            **self._weights())
+            first_step=first_step, **self._weights())
         return loss, aux, gw, gp
 
     def _aux(self, aux):

@@ -159,3 +159,40 @@ def test_cuda_matches_reference_element_fields(cuda_device, name, n, nt, width, 
                                     want_F=False, want_P=False)
     assert F2 is None and P2 is None and np.array_equal(I2.cpu().numpy(), I1b.cpu().numpy())
     eng.close()
+
+
+# ---- path-dependent calls of stateless models: the time loop starts at step 1
+PD = "pathdep_quad4_neohookean_n5_nt4_w20_d2__"
+
+
+def _pd_case():
+    return make_case("quad4_neohookean", n=5, nt=4, width=20, depth=2, t0=0.1)
+
+
+@pytest.mark.parametrize("kind", ["energy", "energy_residual_reaction"])
+def test_oracle_matches_reference_path_dependent_call(kind):
+    L, aux, gw, _ = run_oracle_loss(_pd_case(), kind, first_step=1)
+    assert abs(L - float(G[PD + kind + "__loss"])) <= TOL * abs(L)
+    assert rel(gw, G[PD + kind + "__gw"]) < TOL
+    assert abs(float(aux["energy"]) - float(G[PD + kind + "__aux_energy"])) <= TOL * abs(float(aux["energy"]))
+    if kind != "energy":
+        assert abs(float(aux["residual"]) - float(G[PD + kind + "__aux_residual"])) <= TOL * float(aux["residual"])
+        assert abs(float(aux["global_data_loss"]) - float(G[PD + kind + "__aux_global_data_loss"])) <= \
+            TOL * float(aux["global_data_loss"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["energy", "energy_residual_reaction"])
+def test_cuda_matches_reference_path_dependent_call(cuda_device, kind):
+    from tests.cases import LOSS_WEIGHTS, make_engine
+    case = _pd_case()
+    eng = make_engine(case)
+    loss, aux, gw, _ = eng.loss_and_grad(kind, case.weights, global_outputs=case.global_outputs, first_step=1, **LOSS_WEIGHTS)
+    L, aux = float(loss.cpu()[0]), aux.cpu().numpy()
+    assert abs(L - float(G[PD + kind + "__loss"])) <= TOL * abs(L)
+    assert rel(gw.cpu().numpy(), G[PD + kind + "__gw"]) < TOL
+    assert abs(aux[0] - float(G[PD + kind + "__aux_energy"])) <= TOL * abs(aux[0])
+    if kind != "energy":
+        assert abs(aux[1] - float(G[PD + kind + "__aux_residual"])) <= TOL * aux[1]
+        assert abs(aux[2] - float(G[PD + kind + "__aux_global_data_loss"])) <= TOL * aux[2]
+    eng.close()
