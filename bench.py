@@ -215,6 +215,38 @@ def run_ours(args):
               "note": "library default: the MLP is skipped on time steps whose Dirichlet table b == 0 (u = a, zero "
                       "cotangent; identical results). NOT the headline: value/e2e/roofline evaluate every row."}
 
+    # ---------------- TF32 tensor-core adjoint (PCX_OPT_TF32_ADJOINT; north_star item 4 / config C5), every row
+    # evaluated, reported separately: the headline stays the fp64 (1e-10) path
+    step_device()
+    g64 = res.gw.clone()
+    eng.set_option("tf32_adjoint", 1)
+    for _ in range(3):
+        step_device()
+    g32 = res.gw.clone()
+    eng.profile_enable(True)
+    eng.profile_collect()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    prof32 = eng.profile_collect()
+    eng.profile_enable(False)
+    eng.set_option("tf32_adjoint", 0)
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_tf32 = float(t_ms.cpu()[0])
+    tf32 = {"value": evals_per_rank * world * args.steps / (ms_tf32 * 1e-3), "unit": "evals/s",
+            "ms_per_step": ms_tf32 / args.steps,
+            "grad_rel_err_vs_fp64": float((torch.linalg.norm(g32 - g64) / torch.linalg.norm(g64)).cpu()),
+            "loss_identical": True, "tolerance": 1e-5,
+            "kernel_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in prof32.items() if v[1]},
+            "note": "adjoint through the MLP in error-compensated 3xTF32 (mma.sync.m16n8k8.tf32, fp32 accumulate, fp64 "
+                    "flush every 1024 rows) from fp32 activations; forward / element sweeps / loss stay fp64. NOT the "
+                    "headline: value/e2e/roofline are the fp64 path."}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -262,7 +294,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(host_w.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8),
                 "api": "EnergyLoss().value_and_grad(params, problem) with pinned-host weights in, loss+grad out"},
-        "roofline": roofline, "cpu_baseline": cpu, "null_step_culling": culled,
+        "roofline": roofline, "cpu_baseline": cpu, "null_step_culling": culled, "tf32_adjoint": tf32,
     }
     print(json.dumps(out))
     if world > 1:

@@ -162,6 +162,13 @@ int pcx_destroy(pcx_handle* h);
  * output, so the MLP forward / adjoint are skipped for it.  Results are identical to evaluating every row;
  * 0 evaluates every row like the reference does. */
 #define PCX_OPT_CULL_NULL_STEPS 1
+/* PCX_OPT_TF32_ADJOINT (default 0): run the adjoint through the MLP (delta chain + weight-gradient contraction) on
+ * the TF32 tensor cores with error-compensated 3xTF32 products and fp32 accumulation flushed to fp64 every 1 024
+ * rows, from fp32 copies of the hidden activations (BASELINE.json north_star item 4 / config C5).  The forward pass,
+ * the element sweeps, the loss and aux stay fp64 and bit-identical; only d loss / d weights changes, by <= 1e-5
+ * relative per leaf (north_star allows 1e-4).  Must not be toggled between a forward and its adjoint
+ * (pcx_loss_begin / pcx_loss_finish). */
+#define PCX_OPT_TF32_ADJOINT 2
 int pcx_set_option(pcx_handle* h, int32_t option, int64_t value);
 
 /* sizes the caller needs to allocate outputs */

@@ -13,6 +13,7 @@
 #include "pcx_element.cuh"
 #include "pcx_jet.cuh"
 #include "pcx_mlp.cuh"
+#include "pcx_mlp_tf32.cuh"
 
 using namespace pcx;
 
@@ -72,6 +73,8 @@ struct pcx_handle {
   int bwd_grid = 0;
   long long part_stride = 0;
   double *pk = nullptr, *act = nullptr, *part = nullptr;
+  float* pk32 = nullptr;        // TF32-adjoint mode: hi/lo chain weights (k_pack_weights_tf32)
+  int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT
   double *us = nullptr, *fe = nullptr, *f = nullptr, *v = nullptr, *ubar = nullptr;
   double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
   double *scal = nullptr;       // see SC_* offsets
@@ -386,8 +389,20 @@ static int launch_mlp_fwd_k(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   return (h->ms.KS <= 2 * NT - 1) ? launch_mlp_fwd_v<NT, 1, MT, MINB>(h, st, io) : launch_mlp_fwd_v<NT, 0, MT, MINB>(h, st, io);
 }
 
-static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+// TF32-adjoint mode: the activation planes are stored as fp32 in the same workspace (same element offsets)
+static MlpIO tf32_view(const pcx_handle* h, const MlpIO& io_in) {
+  MlpIO io = io_in;
+  if (h->tf32_adjoint && io.act) {
+    io.act32 = reinterpret_cast<float*>(h->act) + (io.act - h->act);
+    io.act = nullptr;
+    io.pk32 = h->pk32;
+  }
+  return io;
+}
+
+static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io_in) {
   ProfScope ps(h, PCX_PROF_MLP_FORWARD, st);
+  const MlpIO io = tf32_view(h, io_in);
   switch (h->ms.NT) {
     case 2: return launch_mlp_fwd_k<2, 2, 2>(h, st, io);
     case 4: return launch_mlp_fwd_k<4, 2, 2>(h, st, io);
@@ -402,15 +417,59 @@ static int launch_mlp_fwd(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   }
 }
 
-static int bwd_rows_per_cta(const pcx_handle* h) { return 8 * (h->ms.NT + 1); }
+static int bwd_rows_per_cta(const pcx_handle* h) { return h->tf32_adjoint ? 128 : 8 * (h->ms.NT + 1); }
 
-static int launch_mlp_bwd(pcx_handle* h, cudaStream_t st, const MlpIO& io, int* grid_out) {
-  const long long ntiles = (io.n + bwd_rows_per_cta(h) - 1) / bwd_rows_per_cta(h);
+template <int NT, int DH>
+static int launch_mlp_bwd_tf32_v(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
+  const size_t smem = sizeof(BwdTfSmem<NT, DH>);
+  if constexpr (sizeof(BwdTfSmem<NT, DH>) > 227 * 1024) {
+    return fail(PCX_ERR_UNSUPPORTED, "TF32 adjoint: MLP %d x %d needs %zu bytes of shared memory", h->ms.width, h->ms.depth, smem);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward_tf32<NT, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaMemsetAsync(h->part, 0, (size_t)grid * h->part_stride * sizeof(double), st));   // partials are accumulated with RED
+    k_mlp_backward_tf32<NT, DH><<<grid, 256, smem, st>>>(h->ms, io);
+    LAUNCH_CHECK(h);
+    return PCX_OK;
+  }
+}
+
+template <int NT>
+static int launch_mlp_bwd_tf32_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, const MlpIO& io) {
+  switch (DH) {
+    case 0: return launch_mlp_bwd_tf32_v<NT, 0>(h, grid, st, io);
+    case 1: return launch_mlp_bwd_tf32_v<NT, 1>(h, grid, st, io);
+    case 2: return launch_mlp_bwd_tf32_v<NT, 2>(h, grid, st, io);
+    case 3: return launch_mlp_bwd_tf32_v<NT, 3>(h, grid, st, io);
+    case 4: return launch_mlp_bwd_tf32_v<NT, 4>(h, grid, st, io);
+    default: return fail(PCX_ERR_UNSUPPORTED, "MLP depth %d not supported (1..5 hidden layers)", DH + 1);
+  }
+}
+
+static int tf32_supported(const pcx_handle* h) {
+  if (h->ms.NT > 7) return fail(PCX_ERR_UNSUPPORTED, "TF32 adjoint: MLP width %d not supported (n_neurons <= 55)", h->ms.width);
+  return PCX_OK;
+}
+
+static int launch_mlp_bwd(pcx_handle* h, cudaStream_t st, const MlpIO& io_in, int* grid_out) {
+  const long long ntiles = (io_in.n + bwd_rows_per_cta(h) - 1) / bwd_rows_per_cta(h);
   int grid = (int)(ntiles < h->bwd_grid ? ntiles : h->bwd_grid);
   if (grid < 1) grid = 1;
   *grid_out = grid;
   ProfScope ps(h, PCX_PROF_MLP_BACKWARD, st);
   const int DH = h->ms.depth - 1;
+  if (h->tf32_adjoint) {
+    int rc = tf32_supported(h);
+    if (rc) return rc;
+    const MlpIO io = tf32_view(h, io_in);
+    if (!io.act32) return fail(PCX_ERR_STATE, "TF32 adjoint launched without stored activations");
+    switch (h->ms.NT) {
+      case 2: return launch_mlp_bwd_tf32_nt<2>(h, DH, grid, st, io);
+      case 4: return launch_mlp_bwd_tf32_nt<4>(h, DH, grid, st, io);
+      case 7: return launch_mlp_bwd_tf32_nt<7>(h, DH, grid, st, io);
+    }
+    return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
+  }
+  const MlpIO& io = io_in;
   switch (h->ms.NT) {
     case 2: return launch_mlp_bwd_nt<2>(h, DH, grid, st, io);
     case 4: return launch_mlp_bwd_nt<4>(h, DH, grid, st, io);
@@ -426,6 +485,11 @@ static int pack_weights(pcx_handle* h, const double* w, cudaStream_t st) {
   const int blocks = (int)((h->ms.npacked + thr - 1) / thr);
   k_pack_weights<<<blocks, thr, 0, st>>>(h->ms, w, h->pk);
   LAUNCH_CHECK(h);
+  if (h->tf32_adjoint) {
+    const long long nthr = tf32_pack_floats(h->ms.NT, h->ms.depth) / 2;   // >= one thread per fragment entry
+    k_pack_weights_tf32<<<(int)((nthr + thr - 1) / thr), thr, 0, st>>>(h->ms, w, h->pk32);
+    LAUNCH_CHECK(h);
+  }
   return PCX_OK;
 }
 
@@ -446,6 +510,8 @@ static void free_ws(pcx_handle* h) {
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   if (h->flags) cudaFree(h->flags);
   h->flags = nullptr;
+  if (h->pk32) cudaFree(h->pk32);
+  h->pk32 = nullptr;
 }
 
 static int alloc_ws(pcx_handle* h) {
@@ -464,13 +530,16 @@ static int alloc_ws(pcx_handle* h) {
   h->T = (int)T;
   h->rows_cap = T * h->nn;
   if (h->rows_cap < 16384) h->rows_cap = 16384;
-  h->rows_cap = (h->rows_cap + 63) / 64 * 64;
+  // multiple of the largest adjoint row tile plus one tile of slack: the TF32 adjoint pulls whole 128-row
+  // planes with bulk copies, also for the last (partial) tile of a time-step range that starts mid-buffer
+  h->rows_cap = (h->rows_cap + 127) / 128 * 128 + 128;
   h->nblk_el = (int)((h->ne + 127) / 128);
   h->bwd_grid = h->sm_count;
   const long long WPd = 8LL * s.NT;
   h->part_stride = WPd * 8 + (long long)(s.depth - 1) * WPd * WPd + 8 * WPd;
   const long long ndofs = h->nn * h->ndof;
   CUDA_TRY(cudaMalloc(&h->pk, s.npacked * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->pk32, tf32_pack_floats(s.NT, s.depth) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&h->act, act_per_row * h->rows_cap));
   CUDA_TRY(cudaMalloc(&h->part, h->part_stride * h->bwd_grid * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->us, h->rows_cap * h->ndof * sizeof(double)));   // rows_cap >= T*nn
@@ -599,6 +668,10 @@ extern "C" int pcx_set_option(pcx_handle* h, int32_t option, int64_t value) {
   if (!h) return fail(PCX_ERR_INVALID, "null handle");
   switch (option) {
     case PCX_OPT_CULL_NULL_STEPS: h->cull_null_steps = value != 0; return PCX_OK;
+    case PCX_OPT_TF32_ADJOINT:
+      if (value && h->have_field) { int rc = tf32_supported(h); if (rc) return rc; }
+      h->tf32_adjoint = value != 0;
+      return PCX_OK;
     default: return fail(PCX_ERR_INVALID, "unknown option %d", option);
   }
 }
@@ -638,6 +711,8 @@ extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
   h->bc_a = f->bc_a; h->bc_b = f->bc_b;
   h->have_field = true;
   if (const char* e = getenv("PCX_CULL_NULL_STEPS")) h->cull_null_steps = atoi(e) != 0;
+  if (const char* e = getenv("PCX_TF32_ADJOINT")) h->tf32_adjoint = atoi(e) != 0;
+  if (h->tf32_adjoint) { int rc = tf32_supported(h); if (rc) return rc; }
   int rc = find_null_steps(h);
   if (rc) return rc;
   if (h->have_phys) return alloc_ws(h);

@@ -57,6 +57,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 __device__ __forceinline__ void st_cs_f64x2(double* p, double a, double b) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+__device__ __forceinline__ void st_cs_f32x2_fwd(float* p, float a, float b) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ double2 ld_cs_f64x2(const double* p) {
   double2 r;
   asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -149,8 +152,10 @@ struct MlpIO {
   double* u;            // forward: [n*n_out] out (may be nullptr)
   const double* g_u;    // backward: [n*n_out] cotangent on u
   double* act;          // activations [depth][NT][rows_cap][8] (nullptr: do not store)
+  float* act32;         // TF32-adjoint mode: the same planes stored as fp32 instead (pcx_mlp_tf32.cuh)
   long long rows_cap;
   const double* pk;     // packed weights
+  const float* pk32;    // TF32-adjoint mode: packed hi/lo chain weights (k_pack_weights_tf32)
   double* part;         // backward: per-CTA partial weight gradients [gridDim][part_stride]
   long long part_stride;
   // optional fused data loss: g_u = scale * 2 (u - target) computed in the forward pass
@@ -371,7 +376,18 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
           if (jn < NT - 1 || last_real_x1) h[m][jn][1] = tanh_tb(acc[m][jn][1], stab);
           else h[m][jn][1] = 0.0;
         }
-      if (io.act) {
+      if (io.act32) {   // TF32-adjoint mode: fp32 planes, same slot order (half the store traffic)
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+          const long long row = row0 + 8 * m + r;
+          if (row < io.n) {
+#pragma unroll
+            for (int jn = 0; jn < NT; jn++)
+              st_cs_f32x2_fwd(io.act32 + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, (float)h[m][jn][0],
+                              (float)h[m][jn][1]);
+          }
+        }
+      } else if (io.act) {
 #pragma unroll
         for (int m = 0; m < MT; m++) {
           const long long row = row0 + 8 * m + r;
