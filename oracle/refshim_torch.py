@@ -12,7 +12,8 @@ jax itself cannot be installed in this image.  What is NOT the reference's own c
   * ``vmap`` is a Python loop + ``torch.stack``; ``lax.cond`` is an ``if`` on the concrete predicate
     (same value and same selected-branch derivative as jax);
   * ``custom_jvp`` functions are differentiated through the reference's REGISTERED jvp rule (VJP
-    assembled from the rule applied to basis tangents); first order only.
+    assembled from the rule applied to basis tangents, out of differentiable ops, so a second
+    differentiation goes through the rule's own code like jax's does).
 
 Only oracle/gen_golden_ad.py imports this module; nothing at test or run time does.
 """
@@ -286,7 +287,7 @@ def jacfwd(fun, argnums=0, has_aux=False):
 
 
 class custom_jvp:
-    """Differentiates through the REGISTERED rule: VJP(ct) = sum_k <rule(e_k), ct> e_k (first order)."""
+    """Differentiates through the REGISTERED rule: VJP(ct) = sum_k <rule(e_k), ct> e_k."""
 
     def __init__(self, fun, nondiff_argnums=()):
         self.fun, self.jvp_rule, self.nondiff_argnums = fun, None, nondiff_argnums
@@ -310,16 +311,17 @@ class custom_jvp:
 
             @staticmethod
             def backward(ctx, ct):
+                # built from differentiable ops on the saved primal: under create_graph=True (the outer jax.grad of a
+                # loss that already contains jax.grad, base.py:356-385) autograd differentiates the registered rule
+                # itself a second time, with respect to the primal AND the cotangent -- what jax does with a custom_jvp
                 (a,) = ctx.saved_tensors
-                a = a.detach()
-                g = torch.zeros_like(a)
-                with torch.no_grad():
-                    for k in range(a.numel()):
-                        e = torch.zeros_like(a).reshape(-1)
-                        e[k] = 1.0
-                        _, tang = rule((a,), (e.reshape(a.shape),))
-                        g.view(-1)[k] = torch.sum(tang * ct)
-                return g
+                gs = []
+                for k in range(a.numel()):
+                    e = torch.zeros(a.numel(), dtype=a.dtype)
+                    e[k] = 1.0
+                    _, tang = rule((a,), (e.reshape(a.shape),))
+                    gs.append(torch.sum(tang * ct))
+                return torch.stack(gs).reshape(a.shape)
         return Fn.apply(A)
 
 

@@ -880,13 +880,7 @@ static int set_props(pcx_handle* h, const double* prop_raw, cudaStream_t st) {
   return PCX_OK;
 }
 
-static int check_tangent_supported(pcx_handle* h) {
-  if (h->phys.physics == PCX_PHYS_SOLID && h->phys.model == PCX_MODEL_HENCKY)
-    return fail(PCX_ERR_UNSUPPORTED,
-                "Hencky: the second derivative of the log-strain rule (tensor_math.py:343-424) is not on the B200 path; "
-                "residual losses / stiffness action are refused (no fallback)");
-  return PCX_OK;
-}
+static int check_tangent_supported(pcx_handle*) { return PCX_OK; }   // every model has a tangent action
 
 // ------------------------------------------------------------------------------------------ ABI: field ops
 extern "C" int pcx_field_forward(pcx_handle* h, const double* weights, int32_t t_idx, double* us, void* stream) {

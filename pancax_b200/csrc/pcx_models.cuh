@@ -371,8 +371,7 @@ __device__ inline double relative_log_difference(double l1, double l2) {  // ten
 
 // W = 0.5 K tr(E)^2 + G E:E with E = 0.5 log(F^T F) (mtk_log_sqrt, tensor_math.py:337-340).
 // P = 2 F S, S = L(Ebar), Ebar = K tr(E) I + 2 G E, L = the (self-adjoint) derivative rule of
-// mtk_log_sqrt (tensor_math.py:343-424).  Value path only: the second derivative of the custom rule
-// is refused upstream (PCX_ERR_UNSUPPORTED) for residual losses.
+// mtk_log_sqrt (tensor_math.py:343-424).  Value path; the tangent action is the Dual overload below.
 __device__ inline void hencky(const double* F, const Props& pr, double& W, double* P, double* dWdp, bool want_dp) {
   const double K = pr.p[0], G = pr.p[1];
   double C[9];
@@ -431,10 +430,106 @@ __device__ inline void hencky(const double* F, const Props& pr, double& W, doubl
     dWdp[1] = EE;
   }
 }
-__device__ inline void hencky(const Dual*, const Props&, Dual& W, Dual* P, Dual*, bool) {
-  // never instantiated at run time (refused on the host); keeps templates compiling
-  W = Dual(0.0);
-  for (int i = 0; i < 9; i++) P[i] = Dual(0.0);
+// Tangent of the above: dP = (d^2 W / dF^2) : dF, what the reference obtains by differentiating the custom rule a
+// second time (JAX differentiates through eigen_sym33_unit and relative_log_difference; base.py:363-385).
+// Differentiating the eigenvector algorithm with dual numbers would be ill-conditioned wherever two stretches
+// approach each other, and is NaN at F = I (the reference's own result there: every shipped load ramp at t = 0).
+// S = dW/dC is an isotropic tensor function of C, S = sum_i w_i(mu) n_i n_i with mu_i the eigenvalues of C,
+//   w_i = (K trE + 2 G e_i) / (2 mu_i),  e_i = 0.5 ln mu_i,
+// so its derivative has the closed form (in the eigenbasis, D = V^T dC V):
+//   dS_ii = sum_k (dw_i/dmu_k) D_kk,   dw_i/dmu_k = K / (4 mu_i mu_k) + delta_ik (G - K trE - 2 G e_i) / (2 mu_i^2)
+//   dS_ij = [(w_i - w_j) / (mu_i - mu_j)] D_ij
+//         = [-K trE + G (g(x) - 2 e_j)] / (2 mu_i mu_j) D_ij,  x = (mu_i - mu_j) / mu_j,  g(x) = log1p(x) / x
+// -- the divided difference written so that nothing cancels as mu_i -> mu_j (g -> 1 reproduces the diagonal
+// limit), hence finite and exact at repeated stretches and at F = I.  dP = 2 (dF S + F dS).
+__device__ inline void hencky(const Dual* F, const Props& pr, Dual& W, Dual* P, Dual* dWdp, bool want_dp) {
+  const double K = pr.p[0], G = pr.p[1];
+  double Fv[9], dF[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { Fv[i] = F[i].v; dF[i] = F[i].d; }
+  double C[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = Fv[i] * Fv[j] + Fv[3 + i] * Fv[3 + j] + Fv[6 + i] * Fv[6 + j];
+  double mu[3], V[9];
+  eigen_sym33_unit(C, mu, V);
+  const double e[3] = {0.5 * log(mu[0]), 0.5 * log(mu[1]), 0.5 * log(mu[2])};
+  const double trE = e[0] + e[1] + e[2];
+  double w[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) w[i] = (K * trE + 2.0 * G * e[i]) / (2.0 * mu[i]);
+  // FV = F V, dFV = dF V (columns = eigen directions)
+  double FV[9], dFV[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      FV[3 * r + k] = Fv[3 * r] * V[k] + Fv[3 * r + 1] * V[3 + k] + Fv[3 * r + 2] * V[6 + k];
+      dFV[3 * r + k] = dF[3 * r] * V[k] + dF[3 * r + 1] * V[3 + k] + dF[3 * r + 2] * V[6 + k];
+    }
+  // D = V^T (dF^T F + F^T dF) V
+  double D[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; r++) sacc += dFV[3 * r + i] * FV[3 * r + j] + FV[3 * r + i] * dFV[3 * r + j];
+      D[3 * i + j] = sacc;
+    }
+  // M = dS in the eigenbasis
+  double M[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) sacc += K / (4.0 * mu[i] * mu[k]) * D[4 * k];
+    M[4 * i] = sacc + (G - K * trE - 2.0 * G * e[i]) / (2.0 * mu[i] * mu[i]) * D[4 * i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i + 1; j < 3; j++) {
+      const double x = (mu[i] - mu[j]) / mu[j];
+      const double gx = (x == 0.0) ? 1.0 : log1p(x) / x;
+      const double dd = (-K * trE + G * (gx - 2.0 * e[j])) / (2.0 * mu[i] * mu[j]);
+      M[3 * i + j] = M[3 * j + i] = dd * 0.5 * (D[3 * i + j] + D[3 * j + i]);
+    }
+  // dP = 2 (dF S + F dS) = 2 (dFV diag(w) + FV M) V^T ;  P = 2 FV diag(w) V^T
+  double A1[9], A0[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      A0[3 * r + k] = FV[3 * r + k] * w[k];
+      A1[3 * r + k] = dFV[3 * r + k] * w[k] + FV[3 * r] * M[k] + FV[3 * r + 1] * M[3 + k] + FV[3 * r + 2] * M[6 + k];
+    }
+  double dW = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double pv = 2.0 * (A0[3 * r] * V[3 * j] + A0[3 * r + 1] * V[3 * j + 1] + A0[3 * r + 2] * V[3 * j + 2]);
+      const double pd = 2.0 * (A1[3 * r] * V[3 * j] + A1[3 * r + 1] * V[3 * j + 1] + A1[3 * r + 2] * V[3 * j + 2]);
+      P[3 * r + j] = Dual(pv, pd);
+      dW += pv * dF[3 * r + j];
+    }
+  const double EE = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+  W = Dual(0.5 * K * trE * trE + G * EE, dW);
+  if (want_dp) {
+    // d(P:dF)/dK and d(P:dF)/dG: P = K P_K + G P_G with S_K = V diag(trE / (2 mu)) V^T, S_G = V diag(e / mu) V^T
+    double tK = 0.0, tG = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double q = 0.5 * D[4 * i];   // (F V)_i . (dF V)_i
+      tK += trE / mu[i] * q;
+      tG += 2.0 * e[i] / mu[i] * q;
+    }
+    dWdp[0] = Dual(0.5 * trE * trE, tK);
+    dWdp[1] = Dual(EE, tG);
+  }
 }
 
 template <int MODEL, class T>

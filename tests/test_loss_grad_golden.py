@@ -59,8 +59,6 @@ def test_oracle_matches_reference_loss_and_grad(name, n, nt, width, depth, q, ki
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n,nt,width,depth,q,kind", PARAMS)
 def test_cuda_matches_reference_loss_and_grad(cuda_device, name, n, nt, width, depth, q, kind):
-    if "hencky" in name and kind != "energy":
-        pytest.skip("Hencky tangent is refused by the library")
     case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q, t0=T0.get(name, 0.0))
     tag = f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}"
     for det in (True, False):
