@@ -108,7 +108,15 @@ class Parameters:
                  seperate_networks: Optional[bool] = False, n_layers: int = 3, n_neurons: int = 50,
                  device=None):
         if isinstance(key, np.ndarray) and key.ndim == 2:
-            raise NotImplementedError("ensembles (2-D keys) are not on the B200 path")
+            # parameters.py:89-100: an ensemble = the same problem with one independently initialised parameter
+            # set per key row (eqx.filter_vmap over keys).  Here: one member ``Parameters`` per row; every member
+            # shares the problem's Engine (static mesh / physics / field shape), only the weight vectors differ.
+            self.is_ensemble, self.n_ensemble = True, int(key.shape[0])
+            self.members = [Parameters(problem, row, dirichlet_bc_func=dirichlet_bc_func, network_type=network_type,
+                                       seperate_networks=seperate_networks, n_layers=n_layers, n_neurons=n_neurons,
+                                       device=device) for row in key]
+            self.physics, self.state = problem.physics, None
+            return
         self.is_ensemble, self.n_ensemble = False, 1
         self.fields = Field(problem, key, dirichlet_bc_func=dirichlet_bc_func, network_type=network_type,
                             seperate_networks=seperate_networks, n_layers=n_layers, n_neurons=n_neurons,
@@ -128,8 +136,22 @@ class Parameters:
     def __iter__(self):
         return iter((self.fields, self.physics, self.state))
 
+    # ---- ensembles: the stacked leaves of the reference's vmapped pytree, gathered on demand
+    @property
+    def stacked_weights(self):
+        """(n_ensemble, n_weights) -- what ``params.fields.networks`` leaves look like under eqx.filter_vmap."""
+        ms = self.members if self.is_ensemble else [self]
+        return torch.stack([m.fields.networks.weights for m in ms])
+
+    @property
+    def stacked_prop_raw(self):
+        ms = self.members if self.is_ensemble else [self]
+        return torch.stack([m.prop_raw for m in ms])
+
     def properties(self):
         """Current physical property values (trainable ones read back from the device)."""
+        if self.is_ensemble:
+            return [m.properties() for m in self.members]
         out = {}
         model = getattr(self.physics, "constitutive_model", None)
         if model is None:
@@ -158,12 +180,22 @@ class Parameters:
 
     def serialise(self, base_name: str, epoch: int):
         """networks/base.py:80-96 equivalent: {base}_{epoch:07d}.npz with the flat leaves."""
+        if self.is_ensemble:
+            np.savez(f"{base_name}_{str(epoch).zfill(7)}.npz",
+                     weights=self.stacked_weights.detach().cpu().numpy(),
+                     prop_raw=self.stacked_prop_raw.detach().cpu().numpy())
+            return
         np.savez(f"{base_name}_{str(epoch).zfill(7)}.npz",
                  weights=self.fields.networks.weights.detach().cpu().numpy(),
                  prop_raw=self.prop_raw.detach().cpu().numpy())
 
     def deserialise(self, f_name: str):
         d = np.load(f_name)
+        if self.is_ensemble:
+            for k, m in enumerate(self.members):
+                m.fields.networks.set_weights(d["weights"][k])
+                m.prop_raw.copy_(torch.as_tensor(d["prop_raw"][k]))
+            return self
         self.fields.networks.set_weights(d["weights"])
         self.prop_raw.copy_(torch.as_tensor(d["prop_raw"]))
         return self

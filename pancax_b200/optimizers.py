@@ -35,6 +35,9 @@ class Adam:
     def init(self, params, filter_spec: Optional[Any] = None):
         if filter_spec is None:
             filter_spec = params.freeze_physics_normalization_filter()
+        if getattr(params, "is_ensemble", False):
+            # optimizers.py:44-62: one optimiser state over the stacked leaves == one per member with a shared count
+            return OptimizerState([self.init(m, filter_spec) for m in params.members], 0, filter_spec, True)
         w, p = params.fields.networks.weights, params.prop_raw
         opt_state = dict(mu_w=torch.zeros_like(w), nu_w=torch.zeros_like(w),
                          mu_p=torch.zeros_like(p), nu_p=torch.zeros_like(p), count=0,
@@ -46,6 +49,30 @@ class Adam:
         return self.learning_rate * self.decay_rate ** (count / self.transition_steps)
 
     def step(self, params, state: OptimizerState, problem, *args):
+        if state.is_ensemble:
+            return self.ensemble_step(params, state, problem, *args)
+        return self.single_step(params, state, problem, *args)
+
+    def ensemble_step(self, params, state: OptimizerState, problem, *args):
+        """optimizers.py:109-139: eqx.filter_vmap(filter_value_and_grad(loss)) over the ensemble axis, then ONE
+        optax update over the stacked leaves -- element-wise, so it equals the members' own updates with the
+        shared step count.  The members run back to back on the same Engine (each launch already fills the GPU);
+        losses / aux come back stacked along axis 0 like the vmapped reference returns them."""
+        losses, auxs = [], []
+        for m, st in zip(params.members, state.opt_state):
+            _, _, out = self.single_step(m, st, problem, *args)
+            loss, aux = out if self.has_aux else (out, {})
+            losses.append(loss)
+            auxs.append(aux)
+        state.epoch += 1
+        loss = torch.stack([torch.as_tensor(v) for v in losses])
+        if not self.has_aux:
+            return params, state, loss
+        aux = {k: torch.stack([torch.as_tensor(a[k]) for a in auxs]) for k in auxs[0]
+               if all(isinstance(a[k], torch.Tensor) for a in auxs)}
+        return params, state, (loss, aux)
+
+    def single_step(self, params, state: OptimizerState, problem, *args):
         (loss, aux), grads = self.loss_function.value_and_grad(params, problem, *args)
         st = state.opt_state
         gw, gp = grads.fields, grads.props

@@ -166,6 +166,37 @@ def test_trainer_reduces_energy_and_checkpoints(cuda_device, tmp_path):
     assert float(params.fields.networks.weights.abs().sum()) > 0 and not torch.equal(w, params.fields.networks.weights)
 
 
+def test_ensemble_step_equals_independent_members(cuda_device, tmp_path):
+    """optimizers.py:109-139 (ensemble_step = vmap of value_and_grad + one element-wise optax update): every member of
+    the ensemble must follow exactly the trajectory of a single run started from the same key; losses come back
+    stacked along axis 0."""
+    import pancax_b200 as px
+    keys = np.array([[0, 3], [0, 4], [5, 6]], dtype=np.uint32)
+    prob, _ = _build("quad4", n=6, nt=2, t0=0.0)
+    bc = px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 2)
+    ens = px.Parameters(prob, key=keys, dirichlet_bc_func=bc)
+    opt = px.Adam(px.EnergyLoss(), learning_rate=1e-3, has_aux=True)
+    st = opt.init(ens)
+    assert st.is_ensemble
+    for _ in range(4):
+        ens, st, (loss, aux) = opt.step(ens, st, prob)
+    assert loss.shape == (3,) and aux["energy"].shape == (3,) and st.epoch == 4
+    for k in range(3):
+        single = px.Parameters(prob, key=keys[k], dirichlet_bc_func=bc)
+        opt1 = px.Adam(px.EnergyLoss(), learning_rate=1e-3, has_aux=True)
+        s1 = opt1.init(single)
+        for _ in range(4):
+            single, s1, (l1, _) = opt1.step(single, s1, prob)
+        assert torch.equal(single.fields.networks.weights, ens.members[k].fields.networks.weights), k
+        assert float(l1) == float(loss[k])
+    ens.serialise(str(tmp_path / "ens"), 4)
+    w = ens.stacked_weights.clone()
+    for m in ens.members:
+        m.fields.networks.weights.zero_()
+    ens.deserialise(str(tmp_path / "ens_0000004.npz"))
+    assert torch.equal(ens.stacked_weights, w)
+
+
 def test_poisson_example_through_the_api(cuda_device):
     """C1: the reference's Poisson example (examples/forward_problems/poisson/variational_example.py)."""
     import math

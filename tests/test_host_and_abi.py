@@ -137,6 +137,23 @@ def test_problem_and_parameters_shapes():
     assert px.Parameters(prob1, key=0, device="cpu").fields.normalize_time is False
 
 
+def test_ensemble_parameters_structure():
+    """parameters.py:89-100: a 2-D key makes an ensemble, one independently initialised member per key row."""
+    import pancax_b200 as px
+    prob = _problem("quad4")
+    keys = np.array([[0, 1], [0, 2], [7, 7]], dtype=np.uint32)
+    params = px.Parameters(prob, key=keys, device="cpu")
+    assert params.is_ensemble and params.n_ensemble == 3 and len(params.members) == 3
+    W = params.stacked_weights
+    assert W.shape == (3, 5400)
+    assert not np.array_equal(W[0].numpy(), W[1].numpy()) and not np.array_equal(W[1].numpy(), W[2].numpy())
+    single = px.Parameters(prob, key=keys[1], device="cpu")
+    assert np.array_equal(single.fields.networks.weights.numpy(), W[1].numpy())      # member k == the single run with key k
+    assert params.stacked_prop_raw.shape == (3, 1)
+    assert len(params.properties()) == 3
+    assert not px.Parameters(prob, key=0, device="cpu").is_ensemble
+
+
 def test_incompatible_problem_pieces_raise():
     import pancax_b200 as px
     from pancax_b200.problems import DomainPhysicsCompatabilityError
