@@ -42,9 +42,11 @@ extern "C" {
 #define PCX_PHYS_POISSON 0
 #define PCX_PHYS_SOLID   1
 
-/* formulations: pancax/physics_kernels/solid_mechanics.py:20-29 (PlaneStrain), :74-83 (ThreeDimensional) */
+/* formulations: pancax/physics_kernels/solid_mechanics.py:20-29 (PlaneStrain), :32-71 (PlaneStress), :74-83 (ThreeDimensional) */
 #define PCX_FORM_PLANE_STRAIN      0
 #define PCX_FORM_THREE_DIMENSIONAL 1
+#define PCX_FORM_PLANE_STRESS      2   /* solid_mechanics.py:32-71: grad_u_33 = per-point root of sigma_33 = 0
+                                          (math/scalar_root_find.py), differentiated implicitly */
 
 /* constitutive models: pancax/constitutive_models/mechanics/hyperelasticity/*.py
  * property order = dataclass field order of the reference classes:

@@ -39,6 +39,10 @@ CASES = [
     ("tri3_hencky_bounded", 4, 3, 20, 2, 2, ("energy_residual_reaction",)),
     ("quad4_hencky", 3, 3, 20, 2, 2, ("energy_residual",)),
     ("poisson_quad4", 6, 2, 50, 3, 2, ("energy",)),
+    # PlaneStress (solid_mechanics.py:32-71): the reference's own root find + custom_root, per quadrature point
+    ("quad4_neohookean_pstress", 3, 2, 16, 2, 2, ("energy", "energy_residual", "energy_residual_reaction")),
+    ("tri3_gent_pstress_bounded", 3, 3, 16, 2, 2, ("energy_residual_reaction",)),
+    ("quad4_hencky_pstress", 2, 2, 12, 2, 2, ("energy", "energy_residual")),
 ]
 
 
@@ -46,7 +50,8 @@ CASES = [
 # Swanson, and the reference's d||f||/df is NaN there; that case starts at t0 > 0 instead.
 # Hencky: at t = 0 (F = I, repeated stretches) the reference's second derivative through eigen_sym33_unit is NaN as
 # well -- its residual-loss cases start at t0 > 0 too.
-T0 = {"hex8_swanson": 0.25, "hex8_hencky": 0.25, "tri3_hencky_bounded": 0.2, "quad4_hencky": 0.2}
+T0 = {"hex8_swanson": 0.25, "hex8_hencky": 0.25, "tri3_hencky_bounded": 0.2, "quad4_hencky": 0.2,
+      "quad4_hencky_pstress": 0.2}
 
 
 def main():
@@ -57,7 +62,7 @@ def main():
     from pancax.fem.quadrature_rules import QuadratureRule
     from pancax.fem.function_space import NonAllocatedFunctionSpace
     from pancax.constitutive_models import Gent, Hencky, NeoHookean, Swanson, BoundedProperty
-    from pancax.physics_kernels import Poisson, SolidMechanics, PlaneStrain, ThreeDimensional
+    from pancax.physics_kernels import Poisson, SolidMechanics, PlaneStrain, PlaneStress, ThreeDimensional
     from pancax.bvps.uniaxial_tension import UniaxialTensionLinearRamp
     from pancax.loss_functions.weak_form_loss_functions import (EnergyLoss, EnergyAndResidualLoss,
                                                                 EnergyResidualAndReactionLoss)
@@ -95,7 +100,8 @@ def main():
                 else:
                     kw[nme] = float(p)
             model = model_cls[case.model](**kw)
-            form = ThreeDimensional() if case.formulation == "three_dimensional" else PlaneStrain()
+            form = {"three_dimensional": ThreeDimensional, "plane_strain": PlaneStrain,
+                    "plane_stress": PlaneStress}[case.formulation]()
             physics = SolidMechanics(model, form)
             bc = UniaxialTensionLinearRamp(case.bc[1], case.bc[2], case.bc[3], coords.shape[1])
         else:

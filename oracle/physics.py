@@ -30,13 +30,60 @@ class Physics:
             f = self.source(x_q)                                   # (ne, nq)
             # 0.5 * dot(grad_u, grad_u.T) - f*u, summed (1x1)    poisson.py:18-19
             return 0.5 * (grad_u * grad_u).sum((-1, -2)) - f * u_q[..., 0]
+        return models.energy(self.model, self.modify_field_gradient(grad_u), self.props)
+
+    def modify_field_gradient(self, grad_u):
+        """formulation.modify_field_gradient, solid_mechanics.py:26-29 (PlaneStrain), :49-71 (PlaneStress),
+        :80-83 (ThreeDimensional)."""
         if self.formulation == "plane_strain":
-            H = models.tensor_2D_to_3D(grad_u)                     # solid_mechanics.py:26-29
-        elif self.formulation == "three_dimensional":
-            H = grad_u                                             # solid_mechanics.py:80-83
-        else:
-            raise ValueError(self.formulation)
-        return models.energy(self.model, H, self.props)
+            return models.tensor_2D_to_3D(grad_u)
+        if self.formulation == "three_dimensional":
+            return grad_u
+        if self.formulation == "plane_stress":
+            return plane_stress_gradient(self.model, grad_u, self.props)
+        raise ValueError(self.formulation)
+
+
+def plane_stress_gradient(model, grad_u, props):
+    """PlaneStress.modify_field_gradient (solid_mechanics.py:49-71): the out-of-plane entry x = grad_u_33 is the
+    root of sigma_33(x) = 0, found by scalar_root_find.find_root (Newton safeguarded by bisection, guess 0.05,
+    bracket [-0.99, 10], x_tol 1e-13; math/scalar_root_find.py:18-160) and differentiated by the implicit function
+    theorem (jax.lax.custom_root).  sigma_33 = P_33 F_33 / J for this block structure, so the root is that of
+    P_33 = dW/dx.  Here: a batched safeguarded Newton iteration without a tape, then two differentiable Newton
+    steps from the converged root, which reproduce the derivatives of the implicit function up to third order
+    (Newton's map is a second-order contraction at the root) -- what the outer gradients of the residual losses need."""
+    E33 = torch.zeros(3, 3, dtype=F64)
+    E33[2, 2] = 1.0
+
+    def g_and_dg(H2, x, create_graph):
+        W = models.energy(model, models.tensor_2D_to_3D(H2) + x[..., None, None] * E33, props)
+        (g,) = torch.autograd.grad(W.sum(), x, create_graph=True)
+        (dg,) = torch.autograd.grad(g.sum(), x, create_graph=create_graph)
+        return g, dg
+
+    gu = grad_u.detach()
+    lo = torch.full(gu.shape[:-2], -0.99, dtype=F64)
+    hi = torch.full(gu.shape[:-2], 10.0, dtype=F64)
+    # incompressible estimate F33 = 1 / det(F_2D) as the start (the reference starts from 0.05; the root is unique
+    # in the bracket for these models, P_33 is increasing in x)
+    x = (1.0 / torch.linalg.det(gu + torch.eye(2, dtype=F64)) - 1.0).clamp(-0.99, 10.0)
+    for _ in range(60):
+        g, dg = g_and_dg(gu, x.detach().clone().requires_grad_(True), False)
+        g, dg = g.detach(), dg.detach()
+        lo = torch.where(g < 0, x, lo)
+        hi = torch.where(g < 0, hi, x)
+        xn = x - g / dg
+        bad = ~(xn > lo) | ~(xn < hi) | ~(dg > 0)
+        xn = torch.where(bad, 0.5 * (lo + hi), xn)
+        done = bool((xn - x).abs().max() < 1e-15)
+        x = xn
+        if done:
+            break
+    x = x.detach().clone().requires_grad_(True)
+    for _ in range(2):
+        g, dg = g_and_dg(grad_u, x, True)
+        x = x - g / dg
+    return models.tensor_2D_to_3D(grad_u) + x[..., None, None] * E33
 
 
 def element_geometry(pe: ParentElement, X_el):
@@ -115,7 +162,9 @@ def element_fields(physics: Physics, pe: ParentElement, coords, conns, us):
     (constitutive method, mechanics/base.py:112-118)."""
     X_el, U_el = coords[conns], us[conns]
     _, _, grad_u, _ = element_interpolants(pe, X_el, U_el)
-    H = models.tensor_2D_to_3D(grad_u) if physics.formulation == "plane_strain" else grad_u
+    H = physics.modify_field_gradient(grad_u)
+    if physics.formulation == "plane_stress":
+        H = H.detach()
     F = models.deformation_gradient(H)
     I1b = models.I1_bar(H)
     P = models.pk1_stress(physics.model, H, physics.props)

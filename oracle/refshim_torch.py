@@ -152,7 +152,12 @@ def _make_jnp():
     jnp.stack = lambda tup, axis=0: torch.stack([_t(v) for v in tup], dim=axis)
     jnp.column_stack = lambda tup: torch.column_stack([_t(v) for v in tup])
     jnp.concatenate = lambda tup, axis=0: torch.cat([_t(v) for v in tup], dim=axis)
-    jnp.where = lambda c, a, b: torch.where(_t(c), _t(a).to(F64), _t(b).to(F64))
+    def _where(c, a, b):
+        a, b = _t(a), _t(b)
+        if a.dtype == torch.bool and b.dtype == torch.bool:      # boolean selects stay boolean (rtsafe_'s `converged`)
+            return torch.where(_t(c), a, b)
+        return torch.where(_t(c), a.to(F64), b.to(F64))
+    jnp.where = _where
     jnp.maximum = lambda a, b: torch.maximum(_t(a).to(F64), _t(b).to(F64))
     jnp.minimum = lambda a, b: torch.minimum(_t(a).to(F64), _t(b).to(F64))
     jnp.allclose = lambda a, b, **k: bool(torch.allclose(_t(a).to(F64), _t(b).to(F64)))
@@ -480,6 +485,23 @@ def install():
             val = body(i, val)
         return val
     lax.fori_loop = fori_loop
+
+    def custom_root(f, initial_guess, solve, tangent_solve, has_aux=False):
+        """jax.lax.custom_root: the root is found by the caller's ``solve`` (the reference's own rtsafe_) and differentiated by the implicit function theorem.  Here the derivatives are attached with
+        two differentiable Newton steps from the converged root: Newton's map is a contraction of order 2 at the
+        root, so k steps reproduce the derivatives of the implicit function up to order 2^k - 1 = 3 -- enough for the
+        gradient of a residual loss (third-order in the energy)."""
+        res = solve(f, initial_guess)                    # (its own jax.value_and_grad needs a tape; the result is detached)
+        x_star, aux = res if has_aux else (res, None)
+        x = _t(x_star).detach().clone().requires_grad_(True)
+        for _ in range(2):
+            fx = f(x)
+            if not (isinstance(fx, torch.Tensor) and fx.requires_grad):
+                break
+            (dfx,) = torch.autograd.grad(fx, x, create_graph=True)
+            x = x - fx / dfx
+        return (x, aux) if has_aux else x
+    lax.custom_root = custom_root
     jax.lax = lax
     jax.vmap, jax.grad, jax.value_and_grad, jax.custom_jvp = vmap, grad, value_and_grad, custom_jvp
     jax.jit = lambda f, *a, **k: f

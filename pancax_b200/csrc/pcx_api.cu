@@ -630,7 +630,8 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
     if (p->nprops != need[p->model]) return fail(PCX_ERR_INVALID, "model %d takes %d properties, got %d", p->model, need[p->model], p->nprops);
     if (p->formulation == PCX_FORM_PLANE_STRAIN) { if (h->nd != 2 || h->ndof != 2) return fail(PCX_ERR_INVALID, "PlaneStrain needs a 2D mesh and ndof == 2"); }
     else if (p->formulation == PCX_FORM_THREE_DIMENSIONAL) { if (h->nd != 3 || h->ndof != 3) return fail(PCX_ERR_INVALID, "ThreeDimensional needs a 3D mesh and ndof == 3"); }
-    else return fail(PCX_ERR_UNSUPPORTED, "formulation %d is not on the B200 path (PlaneStress needs a per-qp root find)", p->formulation);
+    else if (p->formulation == PCX_FORM_PLANE_STRESS) { if (h->nd != 2 || h->ndof != 2) return fail(PCX_ERR_INVALID, "PlaneStress needs a 2D mesh and ndof == 2"); }
+    else return fail(PCX_ERR_INVALID, "unknown formulation %d", p->formulation);
     if (p->model == PCX_MODEL_SWANSON && p->bounded[7]) return fail(PCX_ERR_INVALID, "Swanson cutoff_strain is static in pancax (swanson.py:26)");
   } else return fail(PCX_ERR_INVALID, "unknown physics %d", p->physics);
   h->phys = *p;
@@ -840,6 +841,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
   a.epart = want_energy ? h->epart : nullptr;
   a.ppart = want_dp ? h->ppart : nullptr;
   a.want_force = want_force ? 1 : 0;
+  a.plane_stress = (h->phys.physics == PCX_PHYS_SOLID && h->phys.formulation == PCX_FORM_PLANE_STRESS) ? 1 : 0;
   const long long ndofs = h->nn * h->ndof;
   if (want_force) {
     if (h->deterministic) { a.fe = h->fe; a.f_atomic = nullptr; }
@@ -1033,7 +1035,8 @@ static int launch_pp_m(pcx_handle* h, const double* us, double* F, double* I1, d
   const int grid = (int)((h->ne + epb - 1) / epb);
   const size_t smem = (size_t)epb * NNPE * sizeof(int32_t);
 #define PCX_PP(M) k_element_pp<NNPE, ND, NDOF, M><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, us, h->props_dev, \
-                                                                           h->phys.nprops, F, I1, P, epb)
+                                                                           h->phys.nprops, F, I1, P, epb, \
+                                                                           h->phys.formulation == PCX_FORM_PLANE_STRESS ? 1 : 0)
   switch (h->phys.model) {
     case PCX_MODEL_NEOHOOKEAN: PCX_PP(PCX_MODEL_NEOHOOKEAN); break;
     case PCX_MODEL_GENT: PCX_PP(PCX_MODEL_GENT); break;

@@ -47,6 +47,7 @@ struct ElemArgs {
   const double* props_dev; // effective properties [PCX_MAX_PROPS] (device: trainable ones change every step)
   int nprops;
   int want_force;
+  int plane_stress;        // PCX_FORM_PLANE_STRESS: F_33 from the per-point root of sigma_33 = 0 (2D solid only)
 };
 
 template <int ND>
@@ -225,6 +226,9 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentT
           for (int i = 0; i < NDOF; i++)
 #pragma unroll
             for (int j = 0; j < ND; j++) F[3 * i + j] += H[i][j];
+          if constexpr (ND == 2) {
+            if (A0.plane_stress && !plane_stress_solve<MODEL>(F, A.props)) bad = true;
+          }
           double W, P[9], dp[PCX_MAX_PROPS];
           model_eval<MODEL, double>(F, A.props, W, P, dp, want_dp);
           if (!(W == W) || fabs(W) > 1.0e300) bad = true;
@@ -247,7 +251,18 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentT
 #pragma unroll
             for (int j = 0; j < ND; j++) { F[3 * i + j].v += H[i][j]; F[3 * i + j].d = dH[i][j]; }
           Dual W, P[9], dp[PCX_MAX_PROPS];
-          model_eval<MODEL, Dual>(F, A.props, W, P, dp, want_dp);
+          bool ps = false;
+          if constexpr (ND == 2) ps = A0.plane_stress != 0;
+          if (ps) {
+            double Fv[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) Fv[i] = F[i].v;
+            if (!plane_stress_solve<MODEL>(Fv, A.props)) bad = true;
+            F[8].v = Fv[8];
+            plane_stress_tangent<MODEL>(F, A.props, W, P, dp, want_dp, A.nprops);
+          } else {
+            model_eval<MODEL, Dual>(F, A.props, W, P, dp, want_dp);
+          }
           if (want_dp) {
             // d(P:dH)/dp = tangent of dW/dp along dH
 #pragma unroll
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(256) k_element_pp(const __grid_constant__ Pare
                                                     const double* __restrict__ coords, const int32_t* __restrict__ conns,
                                                     const double* __restrict__ us, const double* __restrict__ props_dev,
                                                     int nprops, double* __restrict__ Fout, double* __restrict__ I1out,
-                                                    double* __restrict__ Pout, int epb) {
+                                                    double* __restrict__ Pout, int epb, int plane_stress) {
   extern __shared__ int32_t s_conn[];  // [epb][NNPE]
   __shared__ double s_tile[8 * 32 * 9];
   __shared__ double s_dN[TAB_MAX_NQ * 25];   // parent gradients, row stride 25: lanes with different q hit different banks
@@ -442,6 +457,9 @@ __global__ void __launch_bounds__(256) k_element_pp(const __grid_constant__ Pare
         for (int k = 0; k < ND; k++) s = fma(Gu[i][k], Ji[j * ND + k], s);
         F[3 * i + j] += s;
       }
+    if constexpr (ND == 2 && MODEL != 0) {
+      if (plane_stress) plane_stress_solve<MODEL>(F, props);   // solid_mechanics.py:49-71
+    }
     const long long qi = e0 * nq + t;
     if (I1out) {
       // mechanics/base.py:50-63: J^(-2/3) tr(F F^T)

@@ -351,48 +351,59 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
   }
   mbar_wait(&sm.wbar, 0);
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
-    // ---- top: zbar = g_u * bc_b and the inputs tile
+  // top of a tile, publishing half: zbar = g_u * bc_b and the inputs tile into Zb / In[par], the landed h_depth patched
+  auto top_publish = [&](long long tile, int par) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       sm.Zb[lr[e] * 8 + t] = zA[e];
       sm.Zb[lr[e] * 8 + 4 + t] = 0.f;
-      sm.In[parity][lr[e] * 8 + t] = in0[e];
-      sm.In[parity][lr[e] * 8 + 4 + t] = in1[e];
+      sm.In[par][lr[e] * 8 + t] = in0[e];
+      sm.In[par][lr[e] * 8 + 4 + t] = in1[e];
     }
     mbar_wait(&sm.hbar[hb], hph[hb]);
     hph[hb] ^= 1;
     patch_h(tile, hb);
-    fence_proxy_async_smem();
-    SYNC_ARRIVE();     // own rows of H[hb] = h_depth (+ones), Zb, In published
-    TopRaw qn[2];
+  };
+  // top of a tile, register half: d_{depth-1} = (zbar W_out) * (1 - h_depth^2) for the own rows
+  auto top_chain = [&](float (&dC)[NT][4]) {
+    uint32_t ah[4], al[4];
+    split_tf32(zA[0], ah[0], al[0]);
+    split_tf32(zA[1], ah[1], al[1]);
+    ah[2] = al[2] = ah[3] = al[3] = 0u;
+    float dn[NT][4];
 #pragma unroll
-    for (int e = 0; e < 2; e++) qn[e] = issue_top(tile + gridDim.x, lr[e]);
-
-    // d_{depth-1} = (zbar W_out) * (1 - h^2)
-    float dC[NT][4];
-    {
-      uint32_t ah[4], al[4];
-      split_tf32(zA[0], ah[0], al[0]);
-      split_tf32(zA[1], ah[1], al[1]);
-      ah[2] = al[2] = ah[3] = al[3] = 0u;
-      float dn[NT][4];
+    for (int jn = 0; jn < NT; jn++) {
+      float dl[4] = {0.f, 0.f, 0.f, 0.f};
+      dn[jn][0] = dn[jn][1] = dn[jn][2] = dn[jn][3] = 0.f;
+      const float2 w = sm.Wo[jn * 32 + lane];
+      mma_3xtf32(dn[jn], dl, ah, al, __float_as_uint(w.x), 0u, __float_as_uint(w.y), 0u);
 #pragma unroll
-      for (int jn = 0; jn < NT; jn++) {
-        float dl[4] = {0.f, 0.f, 0.f, 0.f};
-        dn[jn][0] = dn[jn][1] = dn[jn][2] = dn[jn][3] = 0.f;
-        const float2 w = sm.Wo[jn * 32 + lane];
-        mma_3xtf32(dn[jn], dl, ah, al, __float_as_uint(w.x), 0u, __float_as_uint(w.y), 0u);
-#pragma unroll
-        for (int x = 0; x < 4; x++) dn[jn][x] += dl[x];
-      }
-      apply_dtanh(dC, dn, hb);
+      for (int x = 0; x < 4; x++) dn[jn][x] += dl[x];
     }
-    SYNC_WAIT();       // everybody is done with the previous tile: H[hb^1] is free, Zb / H[hb] complete
-    if (DH > 0) prefetch_h(tile, DH - 1, hb ^ 1);
-    else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
-    if (m_active && half == 0) contract(gX, 1, sm.H[hb], sm.Zb);   // dW_out^T[slot][o] += sum_rows h_depth[row][slot] zbar[row][o]
+    apply_dtanh(dC, dn, hb);
+  };
 
+  // The layer-0 stage of a tile and the top stage of the CTA's next tile are ONE barrier stage: both contractions are
+  // a single block per M tile (dW_0 on warps 4..7, dW_out on warps 0..3), so fused they keep all four tensor pipes
+  // busy instead of serialising twice behind the barrier.  Prologue: the top stage of the first tile alone.
+  float dC[NT][4];
+  TopRaw qn[2];
+  top_publish(blockIdx.x, parity);
+  fence_proxy_async_smem();
+  SYNC_ARRIVE();
+#pragma unroll
+  for (int e = 0; e < 2; e++) qn[e] = issue_top(blockIdx.x + gridDim.x, lr[e]);
+  top_chain(dC);
+  SYNC_WAIT();
+  if (DH > 0) prefetch_h(blockIdx.x, DH - 1, hb ^ 1);
+  else prefetch_h(blockIdx.x + gridDim.x, s.depth - 1, hb ^ 1);
+  if (m_active && half == 0) contract(gX, 1, sm.H[hb], sm.Zb);   // dW_out^T[slot][o] += sum_rows h_depth[row][slot] zbar[row][o]
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+    if constexpr (DH == 0) {   // no hidden stage separates two fused stages: Zb / In / D of the stage before last
+      SYNC_ARRIVE();           // must have been consumed before they are overwritten below
+      SYNC_WAIT();
+    }
     // ---- hidden layers L = DH .. 1 : d_{L-1} = (d_L W_L) * (1 - h_L^2) ; dW_L = d_L^T h_L
 #pragma unroll
     for (int L = DH; L >= 1; L--) {
@@ -434,15 +445,33 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
       if (m_active) contract(G[L - 1], nb, sm.D[db], sm.H[hb] + nj0 * TS);
       db ^= 1;
     }
-    // ---- layer 0: dW_0 = d_0^T [inputs, 1]
+    // ---- layer 0 of this tile (dW_0 = d_0^T [inputs, 1]) fused with the top stage of the next tile
+    const long long next = tile + gridDim.x;
+    const bool has_next = next < ntiles;
     publish_d(dC, db);
-    SYNC_ARRIVE();
 #pragma unroll
-    for (int e = 0; e < 2; e++) finish_top(tile + gridDim.x, lr[e], qn[e], zA[e], in0[e], in1[e]);
+    for (int e = 0; e < 2; e++) finish_top(next, lr[e], qn[e], zA[e], in0[e], in1[e]);
+    hb ^= 1;           // the next tile's top-layer h is in flight into this buffer
+    if (has_next) {
+      top_publish(next, parity ^ 1);
+      fence_proxy_async_smem();
+    }
+    SYNC_ARRIVE();
+    if (has_next) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) qn[e] = issue_top(next + gridDim.x, lr[e]);
+      top_chain(dC);
+    }
     SYNC_WAIT();
-    if (m_active && half == 1) contract(gX, 1, sm.D[db], sm.In[parity]);
+    if (has_next) {
+      if (DH > 0) prefetch_h(next, DH - 1, hb ^ 1);
+      else prefetch_h(next + gridDim.x, s.depth - 1, hb ^ 1);
+    }
+    if (m_active) {
+      if (half == 1) contract(gX, 1, sm.D[db], sm.In[parity]);
+      else if (has_next) contract(gX, 1, sm.H[hb], sm.Zb);
+    }
     db ^= 1;
-    hb ^= 1;           // the next tile's top-layer h is already in flight into this buffer
     if (++since_flush == TF32_FLUSH_TILES) { flush(); since_flush = 0; }
   }
 #undef SYNC_ARRIVE

@@ -540,4 +540,66 @@ __device__ inline void model_eval(const T* F, const Props& pr, T& W, T* P, T* dW
   else hencky(F, pr, W, P, dWdp, want_dp);
 }
 
+// ------------------------------------------------------------------ PlaneStress (solid_mechanics.py:32-71)
+// The out-of-plane displacement gradient x = grad_u_33 is the root of sigma_33(x) = 0, which the reference finds
+// per quadrature point with scalar_root_find.find_root (Newton safeguarded by bisection, guess 0.05, bracket
+// [-0.99, 10], x_tol 1e-13; math/scalar_root_find.py:18-160).  With F = [[F_2D, 0], [0, 1 + x]],
+// sigma_33 = P_33 F_33 / J, so the root is that of P_33 = dW/dx.  Here: the same safeguarded Newton iteration on
+// P_33, its derivative from one dual-number evaluation seeded on F_33, started from the incompressible estimate
+// F_33 = 1 / det F_2D (2 - 4 iterations instead of the reference's ~8 from 0.05; the root in the bracket is unique,
+// P_33 increases with x), iterated to |dx| < 1e-15 (tighter than the reference's 1e-13, so both agree to 1e-13).
+// F: in-plane entries set, F[8] ignored on entry; on exit F[8] = 1 + x.  Returns false if 60 iterations did not converge.
+template <int MODEL>
+__device__ inline bool plane_stress_solve(double* F, const Props& pr) {
+  const double j2 = F[0] * F[4] - F[1] * F[3];
+  double lo = -0.99, hi = 10.0;
+  double x = fmin(fmax(1.0 / j2 - 1.0, lo), hi);
+  if (!(x == x)) x = 0.05;
+  bool ok = false;
+#pragma unroll 1
+  for (int it = 0; it < 60; it++) {
+    Dual Fd[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Fd[i] = Dual(F[i], 0.0);
+    Fd[8] = Dual(1.0 + x, 1.0);
+    Dual W, P[9], dp[PCX_MAX_PROPS];
+    model_eval<MODEL, Dual>(Fd, pr, W, P, dp, false);
+    const double g = P[8].v, dg = P[8].d;
+    if (g < 0.0) lo = x; else hi = x;
+    double xn = x - g / dg;
+    if (!(xn > lo) || !(xn < hi) || !(dg > 0.0)) xn = 0.5 * (lo + hi);   // bisection step (rtsafe)
+    const double dx = xn - x;
+    x = xn;
+    if (fabs(dx) < 1.0e-15) { ok = true; break; }
+  }
+  F[8] = 1.0 + x;
+  return ok;
+}
+
+// Tangent of the plane-stress response along an in-plane direction dF_2D (Fd[i].d set in-plane, Fd[8].d ignored):
+// the implicit function theorem on P_33(F_2D, x) = 0 gives dx = -(dP_33 | dx = 0) / (dP_33/dx), and every output is
+// linear in the direction, so two dual evaluations (in-plane seed, unit seed on F_33) combine to the total tangent
+//   dP = dP|_(dF_2D, 0) + dx dP|_(0, 1),   d(dW/dp) likewise
+// (what jax.lax.custom_root's tangent rule produces, math/scalar_root_find.py:45-50).  Fd[8].v must hold the root.
+template <int MODEL>
+__device__ inline void plane_stress_tangent(Dual* Fd, const Props& pr, Dual& W, Dual* P, Dual* dWdp, bool want_dp, int nprops) {
+  Fd[8].d = 0.0;
+  model_eval<MODEL, Dual>(Fd, pr, W, P, dWdp, want_dp);
+  Dual Fe[9], We, Pe[9], dpe[PCX_MAX_PROPS];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Fe[i] = Dual(Fd[i].v, 0.0);
+  Fe[8].d = 1.0;
+  model_eval<MODEL, Dual>(Fe, pr, We, Pe, dpe, want_dp);
+  const double dx = -P[8].d / Pe[8].d;
+#pragma unroll
+  for (int i = 0; i < 9; i++) P[i].d = fma(dx, Pe[i].d, P[i].d);
+  W.d = fma(dx, We.d, W.d);
+  if (want_dp) {
+#pragma unroll
+    for (int k = 0; k < PCX_MAX_PROPS; k++)
+      if (k < nprops) dWdp[k].d = fma(dx, dpe[k].d, dWdp[k].d);
+  }
+  Fd[8].d = dx;
+}
+
 }  // namespace pcx

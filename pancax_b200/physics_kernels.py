@@ -22,12 +22,11 @@ class ThreeDimensional(AbstractMechanicsFormulation):
 
 
 class PlaneStress(AbstractMechanicsFormulation):
-    """solid_mechanics.py:32-71 needs a per-quadrature-point root find: not on the B200 path."""
+    """solid_mechanics.py:32-71: grad_u_33 is the per-quadrature-point root of sigma_33 = 0
+    (math/scalar_root_find.py), found and implicitly differentiated inside the element kernels
+    (PCX_FORM_PLANE_STRESS, csrc/pcx_models.cuh: plane_stress_solve / plane_stress_tangent)."""
     n_dimensions = 2
     name = "plane_stress"
-
-    def __init__(self):
-        raise NotImplementedError("PlaneStress is not on the B200 hot path (no fallback)")
 
 
 class BaseEnergyFormPhysics:

@@ -66,6 +66,8 @@ def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=
         mesh = ofem.structured_mesh(elem, n, permute_seed=11 if permute else None)
         trainable = model.endswith("_bounded")
         model = model.replace("_bounded", "")
+        formulation = "plane_stress" if model.endswith("_pstress") else "plane_strain"   # solid_mechanics.py:20-71
+        model = model.replace("_pstress", "")
         props = {"neohookean": [1000.0, 1.0], "gent": [0.833, 0.3846, 3.0],
                  "swanson": list(SWANSON_PROPS.values()), "hencky": [0.833, 0.3846]}[model]
         if trainable:
@@ -73,7 +75,7 @@ def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=
                 [(0.5, 2.0, -0.2), (0.01, 5.0, 0.3)] + props[2:]
         mlp = (3, 2, width, depth)
         c = Case(name, mesh, q_order, times, "solid", 2, mlp,
-                 flatten_mlp(init_mlp(*mlp, seed=seed)), model, "plane_strain", props,
+                 flatten_mlp(init_mlp(*mlp, seed=seed)), model, formulation, props,
                  bc=("uniaxial", 0.5, 1.0, "y"))
         bcs = [("nset_1", 0), ("nset_1", 1), ("nset_3", 0), ("nset_3", 1)]
         c.unknown_idx = ofem.unknown_indices(mesh["coords"].shape[0], 2, mesh["nodesets"], bcs)
