@@ -23,7 +23,7 @@ from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, Energy
                              EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss)
 from .networks import MLP, Field, Parameters  # noqa: F401,E402
 from .optimizers import Adam  # noqa: F401,E402
-from .physics_kernels import HeatEquation, PlaneStrain, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
+from .physics_kernels import HeatEquation, PlaneStrain, PlaneStress, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
 from .post_processor import ExodusPostProcessor, PostProcessor  # noqa: F401,E402
 from .problems import ForwardProblem, InverseProblem  # noqa: F401,E402
 from .trainer import Trainer  # noqa: F401,E402

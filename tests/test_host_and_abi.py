@@ -161,9 +161,10 @@ def test_incompatible_problem_pieces_raise():
     d = px.VariationalDomain(m, np.linspace(0, 1, 2))
     with pytest.raises(DomainPhysicsCompatabilityError):
         px.ForwardProblem(d, object())
-    with pytest.raises(NotImplementedError):
-        from pancax_b200.physics_kernels import PlaneStress
-        PlaneStress()
+    from pancax_b200.physics_kernels import PlaneStress
+    ps = PlaneStress()                       # solid_mechanics.py:32-71: on the path since PCX_FORM_PLANE_STRESS
+    assert ps.n_dimensions == 2 and ps.name == "plane_stress"
+    assert px.SolidMechanics(px.NeoHookean(bulk_modulus=10.0, shear_modulus=1.0), ps).n_dofs == 2
     with pytest.raises(NotImplementedError):
         px.MLP(3, 2, 50, 3, activation="relu", device="cpu")
 
