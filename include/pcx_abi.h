@@ -54,12 +54,14 @@ extern "C" {
  *   GENT        : bulk_modulus, shear_modulus, Jm_parameter          (gent.py:18-20)
  *   SWANSON     : bulk_modulus, A1, P1, B1, Q1, C1, R1, cutoff_strain (swanson.py:18-26; cutoff static)
  *   HENCKY      : bulk_modulus, shear_modulus                        (hencky.py:7-8)
+ *   BLATZ_KO    : shear_modulus                                      (blatz_ko.py:7)
  */
 #define PCX_MODEL_NONE       0
 #define PCX_MODEL_NEOHOOKEAN 1
 #define PCX_MODEL_GENT       2
 #define PCX_MODEL_SWANSON    3
 #define PCX_MODEL_HENCKY     4
+#define PCX_MODEL_BLATZ_KO   5
 #define PCX_MAX_PROPS        8
 
 /* loss kinds: pancax/loss_functions/weak_form_loss_functions.py */

@@ -43,6 +43,9 @@ CASES = [
     ("quad4_neohookean_pstress", 3, 2, 16, 2, 2, ("energy", "energy_residual", "energy_residual_reaction")),
     ("tri3_gent_pstress_bounded", 3, 3, 16, 2, 2, ("energy_residual_reaction",)),
     ("quad4_hencky_pstress", 2, 2, 12, 2, 2, ("energy", "energy_residual")),
+    # Blatz-Ko (hyperelasticity/blatz_ko.py)
+    ("hex8_blatz_ko", 2, 2, 16, 2, 2, ("energy", "energy_residual_reaction")),
+    ("quad4_blatz_ko_bounded", 3, 3, 16, 2, 2, ("energy_residual_reaction",)),
 ]
 
 
@@ -50,7 +53,7 @@ CASES = [
 # Swanson, and the reference's d||f||/df is NaN there; that case starts at t0 > 0 instead.
 # Hencky: at t = 0 (F = I, repeated stretches) the reference's second derivative through eigen_sym33_unit is NaN as
 # well -- its residual-loss cases start at t0 > 0 too.
-T0 = {"hex8_swanson": 0.25, "hex8_hencky": 0.25, "tri3_hencky_bounded": 0.2, "quad4_hencky": 0.2,
+T0 = {"hex8_swanson": 0.25, "hex8_blatz_ko": 0.25, "quad4_blatz_ko_bounded": 0.2, "hex8_hencky": 0.25, "tri3_hencky_bounded": 0.2, "quad4_hencky": 0.2,
       "quad4_hencky_pstress": 0.2}
 
 
@@ -61,7 +64,7 @@ def main():
     from pancax.fem.elements import Hex8Element, Quad4Element, SimplexTriElement
     from pancax.fem.quadrature_rules import QuadratureRule
     from pancax.fem.function_space import NonAllocatedFunctionSpace
-    from pancax.constitutive_models import Gent, Hencky, NeoHookean, Swanson, BoundedProperty
+    from pancax.constitutive_models import BlatzKo, Gent, Hencky, NeoHookean, Swanson, BoundedProperty
     from pancax.physics_kernels import Poisson, SolidMechanics, PlaneStrain, PlaneStress, ThreeDimensional
     from pancax.bvps.uniaxial_tension import UniaxialTensionLinearRamp
     from pancax.loss_functions.weak_form_loss_functions import (EnergyLoss, EnergyAndResidualLoss,
@@ -72,10 +75,11 @@ def main():
     from tests.cases import LOSS_WEIGHTS, make_case, SWANSON_PROPS
 
     elems = {"hex8": Hex8Element(), "quad4": Quad4Element(), "tri3": SimplexTriElement(1)}
-    model_cls = {"neohookean": NeoHookean, "gent": Gent, "swanson": Swanson, "hencky": Hencky}
+    model_cls = {"neohookean": NeoHookean, "gent": Gent, "swanson": Swanson, "hencky": Hencky, "blatz_ko": BlatzKo}
     prop_names = {"neohookean": ("bulk_modulus", "shear_modulus"),
                   "gent": ("bulk_modulus", "shear_modulus", "Jm_parameter"),
-                  "swanson": tuple(SWANSON_PROPS.keys()), "hencky": ("bulk_modulus", "shear_modulus")}
+                  "swanson": tuple(SWANSON_PROPS.keys()), "hencky": ("bulk_modulus", "shear_modulus"),
+                  "blatz_ko": ("shear_modulus",)}
     out = {}
 
     def build(case):

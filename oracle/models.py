@@ -337,7 +337,23 @@ def hencky_energy(grad_u, K, G):
     return 0.5 * K * trE ** 2 + G * torch.einsum("...ij,...ij->...", E, E)
 
 
+def I2(grad_u):
+    """mechanics/base.py:65-71"""
+    F = deformation_gradient(grad_u)
+    C = F.transpose(-1, -2) @ F
+    I1 = torch.einsum("...ii->...", C)
+    return 0.5 * (I1 ** 2 - torch.einsum("...ii->...", C @ C))
+
+
+def blatz_ko_energy(grad_u, G):
+    """hyperelasticity/blatz_ko.py:9-24: W = G/2 (I2/I3 + 2 sqrt(I3) - 5), I3 = J^2 (base.py:82-84)."""
+    J = jacobian(grad_u)
+    I3 = J * J
+    return (G / 2.0) * (I2(grad_u) / I3 + 2.0 * torch.sqrt(I3) - 5.0)
+
+
 MODELS = {
+    "blatz_ko": (blatz_ko_energy, ("shear_modulus",)),
     "neohookean": (neohookean_energy, ("bulk_modulus", "shear_modulus")),
     "gent": (gent_energy, ("bulk_modulus", "shear_modulus", "Jm_parameter")),
     "swanson": (swanson_energy, ("bulk_modulus", "A1", "P1", "B1", "Q1", "C1", "R1",

@@ -14,7 +14,7 @@ __version__ = "0.1.0"
 # pancax's public names for the hot path (same constructors / argument meaning as the reference)
 from .bcs import DirichletBC  # noqa: F401,E402
 from .bvps import BiaxialLinearRamp, SimpleShearLinearRamp, UniaxialTensionLinearRamp  # noqa: F401,E402
-from .constitutive_models import (BoundedProperty, FixedProperty, Gent, Hencky, NeoHookean,  # noqa: F401,E402
+from .constitutive_models import (BlatzKo, BoundedProperty, FixedProperty, Gent, Hencky, NeoHookean,  # noqa: F401,E402
                                   Swanson)
 from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E402
 from .domains import CollocationDomain, VariationalDomain  # noqa: F401,E402

@@ -20,7 +20,7 @@ PROF_CLASSES = ["pack_weights", "mlp_forward", "element_force", "assemble", "ele
 ELEM = {"hex8": 0, "quad4": 1, "tri3": 2}
 PHYS_POISSON, PHYS_SOLID = 0, 1
 FORM = {"plane_strain": 0, "three_dimensional": 1, "plane_stress": 2}
-MODEL = {"none": 0, "neohookean": 1, "gent": 2, "swanson": 3, "hencky": 4}
+MODEL = {"none": 0, "neohookean": 1, "gent": 2, "swanson": 3, "hencky": 4, "blatz_ko": 5}
 LOSS = {"energy": 0, "energy_residual": 1, "energy_residual_reaction": 2}
 
 

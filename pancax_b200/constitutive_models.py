@@ -88,3 +88,10 @@ class Hencky(HyperelasticModel):
     bulk_modulus: Property
     shear_modulus: Property
     name = "hencky"
+
+
+@dataclass
+class BlatzKo(HyperelasticModel):
+    """hyperelasticity/blatz_ko.py:6-24"""
+    shear_modulus: Property
+    name = "blatz_ko"

@@ -312,6 +312,7 @@ static int launch_element_m(int model, bool tangent, dim3 grid, cudaStream_t st,
     case PCX_MODEL_GENT: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_GENT>(tangent, grid, st, tab, a); return 0;
     case PCX_MODEL_SWANSON: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_SWANSON>(tangent, grid, st, tab, a); return 0;
     case PCX_MODEL_HENCKY: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_HENCKY>(tangent, grid, st, tab, a); return 0;
+    case PCX_MODEL_BLATZ_KO: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_BLATZ_KO>(tangent, grid, st, tab, a); return 0;
   }
   return -1;
 }
@@ -625,8 +626,8 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
   if (p->physics == PCX_PHYS_POISSON) {
     if (h->ndof != 1) return fail(PCX_ERR_INVALID, "Poisson needs ndof == 1");
   } else if (p->physics == PCX_PHYS_SOLID) {
-    if (p->model < PCX_MODEL_NEOHOOKEAN || p->model > PCX_MODEL_HENCKY) return fail(PCX_ERR_INVALID, "unknown constitutive model %d", p->model);
-    const int need[5] = {0, 2, 3, 8, 2};
+    if (p->model < PCX_MODEL_NEOHOOKEAN || p->model > PCX_MODEL_BLATZ_KO) return fail(PCX_ERR_INVALID, "unknown constitutive model %d", p->model);
+    const int need[6] = {0, 2, 3, 8, 2, 1};
     if (p->nprops != need[p->model]) return fail(PCX_ERR_INVALID, "model %d takes %d properties, got %d", p->model, need[p->model], p->nprops);
     if (p->formulation == PCX_FORM_PLANE_STRAIN) { if (h->nd != 2 || h->ndof != 2) return fail(PCX_ERR_INVALID, "PlaneStrain needs a 2D mesh and ndof == 2"); }
     else if (p->formulation == PCX_FORM_THREE_DIMENSIONAL) { if (h->nd != 3 || h->ndof != 3) return fail(PCX_ERR_INVALID, "ThreeDimensional needs a 3D mesh and ndof == 3"); }
@@ -1042,6 +1043,7 @@ static int launch_pp_m(pcx_handle* h, const double* us, double* F, double* I1, d
     case PCX_MODEL_GENT: PCX_PP(PCX_MODEL_GENT); break;
     case PCX_MODEL_SWANSON: PCX_PP(PCX_MODEL_SWANSON); break;
     case PCX_MODEL_HENCKY: PCX_PP(PCX_MODEL_HENCKY); break;
+    case PCX_MODEL_BLATZ_KO: PCX_PP(PCX_MODEL_BLATZ_KO); break;
     default: return fail(PCX_ERR_INVALID, "unknown constitutive model %d", h->phys.model);
   }
 #undef PCX_PP

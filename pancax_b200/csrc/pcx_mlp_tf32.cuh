@@ -20,8 +20,9 @@
 //  * the forward kernel stores the hidden activations a second way for this mode: fp32, still in accumulator
 //    slot order, act32[layer][8-wide tile j][row][8 slots] (896 B per row instead of 1 792);
 //  * CTA = 8 warps, persistent over tiles of 128 rows; one elected thread pulls the (layer, tile j) planes of
-//    a row tile -- 4 KB contiguous each -- into shared memory with bulk (TMA) copies one layer ahead,
-//    completion on an mbarrier; no swizzle is needed: with [j][row][8] planes both access patterns (own-row
+//    a row tile -- 4 KB contiguous each -- into a ring of three shared-memory buffers with bulk (TMA) copies TWO
+//    stages ahead (a stage is ~3 000 cycles, DRAM latency + 28 KB at one SM's share of the bandwidth is about as
+//    long: one stage ahead left the mbarrier wait exposed), completion on an mbarrier per ring slot; no swizzle is needed: with [j][row][8] planes both access patterns (own-row
 //    float2 in accumulator layout, and the transposed fragment read rows k0+t / column g of the contraction)
 //    touch 32 distinct banks;
 //  * the m16n8k8 accumulator fragment of layer L (lane (g,t): rows g, g+8; slots 2t, 2t+1 of tile j) is the
@@ -67,8 +68,8 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void mma_3xtf32(float (&ch)[4], float (&cl)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                            uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
   mma_tf32(cl, al[0], al[1], al[2], al[3], bh0, bh1);
-  mma_tf32(cl, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
   mma_tf32(ch, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+  mma_tf32(cl, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -121,13 +122,18 @@ struct BwdTfSmem {
   static constexpr int ROWS = 16 * NW;       // 128 rows per CTA tile
   static constexpr int TS = ROWS * 8;        // floats per (tile j) plane
   static constexpr int NWC = (DH > 0 ? DH : 0) * NT * NT * 32;
+  // bytes of everything but the h ring; the ring takes 3 buffers (loads issued two stages ahead) when that fits
+  // into the 227 KB a CTA may use, else 2 (one stage ahead)
+  static constexpr long long FIXED = (long long)(NWC > 0 ? NWC : 1) * 16 + NT * 32 * 8 + 2LL * NT * TS * 4 + ROWS * 4 * 4 +
+                                     2LL * TS * 4 + 64;
+  static constexpr int NH = (FIXED + 3LL * NT * TS * 4 <= 227 * 1024) ? 3 : 2;
   float4 Wc[NWC > 0 ? NWC : 1];
   float2 Wo[NT * 32];
-  float H[2][NT * TS];
+  float H[NH][NT * TS];
   float D[2][NT * TS];
-  float Zb[TS];
+  float Zb[ROWS * 4];       // zbar, 4 columns (n_out <= 3)
   float In[2][TS];
-  uint64_t wbar, hbar[2], sync;
+  uint64_t wbar, hbar[NH], sync;
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -151,8 +157,7 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
 
   if (threadIdx.x == 0) {
     mbar_init(&sm.wbar, 1);
-    mbar_init(&sm.hbar[0], 1);
-    mbar_init(&sm.hbar[1], 1);
+    for (int i = 0; i < SM::NH; i++) mbar_init(&sm.hbar[i], 1);
     mbar_init(&sm.sync, blockDim.x);
   }
   __syncthreads();
@@ -178,7 +183,19 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
                  (uint32_t)(TS * sizeof(float)), &sm.hbar[buf]);
     }
   };
-  uint32_t hph[2] = {0, 0};
+  // The h loads of a CTA form one sequence q = 0, 1, 2, ...: (tile it, layer depth-1), (it, depth-2), ..., (it, 0),
+  // (it+1, depth-1), ...; load q lands in ring buffer q % NH and is issued NH-1 consuming stages ahead.
+  constexpr int NH = SM::NH;
+  const int depth = DH + 1;
+  auto prefetch_q = [&](long long q) {
+    const long long it = q / depth;
+    prefetch_h(blockIdx.x + it * gridDim.x, depth - 1 - (int)(q - it * depth), (int)(q % NH));
+  };
+  uint32_t hph = 0;   // bit b = phase parity of hbar[b]
+  auto wait_h = [&](int buf) {
+    mbar_wait(&sm.hbar[buf], (hph >> buf) & 1u);
+    hph ^= 1u << buf;
+  };
   uint32_t sphase = 0;
 #define SYNC_ARRIVE() mbar_arrive(&sm.sync)
 #define SYNC_WAIT() do { mbar_wait(&sm.sync, sphase); sphase ^= 1; } while (0)
@@ -296,7 +313,7 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
     }
   };
   // acc[b] += sum_rows A[row][16mi + ..] * B_b[row][..]: A = planes (2mi, 2mi+1) of Ap, B_b = plane b of Bp, b < nblk
-  auto contract = [&](auto& acc, int nblk, const float* __restrict__ Ap, const float* __restrict__ Bp) {
+  auto contract = [&](auto& acc, int nblk, const float* __restrict__ Ap, const float* __restrict__ Bp, bool b_narrow = false) {
     constexpr int NB = sizeof(acc) / sizeof(acc[0]);
     const float* __restrict__ A0 = Ap + (2 * mi) * TS;
     const float* __restrict__ A1 = A0 + TS;
@@ -324,8 +341,14 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
         for (int bb = 0; bb < NB; bb++) {
           if (bb < nblk) {
             uint32_t bh0, bl0, bh1, bl1;
-            split_tf32(Bp[bb * TS + o0], bh0, bl0);
-            split_tf32(Bp[bb * TS + o1], bh1, bl1);
+            if (b_narrow) {   // a [ROWS][4] plane (zbar): columns 4..7 are zero
+              const int r0 = (8 * ks + t) * 4 + g;
+              split_tf32(g < 4 ? Bp[r0] : 0.f, bh0, bl0);
+              split_tf32(g < 4 ? Bp[r0 + 16] : 0.f, bh1, bl1);
+            } else {
+              split_tf32(Bp[bb * TS + o0], bh0, bl0);
+              split_tf32(Bp[bb * TS + o1], bh1, bl1);
+            }
             mma_3xtf32(ch[bb], cl[bb], ah, al, bh0, bh1, bl0, bl1);
           }
         }
@@ -342,7 +365,10 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
   };
 
   int hb = 0, db = 0, parity = 0, since_flush = 0;
-  prefetch_h(blockIdx.x, s.depth - 1, hb);
+  long long hq = 0;   // sequence number of the h load the current stage consumes; hb = hq % NH
+  auto next_h = [&]() { hq++; hb = (hb + 1 == NH) ? 0 : hb + 1; };
+#pragma unroll
+  for (int q = 0; q < NH - 1; q++) prefetch_q(q);
   float zA[2], in0[2], in1[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
@@ -355,13 +381,11 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
   auto top_publish = [&](long long tile, int par) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      sm.Zb[lr[e] * 8 + t] = zA[e];
-      sm.Zb[lr[e] * 8 + 4 + t] = 0.f;
+      sm.Zb[lr[e] * 4 + t] = zA[e];
       sm.In[par][lr[e] * 8 + t] = in0[e];
       sm.In[par][lr[e] * 8 + 4 + t] = in1[e];
     }
-    mbar_wait(&sm.hbar[hb], hph[hb]);
-    hph[hb] ^= 1;
+    wait_h(hb);
     patch_h(tile, hb);
   };
   // top of a tile, register half: d_{depth-1} = (zbar W_out) * (1 - h_depth^2) for the own rows
@@ -395,9 +419,8 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
   for (int e = 0; e < 2; e++) qn[e] = issue_top(blockIdx.x + gridDim.x, lr[e]);
   top_chain(dC);
   SYNC_WAIT();
-  if (DH > 0) prefetch_h(blockIdx.x, DH - 1, hb ^ 1);
-  else prefetch_h(blockIdx.x + gridDim.x, s.depth - 1, hb ^ 1);
-  if (m_active && half == 0) contract(gX, 1, sm.H[hb], sm.Zb);   // dW_out^T[slot][o] += sum_rows h_depth[row][slot] zbar[row][o]
+  prefetch_q(hq + NH - 1);
+  if (m_active && half == 0) contract(gX, 1, sm.H[hb], sm.Zb, true);   // dW_out^T[slot][o] += sum_rows h_depth[row][slot] zbar[row][o]
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     if constexpr (DH == 0) {   // no hidden stage separates two fused stages: Zb / In / D of the stage before last
@@ -408,9 +431,8 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
 #pragma unroll
     for (int L = DH; L >= 1; L--) {
       publish_d(dC, db);
-      mbar_wait(&sm.hbar[hb ^ 1], hph[hb ^ 1]);
-      hph[hb ^ 1] ^= 1;
-      hb ^= 1;
+      next_h();
+      wait_h(hb);
       patch_h(tile, hb);
       fence_proxy_async_smem();
       SYNC_ARRIVE();
@@ -439,9 +461,8 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
 #pragma unroll
         for (int x = 0; x < 4; x++) dn[jn][x] += dl[jn][x];
       apply_dtanh(dC, dn, hb);
-      SYNC_WAIT();     // all rows of D[db] = d_L and H[hb] = h_L are in; H[hb^1] is free
-      if (L > 1) prefetch_h(tile, L - 2, hb ^ 1);
-      else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
+      SYNC_WAIT();     // all rows of D[db] = d_L and H[hb] = h_L are in; the ring slot of the stage before is free
+      prefetch_q(hq + NH - 1);
       if (m_active) contract(G[L - 1], nb, sm.D[db], sm.H[hb] + nj0 * TS);
       db ^= 1;
     }
@@ -451,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
     publish_d(dC, db);
 #pragma unroll
     for (int e = 0; e < 2; e++) finish_top(next, lr[e], qn[e], zA[e], in0[e], in1[e]);
-    hb ^= 1;           // the next tile's top-layer h is in flight into this buffer
+    next_h();          // the next tile's top-layer h is in flight into this ring slot
     if (has_next) {
       top_publish(next, parity ^ 1);
       fence_proxy_async_smem();
@@ -463,13 +484,10 @@ __global__ void __launch_bounds__(256, 1) k_mlp_backward_tf32(const __grid_const
       top_chain(dC);
     }
     SYNC_WAIT();
-    if (has_next) {
-      if (DH > 0) prefetch_h(next, DH - 1, hb ^ 1);
-      else prefetch_h(next + gridDim.x, s.depth - 1, hb ^ 1);
-    }
+    prefetch_q(hq + NH - 1);
     if (m_active) {
       if (half == 1) contract(gX, 1, sm.D[db], sm.In[parity]);
-      else if (has_next) contract(gX, 1, sm.H[hb], sm.Zb);
+      else if (has_next) contract(gX, 1, sm.H[hb], sm.Zb, true);
     }
     db ^= 1;
     if (++since_flush == TF32_FLUSH_TILES) { flush(); since_flush = 0; }

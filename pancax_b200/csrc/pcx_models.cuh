@@ -53,6 +53,15 @@ __host__ __device__ inline Dual s_pow(Dual x, double p) {
   return Dual(r, p * r / x.v * x.d);
 }
 
+// x^p from a precomputed lx = log(x): exp(p lx).  CUDA's pow() carries an extended-precision log internally (~3x the
+// FP64 instructions of log + exp); here |p lx| is O(1), so exp(p log x) is good to a few ulp -- and Swanson raises
+// the same base to two different powers, which then share one log.
+__host__ __device__ inline double s_pow_l(double, double lx, double p) { return exp(p * lx); }
+__host__ __device__ inline Dual s_pow_l(Dual x, Dual lx, double p) {
+  const double r = exp(p * lx.v);
+  return Dual(r, p * r / x.v * x.d);
+}
+
 // x^(-2/3) (x > 0): rcbrt is ~4x cheaper than pow on the FP64 pipe and as accurate (1 ulp)
 __device__ inline double s_pow_m23(double x) { const double r = rcbrt(x); return r * r; }
 __device__ inline Dual s_pow_m23(Dual x) {
@@ -159,10 +168,11 @@ __device__ inline void gent(const T* F, const Props& pr, T& W, T* P, T* dWdp, bo
 template <class T>
 __device__ inline T swanson_term_dexp(T t, double tc, double A, double Pw) {
   // d/dPw of A/(Pw+1) (t^(Pw+1) - tc^(Pw+1))
-  T tp = s_pow(t, Pw + 1.0);
+  T lt = s_log(t);
+  T tp = s_pow_l(t, lt, Pw + 1.0);
   double cp = pow(tc, Pw + 1.0);
   double inv = 1.0 / (Pw + 1.0);
-  return A * ((tp * (s_log(t) * inv - inv * inv)) - cp * (log(tc) * inv - inv * inv));
+  return A * ((tp * (lt * inv - inv * inv)) - cp * (log(tc) * inv - inv * inv));
 }
 
 template <class T>
@@ -190,7 +200,8 @@ __device__ inline void swanson(const T* F, const Props& pr, T& W, T* P, T* dWdp,
   T t2 = (1.0 / 3.0) * I2bar - 1.0 + tc;
   T lJ = s_log(J);
   T wK = J * lJ - J + 1.0;
-  T t1P = s_pow(t1, P1), t1R = s_pow(t1, R1), t2Q = s_pow(t2, Q1);
+  T lt1 = s_log(t1), lt2 = s_log(t2);
+  T t1P = s_pow_l(t1, lt1, P1), t1R = s_pow_l(t1, lt1, R1), t2Q = s_pow_l(t2, lt2, Q1);
   T wA = 1.5 / (P1 + 1.0) * (t1P * t1 - pow(tc, P1 + 1.0));
   T wB = 1.5 / (Q1 + 1.0) * (t2Q * t2 - pow(tc, Q1 + 1.0));
   T wC = 1.5 / (R1 + 1.0) * (t1R * t1 - pow(tc, R1 + 1.0));
@@ -361,17 +372,9 @@ __device__ inline void eigen_sym33_unit(const double* A, double* lam, double* V)
   }
 }
 
-__device__ inline double relative_log_difference(double l1, double l2) {  // tensor_math.py:517-551
-  const bool large = fabs(l1 - l2) > 0.05 * fmin(l1, l2);
-  if (large) return log(l1 / l2) / (l1 - l2);
-  const double frac = (l1 - l2) / (l1 + l2);
-  const double f2 = frac * frac, f4 = f2 * f2;
-  return (2.0 + (2.0 / 3.0) * f2 + (2.0 / 5.0) * f4 + (2.0 / 7.0) * f4 * f2 + (2.0 / 9.0) * f4 * f4) / (l1 + l2);
-}
-
 // W = 0.5 K tr(E)^2 + G E:E with E = 0.5 log(F^T F) (mtk_log_sqrt, tensor_math.py:337-340).
 // P = 2 F S, S = L(Ebar), Ebar = K tr(E) I + 2 G E, L = the (self-adjoint) derivative rule of
-// mtk_log_sqrt (tensor_math.py:343-424).  Value path; the tangent action is the Dual overload below.
+// mtk_log_sqrt (tensor_math.py:343-424), evaluated in the eigenbasis.  The tangent action is the Dual overload below.
 __device__ inline void hencky(const double* F, const Props& pr, double& W, double* P, double* dWdp, bool want_dp) {
   const double K = pr.p[0], G = pr.p[1];
   double C[9];
@@ -381,50 +384,24 @@ __device__ inline void hencky(const double* F, const Props& pr, double& W, doubl
     for (int j = 0; j < 3; j++) C[3 * i + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
   double lam[3], V[9];
   eigen_sym33_unit(C, lam, V);
-  double e[3] = {0.5 * log(lam[0]), 0.5 * log(lam[1]), 0.5 * log(lam[2])};
-  double E[9];
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-      E[3 * i + j] = V[3 * i] * e[0] * V[3 * j] + V[3 * i + 1] * e[1] * V[3 * j + 1] + V[3 * i + 2] * e[2] * V[3 * j + 2];
-  const double trE = E[0] + E[4] + E[8];
-  double EE = 0.0;
-#pragma unroll
-  for (int i = 0; i < 9; i++) EE += E[i] * E[i];
+  // E = V diag(e) V^T, e_i = 0.5 log(lam_i): tr E = sum e_i, E:E = sum e_i^2 (V orthonormal)
+  const double e[3] = {0.5 * log(lam[0]), 0.5 * log(lam[1]), 0.5 * log(lam[2])};
+  const double trE = e[0] + e[1] + e[2];
+  const double EE = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
   W = 0.5 * K * trE * trE + G * EE;
-  // Ebar and its image under L
-  double Eb[9];
+  // S = L(Ebar) with Ebar = K tr(E) I + 2 G E coaxial with C: in the eigenbasis hHat = 0.5 V^T Ebar V is diagonal,
+  // so of the rule's six coefficients (tensor_math.py:369-383) only l_iiii = hHat_ii / lam_i survive -- the
+  // off-diagonal ones multiply entries that vanish identically -- and S = V diag(w) V^T, w_i = (K trE + 2 G e_i) / (2 lam_i)
+  double FV[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) Eb[i] = 2.0 * G * E[i];
-  Eb[0] += K * trE; Eb[4] += K * trE; Eb[8] += K * trE;
-  double T1[9], hh[9];
+  for (int r = 0; r < 3; r++)
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++)
+      FV[3 * r + k] = (F[3 * r] * V[k] + F[3 * r + 1] * V[3 + k] + F[3 * r + 2] * V[6 + k]) * ((K * trE + 2.0 * G * e[k]) / lam[k]);
 #pragma unroll
-    for (int k = 0; k < 3; k++) T1[3 * i + k] = Eb[3 * i] * V[k] + Eb[3 * i + 1] * V[3 + k] + Eb[3 * i + 2] * V[6 + k];
+  for (int r = 0; r < 3; r++)
 #pragma unroll
-  for (int a = 0; a < 3; a++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) hh[3 * a + k] = 0.5 * (V[a] * T1[k] + V[3 + a] * T1[3 + k] + V[6 + a] * T1[6 + k]);
-  double L[9];
-  L[0] = hh[0] / lam[0]; L[4] = hh[4] / lam[1]; L[8] = hh[8] / lam[2];
-  L[1] = L[3] = 0.5 * (hh[1] + hh[3]) * relative_log_difference(lam[0], lam[1]);
-  L[5] = L[7] = 0.5 * (hh[5] + hh[7]) * relative_log_difference(lam[1], lam[2]);
-  L[2] = L[6] = 0.5 * (hh[6] + hh[2]) * relative_log_difference(lam[2], lam[0]);
-  double T2[9], S[9];
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) T2[3 * i + k] = V[3 * i] * L[k] + V[3 * i + 1] * L[3 + k] + V[3 * i + 2] * L[6 + k];
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) S[3 * i + j] = T2[3 * i] * V[3 * j] + T2[3 * i + 1] * V[3 * j + 1] + T2[3 * i + 2] * V[3 * j + 2];
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) P[3 * i + j] = 2.0 * (F[3 * i] * S[j] + F[3 * i + 1] * S[3 + j] + F[3 * i + 2] * S[6 + j]);
+    for (int j = 0; j < 3; j++) P[3 * r + j] = FV[3 * r] * V[3 * j] + FV[3 * r + 1] * V[3 * j + 1] + FV[3 * r + 2] * V[3 * j + 2];
   if (want_dp) {
     dWdp[0] = 0.5 * trE * trE;
     dWdp[1] = EE;
@@ -532,11 +509,47 @@ __device__ inline void hencky(const Dual* F, const Props& pr, Dual& W, Dual* P, 
   }
 }
 
+// ------------------------------------------------------------------ Blatz-Ko (blatz_ko.py:6-24)
+//   W = (G/2) (I2 / I3 + 2 sqrt(I3) - 5),  I2 = (tr(C)^2 - tr(C^2)) / 2,  I3 = J^2  (mechanics/base.py:65-86)
+//   dI2/dF = 2 (I1 F - F C),  d sqrt(I3)/dF = cof F,  dI3/dF = 2 J cof F
+//   P = G [ (I1 F - F C) / J^2 + (1 - I2 / J^3) cof F ]
+template <class T>
+__device__ inline void blatz_ko(const T* F, const Props& pr, T& W, T* P, T* dWdp, bool want_dp) {
+  const double G = pr.p[0];
+  T cof[9];
+  cofactor3(F, cof);
+  T J = F[0] * cof[0] + F[1] * cof[1] + F[2] * cof[2];
+  T C[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
+  T I1 = C[0] + C[4] + C[8];
+  T trC2 = C[0] * C[0] + C[4] * C[4] + C[8] * C[8] + 2.0 * (C[1] * C[1] + C[2] * C[2] + C[5] * C[5]);
+  T I2 = 0.5 * (I1 * I1 - trC2);
+  T Jinv = 1.0 / J;
+  T Jinv2 = Jinv * Jinv;
+  T w = 0.5 * (I2 * Jinv2 + 2.0 * J - 5.0);
+  W = G * w;
+  T cF = G * Jinv2 * I1;
+  T cFC = -(G * Jinv2);
+  T ccof = G * (1.0 - I2 * Jinv2 * Jinv);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      T FC = F[3 * i] * C[j] + F[3 * i + 1] * C[3 + j] + F[3 * i + 2] * C[6 + j];
+      P[3 * i + j] = ccof * cof[3 * i + j] + cF * F[3 * i + j] + cFC * FC;
+    }
+  if (want_dp) dWdp[0] = w;
+}
+
 template <int MODEL, class T>
 __device__ inline void model_eval(const T* F, const Props& pr, T& W, T* P, T* dWdp, bool want_dp) {
   if constexpr (MODEL == PCX_MODEL_NEOHOOKEAN) neohookean(F, pr, W, P, dWdp, want_dp);
   else if constexpr (MODEL == PCX_MODEL_GENT) gent(F, pr, W, P, dWdp, want_dp);
   else if constexpr (MODEL == PCX_MODEL_SWANSON) swanson(F, pr, W, P, dWdp, want_dp);
+  else if constexpr (MODEL == PCX_MODEL_BLATZ_KO) blatz_ko(F, pr, W, P, dWdp, want_dp);
   else hencky(F, pr, W, P, dWdp, want_dp);
 }
 

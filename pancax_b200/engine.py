@@ -24,6 +24,7 @@ MODEL_PROPS = {
     "gent": ("bulk_modulus", "shear_modulus", "Jm_parameter"),
     "swanson": ("bulk_modulus", "A1", "P1", "B1", "Q1", "C1", "R1", "cutoff_strain"),
     "hencky": ("bulk_modulus", "shear_modulus"),
+    "blatz_ko": ("shear_modulus",),
 }
 
 

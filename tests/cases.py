@@ -49,7 +49,7 @@ def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=
     if name.startswith("hex8_"):
         model = name.split("_", 1)[1]
         mesh = ofem.structured_mesh("hex8", n, permute_seed=7 if permute else None)
-        props = {"neohookean": [1000.0, 1.0], "gent": [0.833, 0.3846, 3.0],
+        props = {"neohookean": [1000.0, 1.0], "gent": [0.833, 0.3846, 3.0], "blatz_ko": [0.3846],
                  "swanson": list(SWANSON_PROPS.values()), "hencky": [0.833, 0.3846]}[model]
         mlp = (4, 3, width, depth)
         c = Case(name, mesh, q_order, times, "solid", 3, mlp,
@@ -68,11 +68,11 @@ def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=
         model = model.replace("_bounded", "")
         formulation = "plane_stress" if model.endswith("_pstress") else "plane_strain"   # solid_mechanics.py:20-71
         model = model.replace("_pstress", "")
-        props = {"neohookean": [1000.0, 1.0], "gent": [0.833, 0.3846, 3.0],
+        props = {"neohookean": [1000.0, 1.0], "gent": [0.833, 0.3846, 3.0], "blatz_ko": [0.3846],
                  "swanson": list(SWANSON_PROPS.values()), "hencky": [0.833, 0.3846]}[model]
         if trainable:
-            props = [0.833, (0.01, 5.0, 0.3)] if model == "neohookean" else \
-                [(0.5, 2.0, -0.2), (0.01, 5.0, 0.3)] + props[2:]
+            props = [0.833, (0.01, 5.0, 0.3)] if model == "neohookean" else [(0.01, 5.0, 0.3)] if model == "blatz_ko" \
+                else [(0.5, 2.0, -0.2), (0.01, 5.0, 0.3)] + props[2:]
         mlp = (3, 2, width, depth)
         c = Case(name, mesh, q_order, times, "solid", 2, mlp,
                  flatten_mlp(init_mlp(*mlp, seed=seed)), model, formulation, props,

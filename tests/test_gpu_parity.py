@@ -61,8 +61,9 @@ def test_field_forward_backward(cuda_device, name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "hex8_hencky",
-                                  "quad4_neohookean", "quad4_gent", "quad4_swanson", "quad4_hencky",
+@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "hex8_hencky", "hex8_blatz_ko",
+                                  "quad4_neohookean", "quad4_gent", "quad4_swanson", "quad4_hencky", "quad4_blatz_ko",
+                                  "quad4_blatz_ko_pstress",
                                   "tri3_neohookean", "poisson_quad4", "poisson_tri3", "poisson_hex8"])
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_energy_force(cuda_device, name, deterministic):
@@ -78,9 +79,9 @@ def test_energy_force(cuda_device, name, deterministic):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "hex8_hencky", "quad4_neohookean",
-                                  "quad4_gent", "quad4_swanson", "quad4_hencky", "tri3_hencky", "tri3_neohookean",
-                                  "poisson_quad4"])
+@pytest.mark.parametrize("name", ["hex8_neohookean", "hex8_gent", "hex8_swanson", "hex8_hencky", "hex8_blatz_ko",
+                                  "quad4_neohookean", "quad4_gent", "quad4_swanson", "quad4_hencky", "quad4_blatz_ko",
+                                  "quad4_blatz_ko_pstress", "tri3_hencky", "tri3_neohookean", "poisson_quad4"])
 def test_stiffness_action(cuda_device, name):
     from oracle import losses as ol
     case = make_case(name, n=4, nt=2)
@@ -162,7 +163,8 @@ def test_energy_loss_and_grad(cuda_device, name):
 
 
 @pytest.mark.parametrize("name", ["quad4_neohookean", "quad4_gent", "quad4_swanson", "hex8_neohookean",
-                                  "tri3_neohookean_bounded", "quad4_gent_bounded", "hex8_hencky", "quad4_hencky_bounded"])
+                                  "tri3_neohookean_bounded", "quad4_gent_bounded", "hex8_hencky", "quad4_hencky_bounded",
+                                  "hex8_blatz_ko", "quad4_blatz_ko_bounded"])
 @pytest.mark.parametrize("kind", ["energy_residual", "energy_residual_reaction"])
 def test_residual_losses(cuda_device, name, kind):
     case = make_case(name, n=5, nt=3)

@@ -165,6 +165,7 @@ def test_incompatible_problem_pieces_raise():
     ps = PlaneStress()                       # solid_mechanics.py:32-71: on the path since PCX_FORM_PLANE_STRESS
     assert ps.n_dimensions == 2 and ps.name == "plane_stress"
     assert px.SolidMechanics(px.NeoHookean(bulk_modulus=10.0, shear_modulus=1.0), ps).n_dofs == 2
+    assert px.BlatzKo(shear_modulus=0.4).properties() == ("shear_modulus",) or list(px.BlatzKo(shear_modulus=0.4).properties()) == ["shear_modulus"]
     with pytest.raises(NotImplementedError):
         px.MLP(3, 2, 50, 3, activation="relu", device="cpu")
 
