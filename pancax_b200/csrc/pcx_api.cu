@@ -87,6 +87,7 @@ struct pcx_handle {
   long long launches = 0;
   int sm_count = 148;
   int fwd_variant = 12;   // (MT, min CTAs/SM) of the forward kernel; PCX_FWD_VARIANT overrides (tuning)
+  int fwd_edge = 1;       // last (mostly padding) tile of the hidden layers on the FP64 vector pipe; PCX_FWD_EDGE=0 disables
   bool prof_on = false;
   struct ProfEv { int cat; cudaEvent_t e0, e1; };
   std::vector<ProfEv> prof_events;
@@ -370,23 +371,27 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
   }
 }
 
-template <int NT, int KODD, int MT, int MINB>
+template <int NT, int KODD, int MT, int MINB, int NEDGE = 0>
 static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + EXP2_TAB_N) * sizeof(double);
-  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB, NEDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
   const long long groups = (io.n + 8 * MT - 1) / (8 * MT);
   long long blocks = (groups + 7) / 8;
   const long long maxb = (long long)h->sm_count * MINB;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
-  k_mlp_forward<NT, KODD, MT, MINB><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+  k_mlp_forward<NT, KODD, MT, MINB, NEDGE><<<(int)blocks, 256, smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
 
 template <int NT, int MT, int MINB>
 static int launch_mlp_fwd_k(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  // edge tile on the vector pipe when the last tile holds one or two real features (width 50: 48, 49)
+  const int nedge = h->ms.width - 8 * (NT - 1);
+  if (h->fwd_edge && NT == 7 && MT == 1 && h->ms.KS <= 2 * NT - 1 && (nedge == 1 || nedge == 2))
+    return nedge == 2 ? launch_mlp_fwd_v<NT, 1, MT, MINB, 2>(h, st, io) : launch_mlp_fwd_v<NT, 1, MT, MINB, 1>(h, st, io);
   return (h->ms.KS <= 2 * NT - 1) ? launch_mlp_fwd_v<NT, 1, MT, MINB>(h, st, io) : launch_mlp_fwd_v<NT, 0, MT, MINB>(h, st, io);
 }
 
@@ -581,6 +586,7 @@ extern "C" int pcx_create(pcx_handle** out, const pcx_mesh_desc* m) {
   if (prop.major < 10) { delete h; return fail(PCX_ERR_UNSUPPORTED, "libpancax_b200 requires an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor); }
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("PCX_FWD_VARIANT")) h->fwd_variant = atoi(e);
+  if (const char* e = getenv("PCX_FWD_EDGE")) h->fwd_edge = atoi(e);
   h->elem_type = m->elem_type; h->q_order = m->q_order;
   h->nd = h->tab.nd; h->nnpe = h->tab.nnpe; h->nq = h->tab.nq;
   h->ndof = m->ndof; h->ne = m->ne; h->nn = m->nn; h->nt = m->nt;
@@ -704,6 +710,7 @@ extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
   s.pFH = p; p += (long long)(s.depth - 1) * KSP * NT * 32;
   s.pFO = p; p += KSP * 32;
   s.pFOB = p; p += 64;
+  s.pFE = p; p += (long long)(s.depth - 1) * KSP * 8;
   s.pBO = p; p += NT * 32;
   s.pBH = p; p += (long long)(s.depth - 1) * KSP * NT * 32;
   s.npacked = p;

@@ -37,7 +37,7 @@ struct MlpShape {
   long long offW[MLP_MAX_LAYERS], offB[MLP_MAX_LAYERS];  // offB = -1 if the layer has no bias
   long long nweights;
   // offsets into the packed-fragment buffer
-  long long pF0, pFB, pFH, pFO, pFOB, pBO, pBH, npacked;
+  long long pF0, pFB, pFH, pFO, pFOB, pFE, pBO, pBH, npacked;
   // input normalisation (fields.py:80-86)
   double x_min[3], x_scale[3];  // x_hat = (x - x_min) / (x_max - x_min); x_scale = x_max - x_min
   double t_min, t_scale;
@@ -73,6 +73,8 @@ __device__ __forceinline__ double2 ld_cs_f64x2(const double* p) {
 //   FH  [depth-1][KSP][NT][32] hidden i>=1: W_i[feat(8jn+r')][4ks+c']
 //   FO  [KSP][32]           output:    W_out[r'][4ks+c']                                  (r' < n_out)
 //   FOB [32][2]             output bias (if any) in accumulator layout: b_out[2c+x]
+//   FE  [depth-1][KSP][4][2] hidden i>=1, rows of features 8(NT-1)+f, f < 2: W_i[8(NT-1)+f][4ks+c]  (edge tile on the
+//                           FP64 vector pipe, see k_mlp_forward NEDGE)
 //   BO  [NT][32]            backward top: W_out[c'][feat(8jn+r')]                          (c' < n_out)
 //   BH  [depth-1][KSP][NT][32] backward hidden i>=1: W_i[4ks+c'][feat(8jn+r')]
 // KSP = 2*NT (padded k-step count so offsets do not depend on width).
@@ -112,12 +114,19 @@ __global__ void k_pack_weights(MlpShape s, const double* __restrict__ w, double*
     int r = lane >> 2, c = lane & 3;
     int k = 4 * ks + c;
     if (r < s.n_out && k < W) val = w[s.offW[D] + (long long)r * W + k];
-  } else if (t < s.pBO) {  // FOB
+  } else if (t < s.pFE) {  // FOB
     t -= s.pFOB;
     int x = t & 1, lane = (int)(t >> 1);
     int c = lane & 3;
     int o = 2 * c + x;
     if (o < s.n_out && s.offB[D] >= 0) val = w[s.offB[D] + o];
+  } else if (t < s.pBO) {  // FE: rows of the last tile's (at most two) real features, [depth-1][KSP][4 c][2 f]
+    t -= s.pFE;
+    int f = t & 1, c = (int)(t >> 1) & 3;
+    long long q = t >> 3;
+    int ks = (int)(q % KSP), i = (int)(q / KSP) + 1;
+    int o = 8 * (NT - 1) + f, k = 4 * ks + c;
+    if (o < W && k < W) val = w[s.offW[i] + (long long)o * W + k];
   } else if (t < s.pBH) {  // BO
     t -= s.pBO;
     int lane = t & 31, jn = (int)(t >> 5);
@@ -310,7 +319,12 @@ __device__ __forceinline__ double tanh_tb(double x, const double* __restrict__ T
 // fragments [F0 | FB | FH | FO | FOB] are staged ONCE per CTA into shared memory with a bulk
 // (TMA) copy and read conflict-free (lane-contiguous); activations are streamed to HBM (.cs).
 // ---------------------------------------------------------------------------------------------
-template <int NT, int KODD, int MT, int MINB>
+// NEDGE = 1 or 2: the last 8-wide tile holds only NEDGE real features (width 50: features 48, 49).  Its 13 DMMAs per
+// hidden layer would be 6/8 padding, and DMMA and DFMA share one datapath, so that tile is computed with DFMAs
+// instead: every lane already holds A-fragment element (row r, feature 4ks+c), multiplies it with the two weight
+// rows W[48..49][4ks+c] (one broadcast LDS.128 per k-step), and a 2-step butterfly over the 4 lanes of a row
+// finishes the sums -- 26 DFMA + 4 DADD + 8 SHFL instead of 13 DMMA (= 104 DFMA issue slots).  NEDGE = 0: off.
+template <int NT, int KODD, int MT, int MINB, int NEDGE>
 __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
@@ -411,13 +425,40 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
           acc[m][jn][1] = b2.y;
         }
       }
+      constexpr int NTD = NEDGE ? NT - 1 : NT;   // tiles computed on the tensor pipe
+      double pe[MT][2];
+#pragma unroll
+      for (int m = 0; m < MT; m++) pe[m][0] = pe[m][1] = 0.0;
+      const double2* fe = reinterpret_cast<const double2*>(pk + s.pFE + (long long)i * KSP * 8) + c;
 #pragma unroll
       for (int ks = 0; ks < KS; ks++) {
 #pragma unroll
-        for (int jn = 0; jn < NT; jn++) {
+        for (int jn = 0; jn < NTD; jn++) {
           const double bf = fh[(ks * NT + jn) * 32 + lane];
 #pragma unroll
           for (int m = 0; m < MT; m++) dmma(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
+        }
+        if constexpr (NEDGE > 0) {
+          const double2 we = fe[ks * 4];
+#pragma unroll
+          for (int m = 0; m < MT; m++) {
+            pe[m][0] = fma(h[m][ks >> 1][ks & 1], we.x, pe[m][0]);
+            if (NEDGE > 1) pe[m][1] = fma(h[m][ks >> 1][ks & 1], we.y, pe[m][1]);
+          }
+        }
+      }
+      if constexpr (NEDGE > 0) {
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+#pragma unroll
+          for (int f = 0; f < NEDGE; f++) {
+            pe[m][f] += __shfl_xor_sync(0xffffffffu, pe[m][f], 1);
+            pe[m][f] += __shfl_xor_sync(0xffffffffu, pe[m][f], 2);
+          }
+          // lane c keeps feature 8(NT-1)+c in register 0 (the bias fragment is already there, 0 beyond NEDGE)
+          const double mine = (c == 0) ? pe[m][0] : (NEDGE > 1 && c == 1) ? pe[m][1] : 0.0;
+          acc[m][NT - 1][0] += mine;
+          acc[m][NT - 1][1] = 0.0;
         }
       }
     }
