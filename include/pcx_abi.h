@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PCX_ABI_VERSION 2
+#define PCX_ABI_VERSION 3
 
 /* error codes */
 #define PCX_OK               0
@@ -63,6 +63,7 @@ extern "C" {
 #define PCX_MODEL_HENCKY     4
 #define PCX_MODEL_BLATZ_KO   5
 #define PCX_MAX_PROPS        8
+#define PCX_MAX_PRONY       20
 
 /* loss kinds: pancax/loss_functions/weak_form_loss_functions.py */
 #define PCX_LOSS_ENERGY                   0  /* EnergyLoss.path_independent_call            :74-88   */
@@ -128,6 +129,14 @@ typedef struct {
   double  prop_max[PCX_MAX_PROPS];
   const double* source_q;     /* Poisson: device f64 [ne*nq], f evaluated at the quadrature
                                  points (poisson.py:17; Python callable tabulated once) or NULL */
+  /* SimpleFeFv (pancax/constitutive_models/mechanics/hyperviscoelasticity/simple_fefv.py:11-14): `model` is the
+   * equilibrium model; n_prony > 0 adds that many non-equilibrium Prony branches (PronySeries.moduli /
+   * .relaxation_times, base.py:20-28), each with a 3x3 viscous deformation gradient per quadrature point as state.
+   * The shift factor is 1, as in the reference (simple_fefv.py:27).  Only the path-dependent EnergyLoss
+   * (pcx_loss_desc.first_step = 1, weak_form_loss_functions.py:48-72) is defined for a model with state. */
+  int32_t n_prony;
+  double  prony_moduli[PCX_MAX_PRONY];
+  double  prony_times[PCX_MAX_PRONY];
 } pcx_physics_desc;
 
 typedef struct {

@@ -49,6 +49,14 @@ CASES = [
 ]
 
 
+# State-variable model: SimpleFeFv around the named equilibrium model, EnergyLoss(is_path_dependent=True)
+# (weak_form_loss_functions.py:48-72): (case name, n, nt, width, depth, q_order)
+VISCO_CASES = [
+    ("hex8_visco_neohookean", 2, 4, 12, 2, 2),
+    ("quad4_visco_gent", 3, 3, 12, 2, 2),
+    ("hex8_visco_hencky", 2, 3, 8, 2, 2),
+]
+
 # first time of the load ramp.  At t = 0 the ramped Dirichlet wrapper gives u = 0, hence f = 0 EXACTLY for
 # Swanson, and the reference's d||f||/df is NaN there; that case starts at t0 > 0 instead.
 # Hencky: at t = 0 (F = I, repeated stretches) the reference's second derivative through eigen_sym33_unit is NaN as
@@ -104,6 +112,11 @@ def main():
                 else:
                     kw[nme] = float(p)
             model = model_cls[case.model](**kw)
+            if case.prony is not None:      # simple_fefv.py:11-14 (the converters of PronySeries' fields applied by hand)
+                from pancax.constitutive_models import PronySeries, SimpleFeFv, WLF
+                model = SimpleFeFv(model, PronySeries(moduli=torch.tensor(case.prony[0], dtype=torch.float64),
+                                                      relaxation_times=torch.tensor(case.prony[1], dtype=torch.float64)),
+                                   WLF(C1=17.44, C2=51.6, theta_ref=60.0))
             form = {"three_dimensional": ThreeDimensional, "plane_strain": PlaneStrain,
                     "plane_stress": PlaneStress}[case.formulation]()
             physics = SolidMechanics(model, form)
@@ -227,6 +240,17 @@ def main():
         for k, v in aux.items():
             out[f"pathdep_quad4_neohookean_n5_nt4_w20_d2__{kind}__aux_{k}"] = np.asarray(v.detach().numpy() if isinstance(v, torch.Tensor) else v)
         print("path-dependent", kind, float(loss), np.linalg.norm(gw))
+
+    # ---------------------------------------------------------------- state variables: SimpleFeFv, path-dependent EnergyLoss
+    for name, n, nt, width, depth, q in VISCO_CASES:
+        case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q)
+        tag = f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}"
+        params, problem, leaves, raws = build(case)
+        loss, aux = EnergyLoss(is_path_dependent=True, weight=LOSS_WEIGHTS["energy_weight"])(params, problem)
+        gw, _ = flat_grad(loss, leaves, raws)
+        out[f"{tag}__energy__loss"], out[f"{tag}__energy__gw"] = np.array(float(loss)), gw
+        out[f"{tag}__energy__aux_energy"] = np.asarray(aux["energy"].detach().numpy())
+        print("visco path-dependent", tag, float(loss), np.linalg.norm(gw), flush=True)
 
     # ---------------------------------------------------------------- strong form
     # Poisson: StrongFormResidualLoss.__call__ (strong_form_loss_functions.py:15-27) -> physics.strong_form_residual

@@ -63,6 +63,7 @@ class OracleProblem:
     reaction_nodes: Optional[np.ndarray] = None
     reaction_dof: int = 0
     global_outputs: Optional[np.ndarray] = None            # (nt,)
+    prony: Optional[tuple] = None                          # (moduli, relaxation_times): SimpleFeFv around `model`
 
 
 def _build(problem: OracleProblem, flat_w, prop_raw):
@@ -79,7 +80,7 @@ def _build(problem: OracleProblem, flat_w, prop_raw):
         else:
             props[p.name] = p.value
     phys = Physics(problem.kind, problem.ndof, problem.model, props, problem.formulation,
-                   problem.source)
+                   problem.source, prony=problem.prony)
     pe = ParentElement(problem.elem, problem.q_order)
     return fld, phys, pe
 
@@ -161,6 +162,24 @@ def loss_value(problem: OracleProblem, loss: dict, w, pr):
     # loss["first_step"] = 1: the path-dependent call of a stateless model (weak_form:48-72,242-276): the scan
     # starts at time step 1; residual / reaction terms are still divided by len(times)
     first = int(loss.get("first_step", 0))
+    if problem.prony is not None:
+        # EnergyLoss.path_dependent_call with state variables (weak_form_loss_functions.py:48-72): the state of
+        # every quadrature point starts at initial_state() (Fv = I per Prony branch, simple_fefv.py:72-75) and is
+        # threaded through the steps n = 1 .. nt-1.  dt: times[1]-times[0] for step 1, and -- the update at the END
+        # of the body, :63 -- times[n-1]-times[n-2] for step n >= 2.
+        from .physics import potential_energy_with_state
+        assert kind == "energy" and first == 1, "state variables: path-dependent EnergyLoss only"
+        ne, nq, nb = conns.shape[0], len(pe.w), len(problem.prony[0])
+        Z = torch.eye(3, dtype=F64).expand(ne, nq, nb, 3, 3).clone()
+        ts = problem.times
+        dt = float(ts[1] - ts[0])
+        energy = 0.0
+        for n in range(1, nt):
+            us = fld(coords, float(ts[n]))
+            pi, Z = potential_energy_with_state(phys, pe, coords, conns, us, Z, dt)
+            energy = energy + pi
+            dt = float(ts[n] - ts[n - 1])
+        return we * energy, dict(energy=energy.detach())
     for t in problem.times[first:]:
         us = fld(coords, float(t))                           # weak_form:42,208,304
         if kind == "energy":

@@ -352,6 +352,32 @@ def blatz_ko_energy(grad_u, G):
     return (G / 2.0) * (I2(grad_u) / I3 + 2.0 * torch.sqrt(I3) - 5.0)
 
 
+def simple_fefv_energy(model, grad_u, props, Z_old, dt, moduli, relaxation_times):
+    """hyperviscoelasticity/simple_fefv.py:20-40,85-108 (SimpleFeFv.energy, a_T = 1 as in the reference :27):
+    psi = psi_eq(grad_u) + sum_b [G_b ||dev Ee_b||^2 + G_b tau_b ||dev Dv_b||^2], per Prony branch b
+      Fe_trial = F Fv_old^-1,  Ee_trial = log_sqrt(Fe_trial^T Fe_trial),
+      dEv = dt / (1 + dt / tau) dev(Ee_trial) / tau,  Ee = Ee_trial - dEv,  Dv = dEv / dt,
+      Fv_new = expm(dEv) Fv_old.
+    grad_u (..., 3, 3), Z_old (..., nb, 3, 3) -> (psi (...), Z_new (..., nb, 3, 3))."""
+    psi = energy(model, grad_u, props)
+    F = deformation_gradient(grad_u)
+    eye = torch.eye(3, dtype=F.dtype)
+    news = []
+    for b, (G, tau) in enumerate(zip(moduli, relaxation_times)):
+        Fv_old = Z_old[..., b, :, :]
+        Fe = F @ torch.linalg.inv(Fv_old)
+        Ee_trial = _MtkLogSqrt.apply(Fe.transpose(-1, -2) @ Fe)
+        dev_tr = Ee_trial - torch.einsum("...ii->...", Ee_trial)[..., None, None] / 3.0 * eye
+        dEv = dt * (1.0 / (1.0 + dt / tau)) * dev_tr / tau                    # state_increment :104-108
+        Ee = Ee_trial - dEv
+        Dv = dEv / dt
+        dev_e = Ee - torch.einsum("...ii->...", Ee)[..., None, None] / 3.0 * eye
+        dev_d = Dv - torch.einsum("...ii->...", Dv)[..., None, None] / 3.0 * eye
+        psi = psi + G * (dev_e * dev_e).sum((-1, -2)) + (G * tau) * (dev_d * dev_d).sum((-1, -2))
+        news.append(torch.linalg.matrix_exp(dEv) @ Fv_old)
+    return psi, torch.stack(news, dim=-3)
+
+
 MODELS = {
     "blatz_ko": (blatz_ko_energy, ("shear_modulus",)),
     "neohookean": (neohookean_energy, ("bulk_modulus", "shear_modulus")),

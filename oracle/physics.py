@@ -19,10 +19,16 @@ class Physics:
     scalars) and formulation in {"plane_strain", "three_dimensional"}.
     pancax/physics_kernels/solid_mechanics.py:86-109; poisson.py:8-19."""
 
-    def __init__(self, kind, ndof, model=None, props=None, formulation=None, source=None):
+    def __init__(self, kind, ndof, model=None, props=None, formulation=None, source=None, prony=None):
         self.kind, self.ndof = kind, ndof
         self.model, self.props, self.formulation = model, props, formulation
         self.source = source  # Poisson f(x): callable on (..., nd) tensors
+        self.prony = prony    # (moduli, relaxation_times): SimpleFeFv around `model` (simple_fefv.py:11-14)
+
+    def energy_density_with_state(self, grad_u, Z_old, dt):
+        """(psi (ne, nq), Z_new (ne, nq, nb, 3, 3)) -- SolidMechanics.energy with a SimpleFeFv model."""
+        return models.simple_fefv_energy(self.model, self.modify_field_gradient(grad_u), self.props, Z_old, dt,
+                                         self.prony[0], self.prony[1])
 
     def energy_density(self, x_q, u_q, grad_u):
         """(ne, nq) energy density.  solid_mechanics.py:102-109 / poisson.py:16-19."""
@@ -121,6 +127,14 @@ def potential_energy(physics: Physics, pe: ParentElement, coords, conns, us):
     x_q, u_q, grad_u, JxW = element_interpolants(pe, X_el, U_el)
     W = physics.energy_density(x_q, u_q, grad_u)
     return (JxW * W).sum(dim=1).sum()
+
+
+def potential_energy_with_state(physics: Physics, pe: ParentElement, coords, conns, us, Z_old, dt):
+    """(Pi, Z_new): base.py:297-307,335-354 with state variables threaded through the element integral."""
+    X_el, U_el = coords[conns], us[conns]
+    _, _, grad_u, JxW = element_interpolants(pe, X_el, U_el)
+    W, Z_new = physics.energy_density_with_state(grad_u, Z_old, dt)
+    return (JxW * W).sum(dim=1).sum(), Z_new
 
 
 def potential_energy_and_internal_force(physics, pe, coords, conns, us, create_graph=False):

@@ -517,6 +517,15 @@ def install():
         setattr(jax, nm, lambda f, *a, _n=nm, **k: _na(_n))
     jsp = types.ModuleType("jax.scipy")
     jsp.linalg = types.ModuleType("jax.scipy.linalg")
+    def _expm(A):
+        # simple_fefv.py:94 (state update).  torch.linalg.matrix_exp on ONE small matrix picks too low a Taylor degree
+        # (measured: 1e-10 absolute error at ||A|| ~ 0.01 .. 0.05 against eigh / a 30-term series; the batched code
+        # path is accurate to 2e-15), so a single matrix goes through the batched path
+        A = _t(A)
+        if A.ndim == 2:
+            return torch.linalg.matrix_exp(torch.stack([A, A]))[0]
+        return torch.linalg.matrix_exp(A)
+    jsp.linalg.expm = _expm
     jax.scipy = jsp
     jnn = types.ModuleType("jax.nn")
     jnn.sigmoid = lambda x: torch.sigmoid(_t(x))

@@ -15,7 +15,7 @@ __version__ = "0.1.0"
 from .bcs import DirichletBC  # noqa: F401,E402
 from .bvps import BiaxialLinearRamp, SimpleShearLinearRamp, UniaxialTensionLinearRamp  # noqa: F401,E402
 from .constitutive_models import (BlatzKo, BoundedProperty, FixedProperty, Gent, Hencky, NeoHookean,  # noqa: F401,E402
-                                  Swanson)
+                                  PronySeries, SimpleFeFv, Swanson, WLF)
 from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E402
 from .domains import CollocationDomain, VariationalDomain  # noqa: F401,E402
 from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, write_exodus_mesh  # noqa: F401,E402

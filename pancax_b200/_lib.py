@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpancax_b200.so")
 
 PCX_MAX_PROPS = 8
+PCX_MAX_PRONY = 20
 PCX_AUX_FIXED = 4
 PROF_CLASSES = ["pack_weights", "mlp_forward", "element_force", "assemble", "element_tangent",
                 "mlp_backward", "reduce_wgrad", "other"]
@@ -53,6 +54,8 @@ class PhysicsDesc(C.Structure):
         ("value", C.c_double * PCX_MAX_PROPS), ("bounded", C.c_int32 * PCX_MAX_PROPS),
         ("prop_min", C.c_double * PCX_MAX_PROPS), ("prop_max", C.c_double * PCX_MAX_PROPS),
         ("source_q", C.c_void_p),
+        ("n_prony", C.c_int32),
+        ("prony_moduli", C.c_double * PCX_MAX_PRONY), ("prony_times", C.c_double * PCX_MAX_PRONY),
     ]
 
 

@@ -95,3 +95,53 @@ class BlatzKo(HyperelasticModel):
     """hyperelasticity/blatz_ko.py:6-24"""
     shear_modulus: Property
     name = "blatz_ko"
+
+
+class PronySeries:
+    """hyperviscoelasticity/base.py:20-31"""
+
+    def __init__(self, moduli, relaxation_times) -> None:
+        assert len(moduli) == len(relaxation_times)
+        self.moduli = np.asarray(moduli, dtype=np.float64)
+        self.relaxation_times = np.asarray(relaxation_times, dtype=np.float64)
+
+    def __len__(self) -> int:
+        return len(self.moduli)
+
+
+class WLF:
+    """hyperviscoelasticity/base.py:47-58.  Carried for interface compatibility: SimpleFeFv.energy uses a_T = 1
+    (simple_fefv.py:26-27, the shift-factor call is commented out in the reference)."""
+
+    def __init__(self, C1, C2, theta_ref):
+        self.C1, self.C2, self.theta_ref = C1, C2, theta_ref
+
+    def shift_factor(self, grad_u, theta, state, dt):
+        return 10.0 ** (-self.C1 * (theta - self.theta_ref) / (self.C2 + (theta - self.theta_ref)))
+
+
+class SimpleFeFv:
+    """hyperviscoelasticity/simple_fefv.py:11-108: equilibrium hyperelastic model + Prony branches, one 3x3 viscous
+    deformation gradient per branch and quadrature point as state (initial_state = identities)."""
+    name = "simple_fefv"
+
+    def __init__(self, eq_model, prony_series: PronySeries, shift_factor_model=None):
+        self.eq_model, self.prony_series, self.shift_factor_model = eq_model, prony_series, shift_factor_model
+
+    def num_prony_terms(self) -> int:
+        return len(self.prony_series)
+
+    @property
+    def num_state_variables(self) -> int:
+        return self.num_prony_terms() * 9
+
+    def initial_state(self):
+        return np.tile(np.eye(3).ravel(), self.num_prony_terms())
+
+    def properties(self):
+        return self.eq_model.properties()
+
+    def __getattr__(self, item):          # the equilibrium model's properties (bulk_modulus, ...)
+        if item in ("eq_model", "prony_series", "shift_factor_model"):
+            raise AttributeError(item)
+        return getattr(self.eq_model, item)

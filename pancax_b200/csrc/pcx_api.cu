@@ -74,6 +74,12 @@ struct pcx_handle {
   long long part_stride = 0;
   double *pk = nullptr, *act = nullptr, *part = nullptr;
   float* pk32 = nullptr;        // TF32-adjoint mode: hi/lo chain weights (k_pack_weights_tf32)
+  // SimpleFeFv (state variables): Fv of every (time step, element, qp, Prony branch) and two adjoint buffers,
+  // allocated on the first path-dependent call
+  double *vz = nullptr, *vlam[2] = {nullptr, nullptr};
+  long long vz_per = 0;
+  struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
+                 const double* lam_in; double* lam_out; } vstep;
   int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT
   double *us = nullptr, *fe = nullptr, *f = nullptr, *v = nullptr, *ubar = nullptr;
   double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
@@ -303,6 +309,16 @@ __global__ void k_chain_props(pcx_physics_desc d, const double* __restrict__ pro
 // ------------------------------------------------------------------------------------------ dispatch helpers
 template <int NNPE, int ND, int NDOF, int MODEL>
 static void launch_element_t(bool tangent, dim3 grid, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+  if constexpr (MODEL != 0) {
+    if (a.n_prony > 0) { k_element<NNPE, ND, NDOF, MODEL, false, 2><<<grid, 128, 0, st>>>(tab, a); return; }   // !tangent (sweep checks)
+    if constexpr (ND == 2) {
+      if (a.plane_stress) {
+        if (tangent) k_element<NNPE, ND, NDOF, MODEL, true, 1><<<grid, 128, 0, st>>>(tab, a);
+        else k_element<NNPE, ND, NDOF, MODEL, false, 1><<<grid, 128, 0, st>>>(tab, a);
+        return;
+      }
+    }
+  }
   if (tangent) k_element<NNPE, ND, NDOF, MODEL, true><<<grid, 128, 0, st>>>(tab, a);
   else k_element<NNPE, ND, NDOF, MODEL, false><<<grid, 128, 0, st>>>(tab, a);
 }
@@ -518,6 +534,9 @@ static void free_ws(pcx_handle* h) {
   h->flags = nullptr;
   if (h->pk32) cudaFree(h->pk32);
   h->pk32 = nullptr;
+  if (h->vz) cudaFree(h->vz);
+  for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
+  h->vz = nullptr; h->vz_per = 0;
 }
 
 static int alloc_ws(pcx_handle* h) {
@@ -640,6 +659,14 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
     else if (p->formulation == PCX_FORM_PLANE_STRESS) { if (h->nd != 2 || h->ndof != 2) return fail(PCX_ERR_INVALID, "PlaneStress needs a 2D mesh and ndof == 2"); }
     else return fail(PCX_ERR_INVALID, "unknown formulation %d", p->formulation);
     if (p->model == PCX_MODEL_SWANSON && p->bounded[7]) return fail(PCX_ERR_INVALID, "Swanson cutoff_strain is static in pancax (swanson.py:26)");
+    if (p->n_prony < 0 || p->n_prony > PCX_MAX_PRONY) return fail(PCX_ERR_INVALID, "n_prony must be 0..%d, got %d", PCX_MAX_PRONY, p->n_prony);
+    if (p->n_prony > 0) {
+      for (int b = 0; b < p->n_prony; b++)
+        if (!(p->prony_times[b] > 0.0)) return fail(PCX_ERR_INVALID, "Prony relaxation time %d must be positive", b);
+      for (int i = 0; i < p->nprops; i++)
+        if (p->bounded[i]) return fail(PCX_ERR_UNSUPPORTED, "trainable properties with a state-variable model are not on the B200 path");
+      if (p->formulation == PCX_FORM_PLANE_STRESS) return fail(PCX_ERR_UNSUPPORTED, "PlaneStress with a state-variable model is not on the B200 path");
+    }
   } else return fail(PCX_ERR_INVALID, "unknown physics %d", p->physics);
   h->phys = *p;
   h->ntrain = 0;
@@ -850,6 +877,14 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
   a.ppart = want_dp ? h->ppart : nullptr;
   a.want_force = want_force ? 1 : 0;
   a.plane_stress = (h->phys.physics == PCX_PHYS_SOLID && h->phys.formulation == PCX_FORM_PLANE_STRESS) ? 1 : 0;
+  if (h->phys.physics == PCX_PHYS_SOLID && h->phys.n_prony > 0) {
+    if (!h->vstep.on || tangent)
+      return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
+                                       "only (pcx_loss_and_grad, kind = PCX_LOSS_ENERGY, first_step = 1)");
+    a.n_prony = h->phys.n_prony;
+    for (int b = 0; b < a.n_prony; b++) { a.prony_kappa[b] = h->vstep.kappa[b]; a.prony_c[b] = h->vstep.c[b]; }
+    a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
+  }
   const long long ndofs = h->nn * h->ndof;
   if (want_force) {
     if (h->deterministic) { a.fe = h->fe; a.f_atomic = nullptr; }
@@ -1042,9 +1077,19 @@ static int launch_pp_m(pcx_handle* h, const double* us, double* F, double* I1, d
   const int epb = 64;
   const int grid = (int)((h->ne + epb - 1) / epb);
   const size_t smem = (size_t)epb * NNPE * sizeof(int32_t);
-#define PCX_PP(M) k_element_pp<NNPE, ND, NDOF, M><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, us, h->props_dev, \
-                                                                           h->phys.nprops, F, I1, P, epb, \
-                                                                           h->phys.formulation == PCX_FORM_PLANE_STRESS ? 1 : 0)
+  const bool pstress = h->phys.formulation == PCX_FORM_PLANE_STRESS;
+#define PCX_PP(M)                                                                                                              \
+  do {                                                                                                                         \
+    if constexpr (ND == 2) {                                                                                                   \
+      if (pstress) {                                                                                                           \
+        k_element_pp<NNPE, ND, NDOF, M, true><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, us, h->props_dev,   \
+                                                                       h->phys.nprops, F, I1, P, epb);                         \
+        break;                                                                                                                 \
+      }                                                                                                                        \
+    }                                                                                                                          \
+    k_element_pp<NNPE, ND, NDOF, M><<<grid, 256, smem, st>>>(h->tab, h->ne, h->coords, h->conns, us, h->props_dev,            \
+                                                             h->phys.nprops, F, I1, P, epb);                                  \
+  } while (0)
   switch (h->phys.model) {
     case PCX_MODEL_NEOHOOKEAN: PCX_PP(PCX_MODEL_NEOHOOKEAN); break;
     case PCX_MODEL_GENT: PCX_PP(PCX_MODEL_GENT); break;
@@ -1063,6 +1108,9 @@ extern "C" int pcx_element_fields(pcx_handle* h, const double* prop_raw, const d
   NEED_READY(h);
   if (h->phys.physics != PCX_PHYS_SOLID) return fail(PCX_ERR_UNSUPPORTED, "element fields exist for SolidMechanics only");
   if (!us) return fail(PCX_ERR_INVALID, "pcx_element_fields: us is null");
+  if (h->phys.n_prony > 0 && P)
+    return fail(PCX_ERR_UNSUPPORTED, "pk1_stress of a model with state variables needs the state history; only F and I1_bar "
+                                     "are available from pcx_element_fields");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = set_props(h, prop_raw, st);
   if (rc) return rc;
@@ -1112,10 +1160,100 @@ extern "C" int pcx_residual_reaction(pcx_handle* h, const double* f, double* out
 }
 
 // ------------------------------------------------------------------------------------------ ABI: fused loss + grad
+// ------------------------------------------------------------------------------------------ models with state variables
+// EnergyLoss.path_dependent_call (weak_form_loss_functions.py:48-72) with SimpleFeFv: the state of every quadrature
+// point starts at initial_state() (Fv = I per Prony branch, simple_fefv.py:72-75) and is threaded through the steps
+// n = 1 .. nt-1 by the lax.scan; jax's gradient is the reverse sweep over the same steps.  Here: field at every step
+// -> forward sweep n = 1.. (energy, states kept) -> reverse sweep n = nt-1 .. 1 (recomputes the step from the kept
+// old state, pulls the adjoint of the new state back to the displacement gradient and to the old state, scatters
+// like an internal force) -> ONE adjoint through the MLP over all (time step, node) rows.
+__global__ void k_fill_identity33(double* __restrict__ z, long long nmat) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < nmat * 9) z[i] = (i % 9) % 4 == 0 ? 1.0 : 0.0;
+}
+
+static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
+                               double* loss_out, double* aux, double* g_weights, cudaStream_t st) {
+  if (L->kind != PCX_LOSS_ENERGY || L->first_step != 1)
+    return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
+                                     "only (kind = PCX_LOSS_ENERGY, first_step = 1)");
+  if (h->nt < 2) return fail(PCX_ERR_INVALID, "the path-dependent call needs at least two time steps");
+  if (h->T < h->nt)
+    return fail(PCX_ERR_UNSUPPORTED, "state-variable models keep every time step's activations: %d steps do not fit the "
+                                     "workspace (PCX_WORKSPACE_GB)", h->nt);
+  const bool want_grad = g_weights != nullptr;
+  const int nb = h->phys.n_prony, nt = h->nt;
+  const long long per = h->ne * h->nq * (long long)nb * 9;
+  if (!h->vz || h->vz_per != per) {
+    if (h->vz) cudaFree(h->vz);
+    for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
+    h->vz = nullptr; h->vz_per = 0;
+    CUDA_TRY(cudaMalloc(&h->vz, (size_t)nt * per * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vlam[1], (size_t)per * sizeof(double)));
+    h->vz_per = per;
+  }
+  int rc;
+  const double we = L->energy_weight;
+  const long long ndofs = h->nn * h->ndof;
+  CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(h->scal, 0, SC_SIZE(h) * sizeof(double), st));
+  if ((rc = set_props(h, prop_raw, st))) return rc;
+  if ((rc = pack_weights(h, weights, st))) return rc;
+  if ((rc = field_forward_steps(h, 0, nt, h->us, want_grad, st))) return rc;
+  k_fill_identity33<<<(int)((per + 255) / 256), 256, 0, st>>>(h->vz, per / 9);
+  LAUNCH_CHECK(h);
+  auto step_constants = [&](int n) {
+    // dt of step n: times[1] - times[0] for n = 1, then the update at the END of the scan body (:63)
+    const double dt = n == 1 ? h->times[1] - h->times[0] : h->times[n - 1] - h->times[n - 2];
+    for (int b = 0; b < nb; b++) {
+      const double G = h->phys.prony_moduli[b], tau = h->phys.prony_times[b];
+      const double c = dt / (tau + dt);   // dt * (1 / (1 + dt / tau)) / tau, simple_fefv.py:104-108
+      h->vstep.c[b] = c;
+      h->vstep.kappa[b] = G * ((1.0 - c) * (1.0 - c) + tau * c * c / (dt * dt));
+    }
+  };
+  h->vstep.on = true;
+  rc = PCX_OK;
+  for (int n = 1; n < nt && !rc; n++) {
+    step_constants(n);
+    h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = h->vz + (long long)n * per;
+    h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
+    rc = sweep(h, false, 1, h->us + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, false, false, st);
+    if (!rc) rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
+  }
+  if (!rc && want_grad) {
+    CUDA_TRY(cudaMemsetAsync(h->vlam[0], 0, (size_t)per * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(h->ubar, 0, (size_t)ndofs * sizeof(double), st));      // step 0 is the initial condition
+    int cur = 0;
+    for (int n = nt - 1; n >= 1 && !rc; n--) {
+      step_constants(n);
+      h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = nullptr;
+      h->vstep.lam_in = h->vlam[cur]; h->vstep.lam_out = h->vlam[cur ^ 1];
+      rc = sweep(h, false, 1, h->us + (long long)n * ndofs, nullptr, h->ubar + (long long)n * ndofs, we, nullptr, 0.0, false, false,
+                 true, st);
+      cur ^= 1;
+    }
+  }
+  h->vstep.on = false;
+  if (rc) return rc;
+  if (want_grad) {
+    bool first = true;
+    if ((rc = field_backward_steps(h, 0, nt, h->ubar, g_weights, first, st))) return rc;
+    if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
+  }
+  k_finish<<<1, 32, 0, st>>>(PCX_LOSS_ENERGY, nt, we, 0.0, 0.0, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
+                             h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux, nullptr, 1.0, 1);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
 extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
                                  double* loss_out, double* aux, double* g_weights, double* g_props, void* stream) {
   NEED_READY(h);
   if (!L || !weights || !loss_out || !aux) return fail(PCX_ERR_INVALID, "pcx_loss_and_grad: null argument");
+  if (h->phys.physics == PCX_PHYS_SOLID && h->phys.n_prony > 0)
+    return visco_loss_and_grad(h, L, weights, prop_raw, loss_out, aux, g_weights, (cudaStream_t)stream);
   const bool want_grad = g_weights != nullptr;   // NULL: value + aux only (loss.__call__)
   const int kind = L->kind;
   if (kind < PCX_LOSS_ENERGY || kind > PCX_LOSS_ENERGY_RESIDUAL_REACTION) return fail(PCX_ERR_INVALID, "unknown loss kind %d", kind);

@@ -48,6 +48,15 @@ struct ElemArgs {
   int nprops;
   int want_force;
   int plane_stress;        // PCX_FORM_PLANE_STRESS: F_33 from the per-point root of sigma_33 = 0 (2D solid only)
+  // SimpleFeFv (hyperviscoelasticity/simple_fefv.py): state Fv [ne][nq][n_prony][9] per quadrature point.
+  // Forward sweep of one time step: z_old -> z_new and the energy.  Reverse sweep: z_old and the adjoint lam_in of
+  // the step's new state -> the stress-like S (scattered like P) and lam_out, the adjoint of the old state.
+  int n_prony;
+  double prony_kappa[PCX_MAX_PRONY], prony_c[PCX_MAX_PRONY];
+  const double* z_old;
+  double* z_new;
+  const double* lam_in;
+  double* lam_out;
 };
 
 template <int ND>
@@ -95,7 +104,9 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 
 // MODEL: 0 = Poisson, else PCX_MODEL_*.  TANGENT: false -> energy + internal force,
 // true -> stiffness action K v (forward-mode duals through the same constitutive source).
-template <int NNPE, int ND, int NDOF, int MODEL, bool TANGENT>
+// VAR: 0 = plain; 1 = PlaneStress (2D solid: per-point root find); 2 = SimpleFeFv (state variables, !TANGENT).  Compile-time
+// variants: as run-time branches they cost the plain kernels half of their speed in register spills.
+template <int NNPE, int ND, int NDOF, int MODEL, bool TANGENT, int VAR = 0>
 __global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
   constexpr int NTH = 128;
   __shared__ double sh[NTH / 32];
@@ -226,11 +237,33 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentT
           for (int i = 0; i < NDOF; i++)
 #pragma unroll
             for (int j = 0; j < ND; j++) F[3 * i + j] += H[i][j];
-          if constexpr (ND == 2) {
-            if (A0.plane_stress && !plane_stress_solve<MODEL>(F, A.props)) bad = true;
+          if constexpr (VAR == 1) {
+            if (!plane_stress_solve<MODEL>(F, A.props)) bad = true;
           }
           double W, P[9], dp[PCX_MAX_PROPS];
           model_eval<MODEL, double>(F, A.props, W, P, dp, want_dp);
+          if constexpr (VAR == 2) {   // equilibrium branch above + the non-equilibrium Prony branches (simple_fefv.py:33-40)
+            const long long zq = (e * tab.nq + q) * (long long)A0.n_prony * 9;
+            for (int b = 0; b < A0.n_prony; b++) {
+              double zo[9], zn[9], li[9], lo[9];
+#pragma unroll
+              for (int i = 0; i < 9; i++) zo[i] = A0.z_old[zq + b * 9 + i];
+              if (A0.lam_out) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) li[i] = A0.lam_in[zq + b * 9 + i];
+              }
+              W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], A0.z_new ? zn : nullptr, A0.lam_out ? li : nullptr,
+                               A0.lam_out ? P : nullptr, lo);
+              if (A0.z_new) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
+              }
+              if (A0.lam_out) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = lo[i];
+              }
+            }
+          }
           if (!(W == W) || fabs(W) > 1.0e300) bad = true;
           Wsum = fma(JxW, W, Wsum);
           if (want_dp) {
@@ -251,9 +284,7 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentT
 #pragma unroll
             for (int j = 0; j < ND; j++) { F[3 * i + j].v += H[i][j]; F[3 * i + j].d = dH[i][j]; }
           Dual W, P[9], dp[PCX_MAX_PROPS];
-          bool ps = false;
-          if constexpr (ND == 2) ps = A0.plane_stress != 0;
-          if (ps) {
+          if constexpr (VAR == 1) {
             double Fv[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) Fv[i] = F[i].v;
@@ -397,12 +428,12 @@ __global__ void __launch_bounds__(256) k_geometry(const __grid_constant__ Parent
 // One thread per (element, qp), connectivity rows staged through shared memory; HBM-bound
 // (19 doubles = 152 B written per point).  F, P: [ne][nq][3][3] row-major; I1bar: [ne][nq].
 // ----------------------------------------------------------------------------------------------
-template <int NNPE, int ND, int NDOF, int MODEL>
+template <int NNPE, int ND, int NDOF, int MODEL, bool PSTRESS = false>
 __global__ void __launch_bounds__(256) k_element_pp(const __grid_constant__ ParentTab tab, long long ne,
                                                     const double* __restrict__ coords, const int32_t* __restrict__ conns,
                                                     const double* __restrict__ us, const double* __restrict__ props_dev,
                                                     int nprops, double* __restrict__ Fout, double* __restrict__ I1out,
-                                                    double* __restrict__ Pout, int epb, int plane_stress) {
+                                                    double* __restrict__ Pout, int epb) {
   extern __shared__ int32_t s_conn[];  // [epb][NNPE]
   __shared__ double s_tile[8 * 32 * 9];
   __shared__ double s_dN[TAB_MAX_NQ * 25];   // parent gradients, row stride 25: lanes with different q hit different banks
@@ -457,9 +488,7 @@ __global__ void __launch_bounds__(256) k_element_pp(const __grid_constant__ Pare
         for (int k = 0; k < ND; k++) s = fma(Gu[i][k], Ji[j * ND + k], s);
         F[3 * i + j] += s;
       }
-    if constexpr (ND == 2 && MODEL != 0) {
-      if (plane_stress) plane_stress_solve<MODEL>(F, props);   // solid_mechanics.py:49-71
-    }
+    if constexpr (PSTRESS) plane_stress_solve<MODEL>(F, props);   // solid_mechanics.py:49-71
     const long long qi = e0 * nq + t;
     if (I1out) {
       // mechanics/base.py:50-63: J^(-2/3) tr(F F^T)

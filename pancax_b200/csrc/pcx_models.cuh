@@ -553,6 +553,129 @@ __device__ inline void model_eval(const T* F, const Props& pr, T& W, T* P, T* dW
   else hencky(F, pr, W, P, dWdp, want_dp);
 }
 
+// ------------------------------------------------------------------ SimpleFeFv (hyperviscoelasticity/simple_fefv.py)
+// One Prony branch (G, tau) of the finite-strain viscoelastic model, state Fv (3x3) per quadrature point:
+//   Fe = F Fv_old^-1,  E = log_sqrt(Fe^T Fe) (mtk_log_sqrt, tensor_math.py:337-424),
+//   dEv = dt / (1 + dt/tau) dev(E) / tau = c dev(E),  Ee = E - dEv,  Dv = dEv / dt       (simple_fefv.py:85-108)
+//   psi = G ||dev Ee||^2 + G tau ||dev Dv||^2 = kappa ||dev E||^2,  kappa = G [(1 - c)^2 + tau c^2 / dt^2]
+//   Fv_new = expm(dEv) Fv_old
+// (c and kappa are computed on the host per step).  Everything is a spectral function of Ce = Fe^T Fe, so ONE
+// closed-form eigen decomposition (the reference's own algorithm) serves the energy, the state update and -- for the
+// reverse sweep over time that jax derives by differentiating the lax.scan -- the adjoints:
+//   psi_bar = 1 (the caller scales by JxW) and lam = adjoint of Fv_new  ->  S += d/dF,  lam_old = adjoint of Fv_old
+//   X = c dev E:   Xbar = V (Gamma o sym(V^T (lam Fv_old^T) V)) V^T, Gamma_ij = (e^xi - e^xj) / (xi - xj)   [d expm]
+//   Ebar = 2 kappa dev E + c dev(Xbar);   Cbar = V (Lambda o (V^T Ebar V)) V^T,  Lambda_ii = 1 / (2 mu_i),
+//          Lambda_ij = (ln mu_i - ln mu_j) / (2 (mu_i - mu_j))                                        [d log_sqrt, self-adjoint]
+//   Febar = 2 Fe Cbar;  S += Febar A^T;  Abar = F^T Febar;  lam_old = expm(X) lam - A^T Abar A^T,  A = Fv_old^-1
+// with both divided differences written through expm1 / log1p so that nothing cancels at repeated stretches (F = I).
+
+__device__ inline void mat33_mul(const double* A, const double* B, double* C) {      // C = A B
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ inline void mat33_mul_tn(const double* A, const double* B, double* C) {   // C = A^T B
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+}
+__device__ inline void mat33_mul_nt(const double* A, const double* B, double* C) {   // C = A B^T
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+
+// F, Fv_old: 3x3 row-major.  Fv_new / lam / S / lam_old may be null (forward sweep: Fv_new only; reverse sweep: the
+// last three).  Returns psi of the branch.
+__device__ inline double fefv_branch(const double* F, const double* Fv_old, double kappa, double c, double* Fv_new,
+                                     const double* lam, double* S, double* lam_old) {
+  double cofv[9], A[9];
+  cofactor3(Fv_old, cofv);
+  const double detv = Fv_old[0] * cofv[0] + Fv_old[1] * cofv[1] + Fv_old[2] * cofv[2];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) A[3 * i + j] = cofv[3 * j + i] / detv;   // inverse = cof^T / det
+  double Fe[9], Ce[9];
+  mat33_mul(F, A, Fe);
+  mat33_mul_tn(Fe, Fe, Ce);
+  double mu[3], V[9];
+  eigen_sym33_unit(Ce, mu, V);
+  const double e[3] = {0.5 * log(mu[0]), 0.5 * log(mu[1]), 0.5 * log(mu[2])};
+  const double eb = (e[0] + e[1] + e[2]) / 3.0;
+  const double de[3] = {e[0] - eb, e[1] - eb, e[2] - eb};
+  const double psi = kappa * (de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+  const double x[3] = {c * de[0], c * de[1], c * de[2]};
+  const double ex[3] = {exp(x[0]), exp(x[1]), exp(x[2])};
+  double expX[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) expX[3 * i + j] = V[3 * i] * ex[0] * V[3 * j] + V[3 * i + 1] * ex[1] * V[3 * j + 1] + V[3 * i + 2] * ex[2] * V[3 * j + 2];
+  if (Fv_new) mat33_mul(expX, Fv_old, Fv_new);
+  if (S) {
+    double Eh[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Eh[i] = 0.0;
+    Eh[0] = 2.0 * kappa * de[0]; Eh[4] = 2.0 * kappa * de[1]; Eh[8] = 2.0 * kappa * de[2];
+    if (lam) {
+      double M[9], T[9], Mh[9];
+      mat33_mul_nt(lam, Fv_old, M);     // lam Fv_old^T
+      mat33_mul_tn(V, M, T);            // V^T M
+      mat33_mul(T, V, Mh);              // V^T M V
+      double Xh[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const double d = x[i] - x[j];
+          const double gam = (i == j || d == 0.0) ? ex[j] : ex[j] * expm1(d) / d;
+          Xh[3 * i + j] = gam * 0.5 * (Mh[3 * i + j] + Mh[3 * j + i]);
+        }
+      const double trX = (Xh[0] + Xh[4] + Xh[8]) / 3.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Eh[3 * i + j] += c * (Xh[3 * i + j] - (i == j ? trX : 0.0));
+      mat33_mul(expX, lam, lam_old);    // expm(X)^T lam, expm(X) symmetric
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; i++) lam_old[i] = 0.0;
+    }
+    double Ch[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        double L;
+        if (i == j) L = 0.5 / mu[i];
+        else {
+          const double xr = (mu[i] - mu[j]) / mu[j];
+          L = 0.5 * ((xr == 0.0) ? 1.0 : log1p(xr) / xr) / mu[j];
+        }
+        Ch[3 * i + j] = L * Eh[3 * i + j];
+      }
+    double T1[9], Cb[9], Feb[9], T2[9], Ab[9];
+    mat33_mul(V, Ch, T1);
+    mat33_mul_nt(T1, V, Cb);            // V Ch V^T
+    mat33_mul(Fe, Cb, Feb);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Feb[i] *= 2.0;
+    mat33_mul_nt(Feb, A, T2);           // Febar A^T
+#pragma unroll
+    for (int i = 0; i < 9; i++) S[i] += T2[i];
+    mat33_mul_tn(F, Feb, Ab);           // F^T Febar
+    mat33_mul_tn(A, Ab, T1);            // A^T Abar
+    mat33_mul_nt(T1, A, T2);            // A^T Abar A^T
+#pragma unroll
+    for (int i = 0; i < 9; i++) lam_old[i] -= T2[i];
+  }
+  return psi;
+}
+
 // ------------------------------------------------------------------ PlaneStress (solid_mechanics.py:32-71)
 // The out-of-plane displacement gradient x = grad_u_33 is the root of sigma_33(x) = 0, which the reference finds
 // per quadrature point with scalar_root_find.find_root (Newton safeguarded by bisection, guess 0.05, bracket

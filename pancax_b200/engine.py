@@ -121,9 +121,11 @@ class Engine:
         self._keep = []
 
     # ------------------------------------------------------------------ setup
-    def set_physics(self, kind, model=None, formulation=None, props=None, source_q=None):
+    def set_physics(self, kind, model=None, formulation=None, props=None, source_q=None, prony=None):
         """kind: "poisson" | "solid".  props: list of floats or (prop_min, prop_max) tuples
-        (trainable BoundedProperty) in the model's property order."""
+        (trainable BoundedProperty) in the model's property order.  prony = (moduli, relaxation_times): the model
+        is the equilibrium branch of a SimpleFeFv viscoelastic model with these Prony branches (state variables:
+        path-dependent EnergyLoss only)."""
         pd = PhysicsDesc()
         if kind == "poisson":
             pd.physics, pd.model, pd.formulation, pd.nprops = PHYS_POISSON, 0, 0, 0
@@ -144,6 +146,13 @@ class Engine:
                     pd.prop_min[i], pd.prop_max[i] = float(p[0]), float(p[1])
                 else:
                     pd.value[i] = float(p)
+            if prony is not None:
+                moduli, taus = [float(v) for v in prony[0]], [float(v) for v in prony[1]]
+                if len(moduli) != len(taus):
+                    raise ValueError("PronySeries: moduli and relaxation_times differ in length")
+                pd.n_prony = len(moduli)
+                for b, (g, t) in enumerate(zip(moduli, taus)):
+                    pd.prony_moduli[b], pd.prony_times[b] = g, t
         else:
             raise ValueError(kind)
         with torch.cuda.device(self.device):

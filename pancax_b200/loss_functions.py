@@ -10,7 +10,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .constitutive_models import BoundedProperty
+from .constitutive_models import BoundedProperty, SimpleFeFv
 from .engine import Engine, tabulate_bc
 from .physics_kernels import BaseStrongFormPhysics, HeatEquation, Poisson, SolidMechanics
 
@@ -99,11 +99,15 @@ def get_engine(problem, params, deterministic: bool = True) -> Engine:
         eng.set_physics("poisson", source_q=np.asarray(phys.f(xq.cpu().numpy()), dtype=np.float64))
     elif isinstance(phys, SolidMechanics):
         model = phys.constitutive_model
+        prony = None
+        if isinstance(model, SimpleFeFv):      # equilibrium model + Prony branches (state variables)
+            prony = (model.prony_series.moduli, model.prony_series.relaxation_times)
+            model = model.eq_model
         props = []
         for name in model.properties():
             p = getattr(model, name)
             props.append((p.prop_min, p.prop_max) if isinstance(p, BoundedProperty) else float(p))
-        eng.set_physics("solid", model.name, phys.formulation.name, props)
+        eng.set_physics("solid", model.name, phys.formulation.name, props, prony=prony)
     else:
         raise NotImplementedError(f"physics {type(phys)} is not on the B200 hot path")
     a = b = None
@@ -140,8 +144,8 @@ class PhysicsLossFunction(BaseLossFunction):
             # weak_form_loss_functions.py:48-72,242-276: the scan starts at time step 1.  Without state variables
             # (every hyperelastic model here) that is the only difference from the path-independent call.
             model = getattr(problem.physics, "constitutive_model", None)
-            if model is not None and model.num_state_variables != 0:
-                raise NotImplementedError("models with state variables are not on the B200 path")
+            if model is not None and model.num_state_variables != 0 and self.kind != "energy":
+                raise NotImplementedError("models with state variables: only the path-dependent EnergyLoss is on the B200 path")
             if self.kind == "energy_residual":
                 raise AssertionError("EnergyAndResidualLoss: path-dependent call is disabled in the reference too "
                                      "(weak_form_loss_functions.py:145-147)")

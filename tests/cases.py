@@ -34,6 +34,7 @@ class Case:
     reaction_nodes: np.ndarray = None
     reaction_dof: int = 0
     global_outputs: np.ndarray = None
+    prony: tuple = None             # (moduli, relaxation_times): SimpleFeFv around `model` (names "..._visco_<model>")
 
     @property
     def prop_raw(self):
@@ -44,7 +45,16 @@ def _prop_names(model):
     return olosses.models.MODELS[model][1]
 
 
+PRONY = ([1.0, 0.5], [10.0, 1.0])   # Prony series of the visco cases: moduli, relaxation times
+
+
 def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=2, t0=0.0) -> Case:
+    if "_visco_" in name:            # hyperviscoelasticity/simple_fefv.py around the named equilibrium model
+        c = make_case(name.replace("_visco_", "_"), n, nt, width, depth, seed, permute, q_order, t0)
+        c.name, c.prony = name, PRONY
+        if c.model == "neohookean":
+            c.props = [10.0, 0.855]  # examples/forward_problems/mechanics/example_hyper_visco_3d.py:59-63
+        return c
     times = np.linspace(t0, 1.0, nt)
     if name.startswith("hex8_"):
         model = name.split("_", 1)[1]
@@ -125,7 +135,7 @@ def oracle_problem(case) -> olosses.OracleProblem:
         formulation=case.formulation, props=props, bc_func=oracle_bc(case),
         source=obvps.poisson_example_source if case.kind == "poisson" else None,
         unknown_idx=case.unknown_idx, reaction_nodes=case.reaction_nodes,
-        reaction_dof=case.reaction_dof, global_outputs=case.global_outputs)
+        reaction_dof=case.reaction_dof, global_outputs=case.global_outputs, prony=case.prony)
 
 
 LOSS_WEIGHTS = dict(energy_weight=1.3, residual_weight=0.7, reaction_weight=2.1)
@@ -170,7 +180,7 @@ def make_engine(case, deterministic=True):
         eng.set_physics("poisson", source_q=poisson_source_np(xq.cpu().numpy()))
     else:
         props = [(p[0], p[1]) if isinstance(p, tuple) else p for p in case.props]
-        eng.set_physics("solid", case.model, case.formulation, props)
+        eng.set_physics("solid", case.model, case.formulation, props, prony=case.prony)
     a = b = None
     bc = engine_bc(case)
     if bc is not None:

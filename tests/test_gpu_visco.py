@@ -1,0 +1,115 @@
+"""GPU parity of the state-variable path: SimpleFeFv (pancax/constitutive_models/mechanics/
+hyperviscoelasticity/simple_fefv.py) under the path-dependent EnergyLoss (weak_form_loss_functions.py:48-72) -- the
+forward sweep over time with the states kept and the reverse sweep jax derives from the lax.scan -- against the CPU
+oracle (torch autograd through the same time loop), which is pinned to vectors produced by executing the reference's
+own SimpleFeFv / path_dependent_call on the stand-in (tests/test_loss_grad_golden.py, cases *_visco_*).
+Tolerance 1e-10 relative (fp64)."""
+import numpy as np
+import pytest
+
+from tests.cases import make_case, make_engine, run_engine_loss, run_oracle_loss
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    n = np.linalg.norm(b.ravel())
+    d = np.linalg.norm((a - b).ravel())
+    return d / n if n > 0 else d
+
+
+@pytest.mark.parametrize("name,n,nt", [("hex8_visco_neohookean", 3, 4), ("hex8_visco_gent", 3, 3), ("hex8_visco_hencky", 2, 3),
+                                       ("hex8_visco_swanson", 2, 3), ("hex8_visco_blatz_ko", 2, 4),
+                                       ("quad4_visco_neohookean", 5, 5), ("tri3_visco_gent", 4, 3)])
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_path_dependent_energy_loss_with_state(cuda_device, name, n, nt, deterministic):
+    case = make_case(name, n=n, nt=nt, width=20, depth=3)
+    L, aux, gw, _ = run_engine_loss(case, "energy", deterministic=deterministic, first_step=1)
+    Lo, auxo, gwo, _ = run_oracle_loss(case, "energy", first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo), (name, L, Lo)
+    assert abs(aux[0] - auxo["energy"]) <= TOL * abs(auxo["energy"])
+    assert aux[3] == 0.0
+    assert rel(gw, gwo) < TOL, (name, rel(gw, gwo))
+
+
+def test_non_uniform_time_steps(cuda_device):
+    """dt of step n is times[1]-times[0] for n = 1 and times[n-1]-times[n-2] afterwards (the update at the end of
+    the scan body, weak_form_loss_functions.py:63) -- visible only with non-uniform times."""
+    case = make_case("hex8_visco_neohookean", n=2, nt=5, width=16, depth=2)
+    case.times = np.array([0.0, 0.1, 0.35, 0.5, 1.0])
+    L, aux, gw, _ = run_engine_loss(case, "energy", first_step=1)
+    Lo, auxo, gwo, _ = run_oracle_loss(case, "energy", first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo)
+    assert rel(gw, gwo) < TOL
+
+
+def test_relaxation_limits(cuda_device):
+    """tau -> infinity: no viscous flow within the steps, every branch adds G ||dev E||^2 of the TOTAL log strain (an
+    elastic Hencky-type shear term); tau -> 0: the branch relaxes completely and only the dissipation term
+    G tau ||dev Dv||^2 -> 0 remains, i.e. the equilibrium model alone."""
+    base = make_case("hex8_neohookean", n=3, nt=3, width=16, depth=2)
+    base.props = [10.0, 0.855]
+    Le, _, ge, _ = run_engine_loss(base, "energy", first_step=1)
+    fast = make_case("hex8_visco_neohookean", n=3, nt=3, width=16, depth=2)
+    fast.prony = ([1.0, 0.5], [1e-9, 1e-10])
+    Lf, _, gf, _ = run_engine_loss(fast, "energy", first_step=1)
+    assert abs(Lf - Le) <= 1e-7 * abs(Le) and rel(gf, ge) < 1e-7
+    slow = make_case("hex8_visco_neohookean", n=3, nt=3, width=16, depth=2)
+    slow.prony = ([1.0], [1e12])
+    Ls, _, _, _ = run_engine_loss(slow, "energy", first_step=1)
+    Lso, _, _, _ = run_oracle_loss(slow, "energy", first_step=1)
+    assert Ls > Le and abs(Ls - Lso) <= TOL * abs(Lso)
+
+
+def test_value_only_and_tf32_adjoint(cuda_device):
+    case = make_case("hex8_visco_neohookean", n=3, nt=4, width=20, depth=3)
+    eng = make_engine(case)
+    L, aux, gw, _ = run_engine_loss(case, "energy", eng=eng, first_step=1)
+    loss, aux2, _, _ = eng.loss_and_grad("energy", case.weights, None, want_grad=False, first_step=1, energy_weight=1.3)
+    assert float(loss.cpu()[0]) == L
+    eng.set_option("tf32_adjoint", 1)
+    L32, _, gw32, _ = run_engine_loss(case, "energy", eng=eng, first_step=1)
+    eng.close()
+    assert L32 == L and rel(gw32, gw) < 1e-5 and np.any(gw32 != gw)
+
+
+def test_state_models_are_refused_elsewhere(cuda_device):
+    from pancax_b200._lib import PcxError
+    case = make_case("hex8_visco_neohookean", n=2, nt=3, width=8, depth=2)
+    eng = make_engine(case)
+    us = np.zeros((eng.nn, 3))
+    with pytest.raises(PcxError, match="state variables"):
+        eng.energy_force(us)
+    with pytest.raises(PcxError, match="state variables"):
+        eng.loss_and_grad("energy", case.weights, None)                       # path-independent call
+    with pytest.raises(PcxError, match="state variables"):
+        eng.loss_and_grad("energy_residual", case.weights, None, first_step=1)
+    eng.close()
+
+
+def test_public_api_example_hyper_visco(cuda_device):
+    """examples/forward_problems/mechanics/example_hyper_visco_3d.py: SimpleFeFv(NeoHookean, PronySeries, WLF) with
+    the path-dependent energy loss and Adam."""
+    import pancax_b200 as px
+    import torch
+    mesh = px.create_structured_mesh("hex8", 3)
+    times = np.linspace(0.0, 1.0, 4)
+    domain = px.VariationalDomain(mesh, times)
+    model = px.SimpleFeFv(px.NeoHookean(bulk_modulus=10.0, shear_modulus=0.855),
+                          px.PronySeries(moduli=[1.0], relaxation_times=[10.0]), px.WLF(C1=17.44, C2=51.6, theta_ref=60.0))
+    physics = px.SolidMechanics(model, px.ThreeDimensional())
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)]
+    problem = px.ForwardProblem(domain, physics, [], bcs, [])
+    params = px.Parameters(problem, key=0, dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
+    loss_fn = px.EnergyLoss(is_path_dependent=True)
+    opt = px.Adam(loss_fn, learning_rate=1e-3, has_aux=True)
+    st = opt.init(params)
+    l0 = None
+    for _ in range(20):
+        params, st, (loss, aux) = opt.step(params, st, problem)
+        l0 = float(loss) if l0 is None else l0
+    assert float(loss) < l0 and torch.isfinite(loss)
+    with pytest.raises(Exception):
+        px.EnergyLoss()(params, problem)      # the path-independent call is undefined for a model with state

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.gen_golden_ad import CASES, T0
+from oracle.gen_golden_ad import CASES, T0, VISCO_CASES
 from tests.cases import make_case, run_engine_loss, run_oracle_loss
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_grad.npz"))
@@ -194,3 +194,29 @@ def test_cuda_matches_reference_path_dependent_call(cuda_device, kind):
         assert abs(aux[1] - float(G[PD + kind + "__aux_residual"])) <= TOL * aux[1]
         assert abs(aux[2] - float(G[PD + kind + "__aux_global_data_loss"])) <= TOL * aux[2]
     eng.close()
+
+
+# ---------------------------------------------------------------- state variables (SimpleFeFv, path-dependent EnergyLoss)
+def _check_visco(out, tag):
+    L, aux, gw, _ = out
+    e = aux["energy"] if isinstance(aux, dict) else aux[0]
+    key = f"{tag}__energy__"
+    assert abs(L - float(G[key + "loss"])) <= TOL * abs(float(G[key + "loss"])), (tag, L, float(G[key + "loss"]))
+    assert abs(float(e) - float(G[key + "aux_energy"])) <= TOL * abs(float(G[key + "aux_energy"]))
+    assert rel(gw, G[key + "gw"]) < TOL, (tag, rel(gw, G[key + "gw"]))
+
+
+@pytest.mark.parametrize("name,n,nt,width,depth,q", VISCO_CASES)
+def test_oracle_matches_reference_visco_path_dependent(name, n, nt, width, depth, q):
+    """The reference's own SimpleFeFv.energy / EnergyLoss.path_dependent_call (lax.scan over the steps, state threaded
+    through, jax.scipy.linalg.expm, mtk_log_sqrt with its registered rule) executed on the stand-in."""
+    case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q)
+    _check_visco(run_oracle_loss(case, "energy", first_step=1), f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,nt,width,depth,q", VISCO_CASES)
+def test_cuda_matches_reference_visco_path_dependent(cuda_device, name, n, nt, width, depth, q):
+    case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q)
+    for det in (True, False):
+        _check_visco(run_engine_loss(case, "energy", deterministic=det, first_step=1), f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}")

@@ -137,6 +137,24 @@ def c5(steps, device, ns):
             torch.cuda.empty_cache()
 
 
+def visco(steps, device, n=64, nt=11):
+    """examples/forward_problems/mechanics/example_hyper_visco_3d.py at scale: SimpleFeFv(NeoHookean, one Prony branch),
+    path-dependent EnergyLoss: forward sweep over the steps with the states kept + reverse sweep + one MLP adjoint."""
+    mesh = px.create_structured_mesh("hex8", (n, n, n), lengths=(1.0, 1.0, 1.0))
+    times = np.linspace(0.0, 1.0, nt)
+    domain = px.VariationalDomain(mesh, times, q_order=2)
+    model = px.SimpleFeFv(px.NeoHookean(bulk_modulus=10.0, shear_modulus=0.855),
+                          px.PronySeries(moduli=[1.0], relaxation_times=[10.0]), px.WLF(C1=17.44, C2=51.6, theta_ref=60.0))
+    physics = px.SolidMechanics(model, px.ThreeDimensional())
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)]
+    problem = px.ForwardProblem(domain, physics, dirichlet_bcs=bcs)
+    params = px.Parameters(problem, key=0, n_layers=4, n_neurons=50, device=device,
+                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
+    evals = n ** 3 * 8 * (nt - 1)     # the scan starts at step 1
+    measure(f"visco: Hex8 {n}^3 ({n ** 3 * 8} qp) SimpleFeFv(NeoHookean, 1 Prony branch), nt={nt}, path-dependent EnergyLoss, "
+            "MLP 4->50x4->3", problem, params, px.EnergyLoss(is_path_dependent=True), (), steps, evals)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c2,c4,c5")
@@ -153,6 +171,8 @@ def main():
         c4(args.steps, device)
     if "c5" in cases:
         c5(args.steps, device, [int(x) for x in args.c5_n.split(",")])
+    if "visco" in cases:
+        visco(args.steps, device)
 
 
 if __name__ == "__main__":
