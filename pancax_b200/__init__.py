@@ -22,7 +22,7 @@ from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, wri
 from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, EnergyLoss,  # noqa: F401,E402
                              EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss)
 from .networks import MLP, Field, Parameters  # noqa: F401,E402
-from .optimizers import Adam  # noqa: F401,E402
+from .optimizers import LBFGS, Adam  # noqa: F401,E402
 from .physics_kernels import HeatEquation, PlaneStrain, PlaneStress, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
 from .post_processor import ExodusPostProcessor, PostProcessor  # noqa: F401,E402
 from .problems import ForwardProblem, InverseProblem  # noqa: F401,E402

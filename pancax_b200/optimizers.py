@@ -1,4 +1,4 @@
-"""pancax/optimizers.py: Adam with init/step (:44-68,142-180).  The update itself is one CUDA
+"""pancax/optimizers.py: Adam with init/step (:44-68,142-180) and LBFGS (:189-417).  The update itself is one CUDA
 kernel per leaf (pcx_adam_step) reproducing optax.chain(scale_by_adam(), scale_by_schedule(
 exponential_decay(lr, transition_steps, decay_rate)), scale(-1)) as the reference composes it."""
 from __future__ import annotations
@@ -143,3 +143,105 @@ class Adam:
                 out = self.device_step(params, state, problem, *args)
         torch.cuda.current_stream().wait_stream(s)
         return g, out
+
+
+class LBFGS:
+    """pancax/optimizers.py:189-417: same constructor / init / step interface.  The reference delegates the update to
+    ``optimistix.LBFGS(rtol, atol)`` (third-party, unpinned, not vendored: PARITY UNPINNED); what is restated here is the
+    published algorithm it implements -- limited-memory BFGS direction by the two-loop recursion over the last
+    ``history`` (s, y) pairs, backtracking Armijo line search (slope 0.1, step halving from 1), Cauchy termination
+    ``|df| < atol + rtol |f|`` and ``||dx|| < atol + rtol ||x||`` -- with every vector operation on the device and the
+    loss + gradient coming from the CUDA library.  One ``step`` = one accepted iterate.  Ensembles are refused like in
+    the reference (:409-417)."""
+
+    def __init__(self, loss_function, has_aux: Optional[bool] = False, jit: Optional[bool] = True,
+                 rtol: Optional[float] = 1.0e-3, atol: Optional[float] = 1.0e-3, options=None, tags=None,
+                 history: int = 10, max_backtracks: int = 20) -> None:
+        self.loss_function, self.has_aux, self.jit = loss_function, has_aux, jit
+        self.rtol, self.atol = float(rtol), float(atol)
+        self.options = {} if options is None else options
+        self.tags = frozenset() if tags is None else tags
+        self.history, self.max_backtracks = int(history), int(max_backtracks)
+
+    def init(self, params, filter_spec: Optional[Any] = None):
+        if filter_spec is None:
+            filter_spec = params.freeze_physics_normalization_filter()
+        if getattr(params, "is_ensemble", False):
+            raise NotImplementedError("Per-ensemble LBFGS is not implemented (optimizers.py:409-417)")
+        return OptimizerState(dict(s=[], y=[], f=None, g=None, done=False), 0, filter_spec, False)
+
+    # flat view of the trainable leaves
+    def _leaves(self, params, spec):
+        out = []
+        if spec.get("fields", True):
+            out.append(params.fields.networks.weights)
+        if spec.get("props", True) and params.prop_raw.numel():
+            out.append(params.prop_raw)
+        return out
+
+    def _eval(self, params, spec, problem, args):
+        (loss, aux), grads = self.loss_function.value_and_grad(params, problem, *args)
+        gs = []
+        if spec.get("fields", True):
+            gs.append(grads.fields.reshape(-1))
+        if spec.get("props", True) and params.prop_raw.numel():
+            gs.append(grads.props.reshape(-1)[:params.prop_raw.numel()])
+        return loss, aux, torch.cat(gs).clone()
+
+    def step(self, params, state: OptimizerState, problem, *args):
+        st, spec = state.opt_state, state.filter_spec
+        leaves = self._leaves(params, spec)
+        x0 = torch.cat([v.reshape(-1) for v in leaves]).clone()
+
+        def set_x(x):
+            o = 0
+            for v in leaves:
+                v.copy_(x[o:o + v.numel()].reshape(v.shape))
+                o += v.numel()
+        if st["f"] is None:
+            st["f"], st["aux"], st["g"] = self._eval(params, spec, problem, args)
+        f0, g0 = st["f"], st["g"]
+        # two-loop recursion: d = -H g
+        q = g0.clone()
+        alphas = []
+        for s_k, y_k in zip(reversed(st["s"]), reversed(st["y"])):
+            rho = 1.0 / torch.dot(y_k, s_k)
+            a = rho * torch.dot(s_k, q)
+            alphas.append((a, rho, s_k, y_k))
+            q -= a * y_k
+        if st["s"]:
+            s_k, y_k = st["s"][-1], st["y"][-1]
+            q *= torch.dot(s_k, y_k) / torch.dot(y_k, y_k)
+        for a, rho, s_k, y_k in reversed(alphas):
+            b = rho * torch.dot(y_k, q)
+            q += (a - b) * s_k
+        d = -q
+        slope = torch.dot(g0, d)
+        if not bool(slope < 0):          # not a descent direction (curvature pairs gone bad): restart from steepest descent
+            st["s"], st["y"] = [], []
+            d, slope = -g0, -torch.dot(g0, g0)
+        t, accepted = 1.0 if st["s"] else float(1.0 / max(1.0, float(g0.norm()))), False
+        for _ in range(self.max_backtracks):
+            set_x(x0 + t * d)
+            f1, aux1, g1 = self._eval(params, spec, problem, args)
+            if bool(torch.isfinite(f1)) and bool(f1 <= f0 + 0.1 * t * slope):
+                accepted = True
+                break
+            t *= 0.5
+        if not accepted:
+            set_x(x0)
+            st["done"] = True
+        else:
+            s_new, y_new = t * d, g1 - g0
+            if bool(torch.dot(s_new, y_new) > 1e-12 * s_new.norm() * y_new.norm()):
+                st["s"].append(s_new)
+                st["y"].append(y_new)
+                if len(st["s"]) > self.history:
+                    st["s"].pop(0)
+                    st["y"].pop(0)
+            df, dx = abs(float(f1 - f0)), float(s_new.norm())
+            st["done"] = df < self.atol + self.rtol * abs(float(f1)) and dx < self.atol + self.rtol * float(x0.norm())
+            st["f"], st["aux"], st["g"] = f1, aux1, g1
+        state.epoch += 1
+        loss = st["f"]
+        return params, state, ((loss, st["aux"]) if self.has_aux else loss)

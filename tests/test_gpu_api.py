@@ -197,6 +197,33 @@ def test_ensemble_step_equals_independent_members(cuda_device, tmp_path):
     assert torch.equal(ens.stacked_weights, w)
 
 
+def test_lbfgs_descends_monotonically_and_beats_adam(cuda_device):
+    """optimizers.py:189-417 interface; the update rule restates optimistix.LBFGS's published algorithm (parity
+    unpinned: third-party, not vendored).  Property checks: every accepted step satisfies the Armijo condition (the
+    loss never increases), and on the small Poisson-like energy it gets lower than Adam in the same number of steps."""
+    import pancax_b200 as px
+    prob, params = _build("quad4", n=8, nt=2, t0=0.0)
+    w0 = params.fields.networks.weights.clone()
+    opt = px.LBFGS(px.EnergyLoss(), has_aux=True)
+    st = opt.init(params)
+    losses = []
+    for _ in range(25):
+        params, st, (loss, aux) = opt.step(params, st, prob)
+        losses.append(float(loss))
+        if st.opt_state["done"]:
+            break
+    assert all(b <= a + 1e-14 * abs(a) for a, b in zip(losses, losses[1:])), losses
+    assert "energy" in aux and len(st.opt_state["s"]) <= 10
+    params.fields.networks.weights.copy_(w0)
+    adam = px.Adam(px.EnergyLoss(), learning_rate=1e-3, has_aux=True)
+    sa = adam.init(params)
+    for _ in range(len(losses)):
+        params, sa, (la, _) = adam.step(params, sa, prob)
+    assert losses[-1] < float(la)
+    with pytest.raises(NotImplementedError):
+        opt.init(px.Parameters(prob, key=np.array([[0, 1], [0, 2]], dtype=np.uint32)))
+
+
 def test_poisson_example_through_the_api(cuda_device):
     """C1: the reference's Poisson example (examples/forward_problems/poisson/variational_example.py)."""
     import math
