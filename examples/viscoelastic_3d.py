@@ -10,8 +10,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pancax_b200 import (Adam, DirichletBC, EnergyLoss, ForwardProblem, NeoHookean, Parameters, PronySeries,   # noqa: E402
-                         SimpleFeFv, SolidMechanics, ThreeDimensional, UniaxialTensionLinearRamp, VariationalDomain, WLF,
+from pancax_b200 import (Adam, DirichletBC, EnergyLoss, ForwardProblem, NeoHookean, Parameters, PostProcessor,   # noqa: E402
+                         PronySeries, SimpleFeFv, SolidMechanics, ThreeDimensional, UniaxialTensionLinearRamp, VariationalDomain, WLF,
                          create_structured_mesh)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -34,3 +34,12 @@ for epoch in range(epochs):
     params, opt_st, loss = opt.step(params, opt_st, problem)
     if epoch % 10 == 0:
         print(epoch, float(loss[0]), flush=True)
+
+# results like the reference's script: nodal displacements, deformation gradient and the state variables (Fv)
+out = os.path.join(os.environ.get("PANCAX_WORKDIR", "/tmp/pancax_b200_example"), "output_visco.e")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+pp = PostProcessor(mesh, "exodus")
+pp.init(params, problem, out, node_variables=["field_values"], element_variables=["deformation_gradient", "state_variables"])
+pp.write_outputs(params, problem)
+pp.close()
+print("wrote", out)

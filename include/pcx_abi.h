@@ -293,6 +293,13 @@ int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weights, const do
                                   const double* src, const double* target, int64_t n, double c_t, double c_lap,
                                   double weight, double* loss_out, double* resid_out, double* g_weights, void* stream);
 
+/* State variables after a path-dependent call of a model with state (SimpleFeFv): the viscous deformation gradients
+ * Fv of time step t_idx, device f64 [ne*nq*n_prony*9] in the reference's state layout (ne, nq, n_prony*9) --
+ * what pancax's post-processor writes as `state_variables` (solid_mechanics.py:157-168, is_state_method).  Valid
+ * after pcx_loss_and_grad (first_step = 1) on this handle; step 0 is initial_state() (identities). */
+int64_t pcx_num_state_variables(const pcx_handle* h);   /* n_prony * 9 per quadrature point (0: no state) */
+int pcx_get_state(pcx_handle* h, int32_t t_idx, double* state, void* stream);
+
 /* number of kernels this library has launched on the handle so far (for bench.py "gpu_launches") */
 int64_t pcx_launch_count(const pcx_handle* h);
 

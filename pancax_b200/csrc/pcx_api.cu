@@ -1248,6 +1248,18 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   return PCX_OK;
 }
 
+extern "C" int64_t pcx_num_state_variables(const pcx_handle* h) { return h && h->have_phys ? 9LL * h->phys.n_prony : -1; }
+
+extern "C" int pcx_get_state(pcx_handle* h, int32_t t_idx, double* state, void* stream) {
+  NEED_READY(h);
+  if (h->phys.n_prony <= 0) return fail(PCX_ERR_STATE, "the constitutive model has no state variables");
+  if (!h->vz) return fail(PCX_ERR_STATE, "no state history yet: run the path-dependent pcx_loss_and_grad first");
+  if (t_idx < 0 || t_idx >= h->nt || !state) return fail(PCX_ERR_INVALID, "pcx_get_state: bad time step or null output");
+  CUDA_TRY(cudaMemcpyAsync(state, h->vz + (long long)t_idx * h->vz_per, (size_t)h->vz_per * sizeof(double), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return PCX_OK;
+}
+
 extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
                                  double* loss_out, double* aux, double* g_weights, double* g_props, void* stream) {
   NEED_READY(h);

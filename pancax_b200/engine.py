@@ -341,6 +341,15 @@ class Engine:
             cur[:] = go
         return cur
 
+    def get_state(self, t_idx):
+        """State variables (ne, nq, n_prony*9) of time step ``t_idx`` after a path-dependent call (SimpleFeFv)."""
+        ns = int(self.lib.pcx_num_state_variables(self.h))
+        if ns <= 0:
+            raise ValueError("the constitutive model has no state variables")
+        out = self._empty(self.ne, self.nq, ns)
+        check(self.lib.pcx_get_state(self.h, int(t_idx), _ptr(out), _stream()))
+        return out
+
     def set_option(self, name, value):
         """``cull_null_steps``: skip the MLP on time steps whose Dirichlet table b is identically zero (exact).
         ``tf32_adjoint``: adjoint through the MLP on the TF32 tensor cores (3xTF32, fp32 activations); loss and aux

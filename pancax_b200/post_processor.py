@@ -47,6 +47,9 @@ def variable_names(problem) -> Dict[str, tuple]:
         names["deformation_gradient"] = output_names("F", "full_tensor")
         names["I1_bar"] = output_names("I1_bar", "scalar")
         names["pk1_stress"] = output_names("P", "full_tensor")
+        ns = getattr(problem.physics.constitutive_model, "num_state_variables", 0)
+        if ns:   # solid_mechanics.py:157-168
+            names["state_variables"] = tuple(f"state_variable_{n + 1}" for n in range(ns))
     return names
 
 
@@ -206,6 +209,9 @@ class ExodusPostProcessor(BasePostProcessor):
                 for q in range(nq):
                     elem_vars[f"{comp}_{q + 1}"] = np.empty((nt, eng.ne))
         want = set(self.element_variables)
+        if "state_variables" in want:
+            # the state history of the path-dependent call (weak_form_loss_functions.py:48-72), kept by the library
+            eng.loss_and_grad("energy", w, pr, want_grad=False, first_step=1)
         for n in range(nt):
             us = eng.field_forward(w, n)
             if "field_values" in self.node_variables:
@@ -217,7 +223,12 @@ class ExodusPostProcessor(BasePostProcessor):
                 f = f.cpu().numpy()
                 for i, nm in enumerate(names["internal_force"]):
                     node_vars[nm][n] = f[:, i]
-            if want:
+            if "state_variables" in want:
+                z = eng.get_state(n).cpu().numpy()                       # (ne, nq, ns)
+                for c, comp in enumerate(names["state_variables"]):
+                    for q in range(nq):
+                        elem_vars[f"{comp}_{q + 1}"][n] = z[:, q, c]
+            if want - {"state_variables"}:
                 F, I1b, P = eng.element_fields(us, pr, want_F="deformation_gradient" in want,
                                                want_I1bar="I1_bar" in want, want_P="pk1_stress" in want)
                 for v, arr in (("deformation_gradient", F), ("I1_bar", I1b), ("pk1_stress", P)):

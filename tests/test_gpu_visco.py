@@ -113,3 +113,50 @@ def test_public_api_example_hyper_visco(cuda_device):
     assert float(loss) < l0 and torch.isfinite(loss)
     with pytest.raises(Exception):
         px.EnergyLoss()(params, problem)      # the path-independent call is undefined for a model with state
+
+
+def test_state_variables_output(cuda_device, tmp_path):
+    """pcx_get_state + the post-processor's `state_variables` (solid_mechanics.py:157-168): the kept state history
+    equals the oracle's threaded state, step 0 is initial_state(), and the Exodus file carries
+    state_variable_{k}_{q} element variables like the reference's example_hyper_visco_3d.py asks for."""
+    import torch
+    import pancax_b200 as px
+    from oracle import losses as ol
+    from oracle.physics import potential_energy_with_state
+    from pancax_b200.post_processor import read_exodus_results
+    from tests.cases import oracle_problem
+    case = make_case("hex8_visco_neohookean", n=2, nt=3, width=12, depth=2)
+    eng = make_engine(case)
+    with pytest.raises(Exception, match="no state history"):
+        eng.get_state(1)
+    run_engine_loss(case, "energy", eng=eng, first_step=1)
+    z0, z2 = eng.get_state(0).cpu().numpy(), eng.get_state(2).cpu().numpy()
+    assert z0.shape == (eng.ne, eng.nq, 18)
+    assert np.array_equal(z0, np.tile(np.eye(3).ravel(), (eng.ne, eng.nq, 2)))
+    prob = oracle_problem(case)
+    w, pr = ol._leaves(prob, case.weights, case.prop_raw)
+    fld, phys, pe = ol._build(prob, w, pr)
+    coords, conns = torch.as_tensor(prob.coords), torch.as_tensor(prob.conns, dtype=torch.long)
+    Z = torch.eye(3, dtype=torch.float64).expand(eng.ne, eng.nq, 2, 3, 3).clone()
+    dt = float(case.times[1] - case.times[0])
+    with torch.no_grad():
+        for n in (1, 2):
+            _, Z = potential_energy_with_state(phys, pe, coords, conns, fld(coords, float(case.times[n])), Z, dt)
+    assert rel(z2, Z.reshape(eng.ne, eng.nq, 18).numpy()) < 1e-12
+    eng.close()
+    # through the public post-processor
+    mesh = px.create_structured_mesh("hex8", 2)
+    times = np.linspace(0.0, 1.0, 3)
+    model = px.SimpleFeFv(px.NeoHookean(bulk_modulus=10.0, shear_modulus=0.855), px.PronySeries([1.0], [10.0]), px.WLF(17.44, 51.6, 60.0))
+    problem = px.ForwardProblem(px.VariationalDomain(mesh, times), px.SolidMechanics(model, px.ThreeDimensional()), [],
+                                [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)], [])
+    params = px.Parameters(problem, 0, n_layers=2, n_neurons=12, dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
+    pp = px.PostProcessor(mesh, "exodus")
+    out = str(tmp_path / "visco.e")
+    pp.init(params, problem, out, node_variables=["field_values"], element_variables=["deformation_gradient", "state_variables"])
+    pp.write_outputs(params, problem)
+    pp.close()
+    _, nod, el = read_exodus_results(out)
+    assert "displ_x" in nod and "state_variable_1_1" in el and "state_variable_9_8" in el and "F_xx_1" in el
+    assert np.allclose(el["state_variable_1_1"][0], 1.0) and np.allclose(el["state_variable_2_1"][0], 0.0)
+    assert not np.allclose(el["state_variable_1_1"][2], 1.0)          # the viscous stretch has evolved by the last step
