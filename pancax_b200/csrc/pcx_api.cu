@@ -76,7 +76,7 @@ struct pcx_handle {
   float* pk32 = nullptr;        // TF32-adjoint mode: hi/lo chain weights (k_pack_weights_tf32)
   // SimpleFeFv (state variables): Fv of every (time step, element, qp, Prony branch) and two adjoint buffers,
   // allocated on the first path-dependent call
-  double *vz = nullptr, *vlam[2] = {nullptr, nullptr};
+  double *vz = nullptr, *vlam[2] = {nullptr, nullptr}, *vus = nullptr;
   long long vz_per = 0;
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
                  const double* lam_in; double* lam_out; } vstep;
@@ -535,8 +535,9 @@ static void free_ws(pcx_handle* h) {
   if (h->pk32) cudaFree(h->pk32);
   h->pk32 = nullptr;
   if (h->vz) cudaFree(h->vz);
+  if (h->vus) cudaFree(h->vus);
   for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
-  h->vz = nullptr; h->vz_per = 0;
+  h->vz = nullptr; h->vus = nullptr; h->vz_per = 0;
 }
 
 static int alloc_ws(pcx_handle* h) {
@@ -864,6 +865,26 @@ static int field_backward_steps(pcx_handle* h, int t0, int T, const double* ubar
   return PCX_OK;
 }
 
+// the same for ONE time step whose activations are not resident: forward again (activations only), then the adjoint
+static int field_backward_recompute(pcx_handle* h, int t, const double* ubar, double* g_weights, bool& first, cudaStream_t st) {
+  if (step_is_null(h, t)) return PCX_OK;
+  MlpIO io = node_io(h, t, 1);
+  io.u = nullptr;
+  int rc = launch_mlp_fwd(h, st, io);
+  if (rc) return rc;
+  io.g_u = ubar;
+  int grid = 0;
+  if ((rc = launch_mlp_bwd(h, st, io, &grid))) return rc;
+  if ((rc = reduce_wgrad(h, grid, first ? g_weights : h->gtmp, st))) return rc;
+  if (!first) {
+    const int thr = 256;
+    k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);
+    LAUNCH_CHECK(h);
+  }
+  first = false;
+  return PCX_OK;
+}
+
 // energy (+force) sweep over T time steps of `us` -> f (assembled, scaled by alpha, + beta*add)
 static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const double* v, double* out, double alpha,
                  const double* add, double beta, bool want_energy, bool want_dp, bool want_force, cudaStream_t st) {
@@ -1178,9 +1199,9 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
                                      "only (kind = PCX_LOSS_ENERGY, first_step = 1)");
   if (h->nt < 2) return fail(PCX_ERR_INVALID, "the path-dependent call needs at least two time steps");
-  if (h->T < h->nt)
-    return fail(PCX_ERR_UNSUPPORTED, "state-variable models keep every time step's activations: %d steps do not fit the "
-                                     "workspace (PCX_WORKSPACE_GB)", h->nt);
+  // the MLP activations of every time step stay resident when the workspace holds them (one adjoint launch over all
+  // rows at the end); otherwise each step's activations are recomputed right before its adjoint in the reverse sweep
+  const bool resident = h->T >= h->nt;
   const bool want_grad = g_weights != nullptr;
   const int nb = h->phys.n_prony, nt = h->nt;
   const long long per = h->ne * h->nq * (long long)nb * 9;
@@ -1188,7 +1209,9 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     if (h->vz) cudaFree(h->vz);
     for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
     h->vz = nullptr; h->vz_per = 0;
+    if (h->vus) { cudaFree(h->vus); h->vus = nullptr; }
     CUDA_TRY(cudaMalloc(&h->vz, (size_t)nt * per * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vus, (size_t)nt * h->nn * h->ndof * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vlam[1], (size_t)per * sizeof(double)));
     h->vz_per = per;
@@ -1200,7 +1223,13 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   CUDA_TRY(cudaMemsetAsync(h->scal, 0, SC_SIZE(h) * sizeof(double), st));
   if ((rc = set_props(h, prop_raw, st))) return rc;
   if ((rc = pack_weights(h, weights, st))) return rc;
-  if ((rc = field_forward_steps(h, 0, nt, h->us, want_grad, st))) return rc;
+  double* us_all = resident ? h->us : h->vus;
+  if (resident) {
+    if ((rc = field_forward_steps(h, 0, nt, us_all, want_grad, st))) return rc;
+  } else {
+    for (int n = 1; n < nt; n++)
+      if ((rc = field_forward_steps(h, n, 1, us_all + (long long)n * ndofs, false, st))) return rc;
+  }
   k_fill_identity33<<<(int)((per + 255) / 256), 256, 0, st>>>(h->vz, per / 9);
   LAUNCH_CHECK(h);
   auto step_constants = [&](int n) {
@@ -1219,27 +1248,32 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     step_constants(n);
     h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = h->vz + (long long)n * per;
     h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
-    rc = sweep(h, false, 1, h->us + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, false, false, st);
+    rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, false, false, st);
     if (!rc) rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
   }
+  bool first = true;
   if (!rc && want_grad) {
     CUDA_TRY(cudaMemsetAsync(h->vlam[0], 0, (size_t)per * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(h->ubar, 0, (size_t)ndofs * sizeof(double), st));      // step 0 is the initial condition
+    if (resident) CUDA_TRY(cudaMemsetAsync(h->ubar, 0, (size_t)ndofs * sizeof(double), st));      // step 0 is the initial condition
     int cur = 0;
     for (int n = nt - 1; n >= 1 && !rc; n--) {
       step_constants(n);
       h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = nullptr;
       h->vstep.lam_in = h->vlam[cur]; h->vstep.lam_out = h->vlam[cur ^ 1];
-      rc = sweep(h, false, 1, h->us + (long long)n * ndofs, nullptr, h->ubar + (long long)n * ndofs, we, nullptr, 0.0, false, false,
-                 true, st);
+      double* ubar_n = resident ? h->ubar + (long long)n * ndofs : h->ubar;
+      rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, ubar_n, we, nullptr, 0.0, false, false, true, st);
       cur ^= 1;
+      if (!rc && !resident) {
+        h->vstep.on = false;
+        rc = field_backward_recompute(h, n, ubar_n, g_weights, first, st);
+        h->vstep.on = true;
+      }
     }
   }
   h->vstep.on = false;
   if (rc) return rc;
   if (want_grad) {
-    bool first = true;
-    if ((rc = field_backward_steps(h, 0, nt, h->ubar, g_weights, first, st))) return rc;
+    if (resident && (rc = field_backward_steps(h, 0, nt, h->ubar, g_weights, first, st))) return rc;
     if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   }
   k_finish<<<1, 32, 0, st>>>(PCX_LOSS_ENERGY, nt, we, 0.0, 0.0, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,

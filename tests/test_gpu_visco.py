@@ -160,3 +160,15 @@ def test_state_variables_output(cuda_device, tmp_path):
     assert "displ_x" in nod and "state_variable_1_1" in el and "state_variable_9_8" in el and "F_xx_1" in el
     assert np.allclose(el["state_variable_1_1"][0], 1.0) and np.allclose(el["state_variable_2_1"][0], 0.0)
     assert not np.allclose(el["state_variable_1_1"][2], 1.0)          # the viscous stretch has evolved by the last step
+
+
+def test_recompute_mode_when_the_workspace_cannot_hold_every_step(cuda_device, monkeypatch):
+    """With fewer resident time steps than nt (here forced with PCX_TCHUNK = 1; in production: PCX_WORKSPACE_GB too
+    small for nt x nodes x 1.8 KB of activations) the reverse sweep recomputes each step's activations right before
+    its MLP adjoint instead of keeping them: same loss, same gradient to rounding."""
+    case = make_case("hex8_visco_gent", n=3, nt=4, width=20, depth=3)
+    ref = run_engine_loss(case, "energy", first_step=1)
+    monkeypatch.setenv("PCX_TCHUNK", "1")
+    got = run_engine_loss(case, "energy", first_step=1)
+    assert got[0] == ref[0]
+    assert rel(got[2], ref[2]) < 1e-13
