@@ -235,7 +235,7 @@ def test_deterministic_bitwise_repeat(cuda_device):
     eng.close()
 
 
-@pytest.mark.parametrize("width,depth", [(10, 2), (20, 1), (30, 3), (50, 3), (50, 5), (55, 2), (60, 2)])
+@pytest.mark.parametrize("width,depth", [(10, 2), (20, 1), (30, 3), (49, 3), (50, 3), (50, 5), (51, 2), (55, 2), (60, 2)])
 def test_mlp_shapes(cuda_device, width, depth):
     case = make_case("quad4_neohookean", n=4, nt=2, width=width, depth=depth)
     L, aux, gw, gp = run_engine_loss(case, "energy")

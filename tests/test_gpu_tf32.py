@@ -79,7 +79,7 @@ def test_tf32_adjoint_matches_oracle(cuda_device, name, kind):
     assert max(errs.values()) < TOL_TF32, errs
 
 
-@pytest.mark.parametrize("width,depth", [(7, 1), (15, 2), (24, 3), (31, 5), (50, 4), (55, 3)])
+@pytest.mark.parametrize("width,depth", [(7, 1), (15, 2), (24, 3), (31, 5), (49, 2), (50, 4), (55, 3)])
 def test_tf32_adjoint_network_shapes(cuda_device, width, depth):
     """Every tile count the kernel is instantiated for (NT = 2, 4, 7) and depths 1..5."""
     case = make_case("quad4_neohookean", n=12, nt=2, width=width, depth=depth)
