@@ -106,8 +106,11 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // true -> stiffness action K v (forward-mode duals through the same constitutive source).
 // VAR: 0 = plain; 1 = PlaneStress (2D solid: per-point root find); 2 = SimpleFeFv (state variables, !TANGENT).  Compile-time
 // variants: as run-time branches they cost the plain kernels half of their speed in register spills.
+// resident CTAs per SM asked of the register allocator: the 3D sweeps want every register (1 -> 255 registers; 3 costs
+// Hex8 +47 % in spills), the 2D tangent sweep is 22 % faster with 3 (168 registers, 12 warps per SM) -- measured
+constexpr int elem_min_blocks(int nd, bool tangent) { return (nd == 2 && tangent) ? 3 : 0; }   // 0 = no request
 template <int NNPE, int ND, int NDOF, int MODEL, bool TANGENT, int VAR = 0>
-__global__ void __launch_bounds__(128) k_element(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+__global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
   constexpr int NTH = 128;
   __shared__ double sh[NTH / 32];
   const long long e = blockIdx.x * (long long)NTH + threadIdx.x;
