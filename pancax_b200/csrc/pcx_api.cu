@@ -1242,6 +1242,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
       h->vstep.kappa[b] = G * ((1.0 - c) * (1.0 - c) + tau * c * c / (dt * dt));
     }
   };
+  struct VStepGuard { pcx_handle* h; ~VStepGuard() { h->vstep.on = false; } } vstep_guard{h};   // also on early error returns
   h->vstep.on = true;
   rc = PCX_OK;
   for (int n = 1; n < nt && !rc; n++) {
