@@ -89,7 +89,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(n, nt, rank, world, device, strong=False):
+SWANSON = dict(bulk_modulus=10.0, A1=0.93074321, P1=-0.07673672, B1=0.0, Q1=0.5, C1=0.10448312, R1=1.71691036,
+               cutoff_strain=0.01)   # test/constitutive_models/test_swanson.py:8-14 (config C5)
+
+
+def build_problem(n, nt, rank, world, device, strong=False, model="neohookean"):
     """--scaling strong: ONE n^3 unit cube cut into `world` z slabs of n x n x (n / world) elements (BASELINE config
     3 read literally: "16M quadrature points ... sharded across 8 GPUs").  Default (weak):
     unit-cube slab [0,1]^2 x [rank, rank+1] of n^3 Hex8 elements per rank (weak scaling: the bar
@@ -104,11 +108,15 @@ def build_problem(n, nt, rank, world, device, strong=False):
         mesh = px.create_structured_mesh("hex8", (n, n, n), lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, float(rank)))
     times = np.linspace(0.0, 1.0, nt)
     domain = px.VariationalDomain(mesh, times, q_order=2)
-    physics = px.SolidMechanics(px.NeoHookean(bulk_modulus=K_BULK, shear_modulus=G_SHEAR), px.ThreeDimensional())
+    cm = {"neohookean": lambda: px.NeoHookean(bulk_modulus=K_BULK, shear_modulus=G_SHEAR),
+          "gent": lambda: px.Gent(bulk_modulus=0.833, shear_modulus=0.3846, Jm_parameter=3.0),
+          "swanson": lambda: px.Swanson(**SWANSON),
+          "hencky": lambda: px.Hencky(bulk_modulus=0.833, shear_modulus=0.3846)}[model]()
+    physics = px.SolidMechanics(cm, px.ThreeDimensional())
     bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)]
     problem = px.ForwardProblem(domain, physics, dirichlet_bcs=bcs)
     params = px.Parameters(problem, key=0, n_layers=DEPTH, n_neurons=WIDTH, device=device,
-                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 3))
+                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(1.0 if model == "neohookean" else 0.5, 1.0, "y", 3))
     lo, hi = parallel.global_bounds(mesh.coords)
     params.fields.x_mins, params.fields.x_maxs = lo, hi
     return problem, params
@@ -126,7 +134,7 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     n, nt = args.n, args.nt
     strong = args.scaling == "strong"
-    problem, params = build_problem(n, nt, rank, world, device, strong)
+    problem, params = build_problem(n, nt, rank, world, device, strong, args.model)
     loss_fn = px.EnergyLoss()
     eng = get_engine(problem, params)
     # Headline numbers evaluate EVERY (time step, node) row like the reference does.  The library's default
@@ -295,7 +303,7 @@ def run_ours(args):
         "metric": "quad-pt loss+grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3: 3D NeoHookean Hex8 {n}^3 {'in total' if strong else 'per GPU'} ({eng.ne * eng.nq} qp per GPU x nt={nt}), EnergyLoss, "
+        "config": {"workload": f"{'C3' if args.model in ('neohookean', 'gent') else 'C5'}: 3D {dict(neohookean='NeoHookean', gent='Gent', swanson='Swanson', hencky='Hencky')[args.model]} Hex8 {n}^3 {'in total' if strong else 'per GPU'} ({eng.ne * eng.nq} qp per GPU x nt={nt}), EnergyLoss, "
                                f"MLP {MLP_IN}->{WIDTH}x{DEPTH}->{MLP_OUT} fp64, weights U(+-1/sqrt(fan_in)) seed 0",
                    "elements_per_gpu": eng.ne, "nodes_per_gpu": eng.nn, "qp_per_gpu": eng.ne * eng.nq, "nt": nt,
                    "parallelism": f"qp-sharded dp{world} (z slabs), one allreduce of loss+grads per step",
@@ -376,10 +384,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=128, help="Hex8 elements per direction per GPU (C3: 128)")
+    ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=128, help="Hex8 elements per direction per GPU (C3: 128)")
     ap.add_argument("--nt", type=int, default=2, help="time steps (C3: 2 or 11)")
     ap.add_argument("--cpu-n", type=int, default=32, help="mesh size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="neohookean", choices=["neohookean", "gent", "swanson", "hencky"],
+                    help="constitutive model (default: the C3 headline; swanson / hencky = config C5)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): n^3 elements per GPU; strong: one n^3 block cut into z slabs")
     args = ap.parse_args()
