@@ -132,7 +132,8 @@ typedef struct {
   /* SimpleFeFv (pancax/constitutive_models/mechanics/hyperviscoelasticity/simple_fefv.py:11-14): `model` is the
    * equilibrium model; n_prony > 0 adds that many non-equilibrium Prony branches (PronySeries.moduli /
    * .relaxation_times, base.py:20-28), each with a 3x3 viscous deformation gradient per quadrature point as state.
-   * The shift factor is 1, as in the reference (simple_fefv.py:27).  Only the path-dependent EnergyLoss
+   * The shift factor is 1, as in the reference (simple_fefv.py:27).  value[] / bounded[] describe the equilibrium
+   * model's properties (trainable ones allowed).  Only the path-dependent EnergyLoss
    * (pcx_loss_desc.first_step = 1, weak_form_loss_functions.py:48-72) is defined for a model with state. */
   int32_t n_prony;
   double  prony_moduli[PCX_MAX_PRONY];

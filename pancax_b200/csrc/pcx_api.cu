@@ -664,8 +664,6 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
     if (p->n_prony > 0) {
       for (int b = 0; b < p->n_prony; b++)
         if (!(p->prony_times[b] > 0.0)) return fail(PCX_ERR_INVALID, "Prony relaxation time %d must be positive", b);
-      for (int i = 0; i < p->nprops; i++)
-        if (p->bounded[i]) return fail(PCX_ERR_UNSUPPORTED, "trainable properties with a state-variable model are not on the B200 path");
       if (p->formulation == PCX_FORM_PLANE_STRESS) return fail(PCX_ERR_UNSUPPORTED, "PlaneStress with a state-variable model is not on the B200 path");
     }
   } else return fail(PCX_ERR_INVALID, "unknown physics %d", p->physics);
@@ -1194,7 +1192,7 @@ __global__ void k_fill_identity33(double* __restrict__ z, long long nmat) {
 }
 
 static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
-                               double* loss_out, double* aux, double* g_weights, cudaStream_t st) {
+                               double* loss_out, double* aux, double* g_weights, double* g_props, cudaStream_t st) {
   if (L->kind != PCX_LOSS_ENERGY || L->first_step != 1)
     return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
                                      "only (kind = PCX_LOSS_ENERGY, first_step = 1)");
@@ -1203,6 +1201,9 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   // rows at the end); otherwise each step's activations are recomputed right before its adjoint in the reverse sweep
   const bool resident = h->T >= h->nt;
   const bool want_grad = g_weights != nullptr;
+  // trainable properties belong to the equilibrium model: the Prony branches and the state evolution do not depend on
+  // them, so d loss / d prop is the plain sum of JxW dpsi_eq/dp over the steps of the forward sweep
+  const bool want_dp = want_grad && g_props != nullptr && h->ntrain > 0;
   const int nb = h->phys.n_prony, nt = h->nt;
   const long long per = h->ne * h->nq * (long long)nb * 9;
   if (!h->vz || h->vz_per != per) {
@@ -1249,8 +1250,11 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     step_constants(n);
     h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = h->vz + (long long)n * per;
     h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
-    rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, false, false, st);
+    rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, want_dp, false, st);
     if (!rc) rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
+    if (!rc && want_dp)
+      rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, 1, h->scal + SC_DPI(h) + (long long)n * PCX_MAX_PROPS,
+                       PCX_MAX_PROPS, st);
   }
   bool first = true;
   if (!rc && want_grad) {
@@ -1278,7 +1282,8 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   }
   k_finish<<<1, 32, 0, st>>>(PCX_LOSS_ENERGY, nt, we, 0.0, 0.0, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
-                             h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux, nullptr, 1.0, 1);
+                             h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
+                             want_dp ? g_props : nullptr, 1.0, 1);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
@@ -1300,7 +1305,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   NEED_READY(h);
   if (!L || !weights || !loss_out || !aux) return fail(PCX_ERR_INVALID, "pcx_loss_and_grad: null argument");
   if (h->phys.physics == PCX_PHYS_SOLID && h->phys.n_prony > 0)
-    return visco_loss_and_grad(h, L, weights, prop_raw, loss_out, aux, g_weights, (cudaStream_t)stream);
+    return visco_loss_and_grad(h, L, weights, prop_raw, loss_out, aux, g_weights, g_props, (cudaStream_t)stream);
   const bool want_grad = g_weights != nullptr;   // NULL: value + aux only (loss.__call__)
   const int kind = L->kind;
   if (kind < PCX_LOSS_ENERGY || kind > PCX_LOSS_ENERGY_RESIDUAL_REACTION) return fail(PCX_ERR_INVALID, "unknown loss kind %d", kind);

@@ -52,7 +52,7 @@ def make_case(name, n=4, nt=2, width=50, depth=4, seed=0, permute=True, q_order=
     if "_visco_" in name:            # hyperviscoelasticity/simple_fefv.py around the named equilibrium model
         c = make_case(name.replace("_visco_", "_"), n, nt, width, depth, seed, permute, q_order, t0)
         c.name, c.prony = name, PRONY
-        if c.model == "neohookean":
+        if c.model == "neohookean" and not any(isinstance(p, tuple) for p in c.props):
             c.props = [10.0, 0.855]  # examples/forward_problems/mechanics/example_hyper_visco_3d.py:59-63
         return c
     times = np.linspace(t0, 1.0, nt)

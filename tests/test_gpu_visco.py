@@ -172,3 +172,16 @@ def test_recompute_mode_when_the_workspace_cannot_hold_every_step(cuda_device, m
     got = run_engine_loss(case, "energy", first_step=1)
     assert got[0] == ref[0]
     assert rel(got[2], ref[2]) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["quad4_visco_neohookean_bounded", "quad4_visco_gent_bounded"])
+def test_trainable_equilibrium_properties(cuda_device, name):
+    """BoundedProperty on the equilibrium model of a SimpleFeFv (examples/inverse_problems/mechanics/path-dependent/
+    script.py:38-48): the Prony branches and the state evolution do not depend on it, d loss / d prop_raw is the sum
+    of JxW dpsi_eq/dp over the steps, chained through the sigmoid."""
+    case = make_case(name, n=5, nt=4, width=16, depth=2)
+    L, aux, gw, gp = run_engine_loss(case, "energy", first_step=1)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy", first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo)
+    assert rel(gw, gwo) < TOL
+    assert gpo.size and rel(gp, gpo) < TOL, (gp, gpo)
