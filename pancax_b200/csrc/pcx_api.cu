@@ -77,6 +77,8 @@ struct pcx_handle {
   // SimpleFeFv (state variables): Fv of every (time step, element, qp, Prony branch) and two adjoint buffers,
   // allocated on the first path-dependent call
   double *vz = nullptr, *vlam[2] = {nullptr, nullptr}, *vus = nullptr;
+  double *vq = nullptr, *vpart = nullptr;   // point fluxes [ne*nq][ndof*nd]; block partials [vnblk][1 + PCX_MAX_PROPS]
+  int vnblk = 0;                            // blocks of the per-point sweep: ceil(ne nq / 128)
   long long vz_per = 0;
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
                  const double* lam_in; double* lam_out; } vstep;
@@ -310,7 +312,6 @@ __global__ void k_chain_props(pcx_physics_desc d, const double* __restrict__ pro
 template <int NNPE, int ND, int NDOF, int MODEL>
 static void launch_element_t(bool tangent, dim3 grid, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
   if constexpr (MODEL != 0) {
-    if (a.n_prony > 0) { k_element<NNPE, ND, NDOF, MODEL, false, 2><<<grid, 128, 0, st>>>(tab, a); return; }   // !tangent (sweep checks)
     if constexpr (ND == 2) {
       if (a.plane_stress) {
         if (tangent) k_element<NNPE, ND, NDOF, MODEL, true, 1><<<grid, 128, 0, st>>>(tab, a);
@@ -332,6 +333,38 @@ static int launch_element_m(int model, bool tangent, dim3 grid, cudaStream_t st,
     case PCX_MODEL_BLATZ_KO: launch_element_t<NNPE, ND, NDOF, PCX_MODEL_BLATZ_KO>(tangent, grid, st, tab, a); return 0;
   }
   return -1;
+}
+
+// SimpleFeFv: per-point sweep (+ scatter of the point fluxes in the reverse sweep)
+template <int NNPE, int ND, int NDOF, int MODEL>
+static void launch_visco_t(bool bwd, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+  if (bwd) {
+    k_visco_qp<NNPE, ND, NDOF, MODEL, true><<<nblk_qp, 128, 0, st>>>(tab, a);
+    k_visco_scatter<NNPE, ND, NDOF><<<nblk_el, 128, 0, st>>>(tab, a);
+  } else {
+    k_visco_qp<NNPE, ND, NDOF, MODEL, false><<<nblk_qp, 128, 0, st>>>(tab, a);
+  }
+}
+template <int NNPE, int ND, int NDOF>
+static int launch_visco_m(int model, bool bwd, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+  switch (model) {
+    case PCX_MODEL_NEOHOOKEAN: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_NEOHOOKEAN>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_GENT: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_GENT>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_SWANSON: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_SWANSON>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_HENCKY: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_HENCKY>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_BLATZ_KO: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_BLATZ_KO>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
+  }
+  return -1;
+}
+static int launch_visco(pcx_handle* h, bool bwd, cudaStream_t st, const ElemArgs& a) {
+  ProfScope ps(h, PCX_PROF_ELEMENT_FORCE, st);
+  int rc;
+  if (h->elem_type == PCX_ELEM_HEX8) rc = launch_visco_m<8, 3, 3>(h->phys.model, bwd, h->vnblk, h->nblk_el, st, h->tab, a);
+  else if (h->elem_type == PCX_ELEM_QUAD4) rc = launch_visco_m<4, 2, 2>(h->phys.model, bwd, h->vnblk, h->nblk_el, st, h->tab, a);
+  else rc = launch_visco_m<3, 2, 2>(h->phys.model, bwd, h->vnblk, h->nblk_el, st, h->tab, a);
+  if (rc) return fail(PCX_ERR_INVALID, "no state-variable kernel for this element/model combination");
+  LAUNCH_CHECK(h);
+  return PCX_OK;
 }
 
 static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, const ElemArgs& a) {
@@ -537,7 +570,9 @@ static void free_ws(pcx_handle* h) {
   if (h->vz) cudaFree(h->vz);
   if (h->vus) cudaFree(h->vus);
   for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
-  h->vz = nullptr; h->vus = nullptr; h->vz_per = 0;
+  if (h->vq) cudaFree(h->vq);
+  if (h->vpart) cudaFree(h->vpart);
+  h->vz = nullptr; h->vus = nullptr; h->vq = nullptr; h->vpart = nullptr; h->vz_per = 0; h->vnblk = 0;
 }
 
 static int alloc_ws(pcx_handle* h) {
@@ -903,6 +938,12 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
     a.n_prony = h->phys.n_prony;
     for (int b = 0; b < a.n_prony; b++) { a.prony_kappa[b] = h->vstep.kappa[b]; a.prony_c[b] = h->vstep.c[b]; }
     a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
+    a.qbuf = h->vq;
+    // the per-point sweep has its own grid: partials [vnblk] and [vnblk][PCX_MAX_PROPS]
+    a.epart = want_energy ? h->vpart : nullptr;
+    a.ppart = want_dp ? h->vpart + h->vnblk : nullptr;
+    if (T != 1 || want_force == (a.z_new != nullptr) || !h->vq)
+      return fail(PCX_ERR_STATE, "state-variable sweep: one time step per launch, forward (states) or reverse (forces)");
   }
   const long long ndofs = h->nn * h->ndof;
   if (want_force) {
@@ -912,7 +953,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
       CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)T * ndofs * sizeof(double), st));
     }
   }
-  int rc = launch_element(h, tangent, T, st, a);
+  int rc = a.n_prony > 0 ? launch_visco(h, want_force, st, a) : launch_element(h, tangent, T, st, a);
   if (rc) return rc;
   if (want_force) {
     const long long n = (long long)T * ndofs;
@@ -1211,6 +1252,11 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
     h->vz = nullptr; h->vz_per = 0;
     if (h->vus) { cudaFree(h->vus); h->vus = nullptr; }
+    if (h->vq) { cudaFree(h->vq); h->vq = nullptr; }
+    if (h->vpart) { cudaFree(h->vpart); h->vpart = nullptr; }
+    h->vnblk = (int)((h->ne * h->nq + 127) / 128);
+    CUDA_TRY(cudaMalloc(&h->vq, (size_t)h->ne * h->nq * h->ndof * h->nd * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vpart, (size_t)h->vnblk * (1 + PCX_MAX_PROPS) * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vz, (size_t)nt * per * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vus, (size_t)nt * h->nn * h->ndof * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
@@ -1251,10 +1297,10 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = h->vz + (long long)n * per;
     h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
     rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, want_dp, false, st);
-    if (!rc) rc = reduce_rows(h, h->epart, h->nblk_el, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
+    if (!rc) rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
     if (!rc && want_dp)
-      rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, 1, h->scal + SC_DPI(h) + (long long)n * PCX_MAX_PROPS,
-                       PCX_MAX_PROPS, st);
+      rc = reduce_rows(h, h->vpart + h->vnblk, h->vnblk, PCX_MAX_PROPS, h->phys.nprops, 1,
+                       h->scal + SC_DPI(h) + (long long)n * PCX_MAX_PROPS, PCX_MAX_PROPS, st);
   }
   bool first = true;
   if (!rc && want_grad) {

@@ -57,6 +57,7 @@ struct ElemArgs {
   double* z_new;
   const double* lam_in;
   double* lam_out;
+  double* qbuf;            // [ne][nq][NDOF][ND] parent-space point fluxes (k_visco_qp -> k_visco_scatter)
 };
 
 template <int ND>
@@ -104,8 +105,8 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 
 // MODEL: 0 = Poisson, else PCX_MODEL_*.  TANGENT: false -> energy + internal force,
 // true -> stiffness action K v (forward-mode duals through the same constitutive source).
-// VAR: 0 = plain; 1 = PlaneStress (2D solid: per-point root find); 2 = SimpleFeFv (state variables, !TANGENT).  Compile-time
-// variants: as run-time branches they cost the plain kernels half of their speed in register spills.
+// VAR: 0 = plain; 1 = PlaneStress (2D solid: per-point root find).  SimpleFeFv has its own per-point kernels below
+// (k_visco_qp).  Compile-time variants: as run-time branches they cost the plain kernels half of their speed in register spills.
 // resident CTAs per SM asked of the register allocator: the 3D sweeps want every register (1 -> 255 registers; 3 costs
 // Hex8 +47 % in spills), the 2D tangent sweep is 22 % faster with 3 (168 registers, 12 warps per SM) -- measured
 constexpr int elem_min_blocks(int nd, bool tangent) { return (nd == 2 && tangent) ? 3 : 0; }   // 0 = no request
@@ -245,28 +246,6 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
           }
           double W, P[9], dp[PCX_MAX_PROPS];
           model_eval<MODEL, double>(F, A.props, W, P, dp, want_dp);
-          if constexpr (VAR == 2) {   // equilibrium branch above + the non-equilibrium Prony branches (simple_fefv.py:33-40)
-            const long long zq = (e * tab.nq + q) * (long long)A0.n_prony * 9;
-            for (int b = 0; b < A0.n_prony; b++) {
-              double zo[9], zn[9], li[9], lo[9];
-#pragma unroll
-              for (int i = 0; i < 9; i++) zo[i] = A0.z_old[zq + b * 9 + i];
-              if (A0.lam_out) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) li[i] = A0.lam_in[zq + b * 9 + i];
-              }
-              W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], A0.z_new ? zn : nullptr, A0.lam_out ? li : nullptr,
-                               A0.lam_out ? P : nullptr, lo);
-              if (A0.z_new) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
-              }
-              if (A0.lam_out) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = lo[i];
-              }
-            }
-          }
           if (!(W == W) || fabs(W) > 1.0e300) bad = true;
           Wsum = fma(JxW, W, Wsum);
           if (want_dp) {
@@ -357,6 +336,168 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
     for (int k = 0; k < A.nprops; k++) {
       const double t = block_sum<NTH>(dps[k], sh);
       if (threadIdx.x == 0) A.ppart[(long long)blockIdx.x * PCX_MAX_PROPS + k] = t;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SimpleFeFv sweeps, one thread per (element, quadrature point).  The state update and its reverse sweep are ~10x the
+// arithmetic of a hyperelastic point and hold ~150 live doubles: one thread per ELEMENT (k_element, VAR = 2) keeps the
+// element's X/U/acc (72 doubles for Hex8) live across them and runs only ne threads, so it spills and under-fills the
+// machine.  Here a point's thread owns nothing but its point: geometry -> F -> branches -> (BWD) Q = JxW S J^-T in
+// parent space [ne][nq][NDOF][ND], which k_visco_scatter contracts with the parent gradients into the element vector.
+// BWD = false: z_old -> z_new, energy (and equilibrium property-gradient) partials per block.
+// BWD = true : z_old, lam_in -> lam_out, Q.
+// ----------------------------------------------------------------------------------------------
+template <int NNPE, int ND, int NDOF, int MODEL, bool BWD>
+__global__ void __launch_bounds__(128) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+  constexpr int NTH = 128;
+  __shared__ double sh[NTH / 32];
+  const int nq = tab.nq;
+  const long long npts = A0.ne * nq;
+  const long long t = blockIdx.x * (long long)NTH + threadIdx.x;
+  const bool live = t < npts;
+  Props props;
+#pragma unroll
+  for (int k = 0; k < PCX_MAX_PROPS; k++) props.p[k] = (k < A0.nprops) ? __ldg(A0.props_dev + k) : 0.0;
+  const bool want_dp = !BWD && A0.ppart != nullptr;
+  double Wq = 0.0;
+  double dps[PCX_MAX_PROPS];
+#pragma unroll
+  for (int k = 0; k < PCX_MAX_PROPS; k++) dps[k] = 0.0;
+  bool bad = false;
+  if (live) {
+    const long long e = t / nq;
+    const int q = (int)(t - e * nq);
+    const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
+    double J[ND * ND], Ji[ND * ND], Gu[NDOF][ND];
+#pragma unroll
+    for (int k = 0; k < ND * ND; k++) J[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+      for (int k = 0; k < ND; k++) Gu[i][k] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NNPE; a++) {
+      const long long n = __ldg(A0.conns + e * NNPE + a);
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        const double x = __ldg(A0.coords + n * ND + j);
+#pragma unroll
+        for (int k = 0; k < ND; k++) J[k * ND + j] = fma(dN[a * 3 + k], x, J[k * ND + j]);
+      }
+#pragma unroll
+      for (int i = 0; i < NDOF; i++) {
+        const double u = __ldg(A0.us + n * NDOF + i);
+#pragma unroll
+        for (int k = 0; k < ND; k++) Gu[i][k] = fma(u, dN[a * 3 + k], Gu[i][k]);
+      }
+    }
+    const double detJ = inv_det<ND>(J, Ji);
+    const double JxW = detJ * tab.w[q];
+    double F[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+#pragma unroll
+    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < ND; k++) s = fma(Gu[i][k], Ji[j * ND + k], s);
+        F[3 * i + j] += s;
+      }
+    double W, P[9], dp[PCX_MAX_PROPS];
+    model_eval<MODEL, double>(F, props, W, P, dp, want_dp);   // equilibrium branch (simple_fefv.py:33-40)
+    const long long zq = t * (long long)A0.n_prony * 9;
+    for (int b = 0; b < A0.n_prony; b++) {
+      double zo[9], zn[9], li[9], lo[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) zo[i] = A0.z_old[zq + b * 9 + i];
+      if constexpr (BWD) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) li[i] = A0.lam_in[zq + b * 9 + i];
+        W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], nullptr, li, P, lo);
+#pragma unroll
+        for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = lo[i];
+      } else {
+        W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], zn, nullptr, nullptr, lo);
+#pragma unroll
+        for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
+      }
+    }
+    if (!(W == W) || fabs(W) > 1.0e300) bad = true;
+    if constexpr (BWD) {
+      double* Q = A0.qbuf + t * (NDOF * ND);
+#pragma unroll
+      for (int i = 0; i < NDOF; i++)
+#pragma unroll
+        for (int k = 0; k < ND; k++) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < ND; j++) s = fma(P[3 * i + j], Ji[j * ND + k], s);
+          Q[i * ND + k] = s * JxW;
+        }
+    } else {
+      Wq = JxW * W;
+      if (want_dp) {
+#pragma unroll
+        for (int k = 0; k < PCX_MAX_PROPS; k++)
+          if (k < A0.nprops) dps[k] = JxW * dp[k];
+      }
+    }
+  }
+  if (bad) atomicOr(A0.flags, 1);
+  if constexpr (!BWD) {
+    if (A0.epart) {
+      const double s = block_sum<NTH>(Wq, sh);
+      if (threadIdx.x == 0) A0.epart[blockIdx.x] = s;
+    }
+    if (want_dp) {
+      for (int k = 0; k < A0.nprops; k++) {
+        const double s = block_sum<NTH>(dps[k], sh);
+        if (threadIdx.x == 0) A0.ppart[(long long)blockIdx.x * PCX_MAX_PROPS + k] = s;
+      }
+    }
+  }
+}
+
+// element vector from the parent-space point fluxes: fe[a][i] = sum_q sum_k Q[q][i][k] dN[q][a][k]
+template <int NNPE, int ND, int NDOF>
+__global__ void __launch_bounds__(128) k_visco_scatter(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+  const long long e = blockIdx.x * 128LL + threadIdx.x;
+  if (e >= A0.ne) return;
+  double acc[NNPE][NDOF];
+#pragma unroll
+  for (int a = 0; a < NNPE; a++)
+#pragma unroll
+    for (int i = 0; i < NDOF; i++) acc[a][i] = 0.0;
+  for (int q = 0; q < tab.nq; q++) {
+    const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
+    const double* Qp = A0.qbuf + (e * tab.nq + q) * (NDOF * ND);
+    double Q[NDOF * ND];
+#pragma unroll
+    for (int i = 0; i < NDOF * ND; i++) Q[i] = Qp[i];
+#pragma unroll
+    for (int a = 0; a < NNPE; a++)
+#pragma unroll
+      for (int i = 0; i < NDOF; i++) {
+        double s = acc[a][i];
+#pragma unroll
+        for (int k = 0; k < ND; k++) s = fma(Q[i * ND + k], dN[a * 3 + k], s);
+        acc[a][i] = s;
+      }
+  }
+  if (A0.fe) {
+    double* o = A0.fe + e * (NNPE * NDOF);
+#pragma unroll
+    for (int a = 0; a < NNPE; a++)
+#pragma unroll
+      for (int i = 0; i < NDOF; i++) o[a * NDOF + i] = acc[a][i];
+  } else {
+#pragma unroll
+    for (int a = 0; a < NNPE; a++) {
+      const long long n = __ldg(A0.conns + e * NNPE + a);
+#pragma unroll
+      for (int i = 0; i < NDOF; i++) atomicAdd(A0.f_atomic + n * NDOF + i, acc[a][i]);
     }
   }
 }

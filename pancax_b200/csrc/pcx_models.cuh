@@ -338,21 +338,19 @@ __device__ inline void eigen_sym33_non_unit(const double* A, double* lam, double
     e2[0] = 0.0; e2[1] = 0.0; e2[2] = 1.0;
   }
   // stable ascending sort of (eval0, eval1, eval2) carrying the vectors (argsort, tensor_math.py:276)
-  double ev[3] = {eval0, eval1, eval2};
-  double* vec[3] = {e0, e1, e2};
-  int idx[3] = {0, 1, 2};
-  // insertion sort (stable)
-  if (ev[idx[1]] < ev[idx[0]]) { int t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
-  if (ev[idx[2]] < ev[idx[1]]) {
-    int t = idx[1]; idx[1] = idx[2]; idx[2] = t;
-    if (ev[idx[1]] < ev[idx[0]]) { t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
-  }
+  // (compare-exchanges on named registers: indexing the vectors through a sorted index array would put them in local memory)
+  auto cswap = [](double& la, double* va, double& lb, double* vb) {
+    const bool sw = lb < la;   // strict: equal eigenvalues keep their order (stable)
+    const double tl = sw ? lb : la; lb = sw ? la : lb; la = tl;
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    lam[k] = ev[idx[k]];
-    const double* s = vec[idx[k]];
-    V[k] = s[0]; V[3 + k] = s[1]; V[6 + k] = s[2];
-  }
+    for (int i = 0; i < 3; i++) { const double tv = sw ? vb[i] : va[i]; vb[i] = sw ? va[i] : vb[i]; va[i] = tv; }
+  };
+  cswap(eval0, e0, eval1, e1);
+  cswap(eval1, e1, eval2, e2);
+  cswap(eval0, e0, eval1, e1);
+  lam[0] = eval0; lam[1] = eval1; lam[2] = eval2;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { V[3 * i] = e0[i]; V[3 * i + 1] = e1[i]; V[3 * i + 2] = e2[i]; }
 }
 
 __device__ inline void eigen_sym33_unit(const double* A, double* lam, double* V) {  // tensor_math.py:281-295
@@ -366,8 +364,8 @@ __device__ inline void eigen_sym33_unit(const double* A, double* lam, double* V)
   eigen_sym33_non_unit(S, lam, V);
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    const double n = sqrt(V[k] * V[k] + V[3 + k] * V[3 + k] + V[6 + k] * V[6 + k]);
-    V[k] /= n; V[3 + k] /= n; V[6 + k] /= n;
+    const double rn = 1.0 / sqrt(V[k] * V[k] + V[3 + k] * V[3 + k] + V[6 + k] * V[6 + k]);
+    V[k] *= rn; V[3 + k] *= rn; V[6 + k] *= rn;
     lam[k] *= cmax;
   }
 }
@@ -595,17 +593,18 @@ __device__ inline double fefv_branch(const double* F, const double* Fv_old, doub
   double cofv[9], A[9];
   cofactor3(Fv_old, cofv);
   const double detv = Fv_old[0] * cofv[0] + Fv_old[1] * cofv[1] + Fv_old[2] * cofv[2];
+  const double rdetv = 1.0 / detv;
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int j = 0; j < 3; j++) A[3 * i + j] = cofv[3 * j + i] / detv;   // inverse = cof^T / det
+    for (int j = 0; j < 3; j++) A[3 * i + j] = cofv[3 * j + i] * rdetv;   // inverse = cof^T / det
   double Fe[9], Ce[9];
   mat33_mul(F, A, Fe);
   mat33_mul_tn(Fe, Fe, Ce);
   double mu[3], V[9];
   eigen_sym33_unit(Ce, mu, V);
   const double e[3] = {0.5 * log(mu[0]), 0.5 * log(mu[1]), 0.5 * log(mu[2])};
-  const double eb = (e[0] + e[1] + e[2]) / 3.0;
+  const double eb = (e[0] + e[1] + e[2]) * (1.0 / 3.0);
   const double de[3] = {e[0] - eb, e[1] - eb, e[2] - eb};
   const double psi = kappa * (de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
   const double x[3] = {c * de[0], c * de[1], c * de[2]};
@@ -626,16 +625,19 @@ __device__ inline double fefv_branch(const double* F, const double* Fv_old, doub
       mat33_mul_nt(lam, Fv_old, M);     // lam Fv_old^T
       mat33_mul_tn(V, M, T);            // V^T M
       mat33_mul(T, V, Mh);              // V^T M V
+      // divided differences of exp at the eigenvalues: gam_ij = (ex_i - ex_j) / (x_i - x_j) = ex_j expm1(d) / d, symmetric
       double Xh[9];
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+      for (int i = 0; i < 3; i++) {
+        Xh[4 * i] = ex[i] * Mh[4 * i];
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
+        for (int j = 0; j < i; j++) {
           const double d = x[i] - x[j];
-          const double gam = (i == j || d == 0.0) ? ex[j] : ex[j] * expm1(d) / d;
-          Xh[3 * i + j] = gam * 0.5 * (Mh[3 * i + j] + Mh[3 * j + i]);
+          const double gam = (d == 0.0) ? ex[j] : ex[j] * expm1(d) / d;
+          Xh[3 * i + j] = Xh[3 * j + i] = gam * 0.5 * (Mh[3 * i + j] + Mh[3 * j + i]);
         }
-      const double trX = (Xh[0] + Xh[4] + Xh[8]) / 3.0;
+      }
+      const double trX = (Xh[0] + Xh[4] + Xh[8]) * (1.0 / 3.0);
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -645,19 +647,20 @@ __device__ inline double fefv_branch(const double* F, const double* Fv_old, doub
 #pragma unroll
       for (int i = 0; i < 9; i++) lam_old[i] = 0.0;
     }
+    // divided differences of 0.5 log at the eigenvalues (symmetric): L_ij = 0.5 (log1p(xr) / xr) / mu_j, xr = (mu_i - mu_j) / mu_j
     double Ch[9];
+    const double rmu[3] = {1.0 / mu[0], 1.0 / mu[1], 1.0 / mu[2]};
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      Ch[4 * i] = 0.5 * rmu[i] * Eh[4 * i];
 #pragma unroll
-      for (int j = 0; j < 3; j++) {
-        double L;
-        if (i == j) L = 0.5 / mu[i];
-        else {
-          const double xr = (mu[i] - mu[j]) / mu[j];
-          L = 0.5 * ((xr == 0.0) ? 1.0 : log1p(xr) / xr) / mu[j];
-        }
+      for (int j = 0; j < i; j++) {
+        const double xr = (mu[i] - mu[j]) * rmu[j];
+        const double L = 0.5 * ((xr == 0.0) ? 1.0 : log1p(xr) / xr) * rmu[j];
         Ch[3 * i + j] = L * Eh[3 * i + j];
+        Ch[3 * j + i] = L * Eh[3 * j + i];
       }
+    }
     double T1[9], Cb[9], Feb[9], T2[9], Ab[9];
     mat33_mul(V, Ch, T1);
     mat33_mul_nt(T1, V, Cb);            // V Ch V^T
