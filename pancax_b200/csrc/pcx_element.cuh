@@ -349,8 +349,14 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 // BWD = false: z_old -> z_new, energy (and equilibrium property-gradient) partials per block.
 // BWD = true : z_old, lam_in -> lam_out, Q.
 // ----------------------------------------------------------------------------------------------
+#ifndef PCX_VISCO_MINB_BWD
+#define PCX_VISCO_MINB_BWD 3
+#endif
+#ifndef PCX_VISCO_MINB_FWD
+#define PCX_VISCO_MINB_FWD 4
+#endif
 template <int NNPE, int ND, int NDOF, int MODEL, bool BWD>
-__global__ void __launch_bounds__(128) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+__global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB_FWD) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
   constexpr int NTH = 128;
   __shared__ double sh[NTH / 32];
   const int nq = tab.nq;
