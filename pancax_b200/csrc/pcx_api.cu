@@ -340,7 +340,7 @@ template <int NNPE, int ND, int NDOF, int MODEL>
 static void launch_visco_t(bool bwd, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
   if (bwd) {
     k_visco_qp<NNPE, ND, NDOF, MODEL, true><<<nblk_qp, 128, 0, st>>>(tab, a);
-    k_visco_scatter<NNPE, ND, NDOF><<<nblk_el, 128, 0, st>>>(tab, a);
+    k_visco_scatter<NNPE, ND, NDOF><<<(unsigned)((a.ne + visco_scatter_epb<NNPE>() - 1) / visco_scatter_epb<NNPE>()), 128, 0, st>>>(tab, a);
   } else {
     k_visco_qp<NNPE, ND, NDOF, MODEL, false><<<nblk_qp, 128, 0, st>>>(tab, a);
   }

@@ -466,45 +466,50 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
   }
 }
 
-// element vector from the parent-space point fluxes: fe[a][i] = sum_q sum_k Q[q][i][k] dN[q][a][k]
+// element vector from the parent-space point fluxes: fe[a][i] = sum_q sum_k Q[q][i][k] dN[q][a][k].
+// One thread per (element, node): the block's fluxes (EPB elements, contiguous) are staged through shared memory with
+// coalesced loads, each thread contracts its node's NDOF components and writes them contiguously (HBM-bound:
+// nq NDOF ND + NNPE NDOF doubles per element).
+template <int NNPE>
+__host__ __device__ constexpr int visco_scatter_epb() { return 128 / NNPE; }
 template <int NNPE, int ND, int NDOF>
 __global__ void __launch_bounds__(128) k_visco_scatter(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
-  const long long e = blockIdx.x * 128LL + threadIdx.x;
-  if (e >= A0.ne) return;
-  double acc[NNPE][NDOF];
-#pragma unroll
-  for (int a = 0; a < NNPE; a++)
-#pragma unroll
-    for (int i = 0; i < NDOF; i++) acc[a][i] = 0.0;
-  for (int q = 0; q < tab.nq; q++) {
-    const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
-    const double* Qp = A0.qbuf + (e * tab.nq + q) * (NDOF * ND);
-    double Q[NDOF * ND];
-#pragma unroll
-    for (int i = 0; i < NDOF * ND; i++) Q[i] = Qp[i];
-#pragma unroll
-    for (int a = 0; a < NNPE; a++)
-#pragma unroll
-      for (int i = 0; i < NDOF; i++) {
-        double s = acc[a][i];
-#pragma unroll
-        for (int k = 0; k < ND; k++) s = fma(Q[i * ND + k], dN[a * 3 + k], s);
-        acc[a][i] = s;
-      }
+  constexpr int EPB = visco_scatter_epb<NNPE>();
+  constexpr int QW = NDOF * ND;
+  __shared__ double s_dN[TAB_MAX_NQ * TAB_MAX_NNPE * 3];
+  __shared__ double s_Q[EPB * (TAB_MAX_NQ * QW + 1)];   // +1: elements of one warp on different banks
+  const int nq = tab.nq;
+  const int stride = nq * QW + 1;
+  for (int i = threadIdx.x; i < TAB_MAX_NQ * TAB_MAX_NNPE * 3; i += 128) s_dN[i] = tab.dN[i];
+  const long long e0 = blockIdx.x * (long long)EPB;
+  const int nloc = (int)min((long long)EPB, A0.ne - e0);
+  const double* Qg = A0.qbuf + e0 * nq * QW;
+  for (int i = threadIdx.x; i < nloc * nq * QW; i += 128) {
+    const int el = i / (nq * QW);
+    s_Q[el * stride + (i - el * nq * QW)] = Qg[i];
   }
+  __syncthreads();
+  const int el = threadIdx.x / NNPE, a = threadIdx.x - el * NNPE;
+  if (el >= nloc) return;
+  double acc[NDOF];
+#pragma unroll
+  for (int i = 0; i < NDOF; i++) acc[i] = 0.0;
+  for (int q = 0; q < nq; q++) {
+    const double* Q = s_Q + el * stride + q * QW;
+    const double* dN = s_dN + q * (TAB_MAX_NNPE * 3) + a * 3;
+#pragma unroll
+    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+      for (int k = 0; k < ND; k++) acc[i] = fma(Q[i * ND + k], dN[k], acc[i]);
+  }
+  const long long e = e0 + el;
   if (A0.fe) {
-    double* o = A0.fe + e * (NNPE * NDOF);
 #pragma unroll
-    for (int a = 0; a < NNPE; a++)
-#pragma unroll
-      for (int i = 0; i < NDOF; i++) o[a * NDOF + i] = acc[a][i];
+    for (int i = 0; i < NDOF; i++) A0.fe[(e * NNPE + a) * NDOF + i] = acc[i];
   } else {
+    const long long n = __ldg(A0.conns + e * NNPE + a);
 #pragma unroll
-    for (int a = 0; a < NNPE; a++) {
-      const long long n = __ldg(A0.conns + e * NNPE + a);
-#pragma unroll
-      for (int i = 0; i < NDOF; i++) atomicAdd(A0.f_atomic + n * NDOF + i, acc[a][i]);
-    }
+    for (int i = 0; i < NDOF; i++) atomicAdd(A0.f_atomic + n * NDOF + i, acc[i]);
   }
 }
 
