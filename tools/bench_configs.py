@@ -8,7 +8,9 @@ host-mirror API, in both adjoint modes (fp64 DMMA / TF32 tensor cores).  One JSO
       (analytic uniaxial field + N(0, 1e-4) noise, seed 0) + synthetic global force-displacement data
   C5  3D Swanson / Hencky Hex8 n^3 sweep (1 M .. 128 M qp), EnergyLoss, MLP 4->50x4->3
 
-    python tools/bench_configs.py [--cases c2,c4,c5] [--c5-n 50,100,159,252] [--steps 5]
+  R3D 3D residual / reaction loss on Hex8 100^3 (NeoHookean / Swanson / Hencky): the stiffness-action sweep in 3D
+
+    python tools/bench_configs.py [--cases c2,c4,c5,visco,r3d] [--c5-n 50,100,159,252] [--steps 5]
 
 Every (time step, node) row is evaluated (null-step culling off), deterministic assembly, CUDA events on the
 launching stream, inputs resident.  Not the bench.py contract: no e2e / CPU arm here."""
@@ -137,6 +139,25 @@ def c5(steps, device, ns):
             torch.cuda.empty_cache()
 
 
+def r3d(steps, device, n=100, nt=2):
+    """3D residual / reaction loss (the inverse-problem loss on a Hex8 block): adds the stiffness-action sweep K v."""
+    mesh = px.create_structured_mesh("hex8", (n, n, n), lengths=(1.0, 1.0, 1.0))
+    times = np.linspace(0.0, 1.0, nt)
+    domain = px.VariationalDomain(mesh, times, q_order=2)
+    for model_name, model in (("neohookean", px.NeoHookean(bulk_modulus=0.833, shear_modulus=0.3846)),
+                              ("swanson", px.Swanson(**SWANSON)),
+                              ("hencky", px.Hencky(bulk_modulus=0.833, shear_modulus=0.3846))):
+        physics = px.SolidMechanics(model, px.ThreeDimensional())
+        bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)]
+        gd = px.GlobalData.from_arrays(times, 0.1 * times, mesh.nodeSets["nset_5"], 1)
+        problem = px.InverseProblem(domain, physics, None, gd, dirichlet_bcs=bcs)
+        params = px.Parameters(problem, key=0, n_layers=4, n_neurons=50, device=device,
+                               dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
+        measure(f"R3D Hex8 {n}^3 ({n ** 3 * 8} qp) {model_name}, nt={nt}, EnergyResidualAndReactionLoss, MLP 4->50x4->3",
+                problem, params, px.EnergyResidualAndReactionLoss(), (), steps, n ** 3 * 8 * nt)
+        problem._engines.clear()
+
+
 def visco(steps, device, n=64, nt=11):
     """examples/forward_problems/mechanics/example_hyper_visco_3d.py at scale: SimpleFeFv(NeoHookean, one Prony branch),
     path-dependent EnergyLoss: forward sweep over the steps with the states kept + reverse sweep + one MLP adjoint."""
@@ -173,6 +194,8 @@ def main():
         c5(args.steps, device, [int(x) for x in args.c5_n.split(",")])
     if "visco" in cases:
         visco(args.steps, device)
+    if "r3d" in cases:
+        r3d(args.steps, device)
 
 
 if __name__ == "__main__":
