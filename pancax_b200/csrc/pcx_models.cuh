@@ -431,9 +431,10 @@ __device__ inline void hencky(const Dual* F, const Props& pr, Dual& W, Dual* P, 
   eigen_sym33_unit(C, mu, V);
   const double e[3] = {0.5 * log(mu[0]), 0.5 * log(mu[1]), 0.5 * log(mu[2])};
   const double trE = e[0] + e[1] + e[2];
+  const double rmu[3] = {1.0 / mu[0], 1.0 / mu[1], 1.0 / mu[2]};   // one reciprocal per stretch instead of a division per use
   double w[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) w[i] = (K * trE + 2.0 * G * e[i]) / (2.0 * mu[i]);
+  for (int i = 0; i < 3; i++) w[i] = (K * trE + 2.0 * G * e[i]) * (0.5 * rmu[i]);
   // FV = F V, dFV = dF V (columns = eigen directions)
   double FV[9], dFV[9];
 #pragma unroll
@@ -460,16 +461,16 @@ __device__ inline void hencky(const Dual* F, const Props& pr, Dual& W, Dual* P, 
   for (int i = 0; i < 3; i++) {
     double sacc = 0.0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) sacc += K / (4.0 * mu[i] * mu[k]) * D[4 * k];
-    M[4 * i] = sacc + (G - K * trE - 2.0 * G * e[i]) / (2.0 * mu[i] * mu[i]) * D[4 * i];
+    for (int k = 0; k < 3; k++) sacc += K * (0.25 * rmu[i] * rmu[k]) * D[4 * k];
+    M[4 * i] = sacc + (G - K * trE - 2.0 * G * e[i]) * (0.5 * rmu[i] * rmu[i]) * D[4 * i];
   }
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = i + 1; j < 3; j++) {
-      const double x = (mu[i] - mu[j]) / mu[j];
+      const double x = (mu[i] - mu[j]) * rmu[j];
       const double gx = (x == 0.0) ? 1.0 : log1p(x) / x;
-      const double dd = (-K * trE + G * (gx - 2.0 * e[j])) / (2.0 * mu[i] * mu[j]);
+      const double dd = (-K * trE + G * (gx - 2.0 * e[j])) * (0.5 * rmu[i] * rmu[j]);
       M[3 * i + j] = M[3 * j + i] = dd * 0.5 * (D[3 * i + j] + D[3 * j + i]);
     }
   // dP = 2 (dF S + F dS) = 2 (dFV diag(w) + FV M) V^T ;  P = 2 FV diag(w) V^T
@@ -499,8 +500,8 @@ __device__ inline void hencky(const Dual* F, const Props& pr, Dual& W, Dual* P, 
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       const double q = 0.5 * D[4 * i];   // (F V)_i . (dF V)_i
-      tK += trE / mu[i] * q;
-      tG += 2.0 * e[i] / mu[i] * q;
+      tK += trE * rmu[i] * q;
+      tG += 2.0 * e[i] * rmu[i] * q;
     }
     dWdp[0] = Dual(0.5 * trE * trE, tK);
     dWdp[1] = Dual(EE, tG);
@@ -686,7 +687,7 @@ __device__ inline double fefv_branch(const double* F, const double* Fv_old, doub
 // sigma_33 = P_33 F_33 / J, so the root is that of P_33 = dW/dx.  Here: the same safeguarded Newton iteration on
 // P_33, its derivative from one dual-number evaluation seeded on F_33, started from the incompressible estimate
 // F_33 = 1 / det F_2D (2 - 4 iterations instead of the reference's ~8 from 0.05; the root in the bracket is unique,
-// P_33 increases with x), iterated to |dx| < 1e-15 (tighter than the reference's 1e-13, so both agree to 1e-13).
+// P_33 increases with x), iterated to |dx| < 1e-15 or to the rounding floor (tighter than the reference's 1e-13, so both agree to 1e-13).
 // F: in-plane entries set, F[8] ignored on entry; on exit F[8] = 1 + x.  Returns false if 60 iterations did not converge.
 template <int MODEL>
 __device__ inline bool plane_stress_solve(double* F, const Props& pr) {
@@ -695,6 +696,7 @@ __device__ inline bool plane_stress_solve(double* F, const Props& pr) {
   double x = fmin(fmax(1.0 / j2 - 1.0, lo), hi);
   if (!(x == x)) x = 0.05;
   bool ok = false;
+  double dx_prev = 1.0e300;
 #pragma unroll 1
   for (int it = 0; it < 60; it++) {
     Dual Fd[9];
@@ -706,10 +708,18 @@ __device__ inline bool plane_stress_solve(double* F, const Props& pr) {
     const double g = P[8].v, dg = P[8].d;
     if (g < 0.0) lo = x; else hi = x;
     double xn = x - g / dg;
-    if (!(xn > lo) || !(xn < hi) || !(dg > 0.0)) xn = 0.5 * (lo + hi);   // bisection step (rtsafe)
-    const double dx = xn - x;
+    // a Newton step that lands ON a bracket end (an earlier iterate sat on the root to rounding and became that end) is
+    // the root, not an escape: taking it ends the iteration, bisecting instead would halve the bracket ~50 more times
+    const double slack = 8.0 * 2.220446049250313e-16 * fmax(1.0, fabs(x));
+    if (dg > 0.0 && xn <= lo && xn >= lo - slack) xn = lo;
+    else if (dg > 0.0 && xn >= hi && xn <= hi + slack) xn = hi;
+    else if (!(xn > lo) || !(xn < hi) || !(dg > 0.0)) xn = 0.5 * (lo + hi);   // bisection step (rtsafe)
+    const double dx = fabs(xn - x);
     x = xn;
-    if (fabs(dx) < 1.0e-15) { ok = true; break; }
+    // converged: step below 1e-15, or below 1e-13 and no longer contracting (a bisection step halves it) -- the quadratic phase has hit the rounding
+    // floor of P_33 (a few 1e-16 through the eigen decomposition of Hencky), where steps only jitter
+    if (dx < 1.0e-15 || (dx < 1.0e-13 && dx > 0.75 * dx_prev)) { ok = true; break; }
+    dx_prev = dx;
   }
   F[8] = 1.0 + x;
   return ok;

@@ -10,7 +10,7 @@ host-mirror API, in both adjoint modes (fp64 DMMA / TF32 tensor cores).  One JSO
 
   R3D 3D residual / reaction loss on Hex8 100^3 (NeoHookean / Swanson / Hencky): the stiffness-action sweep in 3D
 
-    python tools/bench_configs.py [--cases c2,c4,c5,visco,r3d] [--c5-n 50,100,159,252] [--steps 5]
+    python tools/bench_configs.py [--cases c2,c4,c5,visco,r3d,pstress] [--c5-n 50,100,159,252] [--steps 5]
 
 Every (time step, node) row is evaluated (null-step culling off), deterministic assembly, CUDA events on the
 launching stream, inputs resident.  Not the bench.py contract: no e2e / CPU arm here."""
@@ -158,6 +158,24 @@ def r3d(steps, device, n=100, nt=2):
         problem._engines.clear()
 
 
+def pstress(steps, device, n=512, nt=11):
+    """C2's mesh under PlaneStress (per-point root find of P_33 = 0, solid_mechanics.py:32-71)."""
+    mesh = px.create_structured_mesh("quad4", (n, n), lengths=(1.0, 1.0))
+    times = np.linspace(0.0, 1.0, nt)
+    domain = px.VariationalDomain(mesh, times, q_order=2)
+    for model_name, model in (("neohookean", px.NeoHookean(bulk_modulus=10.0, shear_modulus=1.0)),
+                              ("hencky", px.Hencky(bulk_modulus=10.0, shear_modulus=1.0))):
+        physics = px.SolidMechanics(model, px.PlaneStress())
+        bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_1") for c in range(2)]
+        gd = px.GlobalData.from_arrays(times, np.zeros(nt), mesh.nodeSets["nset_1"], 1)
+        problem = px.InverseProblem(domain, physics, None, gd, dirichlet_bcs=bcs)
+        params = px.Parameters(problem, key=0, n_layers=3, n_neurons=50, device=device,
+                               dirichlet_bc_func=px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 2))
+        measure(f"PSTRESS Quad4 {n}^2 {model_name} plane stress, nt={nt}, EnergyResidualAndReactionLoss, MLP 3->50x3->2",
+                problem, params, px.EnergyResidualAndReactionLoss(), (), steps, n * n * 4 * nt)
+        problem._engines.clear()
+
+
 def visco(steps, device, n=64, nt=11):
     """examples/forward_problems/mechanics/example_hyper_visco_3d.py at scale: SimpleFeFv(NeoHookean, one Prony branch),
     path-dependent EnergyLoss: forward sweep over the steps with the states kept + reverse sweep + one MLP adjoint."""
@@ -196,6 +214,8 @@ def main():
         visco(args.steps, device)
     if "r3d" in cases:
         r3d(args.steps, device)
+    if "pstress" in cases:
+        pstress(args.steps, device)
 
 
 if __name__ == "__main__":
