@@ -77,6 +77,8 @@ struct pcx_handle {
   // SimpleFeFv (state variables): Fv of every (time step, element, qp, Prony branch) and two adjoint buffers,
   // allocated on the first path-dependent call
   double *vz = nullptr, *vlam[2] = {nullptr, nullptr}, *vus = nullptr;
+  double* f33 = nullptr;                    // PlaneStress: roots of the last force sweep [T][ne][nq] (reused by the tangent sweep)
+  long long f33_cap = 0;
   double *vq = nullptr, *vpart = nullptr;   // point fluxes [ne*nq][ndof*nd]; block partials [vnblk][1 + PCX_MAX_PROPS]
   int vnblk = 0;                            // blocks of the per-point sweep: ceil(ne nq / 128)
   long long vz_per = 0;
@@ -572,6 +574,8 @@ static void free_ws(pcx_handle* h) {
   for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
   if (h->vq) cudaFree(h->vq);
   if (h->vpart) cudaFree(h->vpart);
+  if (h->f33) cudaFree(h->f33);
+  h->f33 = nullptr; h->f33_cap = 0;
   h->vz = nullptr; h->vus = nullptr; h->vq = nullptr; h->vpart = nullptr; h->vz_per = 0; h->vnblk = 0;
 }
 
@@ -919,8 +923,10 @@ static int field_backward_recompute(pcx_handle* h, int t, const double* ubar, do
 }
 
 // energy (+force) sweep over T time steps of `us` -> f (assembled, scaled by alpha, + beta*add)
+// reuse_f33 (PlaneStress, tangent): the force sweep of the SAME us and T ran right before -- take its roots instead of solving again
 static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const double* v, double* out, double alpha,
-                 const double* add, double beta, bool want_energy, bool want_dp, bool want_force, cudaStream_t st) {
+                 const double* add, double beta, bool want_energy, bool want_dp, bool want_force, cudaStream_t st,
+                 bool reuse_f33 = false) {
   ElemArgs a;
   memset(&a, 0, sizeof(a));
   a.ne = h->ne; a.coords = h->coords; a.conns = h->conns; a.us = us; a.v = v;
@@ -931,6 +937,20 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
   a.ppart = want_dp ? h->ppart : nullptr;
   a.want_force = want_force ? 1 : 0;
   a.plane_stress = (h->phys.physics == PCX_PHYS_SOLID && h->phys.formulation == PCX_FORM_PLANE_STRESS) ? 1 : 0;
+  if (a.plane_stress) {
+    const long long need = (long long)T * h->ne * h->nq;
+    if (!tangent) {
+      if (h->f33_cap < need) {
+        if (h->f33) cudaFree(h->f33);
+        h->f33 = nullptr; h->f33_cap = 0;
+        if (cudaMalloc(&h->f33, (size_t)need * sizeof(double)) == cudaSuccess) h->f33_cap = need;
+        else (void)cudaGetLastError();   // no room: the tangent sweep solves again
+      }
+      a.f33_out = h->f33;
+    } else if (reuse_f33 && h->f33 && h->f33_cap >= need) {
+      a.f33_in = h->f33;
+    }
+  }
   if (h->phys.physics == PCX_PHYS_SOLID && h->phys.n_prony > 0) {
     if (!h->vstep.on || tangent)
       return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
@@ -1416,7 +1436,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
           LAUNCH_CHECK(h);
         }
       }
-      if ((rc = sweep(h, true, T, h->us, h->v, h->ubar, 1.0, h->f, we, false, want_dp, true, st))) return rc;
+      if ((rc = sweep(h, true, T, h->us, h->v, h->ubar, 1.0, h->f, we, false, want_dp, true, st, true))) return rc;
       if (want_dp)
         if ((rc = reduce_rows(h, h->ppart, h->nblk_el, PCX_MAX_PROPS, h->phys.nprops, T,
                               h->scal + SC_DFV(h) + (long long)t0 * PCX_MAX_PROPS, PCX_MAX_PROPS, st))) return rc;

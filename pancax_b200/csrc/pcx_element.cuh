@@ -48,6 +48,8 @@ struct ElemArgs {
   int nprops;
   int want_force;
   int plane_stress;        // PCX_FORM_PLANE_STRESS: F_33 from the per-point root of sigma_33 = 0 (2D solid only)
+  double* f33_out;         // [T][ne][nq] the roots found by the force sweep, kept for ...
+  const double* f33_in;    // ... the tangent sweep at the same displacements (nullptr: solve again)
   // SimpleFeFv (hyperviscoelasticity/simple_fefv.py): state Fv [ne][nq][n_prony][9] per quadrature point.
   // Forward sweep of one time step: z_old -> z_new and the energy.  Reverse sweep: z_old and the adjoint lam_in of
   // the step's new state -> the stress-like S (scattered like P) and lam_out, the adjoint of the old state.
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
             for (int j = 0; j < ND; j++) F[3 * i + j] += H[i][j];
           if constexpr (VAR == 1) {
             if (!plane_stress_solve<MODEL>(F, A.props)) bad = true;
+            if (A0.f33_out) A0.f33_out[((long long)blockIdx.y * A0.ne + e) * tab.nq + q] = F[8];
           }
           double W, P[9], dp[PCX_MAX_PROPS];
           model_eval<MODEL, double>(F, A.props, W, P, dp, want_dp);
@@ -270,7 +273,8 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
             double Fv[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) Fv[i] = F[i].v;
-            if (!plane_stress_solve<MODEL>(Fv, A.props)) bad = true;
+            if (A0.f33_in) Fv[8] = A0.f33_in[((long long)blockIdx.y * A0.ne + e) * tab.nq + q];
+            else if (!plane_stress_solve<MODEL>(Fv, A.props)) bad = true;
             F[8].v = Fv[8];
             plane_stress_tangent<MODEL>(F, A.props, W, P, dp, want_dp, A.nprops);
           } else {
