@@ -693,7 +693,13 @@ template <int MODEL>
 __device__ inline bool plane_stress_solve(double* F, const Props& pr) {
   const double j2 = F[0] * F[4] - F[1] * F[3];
   double lo = -0.99, hi = 10.0;
-  double x = fmin(fmax(1.0 / j2 - 1.0, lo), hi);
+  double x = 1.0 / j2 - 1.0;
+  if constexpr (MODEL == PCX_MODEL_HENCKY) {
+    // closed form: F = diag(F_2D, l3) has tr E = ln det F_2D + ln l3, and P_33 = (K tr E + 2 G ln l3) / l3 = 0 gives
+    // l3 = (det F_2D)^(-K / (K + 2 G)); the iteration below then only confirms it
+    x = exp(-pr.p[0] / (pr.p[0] + 2.0 * pr.p[1]) * log(j2)) - 1.0;
+  }
+  x = fmin(fmax(x, lo), hi);
   if (!(x == x)) x = 0.05;
   bool ok = false;
   double dx_prev = 1.0e300;
