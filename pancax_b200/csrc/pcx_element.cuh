@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
     A.ppart = A0.ppart ? A0.ppart + ts * (long long)gridDim.x * PCX_MAX_PROPS : nullptr;
 #pragma unroll
     for (int k = 0; k < PCX_MAX_PROPS; k++) A.props.p[k] = (MODEL != 0 && k < A0.nprops) ? __ldg(A0.props_dev + k) : 0.0;
+    props_derive<MODEL>(A.props);
   }
   const bool live = e < A.ne;
   double Wsum = 0.0;
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
   Props props;
 #pragma unroll
   for (int k = 0; k < PCX_MAX_PROPS; k++) props.p[k] = (k < A0.nprops) ? __ldg(A0.props_dev + k) : 0.0;
+  props_derive<MODEL>(props);
   const bool want_dp = !BWD && A0.ppart != nullptr;
   double Wq = 0.0;
   double dps[PCX_MAX_PROPS];
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(256) k_element_pp(const __grid_constant__ Pare
   Props props;
 #pragma unroll
   for (int k = 0; k < PCX_MAX_PROPS; k++) props.p[k] = (k < nprops) ? __ldg(props_dev + k) : 0.0;
+  props_derive<MODEL>(props);
   __syncthreads();
   const int nq = tab.nq;
   const int npts = nloc * nq;

@@ -85,6 +85,7 @@ __host__ __device__ inline void cofactor3(const T* F, T* C) {
 
 struct Props {
   double p[PCX_MAX_PROPS];
+  double aux[6];   // per-model constants derived from p once per thread (props_derive), not once per quadrature point
 };
 
 // Volumetric part shared by NeoHookean and Gent: W_vol = 0.5 K (0.5 (J^2 - 1) - ln J)
@@ -202,9 +203,9 @@ __device__ inline void swanson(const T* F, const Props& pr, T& W, T* P, T* dWdp,
   T wK = J * lJ - J + 1.0;
   T lt1 = s_log(t1), lt2 = s_log(t2);
   T t1P = s_pow_l(t1, lt1, P1), t1R = s_pow_l(t1, lt1, R1), t2Q = s_pow_l(t2, lt2, Q1);
-  T wA = 1.5 / (P1 + 1.0) * (t1P * t1 - pow(tc, P1 + 1.0));
-  T wB = 1.5 / (Q1 + 1.0) * (t2Q * t2 - pow(tc, Q1 + 1.0));
-  T wC = 1.5 / (R1 + 1.0) * (t1R * t1 - pow(tc, R1 + 1.0));
+  T wA = pr.aux[3] * (t1P * t1 - pr.aux[0]);   // 1.5 / (P1 + 1) (t1^(P1+1) - tc^(P1+1)), constants from props_derive
+  T wB = pr.aux[4] * (t2Q * t2 - pr.aux[1]);
+  T wC = pr.aux[5] * (t1R * t1 - pr.aux[2]);
   W = K * wK + A1 * wA + B1 * wB + C1 * wC;
   T dJ = K * lJ;
   T d1 = 0.5 * (A1 * t1P + C1 * t1R);
@@ -230,6 +231,22 @@ __device__ inline void swanson(const T* F, const Props& pr, T& W, T* P, T* dWdp,
     dWdp[5] = wC;
     dWdp[6] = 1.5 * swanson_term_dexp(t1, tc, C1, R1);
     dWdp[7] = T(0.0);
+  }
+}
+
+// constants of a model that depend on the properties only: evaluated once per thread, before the quadrature loop
+template <int MODEL>
+__device__ inline void props_derive(Props& pr) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) pr.aux[k] = 0.0;
+  if constexpr (MODEL == PCX_MODEL_SWANSON) {
+    const double cs = pr.p[7], tc = (1.0 / 3.0) * (3.0 + cs * cs) - 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double e1 = pr.p[2 + 2 * k] + 1.0;   // P1 + 1, Q1 + 1, R1 + 1
+      pr.aux[k] = pow(tc, e1);
+      pr.aux[3 + k] = 1.5 / e1;
+    }
   }
 }
 
