@@ -103,3 +103,18 @@ def test_plane_stress_needs_a_2d_mesh(cuda_device):
     with pytest.raises(PcxError, match="PlaneStress"):
         eng.set_physics("solid", "neohookean", "plane_stress", [1000.0, 1.0])
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["quad4_neohookean_pstress", "quad4_gent_pstress", "quad4_swanson_pstress",
+                                  "quad4_hencky_pstress"])
+def test_root_find_converges_everywhere(cuda_device, name):
+    """4 096 quadrature points x 4 load levels: every per-point root find must report convergence (aux[3] == 0) --
+    a Newton iterate that sits on the root to rounding becomes a bracket end, and the later Newton steps that land on
+    that end must be taken, not bisected away (Hencky ran out of its iteration budget there before)."""
+    case = make_case(name, n=32, nt=4)
+    case.times = np.linspace(0.25, 1.0, 4)
+    L, aux, gw, gp = run_engine_loss(case, "energy_residual")
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy_residual")
+    assert aux[3] == 0.0, "root find did not converge somewhere"
+    assert abs(L - Lo) <= TOL * abs(Lo), name
+    assert rel(gw, gwo) < 1e-9, name
