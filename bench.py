@@ -93,17 +93,31 @@ SWANSON = dict(bulk_modulus=10.0, A1=0.93074321, P1=-0.07673672, B1=0.0, Q1=0.5,
                cutoff_strain=0.01)   # test/constitutive_models/test_swanson.py:8-14 (config C5)
 
 
+def strong_grid(world):
+    """Near-cubic process grid (px, py, pz) for cutting ONE cube into `world` blocks: fewer duplicated closure nodes
+    than z slabs (128^3 over 8 ranks: 65^3 / 64^3 = +4.8 % nodes per rank instead of 129*129*17 / (128*128*16) = +7.9 %)."""
+    g = [1, 1, 1]
+    k, w = 2, world
+    while w > 1:          # world is a power of two on one box (1, 2, 4, 8); peel factors largest axis last
+        g[k] *= 2
+        w //= 2
+        k = (k - 1) % 3
+    return tuple(g)
+
+
 def build_problem(n, nt, rank, world, device, strong=False, model="neohookean"):
-    """--scaling strong: ONE n^3 unit cube cut into `world` z slabs of n x n x (n / world) elements (BASELINE config
-    3 read literally: "16M quadrature points ... sharded across 8 GPUs").  Default (weak):
+    """--scaling strong: ONE n^3 unit cube cut into `world` near-cubic blocks (BASELINE config 3 read literally:
+    "16M quadrature points ... sharded across 8 GPUs").  Default (weak):
     unit-cube slab [0,1]^2 x [rank, rank+1] of n^3 Hex8 elements per rank (weak scaling: the bar
     grows along z with the GPU count), 3D NeoHookean, uniaxial-tension Dirichlet wrapper."""
     import pancax_b200 as px
     from pancax_b200 import parallel
     if strong:
-        assert n % world == 0, "--scaling strong needs n divisible by the GPU count"
-        mesh = px.create_structured_mesh("hex8", (n, n, n // world), lengths=(1.0, 1.0, 1.0 / world),
-                                         origin=(0.0, 0.0, rank / world))
+        gx, gy, gz = strong_grid(world)
+        assert n % gx == 0 and n % gy == 0 and n % gz == 0, "--scaling strong needs n divisible by the process grid"
+        ix, iy, iz = rank % gx, (rank // gx) % gy, rank // (gx * gy)
+        mesh = px.create_structured_mesh("hex8", (n // gx, n // gy, n // gz), lengths=(1.0 / gx, 1.0 / gy, 1.0 / gz),
+                                         origin=(ix / gx, iy / gy, iz / gz))
     else:
         mesh = px.create_structured_mesh("hex8", (n, n, n), lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, float(rank)))
     times = np.linspace(0.0, 1.0, nt)
@@ -120,6 +134,197 @@ def build_problem(n, nt, rank, world, device, strong=False, model="neohookean"):
     lo, hi = parallel.global_bounds(mesh.coords)
     params.fields.x_mins, params.fields.x_maxs = lo, hi
     return problem, params
+
+
+def _max_over_ranks(ms, device, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.cpu()[0])
+
+
+def _timed(step, steps, warmup, device, world):
+    """warmup untimed steps, then `steps` steps between barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks.  Returns total ms."""
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    return _max_over_ranks(e0.elapsed_time(e1), device, world)
+
+
+def _try_graph(step, device):
+    """Capture one step (the library's launches + the NCCL allreduce) in a CUDA graph; returns a replay callable or
+    None when the capture is refused (then the eager step is timed).  The C ABI never allocates / synchronises inside a
+    compute call, so the whole step is capturable; it matters where the step is short (strong scaling at 8 GPUs:
+    ~1.5 ms, 9 launches + one 64 KB allreduce)."""
+    if os.environ.get("PCX_BENCH_NO_GRAPH"):
+        return None
+    try:
+        g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=device)
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            step()                                  # same stream as the capture: NCCL's per-stream set-up happens here
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
+                step()
+        torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        return g.replay
+    except Exception as e:      # noqa: BLE001
+        print(f"[bench] CUDA-graph capture of the step refused ({type(e).__name__}: {e}); timing the eager step", file=sys.stderr)
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        return None
+
+
+def strong_scaling_leg(args, rank, world, device, weak_value):
+    """BASELINE config 3 read literally: ONE n^3 block (16.8 M quadrature points at n = 128) cut over the N GPUs.
+    Reported at every N next to the (weak) headline so the driver's 1/2/4/8 runs carry the strong curve too."""
+    import pancax_b200 as px
+    from pancax_b200 import parallel
+    from pancax_b200.loss_functions import get_engine
+    n, nt = args.n, args.nt
+    if world == 1:
+        return None      # same workload as the headline line: filled in by the caller
+    problem, params = build_problem(n, nt, rank, world, device, True, args.model)
+    eng = get_engine(problem, params)
+    eng.set_option("cull_null_steps", 0)
+    w = params.fields.networks.weights
+    res = parallel.PackedResult(4 + nt, eng.n_weights, eng.n_train, device)
+
+    def step():
+        eng.loss_and_grad("energy", w, out=res.as_out())
+        res.allreduce()
+    ms_eager = _timed(step, args.steps, 3, device, world)
+    replay = _try_graph(step, device)
+    ok = torch.tensor([1.0 if replay is not None else 0.0], device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # replay only if EVERY rank captured
+    ms_graph = _timed(replay, args.steps, 3, device, world) if float(ok.cpu()[0]) > 0 else None
+    ms = min(ms_eager, ms_graph) if ms_graph else ms_eager
+    total = n ** 3 * 8 * nt
+    value = total * args.steps / (ms * 1e-3)
+    out = {"value": value, "unit": "evals/s", "ms_per_step": ms / args.steps, "ms_per_step_eager": ms_eager / args.steps,
+           "ms_per_step_cuda_graph": (ms_graph / args.steps) if ms_graph else None, "n_gpus": world,
+           "workload": f"ONE Hex8 {n}^3 block ({n ** 3 * 8} qp x nt={nt}) cut into {'x'.join(map(str, strong_grid(world)))} "
+                       f"blocks, {eng.ne * eng.nq} qp and {eng.nn} closure nodes per GPU",
+           "per_gpu_rate_vs_weak_line": value / weak_value if weak_value else None,
+           "note": "strong scaling of the literal C3; per_gpu_rate_vs_weak_line = this value / the headline (weak) value of "
+                   "the same run = per-GPU throughput on a 1/N-size shard relative to a full 128^3 shard (includes the "
+                   "duplicated closure nodes and the exposed allreduce)"}
+    eng.close()
+    problem._engines.clear()
+    del problem, params, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def residual_sharded_leg(args, rank, world, device):
+    """Config C2 on N element shards: 2D plane-strain NeoHookean Quad4 n^2 (512^2 = 1 048 576 qp), nt = 11,
+    EnergyResidualAndReactionLoss through the phased ABI (pcx_loss_begin / _mid / _finish) with the two exchanges
+    between the phases, against the SAME loss on the whole mesh (rank 0).  At N = 1 the whole-mesh step is the timed
+    one and the sharded path is checked with two shards driven in lock-step on the one GPU."""
+    import torch.distributed as dist
+    import pancax_b200 as px
+    from pancax_b200 import parallel
+    from pancax_b200.loss_functions import get_engine
+    n, nt = args.c2_n, 11
+    times = np.linspace(0.0, 1.0, nt)
+    full = px.create_structured_mesh("quad4", (n, n), lengths=(1.0, 1.0))
+    gout = 0.05 * times
+    lw = dict(energy_weight=1.0, residual_weight=1.0, reaction_weight=1.0)
+
+    def build(mesh):
+        domain = px.VariationalDomain(mesh, times, q_order=2)
+        physics = px.SolidMechanics(px.NeoHookean(bulk_modulus=1000.0, shear_modulus=1.0), px.PlaneStrain())
+        bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_1") for c in range(2)]
+        gd = px.GlobalData.from_arrays(times, gout, mesh.nodeSets["nset_1"], 1)
+        problem = px.InverseProblem(domain, physics, None, gd, dirichlet_bcs=bcs)
+        return problem
+
+    def make_params(problem):
+        return px.Parameters(problem, key=0, n_layers=3, n_neurons=50, device=device,
+                             dirichlet_bc_func=px.UniaxialTensionLinearRamp(1.0, 1.0, "y", 2))
+    loss_fn = px.EnergyResidualAndReactionLoss(**lw)
+    evals = n * n * 4 * nt
+    whole = None
+    if rank == 0:
+        fp = build(full)
+        fparams = make_params(fp)
+        get_engine(fp, fparams).set_option("cull_null_steps", 0)
+        (L1, a1), g1 = loss_fn.value_and_grad(fparams, fp)
+        whole = (fp, fparams, L1.clone(), a1["residual"].clone(), a1["reactions"].clone(), g1.fields.clone())
+    out = {"workload": f"C2: Quad4 {n}^2 ({n * n * 4} qp), plane-strain NeoHookean K=1000 G=1, nt={nt}, "
+                       "EnergyResidualAndReactionLoss with reaction on the top node set, MLP 3->50x3->2 fp64",
+           "unit": "evals/s", "n_gpus": world}
+    if world == 1:
+        fp, fparams = whole[0], whole[1]
+
+        def step():
+            return loss_fn.value_and_grad(fparams, fp)
+        ms = _timed(step, args.steps, 3, device, 1)
+        # the sharded path on this one GPU: two element shards in lock-step through the phased ABI
+        subs = [parallel.partition_mesh(full, r, 2) for r in range(2)]
+        plans = parallel.make_shard_plans([l2g for _, l2g in subs])
+        lo, hi = full.coords.min(axis=0), full.coords.max(axis=0)
+        engines = []
+        for (sub, _), plan in zip(subs, plans):
+            sp = build(sub)
+            sp.shard = parallel.ShardInfo(plan, None, lo, hi)
+            sp._engines = {}
+            e = get_engine(sp, make_params(sp))
+            e.set_option("cull_null_steps", 0)
+            engines.append(e)
+        L, aux, gw, _ = parallel.run_shards_in_process(engines, plans, "energy_residual_reaction", fparams.fields.networks.weights,
+                                                       None, global_outputs=gout, **lw)
+        out.update({"n_shards": 2, "shards": "2 element shards driven in lock-step on the one GPU (phased ABI + exchanges)",
+                    "shared_nodes": int(plans[0].n_shared)})
+        for e in engines:
+            e.close()
+    else:
+        sub, l2g = parallel.partition_mesh(full, rank, world)
+        sp = build(sub)
+        parallel.shard_problem(sp, l2g, device)
+        sparams = make_params(sp)
+        get_engine(sp, sparams).set_option("cull_null_steps", 0)
+        res = parallel.PackedResult(4 + nt, sparams.fields.networks.weights.numel(), 0, device)
+
+        def step():
+            (loss, aux), grads = loss_fn.value_and_grad(sparams, sp)
+            res.loss.copy_(loss.reshape(1))
+            res.aux[1:2].copy_(aux["residual"].reshape(1)); res.aux[4:].copy_(aux["reactions"])
+            res.gw.copy_(grads.fields)
+            res.allreduce()
+        ms = _timed(step, args.steps, 3, device, world)
+        L, aux, gw = res.loss[0], res.aux, res.gw
+        out.update({"n_shards": world, "shards": "one element shard per GPU (contiguous element ranges = y slabs), NCCL exchanges",
+                    "shared_nodes": int(sp.shard.plan.n_shared)})
+    out.update({"value": evals * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps})
+    if rank == 0:
+        _, _, L1, R1, re1, g1 = whole
+        out["rel_err_vs_whole_mesh"] = {
+            "loss": abs(float(L) - float(L1)) / abs(float(L1)),
+            "residual": abs(float(aux[1]) - float(R1)) / abs(float(R1)),
+            "reactions": float((aux[4:] - re1).norm() / re1.norm()),
+            "grad": float((gw - g1).norm() / g1.norm())}
+        out["loss"] = float(L1)
+    return out
 
 
 def run_ours(args):
@@ -266,6 +471,14 @@ def run_ours(args):
                     "flush every 1024 rows) from fp32 activations; forward / element sweeps / loss stay fp64. NOT the "
                     "headline: value/e2e/roofline are the fp64 path."}
 
+    # ---------------- strong scaling of the literal C3 and the sharded residual loss (C2), every N
+    strong_leg = resid_leg = None
+    if not args.no_extra_legs and args.scaling == "weak":
+        strong_leg = strong_scaling_leg(args, rank, world, device, value)
+        if world == 1:
+            strong_leg = {"value": value, "unit": "evals/s", "ms_per_step": ms / args.steps, "n_gpus": 1,
+                          "workload": f"ONE Hex8 {n}^3 block on one GPU = the headline line", "per_gpu_rate_vs_weak_line": 1.0}
+        resid_leg = residual_sharded_leg(args, rank, world, device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,7 +511,7 @@ def run_ours(args):
     # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.cpu_n, nt, max_seconds=25.0)
+        cpu = cpu_baseline(args.cpu_n, nt, max_seconds=25.0, threads=args.cpu_threads)
     out = {
         "metric": "quad-pt loss+grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -314,10 +527,19 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(host_w.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8),
                 "api": "EnergyLoss().value_and_grad(params, problem) with pinned-host weights in, loss+grad out"},
         "roofline": roofline, "cpu_baseline": cpu, "null_step_culling": culled, "tf32_adjoint": tf32,
+        "strong_scaling": strong_leg, "residual_sharded": resid_leg,
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cpu_threads(requested=None):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: without this the reference arm at N > 1 ran on ONE core
+    (VERDICT r1).  All host cores at every N, or --cpu-threads."""
+    n = int(requested) if requested else (os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 def _oracle_case(n, nt):
@@ -329,8 +551,7 @@ def cpu_baseline(n, nt, max_seconds=25.0, threads=None):
     """The CPU restatement of pancax's path (oracle/, torch fp64, all host threads) timed on a bounded
     sample of the SAME workload (smaller mesh, same physics / network / loss)."""
     from tests.cases import run_oracle_loss
-    if threads:
-        torch.set_num_threads(threads)
+    _cpu_threads(threads)
     case = _oracle_case(n, nt)
     evals = case.mesh["conns"].shape[0] * 8 * nt
     run_oracle_loss(case, "energy", energy_weight=1.0)      # warm-up
@@ -354,6 +575,7 @@ def run_reference(args):
     if rank != 0:
         return
     from tests.cases import run_oracle_loss
+    _cpu_threads(args.cpu_threads)
     n, nt = args.cpu_n, args.nt
     case = _oracle_case(n, nt)
     evals = case.mesh["conns"].shape[0] * 8 * nt
@@ -388,6 +610,9 @@ def main():
     ap.add_argument("--nt", type=int, default=2, help="time steps (C3: 2 or 11)")
     ap.add_argument("--cpu-n", type=int, default=32, help="mesh size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=None, help="host threads of the CPU arms (default: all cores, at every N)")
+    ap.add_argument("--c2-n", type=int, default=512, help="Quad4 elements per side of the sharded residual-loss leg (C2: 512)")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the strong_scaling / residual_sharded legs")
     ap.add_argument("--model", default="neohookean", choices=["neohookean", "gent", "swanson", "hencky"],
                     help="constitutive model (default: the C3 headline; swanson / hencky = config C5)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PCX_ABI_VERSION 3
+#define PCX_ABI_VERSION 4
 
 /* error codes */
 #define PCX_OK               0
@@ -145,7 +145,8 @@ typedef struct {
   double  energy_weight;
   double  residual_weight;
   double  reaction_weight;
-  const double* global_outputs; /* HOST f64 [nt] (problem.global_data.outputs) or NULL          */
+  const double* global_outputs; /* DEVICE f64 [nt] (problem.global_data.outputs) or NULL; read by the kernels
+                                   of the call, never staged (ABI v4; v3 took a host pointer)       */
   int32_t first_step;         /* 0: path-independent call (vmap over all times); 1: the path-dependent call of a
                                  model without state variables (weak_form_loss_functions.py:48-72,242-276): the
                                  loop starts at time step 1 ("time step 0 is the initial condition"), residual and
@@ -184,6 +185,13 @@ int pcx_destroy(pcx_handle* h);
  * (pcx_loss_begin / pcx_loss_finish). */
 #define PCX_OPT_TF32_ADJOINT 2
 int pcx_set_option(pcx_handle* h, int32_t option, int64_t value);
+
+/* Set-up call for workspaces whose size depends on the caller's batch (everything else is sized by pcx_set_physics /
+ * pcx_set_field): PCX_RESERVE_POINTS = the strong-form / collocation path for batches of up to n points.  Allocates
+ * and may synchronise: call it outside traced / captured regions.  Compute calls never allocate; one that needs more
+ * than was reserved returns PCX_ERR_STATE. */
+#define PCX_RESERVE_POINTS 1
+int pcx_reserve(pcx_handle* h, int32_t what, int64_t n);
 
 /* sizes the caller needs to allocate outputs */
 int64_t pcx_num_weights(const pcx_handle* h);     /* flat MLP parameter count          */
@@ -258,7 +266,9 @@ int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* loss, const double* we
  *   -- caller: rr_total = sum over shards of rr_partial (may be in place).
  *   pcx_loss_finish: v, tangent action, adjoint.  Outputs are the shard's PARTIAL loss / aux / gradients:
  *     their SUM over shards is the value pcx_loss_and_grad returns on the whole mesh, provided
- *     replicated_scale = 1 / n_shards (it weights the terms all shards compute identically). */
+ *     replicated_scale = 1 / n_shards (it weights the terms all shards compute identically).
+ *     Exception: aux[PCX_AUX_FLAGS] is the shard's own flag word (a bit mask): combine it with OR / MAX, or read a
+ *     summed value as "non-zero = anomaly on some shard". */
 int pcx_set_ownership(pcx_handle* h, int64_t n_unknown_owned, int64_t n_reaction_owned);
 int pcx_loss_begin(pcx_handle* h, const pcx_loss_desc* loss, const double* weights, const double* prop_raw,
                    double* f_partial, void* stream);

@@ -48,7 +48,7 @@ struct pcx_handle {
   int phase = 0;                // phased (sharded) loss: 0 idle, 1 after begin, 2 after mid
   // strong-form (jet) workspace, allocated on first use
   double *jet_post = nullptr, *jet_pre = nullptr, *jet_adj = nullptr, *jet_zjet = nullptr, *jet_obar = nullptr, *jet_lpart = nullptr;
-  long long jet_rows_cap = 0, jet_lpart_n = 0;
+  long long jet_rows_cap = 0, jet_lpart_n = 0, jet_reserved_n = 0;
   std::vector<char> step_null;  // time steps whose Dirichlet table b is identically 0: u = a, zero cotangent
   int cull_null_steps = 1;      // skip the MLP on those steps (exact); PCX_OPT_CULL_NULL_STEPS / env PCX_CULL_NULL_STEPS
   const double* coords = nullptr;
@@ -89,7 +89,7 @@ struct pcx_handle {
   double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
   double *scal = nullptr;       // see SC_* offsets
   double *props_dev = nullptr;  // effective properties [PCX_MAX_PROPS] + d p/d raw [PCX_MAX_PROPS]
-  double *times_dev = nullptr, *gout_dev = nullptr;
+  double *times_dev = nullptr;
   double *gtmp = nullptr;       // [nweights] scratch
   int* flags = nullptr;
   long long* adj_ptr = nullptr;
@@ -219,7 +219,7 @@ __global__ void k_props(pcx_physics_desc d, const double* __restrict__ raw, doub
 __global__ void k_resid_coeffs(int t0, int T, int nt, double wr, double wg, const double* __restrict__ rr,
                                const double* __restrict__ gout, double* __restrict__ R, double* __restrict__ react,
                                double* __restrict__ c1, double* __restrict__ c2) {
-  const int i = threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per time step of the batch (any T)
   if (i >= T) return;
   const int t = t0 + i;
   const double r2 = rr[2 * i], re = rr[2 * i + 1];
@@ -563,7 +563,7 @@ static int reduce_wgrad(pcx_handle* h, int nparts, double* g, cudaStream_t st) {
 static void jet_free(pcx_handle* h);
 static void free_ws(pcx_handle* h) {
   double** ptrs[] = {&h->pk, &h->act, &h->part, &h->us, &h->fe, &h->f, &h->v, &h->ubar, &h->epart, &h->ppart,
-                     &h->rpart, &h->scal, &h->props_dev, &h->times_dev, &h->gout_dev, &h->gtmp};
+                     &h->rpart, &h->scal, &h->props_dev, &h->times_dev, &h->gtmp};
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   if (h->flags) cudaFree(h->flags);
   h->flags = nullptr;
@@ -620,9 +620,24 @@ static int alloc_ws(pcx_handle* h) {
   CUDA_TRY(cudaMalloc(&h->props_dev, 2 * PCX_MAX_PROPS * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->times_dev, h->nt * sizeof(double)));
   CUDA_TRY(cudaMemcpy(h->times_dev, h->times.data(), h->nt * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&h->gout_dev, h->nt * sizeof(double)));
-  CUDA_TRY(cudaMemset(h->gout_dev, 0, h->nt * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->gtmp, s.nweights * sizeof(double)));
+  // workspaces that only some physics need are allocated HERE, never inside a compute call (pcx_abi.h: compute calls
+  // do not allocate): the PlaneStress roots of the last force sweep, the SimpleFeFv state history and adjoints
+  if (h->phys.physics == PCX_PHYS_SOLID && h->phys.formulation == PCX_FORM_PLANE_STRESS) {
+    h->f33_cap = T * h->ne * h->nq;
+    CUDA_TRY(cudaMalloc(&h->f33, (size_t)h->f33_cap * sizeof(double)));
+  }
+  if (h->phys.physics == PCX_PHYS_SOLID && h->phys.n_prony > 0) {
+    const long long per = h->ne * h->nq * (long long)h->phys.n_prony * 9;
+    h->vnblk = (int)((h->ne * h->nq + 127) / 128);
+    CUDA_TRY(cudaMalloc(&h->vq, (size_t)h->ne * h->nq * h->ndof * h->nd * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vpart, (size_t)h->vnblk * (1 + PCX_MAX_PROPS) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vz, (size_t)h->nt * per * sizeof(double)));
+    if (h->T < h->nt) CUDA_TRY(cudaMalloc(&h->vus, (size_t)h->nt * h->nn * h->ndof * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->vlam[1], (size_t)per * sizeof(double)));
+    h->vz_per = per;
+  }
   CUDA_TRY(cudaMalloc(&h->flags, sizeof(int)));
   CUDA_TRY(cudaMemset(h->flags, 0, sizeof(int)));
   return PCX_OK;
@@ -938,15 +953,9 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
   a.want_force = want_force ? 1 : 0;
   a.plane_stress = (h->phys.physics == PCX_PHYS_SOLID && h->phys.formulation == PCX_FORM_PLANE_STRESS) ? 1 : 0;
   if (a.plane_stress) {
-    const long long need = (long long)T * h->ne * h->nq;
+    const long long need = (long long)T * h->ne * h->nq;   // <= f33_cap: allocated by alloc_ws for h->T steps
     if (!tangent) {
-      if (h->f33_cap < need) {
-        if (h->f33) cudaFree(h->f33);
-        h->f33 = nullptr; h->f33_cap = 0;
-        if (cudaMalloc(&h->f33, (size_t)need * sizeof(double)) == cudaSuccess) h->f33_cap = need;
-        else (void)cudaGetLastError();   // no room: the tangent sweep solves again
-      }
-      a.f33_out = h->f33;
+      a.f33_out = (h->f33 && h->f33_cap >= need) ? h->f33 : nullptr;
     } else if (reuse_f33 && h->f33 && h->f33_cap >= need) {
       a.f33_in = h->f33;
     }
@@ -1267,22 +1276,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   const bool want_dp = want_grad && g_props != nullptr && h->ntrain > 0;
   const int nb = h->phys.n_prony, nt = h->nt;
   const long long per = h->ne * h->nq * (long long)nb * 9;
-  if (!h->vz || h->vz_per != per) {
-    if (h->vz) cudaFree(h->vz);
-    for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
-    h->vz = nullptr; h->vz_per = 0;
-    if (h->vus) { cudaFree(h->vus); h->vus = nullptr; }
-    if (h->vq) { cudaFree(h->vq); h->vq = nullptr; }
-    if (h->vpart) { cudaFree(h->vpart); h->vpart = nullptr; }
-    h->vnblk = (int)((h->ne * h->nq + 127) / 128);
-    CUDA_TRY(cudaMalloc(&h->vq, (size_t)h->ne * h->nq * h->ndof * h->nd * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->vpart, (size_t)h->vnblk * (1 + PCX_MAX_PROPS) * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->vz, (size_t)nt * per * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->vus, (size_t)nt * h->nn * h->ndof * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->vlam[1], (size_t)per * sizeof(double)));
-    h->vz_per = per;
-  }
+  if (!h->vz || h->vz_per != per) return fail(PCX_ERR_STATE, "state-variable workspace missing (pcx_set_physics / pcx_set_field allocate it)");
   int rc;
   const double we = L->energy_weight;
   const long long ndofs = h->nn * h->ndof;
@@ -1347,7 +1341,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     if (resident && (rc = field_backward_steps(h, 0, nt, h->ubar, g_weights, first, st))) return rc;
     if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   }
-  k_finish<<<1, 32, 0, st>>>(PCX_LOSS_ENERGY, nt, we, 0.0, 0.0, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
+  k_finish<<<1, 32, 0, st>>>(PCX_LOSS_ENERGY, nt, we, 0.0, 0.0, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), nullptr,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr, 1.0, 1);
   LAUNCH_CHECK(h);
@@ -1388,8 +1382,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
   const double we = L->energy_weight, wr = resid ? L->residual_weight : 0.0;
   const double wg = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->reaction_weight : 0.0;
   int rc;
-  if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION)
-    CUDA_TRY(cudaMemcpyAsync(h->gout_dev, L->global_outputs, h->nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double* gout = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->global_outputs : nullptr;   // device [nt]
   CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
   if ((rc = set_props(h, prop_raw, st))) return rc;
   if ((rc = pack_weights(h, weights, st))) return rc;
@@ -1416,8 +1409,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
     if (resid) {
       // residual norm, reaction, v_t, tangent action, ubar = we f + K v
       if ((rc = resid_react(h, T, h->f, h->scal + SC_RR(h), st))) return rc;
-      k_resid_coeffs<<<1, 64, 0, st>>>(t0, T, h->nt, wr, wg, h->scal + SC_RR(h),
-                                       kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? h->gout_dev : nullptr,
+      k_resid_coeffs<<<(T + 63) / 64, 64, 0, st>>>(t0, T, h->nt, wr, wg, h->scal + SC_RR(h), gout,
                                        h->scal + SC_R(h), h->scal + SC_REACT(h), h->scal + SC_C1(h), h->scal + SC_C2(h));
       LAUNCH_CHECK(h);
       if (!want_grad) continue;
@@ -1446,7 +1438,7 @@ extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const do
     if ((rc = field_backward_steps(h, t0, T, h->ubar, g_weights, first, st))) return rc;
   }
   if (want_grad && first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
-  k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
+  k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), gout,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr, 1.0, t_first);
   LAUNCH_CHECK(h);
@@ -1491,8 +1483,6 @@ extern "C" int pcx_loss_begin(pcx_handle* h, const pcx_loss_desc* L, const doubl
   if (!weights || !f_partial) return fail(PCX_ERR_INVALID, "pcx_loss_begin: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int T = h->nt;
-  if (L->kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION)
-    CUDA_TRY(cudaMemcpyAsync(h->gout_dev, L->global_outputs, h->nt * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
   if ((rc = set_props(h, prop_raw, st))) return rc;
   if ((rc = pack_weights(h, weights, st))) return rc;
@@ -1532,7 +1522,8 @@ extern "C" int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* L, const doub
   const double wg = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->reaction_weight : 0.0;
   const bool want_dp = g_props != nullptr && h->ntrain > 0;
   const long long ndofs = h->nn * h->ndof;
-  k_resid_coeffs<<<1, 64, 0, st>>>(0, T, h->nt, wr, wg, rr_total, kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? h->gout_dev : nullptr,
+  const double* gout = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->global_outputs : nullptr;   // device [nt]
+  k_resid_coeffs<<<(T + 63) / 64, 64, 0, st>>>(0, T, h->nt, wr, wg, rr_total, gout,
                                    h->scal + SC_R(h), h->scal + SC_REACT(h), h->scal + SC_C1(h), h->scal + SC_C2(h));
   LAUNCH_CHECK(h);
   CUDA_TRY(cudaMemsetAsync(h->v, 0, (size_t)T * ndofs * sizeof(double), st));
@@ -1557,7 +1548,7 @@ extern "C" int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* L, const doub
   bool first = true;
   if ((rc = field_backward_steps(h, 0, T, h->ubar, g_weights, first, st))) return rc;
   if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
-  k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), h->gout_dev,
+  k_finish<<<1, 32, 0, st>>>(kind, h->nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), gout,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr, replicated_scale);
   LAUNCH_CHECK(h);
@@ -1568,7 +1559,7 @@ extern "C" int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* L, const doub
 static void jet_free(pcx_handle* h) {
   double** ptrs[] = {&h->jet_post, &h->jet_pre, &h->jet_adj, &h->jet_zjet, &h->jet_obar, &h->jet_lpart};
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
-  h->jet_rows_cap = 0; h->jet_lpart_n = 0;
+  h->jet_rows_cap = 0; h->jet_lpart_n = 0; h->jet_reserved_n = 0;
 }
 
 static int jet_alloc(pcx_handle* h, long long n) {
@@ -1589,6 +1580,33 @@ static int jet_alloc(pcx_handle* h, long long n) {
   CUDA_TRY(cudaMalloc(&h->jet_zjet, (size_t)want * S * h->ndof * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->jet_obar, (size_t)want * S * h->ndof * sizeof(double)));
   h->jet_rows_cap = want;
+  return PCX_OK;
+}
+
+// Set-up call (allocates; never inside a captured / traced region): workspace of the strong-form path for batches
+// of up to n points.  Compute calls on more points than reserved are refused.
+extern "C" int pcx_reserve(pcx_handle* h, int32_t what, int64_t n) {
+  NEED_READY(h);
+  if (what != PCX_RESERVE_POINTS) return fail(PCX_ERR_INVALID, "pcx_reserve: unknown workspace kind %d", what);
+  if (n <= 0) return fail(PCX_ERR_INVALID, "pcx_reserve: n must be positive");
+  if (n <= h->jet_reserved_n) return PCX_OK;
+  int rc = jet_alloc(h, n);
+  if (rc) return rc;
+  const long long nchunks = (n + h->jet_rows_cap - 1) / h->jet_rows_cap;
+  const int pgrid = 256;
+  if (h->jet_lpart_n < nchunks * pgrid) {
+    if (h->jet_lpart) cudaFree(h->jet_lpart);
+    h->jet_lpart = nullptr;
+    CUDA_TRY(cudaMalloc(&h->jet_lpart, (size_t)nchunks * pgrid * sizeof(double)));
+    h->jet_lpart_n = nchunks * pgrid;
+  }
+  h->jet_reserved_n = n;
+  return PCX_OK;
+}
+static int jet_need(pcx_handle* h, long long n) {
+  if (n > h->jet_reserved_n)
+    return fail(PCX_ERR_STATE, "strong-form workspace holds %lld points, the call has %lld: pcx_reserve(h, PCX_RESERVE_POINTS, n) "
+                               "at set-up (compute calls never allocate)", h->jet_reserved_n, n);
   return PCX_OK;
 }
 
@@ -1666,7 +1684,7 @@ extern "C" int pcx_points_jet(pcx_handle* h, const double* weights, const double
   NEED_READY(h);
   if (!weights || !pts || n <= 0) return fail(PCX_ERR_INVALID, "pcx_points_jet: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = jet_alloc(h, n);
+  int rc = jet_need(h, n);
   if (rc) return rc;
   if ((rc = pack_weights(h, weights, st))) return rc;
   for (long long o = 0; o < n; o += h->jet_rows_cap) {
@@ -1692,16 +1710,10 @@ extern "C" int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weight
   NEED_READY(h);
   if (!weights || !pts || !loss_out || n <= 0) return fail(PCX_ERR_INVALID, "pcx_strong_form_loss_and_grad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = jet_alloc(h, n);
+  int rc = jet_need(h, n);
   if (rc) return rc;
   const long long nchunks = (n + h->jet_rows_cap - 1) / h->jet_rows_cap;
   const int pgrid = 256;
-  if (h->jet_lpart_n < nchunks * pgrid) {
-    if (h->jet_lpart) cudaFree(h->jet_lpart);
-    h->jet_lpart = nullptr;
-    CUDA_TRY(cudaMalloc(&h->jet_lpart, (size_t)nchunks * pgrid * sizeof(double)));
-    h->jet_lpart_n = nchunks * pgrid;
-  }
   if ((rc = pack_weights(h, weights, st))) return rc;
   const int S = h->nd + 3, NT = h->ms.NT, WPd = 8 * NT, DH = h->ms.depth - 1;
   const long long PL = (long long)NT * h->jet_rows_cap * 8;

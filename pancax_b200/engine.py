@@ -263,11 +263,20 @@ class Engine:
         return F, I1, P
 
     # ---- strong-form / collocation path
+    def reserve_points(self, n):
+        """Set-up: workspace of the strong-form path for batches of up to ``n`` points (pcx_reserve; the compute
+        calls never allocate).  Grows only; a no-op once enough is reserved."""
+        if n > getattr(self, "_points_reserved", 0):
+            with torch.cuda.device(self.device):
+                check(self.lib.pcx_reserve(self.h, 1, int(n)))
+            self._points_reserved = int(n)
+
     def points_jet(self, weights, pts, tab=None, want=("u", "grad_u", "lap_u", "u_t")):
         """(u (n,ndof), grad_u (n,ndof,nd), lap_u (n,ndof), u_t (n,ndof)) of the Field at points
         pts (n, nd+1) = (x..., t); ``tab`` (n, ndof, 2*(nd+3)) = Dirichlet wrapper tables or None."""
         w, p, tb = self._dev(weights), self._dev(pts), self._dev(tab)
         n = p.shape[0]
+        self.reserve_points(n)
         u = self._empty(n, self.ndof) if "u" in want else None
         gu = self._empty(n, self.ndof, self.nd) if "grad_u" in want else None
         lu = self._empty(n, self.ndof) if "lap_u" in want else None
@@ -281,6 +290,7 @@ class Engine:
         """weight * mean((c_t u_t - c_lap lap u - src - target)^2) over the batch and its weight gradient."""
         w, p, tb, sr, tg = (self._dev(weights), self._dev(pts), self._dev(tab), self._dev(src), self._dev(target))
         n = p.shape[0]
+        self.reserve_points(n)
         loss = self._empty(1)
         res = self._empty(n, self.ndof) if want_resid else None
         gw = self._empty(self.n_weights) if want_grad else None
@@ -305,10 +315,8 @@ class Engine:
         ld.first_step = int(first_step)
         ld.energy_weight, ld.residual_weight, ld.reaction_weight = \
             float(energy_weight), float(residual_weight), float(reaction_weight)
-        go = None
         if global_outputs is not None:
-            go = self._host_outputs(global_outputs)
-            ld.global_outputs = go.ctypes.data_as(C.POINTER(C.c_double))
+            ld.global_outputs = self._dev_outputs(global_outputs).data_ptr()
         if out is None:
             loss = self._empty(1)
             aux = self._empty(PCX_AUX_FIXED + self.nt)
@@ -318,8 +326,6 @@ class Engine:
             loss, aux, gw, gp = out
         check(self.lib.pcx_loss_and_grad(self.h, C.byref(ld), _ptr(w), _ptr(pr), _ptr(loss), _ptr(aux),
                                          _ptr(gw), _ptr(gp) if self.n_train > 0 else None, _stream()))
-        # (cudaMemcpyAsync from pageable host memory returns once the source has been staged,
-        #  so `go` may be released here)
         return loss, aux, gw, gp[: self.n_train]
 
     def null_steps(self):
@@ -328,18 +334,29 @@ class Engine:
             return np.zeros(self.nt, dtype=bool)
         return self._bc_b_host_zero
 
-    def _host_outputs(self, global_outputs):
-        """Host copy of problem.global_data.outputs that lives as long as the engine: the library copies it
-        to the device inside the call, and a captured CUDA graph re-reads the same host address on replay."""
-        go = np.ascontiguousarray(global_outputs, dtype=np.float64)
+    def _dev_outputs(self, global_outputs):
+        """Device copy of problem.global_data.outputs (ABI v4: pcx_loss_desc.global_outputs is a device pointer the
+        kernels read directly).  A device tensor is used as is; host data is uploaded once into a buffer that lives
+        as long as the engine and re-uploaded only when its values change, so a captured CUDA graph keeps reading
+        the same address."""
+        if isinstance(global_outputs, torch.Tensor) and global_outputs.is_cuda:
+            go = global_outputs.to(dtype=torch.float64).contiguous()
+            if go.numel() != self.nt:
+                raise ValueError("global_outputs must have nt entries")
+            self._go_user = go          # keep it alive while work that reads it may be in flight
+            return go
+        go = np.ascontiguousarray(global_outputs.cpu().numpy() if isinstance(global_outputs, torch.Tensor)
+                                  else global_outputs, dtype=np.float64).reshape(-1)
         if go.shape[0] != self.nt:
             raise ValueError("global_outputs must have nt entries")
         cur = getattr(self, "_go_host", None)
-        if cur is None:
-            self._go_host = cur = go.copy()
-        elif not np.array_equal(cur, go):
-            cur[:] = go
-        return cur
+        if cur is None or not np.array_equal(cur, go):
+            self._go_host = go.copy()
+            if getattr(self, "_go_dev", None) is None:
+                self._go_dev = torch.from_numpy(self._go_host).to(self.device)
+            else:
+                self._go_dev.copy_(torch.from_numpy(self._go_host))
+        return self._go_dev
 
     def get_state(self, t_idx):
         """State variables (ne, nq, n_prony*9) of time step ``t_idx`` after a path-dependent call (SimpleFeFv)."""
@@ -367,8 +384,8 @@ class Engine:
             float(energy_weight), float(residual_weight), float(reaction_weight)
         go = None
         if global_outputs is not None:
-            go = self._host_outputs(global_outputs)
-            ld.global_outputs = go.ctypes.data_as(C.POINTER(C.c_double))
+            go = self._dev_outputs(global_outputs)
+            ld.global_outputs = go.data_ptr()
         return ld, go
 
     def loss_begin(self, kind, weights, prop_raw=None, energy_weight=1.0, residual_weight=1.0,

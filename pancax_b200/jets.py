@@ -198,15 +198,21 @@ def tabulate_bc_jet(bc_func, pts, ndof):
         if len(comps) != ndof:
             raise ValueError(f"dirichlet_bc_func returned {len(comps)} components, expected {ndof}")
         return [c if isinstance(c, Jet) else Jet.const(c, t) for c in comps]
-    g0, g1, g2 = evaluate(0.0), evaluate(1.0), evaluate(-0.7)
+    g0, g1 = evaluate(0.0), evaluate(1.0)
+    # affinity AND diagonality: a different probe value per component, so a wrapper that mixes components
+    # (u_i depending on z_j, j != i) fails the check instead of passing with every z_j equal
+    probe = [-0.7 + 0.45 * i for i in range(ndof)]
+    out2 = bc_func(x, t, Vec(probe))
+    comps2 = list(out2) if isinstance(out2, (Vec, list, tuple)) else [out2]
+    g2 = [c if isinstance(c, Jet) else Jet.const(c, t) for c in comps2]
     tab = np.zeros((n, ndof, 2 * K))
     for i in range(ndof):
         a, b = g0[i], g1[i] - g0[i]
-        chk = a + b * (-0.7) - g2[i]
+        chk = a + b * probe[i] - g2[i]
         scale = max(1.0, float(np.abs(g2[i].v).max()))
         if max(np.abs(chk.v).max(), np.abs(chk.l).max()) > 1e-9 * scale:
-            raise NotImplementedError("dirichlet_bc_func is not affine in the network output z; pancax_b200 "
-                                      "tabulates u = a(x,t) + b(x,t) z and its derivatives")
+            raise NotImplementedError("dirichlet_bc_func is not diagonal-affine in the network output z; pancax_b200 "
+                                      "tabulates u_i = a_i(x,t) + b_i(x,t) z_i and its derivatives")
         for off, q in ((0, a), (K, b)):
             tab[:, i, off] = q.v
             tab[:, i, off + 1:off + 1 + nd] = q.g[:, :nd]

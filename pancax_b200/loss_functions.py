@@ -73,8 +73,20 @@ def get_engine(problem, params, deterministic: bool = True) -> Engine:
     traced call of a jitted step."""
     fld = params.fields
     net = fld.networks
+    shard = getattr(problem, "shard", None)
+    if shard is not None and getattr(shard, "x_mins", None) is not None:
+        # fields.py:70-71 normalises with the bounds of the WHOLE mesh.  A Field built on a shard took the shard's
+        # own bounds from problem.coords: every rank would then evaluate a different u(x, t) from the same weights.
+        # A Field whose bounds were set by hand to something else is left alone.
+        loc_lo, loc_hi = np.min(problem.coords, axis=0), np.max(problem.coords, axis=0)
+        if np.array_equal(fld.x_mins, loc_lo) and np.array_equal(fld.x_maxs, loc_hi):
+            fld.x_mins, fld.x_maxs = shard.x_mins.copy(), shard.x_maxs.copy()
+    # everything baked into the pcx_handle at set-up is part of the key; the wrapper itself (not its id(), which can
+    # be reused after garbage collection) is held by the key
     key = (net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers, net.use_final_bias,
-           id(fld.dirichlet_bc_func), deterministic)
+           fld.dirichlet_bc_func, deterministic,
+           tuple(np.asarray(fld.x_mins, dtype=np.float64).tolist()), tuple(np.asarray(fld.x_maxs, dtype=np.float64).tolist()),
+           float(fld.t_min), float(fld.t_max), bool(fld.normalize_time))
     eng = problem._engines.get(key)
     if eng is not None:
         return eng
@@ -82,7 +94,6 @@ def get_engine(problem, params, deterministic: bool = True) -> Engine:
     gd = getattr(problem, "global_data", None)
     unk = None if dom.dof_manager is None else dom.dof_manager.unknownIndices
     rn = None if gd is None else gd.reaction_nodes
-    shard = getattr(problem, "shard", None)
     if shard is not None:     # entries owned by this shard first (pcx_set_ownership)
         unk, n_uo, rn, n_ro = shard.plan.order_owned_first(unk, rn, problem.n_dofs)
     eng = Engine(dom.coords, dom.conns, dom.mesh.elem_type, dom.q_order, problem.n_dofs, dom.times,

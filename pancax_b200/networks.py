@@ -95,8 +95,14 @@ class Field:
                             ensure_positivity=ensure_positivity, device=device)
         self.seperate_networks = False
         self.t_min, self.t_max = float(np.min(problem.times)), float(np.max(problem.times))
-        self.x_mins = np.min(problem.coords, axis=0)
-        self.x_maxs = np.max(problem.coords, axis=0)
+        shard = getattr(problem, "shard", None)
+        if shard is not None and getattr(shard, "x_mins", None) is not None:
+            # one element shard of a larger mesh (parallel.shard_problem): the reference normalises with the bounds
+            # of the whole mesh, never the shard's
+            self.x_mins, self.x_maxs = shard.x_mins.copy(), shard.x_maxs.copy()
+        else:
+            self.x_mins = np.min(problem.coords, axis=0)
+            self.x_maxs = np.max(problem.coords, axis=0)
         self.normalize_time = not np.allclose(self.t_min, self.t_max)   # fields.py:73-76
 
 
@@ -178,19 +184,45 @@ class Parameters:
     def freeze_fields_filter(self):
         return dict(fields=False, props=True)
 
+    def _meta(self):
+        """What a checkpoint must agree on with the Parameters it is restored onto: the net shape and the Field's
+        normalisation constants (leaves of the reference's Parameters pytree, fields.py:66-76; restoring weights onto
+        other bounds silently changes the field)."""
+        m = self.members[0] if self.is_ensemble else self
+        net, fld = m.fields.networks, m.fields
+        return dict(net_shape=np.array([net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers,
+                                        int(net.use_final_bias)], dtype=np.int64),
+                    x_mins=np.asarray(fld.x_mins, dtype=np.float64), x_maxs=np.asarray(fld.x_maxs, dtype=np.float64),
+                    t_range=np.array([fld.t_min, fld.t_max], dtype=np.float64),
+                    normalize_time=np.array([int(bool(fld.normalize_time))], dtype=np.int64))
+
     def serialise(self, base_name: str, epoch: int):
-        """networks/base.py:80-96 equivalent: {base}_{epoch:07d}.npz with the flat leaves."""
+        """networks/base.py:80-96 equivalent: {base}_{epoch:07d}.npz with the flat leaves (weights in equinox leaf
+        order, raw trainable properties) plus the net shape and normalisation constants.  NOT the reference's
+        ``.eqx`` container (eqx.tree_serialise_leaves over the whole pytree); the two formats cannot read each
+        other -- the flat ``weights`` vector is the leaves of ``params.fields.networks`` in equinox order, which is
+        what an importer on the JAX side needs (integration/kernels_b200.py: flat_to_pytree)."""
         if self.is_ensemble:
             np.savez(f"{base_name}_{str(epoch).zfill(7)}.npz",
                      weights=self.stacked_weights.detach().cpu().numpy(),
-                     prop_raw=self.stacked_prop_raw.detach().cpu().numpy())
+                     prop_raw=self.stacked_prop_raw.detach().cpu().numpy(), **self._meta())
             return
         np.savez(f"{base_name}_{str(epoch).zfill(7)}.npz",
                  weights=self.fields.networks.weights.detach().cpu().numpy(),
-                 prop_raw=self.prop_raw.detach().cpu().numpy())
+                 prop_raw=self.prop_raw.detach().cpu().numpy(), **self._meta())
 
     def deserialise(self, f_name: str):
         d = np.load(f_name)
+        if "net_shape" in d.files:       # checkpoints written before the metadata existed carry none: accepted as is
+            meta = self._meta()
+            if not np.array_equal(d["net_shape"], meta["net_shape"]):
+                raise ValueError(f"checkpoint {f_name}: network shape {d['net_shape'].tolist()} != "
+                                 f"{meta['net_shape'].tolist()} (n_in, n_out, n_neurons, n_layers, use_final_bias)")
+            for k in ("x_mins", "x_maxs", "t_range", "normalize_time"):
+                if not np.allclose(d[k], meta[k], rtol=1e-12, atol=0.0):
+                    raise ValueError(f"checkpoint {f_name}: Field normalisation constant {k} = {d[k].tolist()} differs "
+                                     f"from this problem's {np.asarray(meta[k]).tolist()}; the weights would describe a "
+                                     "different field")
         if self.is_ensemble:
             for k, m in enumerate(self.members):
                 m.fields.networks.set_weights(d["weights"][k])

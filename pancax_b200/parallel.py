@@ -88,6 +88,10 @@ class PackedResult:
     def allreduce(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            # aux[PCX_AUX_FLAGS] is a bit mask (only bit0 is defined), not a quantity: the sum over ranks counts the
+            # ranks that raised it -- fold it back to the OR
+            if self.na > 3:
+                self.aux[3:4].clamp_(max=1.0)
         return self
 
 
@@ -187,19 +191,25 @@ class ShardExchange:
 
 
 class ShardInfo:
-    def __init__(self, plan, exchange):
+    def __init__(self, plan, exchange, x_mins=None, x_maxs=None):
         self.plan, self.exchange = plan, exchange
+        self.x_mins, self.x_maxs = x_mins, x_maxs      # Field normalisation bounds of the WHOLE mesh
 
 
-def shard_problem(problem, local_to_global, device=None):
+def shard_problem(problem, local_to_global, device=None, bounds=None):
     """Declare ``problem`` (built on this rank's element shard, nodes numbered locally) to be one shard
     of a larger mesh: ``local_to_global`` maps its nodes to mesh-wide node ids.  Residual / reaction
     losses evaluated on it then go through the phased ABI with the two exchanges; EnergyLoss needs
-    nothing.  Collective: every rank must call it."""
+    nothing.  The Field normalisation bounds of the WHOLE mesh (fields.py:70-71) are computed here
+    (``bounds = (x_mins, x_maxs)`` overrides them: shards driven from one process) and used by every Field
+    built on, or evaluated with, the sharded problem.  Collective: every rank must call it."""
     plan = make_shard_plan(local_to_global)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
-    problem.shard = ShardInfo(plan, ShardExchange(plan, device))
+    if bounds is None:
+        bounds = global_bounds(np.asarray(problem.coords))     # MIN / MAX allreduce over the ranks
+    problem.shard = ShardInfo(plan, ShardExchange(plan, device), np.asarray(bounds[0], dtype=np.float64),
+                              np.asarray(bounds[1], dtype=np.float64))
     problem._engines = {}
     return problem
 

@@ -334,37 +334,75 @@ def test_post_processor_writes_reference_layout(cuda_device, tmp_path):
         assert np.linalg.norm(el["P_zz_4"][n] - P[:, 3, 2, 2]) <= 1e-10 * np.linalg.norm(P) + 1e-13
 
 
-def test_loss_and_grad_is_cuda_graph_capturable(cuda_device):
-    """The C ABI never allocates, synchronises or reads back inside a compute call, so a whole loss+gradient
-    step can be captured in a CUDA graph by the caller (launch-bound small meshes; tools/bench_small.py)."""
+@pytest.mark.parametrize("name,kind,first_step", [
+    ("quad4_neohookean", "energy_residual_reaction", 0),
+    ("quad4_neohookean_pstress", "energy_residual_reaction", 0),     # PlaneStress: root workspace sized at set-up
+    ("hex8_visco_neohookean", "energy", 1),                          # SimpleFeFv: state history sized at set-up
+    ("hex8_neohookean", "energy_residual_reaction", 0),
+])
+def test_loss_and_grad_is_cuda_graph_capturable(cuda_device, name, kind, first_step):
+    """The C ABI never allocates, synchronises or reads back inside a compute call (pcx_abi.h), so a whole
+    loss+gradient step can be captured in a CUDA graph by the caller.  The captured handle has NEVER run before the
+    capture (a second handle of the same case warms the kernels up), so any workspace allocated lazily inside a
+    compute call -- or a host buffer staged inside it -- would break the capture."""
     import torch
     from tests.cases import make_case, make_engine
-    case = make_case("quad4_neohookean", n=6, nt=3, width=20, depth=2)
-    eng = make_engine(case)
+    case = make_case(name, n=4 if name.startswith("hex8") else 6, nt=3, width=20, depth=2)
+    if first_step == 0:
+        case.times = np.linspace(0.25, 1.0, 3)
+    warm, eng = make_engine(case), make_engine(case)
     w = torch.as_tensor(case.weights, device=eng.device)
+    pr = torch.as_tensor(case.prop_raw, device=eng.device) if eng.n_train else None
+    gout = torch.as_tensor(case.global_outputs, device=eng.device)       # device pointer in pcx_loss_desc (ABI v4)
     out = tuple(torch.empty(k, dtype=torch.float64, device=eng.device) for k in (1, 4 + 3, eng.n_weights, 1))
-    kw = dict(global_outputs=case.global_outputs, energy_weight=1.3, residual_weight=0.7, reaction_weight=2.1)
-    eng.loss_and_grad("energy_residual_reaction", w, out=out, **kw)
-    ref = [o.clone() for o in out]
+    kw = dict(global_outputs=gout, energy_weight=1.3, residual_weight=0.7, reaction_weight=2.1, first_step=first_step)
+    ref = warm.loss_and_grad(kind, w, pr, **kw)
+    ref = [o.clone() for o in ref]
+    torch.cuda.synchronize()
     g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        eng.loss_and_grad("energy_residual_reaction", w, out=out, **kw)
         with torch.cuda.graph(g, stream=s):
-            eng.loss_and_grad("energy_residual_reaction", w, out=out, **kw)
+            eng.loss_and_grad(kind, w, pr, out=out, **kw)
     torch.cuda.current_stream().wait_stream(s)
     for o in out:
         o.zero_()
-    w2 = w * 1.01
     g.replay()
     torch.cuda.synchronize()
-    assert all(torch.equal(a, b) for a, b in zip(out, ref))
-    # new weights through the same graph: the captured pointers are the caller's buffers
+    assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1]) and torch.equal(out[2], ref[2])
+    # new weights and new global data through the same graph: the captured pointers are the caller's buffers
+    w2, gout2 = w * 1.01, gout * 0.5 + 0.01
     w.copy_(w2)
+    gout.copy_(gout2)
     g.replay()
     torch.cuda.synchronize()
-    L2, _, g2, _ = eng.loss_and_grad("energy_residual_reaction", w2, **kw)
-    assert torch.equal(out[0], L2) and torch.equal(out[2], g2)
+    L2, a2, g2, _ = warm.loss_and_grad(kind, w2, pr, **dict(kw, global_outputs=gout2))
+    assert torch.equal(out[0], L2) and torch.equal(out[1], a2) and torch.equal(out[2], g2)
+    eng.close()
+    warm.close()
+
+
+def test_strong_form_workspace_is_reserved_at_setup(cuda_device):
+    """pcx_reserve: the strong-form workspace is a set-up allocation; a compute call on more points than reserved is
+    refused (PCX_ERR_STATE) instead of allocating."""
+    import torch
+    from pancax_b200._lib import PcxError, check
+    from tests.cases import make_case, make_engine
+    import ctypes as C
+    case = make_case("poisson_quad4", n=4, nt=2, width=20, depth=2)
+    eng = make_engine(case)
+    w = torch.as_tensor(case.weights, device=eng.device)
+    pts = torch.rand(300, 3, dtype=torch.float64, device=eng.device)
+    u = torch.empty(300, 1, dtype=torch.float64, device=eng.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    args = (eng.h, C.c_void_p(w.data_ptr()), C.c_void_p(pts.data_ptr()), None, 300, C.c_void_p(u.data_ptr()), None, None, None, st)
+    with pytest.raises(PcxError, match="pcx_reserve"):
+        check(eng.lib.pcx_points_jet(*args))
+    check(eng.lib.pcx_reserve(eng.h, 1, 300))
+    check(eng.lib.pcx_points_jet(*args))
+    u_ref = eng.points_forward(w, pts)
+    torch.cuda.synchronize()
+    assert torch.allclose(u, u_ref, rtol=1e-12, atol=1e-14)
     eng.close()
 
 

@@ -193,6 +193,35 @@ def test_residual_loss_at_t0_is_finite(cuda_device):
     assert rel(gw, gwo) < TOL
 
 
+@pytest.mark.parametrize("kind", ["energy_residual", "energy_residual_reaction"])
+def test_residual_losses_with_more_than_64_time_steps(cuda_device, kind):
+    """The per-step residual coefficients are computed by one thread per time step of the batch: a batch of more
+    than 64 steps must fill all of them (a <<<1, 64>>> launch left steps >= 64 at zero)."""
+    case = make_case("quad4_neohookean", n=3, nt=70, width=12, depth=2)
+    case.times = np.linspace(0.2, 1.0, 70)
+    case.global_outputs = np.linspace(0.0, 0.2, 70)
+    L, aux, gw, gp = run_engine_loss(case, kind)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, kind)
+    assert abs(L - Lo) <= TOL * abs(Lo)
+    assert abs(aux[1] - auxo["residual"]) <= TOL * abs(auxo["residual"])
+    if kind == "energy_residual_reaction":
+        assert rel(aux[4:], auxo["reactions"]) < TOL
+        assert np.all(aux[4 + 64:] != 0.0)
+    assert rel(gw, gwo) < TOL
+
+
+def test_time_chunk_not_dividing_nt(cuda_device, monkeypatch):
+    case = make_case("quad4_neohookean", n=4, nt=7, width=16, depth=2)
+    case.times = np.linspace(0.2, 1.0, 7)
+    case.global_outputs = np.linspace(0.0, 0.2, 7)
+    ref = run_oracle_loss(case, "energy_residual_reaction")
+    monkeypatch.setenv("PCX_TCHUNK", "3")
+    out = run_engine_loss(case, "energy_residual_reaction")
+    assert abs(ref[0] - out[0]) <= TOL * abs(ref[0])
+    assert rel(out[1][4:], ref[1]["reactions"]) < TOL
+    assert rel(out[2], ref[2]) < TOL
+
+
 def test_time_chunking_matches(cuda_device, monkeypatch):
     case = make_case("quad4_neohookean", n=5, nt=5)
     case.times = np.linspace(0.2, 1.0, 5)
