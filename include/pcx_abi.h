@@ -184,6 +184,18 @@ int pcx_destroy(pcx_handle* h);
  * relative per leaf (north_star allows 1e-4).  Must not be toggled between a forward and its adjoint
  * (pcx_loss_begin / pcx_loss_finish). */
 #define PCX_OPT_TF32_ADJOINT 2
+/* Kernel-variant switches for A/B measurements (tools/kernel_ab.py); every variant computes the same function to
+ * rounding.  FWD_TANH: 1 (default) replicated conflict-free exp2 table + 13-instruction tanh, 0 single table, 2 replicated
+ * table with the old range reduction.  FWD_EDGE / BWD_EDGE: 1 (default) the mostly-padding last feature tile of the hidden
+ * layers on the FP64 vector pipe instead of the tensor pipe.  FWD_VARIANT: (row tiles per warp, min CTAs per SM) = 12|21|22. */
+#define PCX_OPT_TUNE_FWD_TANH    100
+#define PCX_OPT_TUNE_FWD_EDGE    101
+#define PCX_OPT_TUNE_BWD_EDGE    102
+#define PCX_OPT_TUNE_FWD_VARIANT 103
+#define PCX_OPT_TUNE_FWD_DYNAMIC 105   /* 1 (default): forward row groups handed out by a global counter; 0: static grid stride */
+#define PCX_OPT_TUNE_L2PF        107   /* 1 (default): the adjoint pulls its next tile's stored activations into L2 a tile ahead */
+#define PCX_OPT_TUNE_STAMPS      104   /* value = device pointer to u64[3 * 2 * SM count] or 0: the MLP kernels over the mesh
+                                          nodes write per-CTA (start, end, smid) %globaltimer stamps of their last launch there */
 int pcx_set_option(pcx_handle* h, int32_t option, int64_t value);
 
 /* Set-up call for workspaces whose size depends on the caller's batch (everything else is sized by pcx_set_physics /

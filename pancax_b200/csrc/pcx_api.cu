@@ -82,6 +82,7 @@ struct pcx_handle {
   double *vq = nullptr, *vpart = nullptr;   // point fluxes [ne*nq][ndof*nd]; block partials [vnblk][1 + PCX_MAX_PROPS]
   int vnblk = 0;                            // blocks of the per-point sweep: ceil(ne nq / 128)
   long long vz_per = 0;
+  bool vz_filled = false;                   // a path-dependent call has written the state history
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
                  const double* lam_in; double* lam_out; } vstep;
   int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT
@@ -97,6 +98,12 @@ struct pcx_handle {
   long long launches = 0;
   int sm_count = 148;
   int fwd_variant = 12;   // (MT, min CTAs/SM) of the forward kernel; PCX_FWD_VARIANT overrides (tuning)
+  int fwd_tanh = 1;       // 1: replicated conflict-free exp2 table + 13-instruction tanh; 0: single table (PCX_FWD_TANH)
+  int l2pf = 1;                           // PCX_OPT_TUNE_L2PF
+  unsigned int* sched = nullptr;          // group counter of the forward kernel's dynamic scheduler
+  int fwd_dynamic = 1;                    // PCX_OPT_TUNE_FWD_DYNAMIC
+  unsigned long long* stamps = nullptr;   // tuning: per-CTA time stamps of the last MLP launch (PCX_OPT_TUNE_STAMPS)
+  int bwd_edge = 1;       // the same for the adjoint's delta chain; PCX_BWD_EDGE=0 disables
   int fwd_edge = 1;       // last (mostly padding) tile of the hidden layers on the FP64 vector pipe; PCX_FWD_EDGE=0 disables
   bool prof_on = false;
   struct ProfEv { int cat; cudaEvent_t e0, e1; };
@@ -387,17 +394,27 @@ static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, c
   return PCX_OK;
 }
 
-template <int NT, int KODD, int DH, bool WSMEM>
-static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
+template <int NT, int KODD, int DH, bool WSMEM, int BEDGE>
+static int launch_mlp_bwd_e(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
   const size_t smem = sizeof(BwdSmem<NT, DH, WSMEM>);
   if (smem > 227 * 1024)
     return fail(PCX_ERR_UNSUPPORTED, "MLP %d x %d needs %zu bytes of shared memory in the adjoint kernel", h->ms.width,
                 h->ms.depth, smem);
   // per device and cheap: set it on every launch (a process may drive several devices)
-  CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_mlp_backward<NT, KODD, DH, WSMEM><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM, BEDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mlp_backward<NT, KODD, DH, WSMEM, BEDGE><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
+}
+template <int NT, int KODD, int DH, bool WSMEM>
+static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
+  // edge tile of the delta chain on the vector pipe when the last tile holds one or two real features (width 50: 48, 49)
+  if constexpr (NT == 7 && KODD == 1 && DH > 0) {
+    const int nedge = h->ms.width - 8 * (NT - 1);
+    if (h->bwd_edge && nedge == 2) return launch_mlp_bwd_e<NT, KODD, DH, WSMEM, 2>(h, grid, st, io);
+    if (h->bwd_edge && nedge == 1) return launch_mlp_bwd_e<NT, KODD, DH, WSMEM, 1>(h, grid, st, io);
+  }
+  return launch_mlp_bwd_e<NT, KODD, DH, WSMEM, 0>(h, grid, st, io);
 }
 
 template <int NT, int DH>
@@ -422,19 +439,34 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
   }
 }
 
-template <int NT, int KODD, int MT, int MINB, int NEDGE = 0>
-static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
-  const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + EXP2_TAB_N) * sizeof(double);
-  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB, NEDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV, int NTHR = 256>
+static int launch_mlp_fwd_t(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + fwd_table_doubles(TV)) * sizeof(double);
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB, NEDGE, TV, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
   const long long groups = (io.n + 8 * MT - 1) / (8 * MT);
-  long long blocks = (groups + 7) / 8;
+  long long blocks = (groups + NTHR / 32 - 1) / (NTHR / 32);
   const long long maxb = (long long)h->sm_count * MINB;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
-  k_mlp_forward<NT, KODD, MT, MINB, NEDGE><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+  MlpIO iod = io;
+  iod.sched = h->fwd_dynamic ? h->sched : nullptr;
+  if (iod.sched) CUDA_TRY(cudaMemsetAsync(h->sched, 0, sizeof(unsigned int), st));
+  k_mlp_forward<NT, KODD, MT, MINB, NEDGE, TV, NTHR><<<(int)blocks, NTHR, smem, st>>>(h->ms, iod);
   LAUNCH_CHECK(h);
   return PCX_OK;
+}
+template <int NT, int KODD, int MT, int MINB, int NEDGE = 0>
+static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
+  // the replicated table costs 8 KB per CTA: taken when two CTAs per SM still fit (they do up to width 55), else the
+  // single 1 KB table
+  const size_t smem1 = (size_t)(h->ms.pBO - h->ms.pF0 + fwd_table_doubles(1)) * sizeof(double);
+  if constexpr (NT == 7 && MT == 1 && MINB == 2 && NEDGE == 2) {   // tuning: more warps per CTA (fewer registers each)
+    if (h->fwd_variant == 13) return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 1, 320>(h, st, io);
+    if (h->fwd_variant == 14) return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 1, 384>(h, st, io);
+  }
+  if (h->fwd_tanh == 1 && (smem1 + 1024) * MINB <= 227 * 1024) return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 1>(h, st, io);
+  return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 0>(h, st, io);
 }
 
 template <int NT, int MT, int MINB>
@@ -567,6 +599,8 @@ static void free_ws(pcx_handle* h) {
   for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   if (h->flags) cudaFree(h->flags);
   h->flags = nullptr;
+  if (h->sched) cudaFree(h->sched);
+  h->sched = nullptr;
   if (h->pk32) cudaFree(h->pk32);
   h->pk32 = nullptr;
   if (h->vz) cudaFree(h->vz);
@@ -576,7 +610,7 @@ static void free_ws(pcx_handle* h) {
   if (h->vpart) cudaFree(h->vpart);
   if (h->f33) cudaFree(h->f33);
   h->f33 = nullptr; h->f33_cap = 0;
-  h->vz = nullptr; h->vus = nullptr; h->vq = nullptr; h->vpart = nullptr; h->vz_per = 0; h->vnblk = 0;
+  h->vz = nullptr; h->vus = nullptr; h->vq = nullptr; h->vpart = nullptr; h->vz_per = 0; h->vnblk = 0; h->vz_filled = false;
 }
 
 static int alloc_ws(pcx_handle* h) {
@@ -640,6 +674,7 @@ static int alloc_ws(pcx_handle* h) {
   }
   CUDA_TRY(cudaMalloc(&h->flags, sizeof(int)));
   CUDA_TRY(cudaMemset(h->flags, 0, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&h->sched, 4 * sizeof(unsigned int)));
   return PCX_OK;
 }
 
@@ -661,6 +696,8 @@ extern "C" int pcx_create(pcx_handle** out, const pcx_mesh_desc* m) {
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("PCX_FWD_VARIANT")) h->fwd_variant = atoi(e);
   if (const char* e = getenv("PCX_FWD_EDGE")) h->fwd_edge = atoi(e);
+  if (const char* e = getenv("PCX_FWD_TANH")) h->fwd_tanh = atoi(e);
+  if (const char* e = getenv("PCX_BWD_EDGE")) h->bwd_edge = atoi(e);
   h->elem_type = m->elem_type; h->q_order = m->q_order;
   h->nd = h->tab.nd; h->nnpe = h->tab.nnpe; h->nq = h->tab.nq;
   h->ndof = m->ndof; h->ne = m->ne; h->nn = m->nn; h->nt = m->nt;
@@ -760,6 +797,14 @@ extern "C" int pcx_set_option(pcx_handle* h, int32_t option, int64_t value) {
       if (value && h->have_field) { int rc = tf32_supported(h); if (rc) return rc; }
       h->tf32_adjoint = value != 0;
       return PCX_OK;
+    // kernel-variant switches (tuning / A-B measurements; every variant computes the same function)
+    case PCX_OPT_TUNE_FWD_TANH: h->fwd_tanh = (int)value; return PCX_OK;
+    case PCX_OPT_TUNE_FWD_EDGE: h->fwd_edge = (int)value; return PCX_OK;
+    case PCX_OPT_TUNE_BWD_EDGE: h->bwd_edge = (int)value; return PCX_OK;
+    case PCX_OPT_TUNE_FWD_VARIANT: h->fwd_variant = (int)value; return PCX_OK;
+    case PCX_OPT_TUNE_FWD_DYNAMIC: h->fwd_dynamic = value != 0; return PCX_OK;
+    case PCX_OPT_TUNE_L2PF: h->l2pf = value != 0; return PCX_OK;
+    case PCX_OPT_TUNE_STAMPS: h->stamps = reinterpret_cast<unsigned long long*>(value); return PCX_OK;
     default: return fail(PCX_ERR_INVALID, "unknown option %d", option);
   }
 }
@@ -856,6 +901,8 @@ static MlpIO node_io(pcx_handle* h, int t0, int T) {
   io.bc_a = h->bc_a ? h->bc_a + (long long)t0 * h->nn * h->ndof : nullptr;
   io.bc_b = h->bc_b ? h->bc_b + (long long)t0 * h->nn * h->ndof : nullptr;
   io.act = h->act; io.rows_cap = h->rows_cap; io.pk = h->pk; io.part = h->part; io.part_stride = h->part_stride;
+  io.dbg = h->stamps;
+  io.l2pf = h->l2pf;
   return io;
 }
 
@@ -1337,6 +1384,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   }
   h->vstep.on = false;
   if (rc) return rc;
+  h->vz_filled = true;
   if (want_grad) {
     if (resident && (rc = field_backward_steps(h, 0, nt, h->ubar, g_weights, first, st))) return rc;
     if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
@@ -1353,7 +1401,7 @@ extern "C" int64_t pcx_num_state_variables(const pcx_handle* h) { return h && h-
 extern "C" int pcx_get_state(pcx_handle* h, int32_t t_idx, double* state, void* stream) {
   NEED_READY(h);
   if (h->phys.n_prony <= 0) return fail(PCX_ERR_STATE, "the constitutive model has no state variables");
-  if (!h->vz) return fail(PCX_ERR_STATE, "no state history yet: run the path-dependent pcx_loss_and_grad first");
+  if (!h->vz || !h->vz_filled) return fail(PCX_ERR_STATE, "no state history yet: run the path-dependent pcx_loss_and_grad first");
   if (t_idx < 0 || t_idx >= h->nt || !state) return fail(PCX_ERR_INVALID, "pcx_get_state: bad time step or null output");
   CUDA_TRY(cudaMemcpyAsync(state, h->vz + (long long)t_idx * h->vz_per, (size_t)h->vz_per * sizeof(double), cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));

@@ -77,6 +77,11 @@ __device__ __forceinline__ double2 ld_cs_f64x2(const double* p) {
 //                           FP64 vector pipe, see k_mlp_forward NEDGE)
 //   BO  [NT][32]            backward top: W_out[c'][feat(8jn+r')]                          (c' < n_out)
 //   BH  [depth-1][KSP][NT][32] backward hidden i>=1: W_i[4ks+c'][feat(8jn+r')]
+//   BE  [depth-1][KSP][4][2] backward hidden i>=1, columns of input features 8(NT-1)+f, f < 2: W_i[4ks+c][8(NT-1)+f]
+//                           (edge tile of the delta chain on the FP64 vector pipe, see k_mlp_backward BEDGE).  It has no
+//                           section of its own: when the width leaves k-step KSP-1 of BH unused (KS < KSP, all zeros),
+//                           BE of layer i sits in the first 8*KSP doubles of that k-step, so the adjoint kernel finds it
+//                           in the shared-memory copy of BH it stages anyway.
 // KSP = 2*NT (padded k-step count so offsets do not depend on width).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_weights(MlpShape s, const double* __restrict__ w, double* __restrict__ pk) {
@@ -133,7 +138,7 @@ __global__ void k_pack_weights(MlpShape s, const double* __restrict__ w, double*
     int r = lane >> 2, c = lane & 3;
     int k = slot_to_feat(8 * jn + r);
     if (c < s.n_out && k < W) val = w[s.offW[D] + (long long)c * W + k];
-  } else {  // BH
+  } else {  // BH (+ BE in its unused last k-step)
     t -= s.pBH;
     int lane = t & 31;
     long long q = t >> 5;
@@ -143,6 +148,12 @@ __global__ void k_pack_weights(MlpShape s, const double* __restrict__ w, double*
     int r = lane >> 2, c = lane & 3;
     int o = 4 * ks + c, k = slot_to_feat(8 * jn + r);
     if (o < W && k < W) val = w[s.offW[i] + (long long)o * W + k];
+    const int e = jn * 32 + lane;       // position inside the k-step
+    if (s.KS < KSP && ks == KSP - 1 && e < KSP * 8) {
+      const int f = e & 1, cc = (e >> 1) & 3, kb = e >> 3;
+      const int ob = 4 * kb + cc, kk = 8 * (NT - 1) + f;
+      val = (ob < W && kk < W) ? w[s.offW[i] + (long long)ob * W + kk] : 0.0;
+    }
   }
   pk[tid] = val;
 }
@@ -167,8 +178,16 @@ struct MlpIO {
   const float* pk32;    // TF32-adjoint mode: packed hi/lo chain weights (k_pack_weights_tf32)
   double* part;         // backward: per-CTA partial weight gradients [gridDim][part_stride]
   long long part_stride;
-  // optional fused data loss: g_u = scale * 2 (u - target) computed in the forward pass
+  unsigned int* sched;       // forward: group counter of the dynamic scheduler (zeroed before the launch) or nullptr
+  int l2pf;                  // adjoint: L2 prefetch of the next tile's activations
+  unsigned long long* dbg;   // tuning: per-CTA (start, end, smid) stamps [3*gridDim] or nullptr (PCX_OPT_TUNE_STAMPS)
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ double mlp_input(const MlpShape& s, const MlpIO& io, long long row, int c) {
   // fields.py:80-88: inputs = hstack(x_norm, t_norm)
@@ -232,6 +251,10 @@ __device__ __forceinline__ void stage_weights(double* dst, const double* src, lo
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   const uint32_t sz = valid ? 16u : 0u;   // src-size 0 => zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+// L2 prefetch of a contiguous global range (TMA engine, no shared memory involved)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -314,6 +337,43 @@ __device__ __forceinline__ double tanh_tb(double x, const double* __restrict__ T
   return copysign(q, x);
 }
 
+// Forward-kernel variant of the same tanh: 13 FP64-pipe instructions instead of 15 and a conflict-free table.
+//  * the 2^(j/64) table is replicated 16 times, entry j of copy l at T[16 j + l]: the 16 lanes of a half warp (one
+//    shared-memory wavefront of an LDS.64) read 16 different bank pairs whatever their j -- the 128-entry single copy
+//    cost 2.75 extra wavefronts per lookup on random j (ncu r01: 73.9 M bank conflicts per forward launch);
+//    64 entries: |s| <= 1/2 in units of ln2/64, degree-5 truncation (ln2/128)^6/720 = 3.5e-17 relative;
+//  * the clamp |x| <= 22 is an integer min on the high word (ALU pipe), not a DSETP/select pair on the FP64 pipe;
+//  * s = a C - k takes k back from the integer pipe (I2F, conversion unit) instead of a DADD on the FP64 pipe.
+constexpr int EXP2_REP_N = 64, EXP2_REP_COPIES = 16;
+template <bool CHEAP = true>   // false (tuning only): the table alone, clamp and s as in tanh_tb
+__device__ __forceinline__ double tanh_rep(double x, const double* __restrict__ T /* + (lane & 15) */) {
+  const int xh = __double2hiint(x);
+  const int ah = min(xh & 0x7fffffff, 0x40360000);                 // |x| clamped to [0, 22 + 2^-16): E underflows to ~0 anyway
+  const double a = CHEAP ? __hiloint2double(ah, __double2loint(x)) : fmin(fabs(x), 22.0);
+  const double MAGIC = 6755399441055744.0;
+  const double C = -0x1.71547652b82fep+7;                          // -2 log2(e) * 64
+  const double t = fma(a, C, MAGIC);
+  const int k = __double2loint(t);                                 // <= 0
+  const double s = CHEAP ? fma(a, C, -(double)k) : fma(a, C, MAGIC - t);   // exact: k is the rounded product
+  double p = 0x1.5d87fe78a6731p-40;                                // (ln2/64)^5/5!
+  p = fma(p, s, 0x1.3b2ab6fba4e77p-31);                            // (ln2/64)^4/4!
+  p = fma(p, s, 0x1.c6b08d704a0c0p-23);                            // (ln2/64)^3/3!
+  p = fma(p, s, 0x1.ebfbdff82c58fp-15);                            // (ln2/64)^2/2!
+  p = fma(p, s, 0x1.62e42fefa39efp-7);                             // ln2/64
+  p = fma(p, s, 1.0);
+  const double m = T[(k & (EXP2_REP_N - 1)) * EXP2_REP_COPIES] * p;
+  const int n = k >> 6;
+  const int mh = __double2hiint(m), ml = __double2loint(m);
+  const double E = __hiloint2double(mh + (n << 20), ml);
+  const double m2E = __hiloint2double((mh + ((n + 1) << 20)) ^ 0x80000000, ml);   // -2E
+  const double den = 1.0 + E;
+  const double r0 = rcp_approx_f64(den);
+  const double e = fma(-den, r0, 1.0);
+  const double r1 = fma(r0, fma(e, e, e), r0);
+  const double q = fma(m2E, r1, 1.0);
+  return __hiloint2double((__double2hiint(q) & 0x7fffffff) | (xh & 0x80000000), __double2loint(q));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward.  One warp = MT tiles of 8 rows; grid-stride over row groups.  The forward weight
 // fragments [F0 | FB | FH | FO | FOB] are staged ONCE per CTA into shared memory with a bulk
@@ -324,41 +384,102 @@ __device__ __forceinline__ double tanh_tb(double x, const double* __restrict__ T
 // instead: every lane already holds A-fragment element (row r, feature 4ks+c), multiplies it with the two weight
 // rows W[48..49][4ks+c] (one broadcast LDS.128 per k-step), and a 2-step butterfly over the 4 lanes of a row
 // finishes the sums -- 26 DFMA + 4 DADD + 8 SHFL instead of 13 DMMA (= 104 DFMA issue slots).  NEDGE = 0: off.
-template <int NT, int KODD, int MT, int MINB, int NEDGE>
-__global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
+//
+// Per-group prologue (r2): raw coordinate / time loads are issued a whole group ahead and normalised at use (the
+// load -> subtract -> divide chain sat exposed in front of layer 0: 3.4 % of the samples on one DADD), the lane's
+// normalisation constants are hoisted, and (time step, node) of a row is tracked incrementally instead of a 64-bit
+// division and modulo per group.
+// TV = 0: tanh_tb (single 128-entry table); TV = 1: tanh_rep (replicated conflict-free table, 13 FP64 instructions);
+// TV = 2 (tuning): replicated table with tanh_tb's clamp / range reduction
+constexpr int fwd_table_doubles(int tv) { return tv ? EXP2_REP_N * EXP2_REP_COPIES : EXP2_TAB_N; }
+template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV = 1, int NTHR = 256>
+__global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
+  if (io.dbg && threadIdx.x == 0) { io.dbg[3 * blockIdx.x] = globaltimer_ns(); unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); io.dbg[3 * blockIdx.x + 2] = sm; }
   double* sw = reinterpret_cast<double*>(smem_raw);
-  double* stab = sw + (s.pBO - s.pF0);          // 2^(j/128) table behind the weight fragments
-  if (threadIdx.x < EXP2_TAB_N) stab[threadIdx.x] = g_exp2_tab[threadIdx.x];
+  double* stab = sw + (s.pBO - s.pF0);          // exp2 table behind the weight fragments
+  if constexpr (TV == 0) {
+    if (threadIdx.x < EXP2_TAB_N) stab[threadIdx.x] = g_exp2_tab[threadIdx.x];
+  } else {
+    for (int i = threadIdx.x; i < EXP2_REP_N * EXP2_REP_COPIES; i += blockDim.x)
+      stab[i] = g_exp2_tab[(i / EXP2_REP_COPIES) * (EXP2_TAB_N / EXP2_REP_N)];
+  }
   stage_weights(sw, io.pk + s.pF0, s.pBO - s.pF0, &wbar);   // (contains a __syncthreads)
   const double* __restrict__ pk = sw - s.pF0;   // same offsets as the global buffer
 
   const int lane = threadIdx.x & 31;
+  if constexpr (TV != 0) stab += lane & (EXP2_REP_COPIES - 1);
+  auto act_fn = [&](double z) { if constexpr (TV == 0) return tanh_tb(z, stab); else return tanh_rep<TV == 1>(z, stab); };
   const int r = lane >> 2, c = lane & 3;
   constexpr int KSP = 2 * NT;
   constexpr int KS = 2 * NT - KODD;   // compile-time k-step count: no per-step branch, loads pipeline freely
+  constexpr int NE = 2 * NT;          // A-fragment elements (k-steps' worth of features) per row tile
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
   const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long ngroups = (io.n + 8 * MT - 1) / (8 * MT);
   // slots of the last tile whose features are all padding need no tanh (their pre-activation is 0)
   const int last_real_x1 = (8 * (NT - 1) + 4 < s.width);   // reg x=1 of tile NT-1 holds features 8(NT-1)+4+c
 
-  // inputs of the next row group are loaded one iteration ahead; the Dirichlet tables of this group
-  // at the top of the iteration (consumed after the whole layer chain): no exposed DRAM latency
-  double a0n[MT];
+  // fields.py:80-88: inputs = hstack(x_norm, t_norm); lane c owns input column c.  (raw - in_min) / in_scale with
+  // in_min = 0, in_scale = 1 where nothing is normalised (exact); padding columns read raw = 0.
+  const bool is_x = c < s.nd, is_t = c == s.nd;
+  const double in_min = is_x ? s.x_min[c] : (is_t && s.normalize_time) ? s.t_min : 0.0;
+  const double in_scale = is_x ? s.x_scale[c] : (is_t && s.normalize_time) ? s.t_scale : 1.0;
+  // Dynamic group scheduler (r2).  The two CTAs resident on an SM do not progress at the same rate -- with the static
+  // grid-stride split, on EVERY SM one CTA finished after 78 % of the kernel and the other ran the last 22 % alone, at
+  // half the warps per scheduler (per-CTA %globaltimer stamps, tools/cta_stamps.py) -- so warps take their next group of
+  // 8*MT rows from a global counter (io.sched, zeroed before the launch), one group ahead so the atomic's latency never
+  // shows.  Rows are independent: results do not depend on who computes them.  io.sched == nullptr: static stride.
+  auto grab = [&](long long prev) -> long long {
+    if (!io.sched) return prev + warps_total;
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(io.sched, 1u);
+    return (long long)__shfl_sync(0xffffffffu, v, 0) + warps_total;   // the first warps_total groups are handed out statically
+  };
+  // rows of the NEXT group of this lane: row, and (time step, node) when rows are (time step, node) pairs
+  long long rowN[MT], nodeN[MT];
+  int tqN[MT];
+  const bool small = io.n < 0x7fffffffLL;
+  auto seek = [&](long long gnext) {
 #pragma unroll
-  for (int m = 0; m < MT; m++) a0n[m] = mlp_input(s, io, warp_id * (8 * MT) + 8 * m + r, c);
-  for (long long g = warp_id; g < ngroups; g += warps_total) {
+    for (int m = 0; m < MT; m++) {
+      rowN[m] = gnext * (8 * MT) + 8 * m + r;
+      if (io.nn_mod > 0 && rowN[m] < io.n) {
+        if (small) tqN[m] = (int)((unsigned)rowN[m] / (unsigned)io.nn_mod);
+        else tqN[m] = (int)(rowN[m] / io.nn_mod);
+        nodeN[m] = rowN[m] - (long long)tqN[m] * io.nn_mod;
+      } else {
+        tqN[m] = 0;
+        nodeN[m] = rowN[m];
+      }
+    }
+  };
+  auto load_raw = [&](int m) -> double {
+    if (rowN[m] >= io.n) return in_min;      // normalises to 0
+    if (is_x) return io.x[nodeN[m] * io.x_stride + c];
+    if (is_t) return io.nn_mod > 0 ? io.times[tqN[m]] : (io.trow ? io.trow[rowN[m] * io.x_stride] : io.t);
+    return 0.0;
+  };
+  long long g = warp_id;
+  long long gnext = grab(g);
+  seek(g);
+  double rawn[MT];
+#pragma unroll
+  for (int m = 0; m < MT; m++) rawn[m] = load_raw(m);
+
+  for (; g < ngroups; g = gnext, gnext = grab(g)) {
     const long long row0 = g * (8 * MT);
     double h[MT][NT][2], acc[MT][NT][2];
     // ---- layer 0
     double a0[MT];
     double bcA[MT][2], bcB[MT][2];
+    seek(gnext);   // next group's raw input: a whole layer chain to arrive
 #pragma unroll
     for (int m = 0; m < MT; m++) {
-      a0[m] = a0n[m];
-      a0n[m] = mlp_input(s, io, (g + warps_total) * (8 * MT) + 8 * m + r, c);   // rows >= n give 0
+      const double rw = rawn[m];
+      rawn[m] = load_raw(m);
+      a0[m] = (rw - in_min) / in_scale;
       const long long row = row0 + 8 * m + r;
 #pragma unroll
       for (int x = 0; x < 2; x++) {
@@ -379,39 +500,43 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
         dmma(acc[m][jn][0], acc[m][jn][1], a0[m], bf);
       }
     }
-#pragma unroll 1
-    for (int i = 0;; i++) {
-      // activation of layer i
+    // activation of element e of every row tile (element e = register e&1 of tile e>>1 = features 4e..4e+3)
+    auto activate = [&](int e) {
 #pragma unroll
-      for (int m = 0; m < MT; m++)
-#pragma unroll
-        for (int jn = 0; jn < NT; jn++) {
-          h[m][jn][0] = tanh_tb(acc[m][jn][0], stab);
-          if (jn < NT - 1 || last_real_x1) h[m][jn][1] = tanh_tb(acc[m][jn][1], stab);
-          else h[m][jn][1] = 0.0;
-        }
+      for (int m = 0; m < MT; m++) {
+        if (e < NE - 1 || last_real_x1) h[m][e >> 1][e & 1] = act_fn(acc[m][e >> 1][e & 1]);
+        else h[m][e >> 1][e & 1] = 0.0;
+      }
+    };
+    // stored for the adjoint once both elements of a tile exist (one coalesced 512 B row block per warp and tile)
+    auto store_tile = [&](int i, int jn) {
       if (io.act32) {   // TF32-adjoint mode: fp32 planes, same slot order (half the store traffic)
 #pragma unroll
         for (int m = 0; m < MT; m++) {
           const long long row = row0 + 8 * m + r;
-          if (row < io.n) {
-#pragma unroll
-            for (int jn = 0; jn < NT; jn++)
-              st_cs_f32x2_fwd(io.act32 + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, (float)h[m][jn][0],
-                              (float)h[m][jn][1]);
-          }
+          if (row < io.n)
+            st_cs_f32x2_fwd(io.act32 + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, (float)h[m][jn][0],
+                            (float)h[m][jn][1]);
         }
       } else if (io.act) {
 #pragma unroll
         for (int m = 0; m < MT; m++) {
           const long long row = row0 + 8 * m + r;
-          if (row < io.n) {
-#pragma unroll
-            for (int jn = 0; jn < NT; jn++)
-              st_cs_f64x2(io.act + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, h[m][jn][0], h[m][jn][1]);
-          }
+          if (row < io.n) st_cs_f64x2(io.act + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, h[m][jn][0], h[m][jn][1]);
         }
       }
+    };
+#pragma unroll 1
+    for (int i = 0;; i++) {
+      // activation of layer i: a phase of its own.  (Tried in r2 and measured slower, 3.64 -> 3.93 ms: computing the
+      // activation of element e two k-steps ahead of the DMMAs that consume it, in one interleaved stream -- a warp
+      // issues in order, so the DMMAs then queue behind the dependent DFMA chain of the tanh in front of them; as
+      // separate phases one warp's DMMA phase is a clean stream of independent instructions that fills the pipe while
+      // the other warps of the scheduler sit in their tanh chains.)
+#pragma unroll
+      for (int e = 0; e < NE; e++) activate(e);
+#pragma unroll
+      for (int jn = 0; jn < NT; jn++) store_tile(i, jn);
       if (i == s.depth - 1) break;
       // ---- hidden layer i+1
       const double* fb = pk + s.pFB + (long long)(i + 1) * NT * 64;
@@ -497,6 +622,10 @@ __global__ void __launch_bounds__(256, MINB) k_mlp_forward(const __grid_constant
       }
     }
   }
+  if (io.dbg) {
+    __syncthreads();
+    if (threadIdx.x == 0) io.dbg[3 * blockIdx.x + 1] = globaltimer_ns();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -534,13 +663,19 @@ struct BwdSmem {
   uint64_t sync;   // split-phase CTA barrier (arrive early, wait late): count = blockDim.x
 };
 
-template <int NT, int KODD, int DH, bool WSMEM>
+// BEDGE = 1 or 2: the last 8-wide tile holds only BEDGE real features (width 50: 48, 49).  The 13 DMMAs per hidden layer
+// that produce the delta chain's entries for that tile would be 6/8 padding; like the forward kernel's NEDGE they are
+// replaced by DFMAs on the lane-local A-fragment elements (row r, out feature 4ks+c) times the two weight columns
+// W[4ks+c][48..49] (one 16-byte read-only load per k-step, L1-resident) and a 2-step butterfly over the 4 lanes of a row:
+// 26 DFMA + 4 DADD + 8 SHFL instead of 13 DMMA.  BEDGE = 0: off.
+template <int NT, int KODD, int DH, bool WSMEM, int BEDGE = 0>
 __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   using SM = BwdSmem<NT, DH, WSMEM>;
   constexpr int ROWS = SM::ROWS, S = SM::S, SN = SM::SN;
   constexpr int KSP = 2 * NT;
   constexpr int KS = 2 * NT - KODD;
-  constexpr int KR = ROWS / 4;  // k-steps over rows in the weight-gradient contraction
+  constexpr int KR = ROWS / 4;  // k-steps over rows in the weight-gradient contraction (even: ROWS = 8 (NT + 1))
+  static_assert(BEDGE == 0 || KODD == 1, "the edge weights live in the unused last k-step of BH");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
@@ -550,7 +685,12 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
   const int gl = swz(lrow);        // its swizzle (row writes / own-row reads)
   const int gc = swz(c);           // swizzle of fragment reads: rows 4ks + c  => (row & 3) == c
   const int ones_slot = feat_to_slot(s.width);
+  if (io.dbg && threadIdx.x == 0) { io.dbg[3 * blockIdx.x] = globaltimer_ns(); unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); io.dbg[3 * blockIdx.x + 2] = sm; }
 
+  // the layer-0 contraction of a tile runs together with the top-layer contraction of the CTA's NEXT tile (below): the
+  // first tile then contracts these zeros
+  for (int i = threadIdx.x; i < ROWS * S; i += blockDim.x) sm.D[1][i] = 0.0;
+  for (int i = threadIdx.x; i < ROWS * SN; i += blockDim.x) sm.In[1][i] = 0.0;
   if constexpr (WSMEM) stage_weights(sm.W, io.pk + s.pBO, SM::NWB, &sm.bar);
   const double* __restrict__ wBO = WSMEM ? sm.W : io.pk + s.pBO;
   const double* __restrict__ wBH = wBO + NT * 32;
@@ -597,42 +737,50 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
 #define SYNC_WAIT() do { mbar_wait(&sm.sync, sphase); sphase ^= 1; } while (0)
 
   // per-tile top inputs (cotangent column and normalised inputs): the raw global loads are issued
-  // a whole tile ahead (4 registers in flight), the arithmetic happens when the tile starts
-  struct TopRaw { double g, b, x, t; };
-  auto issue_top = [&](long long tile) {
-    TopRaw q = {0.0, 1.0, 0.0, 0.0};
-    const long long row = tile * ROWS + lrow;
-    if (tile < ntiles && row < io.n) {
+  // a whole tile ahead (4 registers in flight), the arithmetic happens when the tile starts.  (time step, node) of
+  // the lane's row is tracked incrementally from tile to tile (no 64-bit division / modulo per tile).
+  const long long tstride = (long long)gridDim.x * ROWS;
+  long long rowT = (long long)blockIdx.x * ROWS + lrow;            // this lane's row in the next tile to be issued
+  int tqT = io.nn_mod > 0 ? (int)(rowT / io.nn_mod) : 0;
+  long long nodeT = io.nn_mod > 0 ? rowT - (long long)tqT * io.nn_mod : rowT;
+  const double in_min = c < s.nd ? s.x_min[c] : (c == s.nd && s.normalize_time) ? s.t_min : 0.0;
+  const double in_scale = c < s.nd ? s.x_scale[c] : (c == s.nd && s.normalize_time) ? s.t_scale : 1.0;
+  struct TopRaw { double g, b, x; bool live; };
+  auto issue_top = [&]() {      // for the tile whose row is rowT; then advances to the CTA's following tile
+    TopRaw q = {0.0, 1.0, in_min, false};
+    if (rowT < io.n) {
+      q.live = true;
       if (c < s.n_out) {
-        const long long k = row * s.n_out + c;
+        const long long k = rowT * s.n_out + c;
         q.g = io.g_u[k];
         if (io.bc_b) q.b = io.bc_b[k];
       }
-      const long long xr = io.nn_mod > 0 ? row % io.nn_mod : row;
-      if (c < s.nd) q.x = io.x[xr * io.x_stride + c];
-      else if (c == s.nd) q.t = io.nn_mod > 0 ? io.times[row / io.nn_mod] : (io.trow ? io.trow[row * io.x_stride] : io.t);
+      if (c < s.nd) q.x = io.x[nodeT * io.x_stride + c];
+      else if (c == s.nd) q.x = io.nn_mod > 0 ? io.times[tqT] : (io.trow ? io.trow[rowT * io.x_stride] : io.t);
+      else q.x = 0.0;
+    }
+    rowT += tstride;
+    if (io.nn_mod > 0) {
+      nodeT += tstride;
+      while (nodeT >= io.nn_mod) { nodeT -= io.nn_mod; tqT++; }
     }
     return q;
   };
-  auto finish_top = [&](long long tile, const TopRaw& q, double& zA, double& v0, double& v1) {
-    const long long row = tile * ROWS + lrow;
-    const bool live = tile < ntiles && row < io.n;
+  auto finish_top = [&](const TopRaw& q, double& zA, double& v0, double& v1) {
     zA = q.g * q.b;
-    // fields.py:80-88: inputs = hstack(x_norm, t_norm)  (same arithmetic as mlp_input)
-    v0 = 0.0;
-    if (c < s.nd) v0 = (q.x - s.x_min[c]) / s.x_scale[c];
-    else if (c == s.nd) v0 = s.normalize_time ? (q.t - s.t_min) / s.t_scale : q.t;
+    // fields.py:80-88: inputs = hstack(x_norm, t_norm)  (same arithmetic as the forward kernel)
+    v0 = (q.x - in_min) / in_scale;
     v1 = (4 + c == s.n_in) ? 1.0 : 0.0;
     if (c == s.n_in) v0 = 1.0;  // n_in < 4
-    if (!live) { zA = 0.0; v0 = 0.0; v1 = 0.0; }
+    if (!q.live) { zA = 0.0; v0 = 0.0; v1 = 0.0; }
   };
 
   int hb = 0, db = 0;
   prefetch_h(blockIdx.x, s.depth - 1, hb);
   double zA, in0, in1;
   {
-    const TopRaw q0 = issue_top(blockIdx.x);
-    finish_top(blockIdx.x, q0, zA, in0, in1);
+    const TopRaw q0 = issue_top();
+    finish_top(q0, zA, in0, in1);
   }
   int parity = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
@@ -647,8 +795,16 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
     cp_async_wait_all();
     if (live && c == ((ones_slot & 7) >> 1)) sm.H[hb][lrow * S + (ones_slot ^ gl)] = 1.0;
     __syncwarp();      // the ones patch is read back by the other lanes of this row below
-    SYNC_ARRIVE();     // own rows of H[hb] = h_depth (+ones), Zb, In published
-    const TopRaw qn = issue_top(tile + gridDim.x);   // next tile's global loads fly during this whole tile
+    SYNC_ARRIVE();     // own rows of H[hb] = h_depth (+ones), Zb, In -- and of D[db^1] = d_0 of the previous tile -- published
+    const TopRaw qn = issue_top();   // next tile's global loads fly during this whole tile
+    // the stored activations of the CTA's NEXT tile (depth x NT planes of ROWS x 64 B, contiguous each) are pulled into L2
+    // a whole tile ahead: the cp.async prefetches below have half a stage to land and then find them there instead of
+    // in HBM (PCX_OPT_TUNE_L2PF)
+    if (io.l2pf && threadIdx.x < s.depth * NT) {
+      const long long nrow = (tile + gridDim.x) * ROWS;
+      if (nrow + ROWS <= io.n)
+        bulk_prefetch_l2(io.act + ((long long)threadIdx.x * io.rows_cap + nrow) * 8, ROWS * 64);
+    }
 
     // d_{depth-1} = (zbar W_out) * (1 - h^2), h read back from the own row of the tile
     double dC[NT][2];
@@ -661,15 +817,27 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
       dC[jn][0] = p0 ? 0.0 : a0 * (1.0 - hv.x * hv.x);
       dC[jn][1] = p1 ? 0.0 : a1 * (1.0 - hv.y * hv.y);
     }
-    SYNC_WAIT();       // everybody is done with the previous tile: H[hb^1] is free, Zb / H[hb] complete
+    SYNC_WAIT();       // everybody is done with the previous tile: H[hb^1] is free, Zb / H[hb] / D[db^1] complete
     // prefetch the next h: layer DH-1 of this tile, or (depth == 1) the next tile's top layer
     if (DH > 0) prefetch_h(tile, DH - 1, hb ^ 1);
     else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
     if (warp < NT) {
-      // dW_out[o][slot] += sum_rows zbar[row][o] * h_depth[row][slot], in-slot tile `warp`
-#pragma unroll 4
-      for (int ks = 0; ks < KR; ks++)
+      // dW_out[o][slot] += sum_rows zbar[row][o] * h_depth[row][slot], in-slot tile `warp`, TOGETHER with the layer-0
+      // contraction of the CTA's previous tile, dW_0 += d_0^T [inputs, 1]: each is one dependent accumulator chain of
+      // KR DMMAs -- latency-bound on its own (ncu r1: the two stages held 16 % of the time for 6 % of the DMMAs) -- so
+      // they are interleaved and split over even / odd row k-steps: four independent chains, one barrier round less
+      double gOb[2] = {0.0, 0.0}, g0b[2] = {0.0, 0.0};
+      const double* Dp = sm.D[db ^ 1];
+      const double* Ip = sm.In[parity ^ 1];
+#pragma unroll 2
+      for (int ks = 0; ks < KR; ks += 2) {
         dmma(gO[0], gO[1], sm.Zb[(4 * ks + c) * SN + r], sm.H[hb][(4 * ks + c) * S + ((8 * warp + r) ^ gc)]);
+        dmma(g0[0], g0[1], Dp[(4 * ks + c) * S + ((8 * warp + r) ^ gc)], Ip[(4 * ks + c) * SN + r]);
+        dmma(gOb[0], gOb[1], sm.Zb[(4 * ks + 4 + c) * SN + r], sm.H[hb][(4 * ks + 4 + c) * S + ((8 * warp + r) ^ gc)]);
+        dmma(g0b[0], g0b[1], Dp[(4 * ks + 4 + c) * S + ((8 * warp + r) ^ gc)], Ip[(4 * ks + 4 + c) * SN + r]);
+      }
+      gO[0] += gOb[0]; gO[1] += gOb[1];
+      g0[0] += g0b[0]; g0[1] += g0b[1];
     }
     // ---- hidden layers L = DH .. 1 : d_{L-1} = (d_L W_L) * (1 - h_L^2) ; dW_L = d_L^T h_L
 #pragma unroll
@@ -687,10 +855,29 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) dn[jn][0] = dn[jn][1] = 0.0;
       const double* bh = wBH + (long long)(L - 1) * KSP * NT * 32;
+      constexpr int NTD = BEDGE ? NT - 1 : NT;   // tiles computed on the tensor pipe
+      double pe0 = 0.0, pe1 = 0.0;
+      const double2* be = reinterpret_cast<const double2*>(bh + (KSP - 1) * NT * 32) + c;   // BE: see k_pack_weights
 #pragma unroll
       for (int ks = 0; ks < KS; ks++) {
 #pragma unroll
-        for (int jn = 0; jn < NT; jn++) dmma(dn[jn][0], dn[jn][1], dC[ks >> 1][ks & 1], bh[(ks * NT + jn) * 32 + lane]);
+        for (int jn = 0; jn < NTD; jn++) dmma(dn[jn][0], dn[jn][1], dC[ks >> 1][ks & 1], bh[(ks * NT + jn) * 32 + lane]);
+        if constexpr (BEDGE > 0) {
+          const double2 we = be[ks * 4];
+          pe0 = fma(dC[ks >> 1][ks & 1], we.x, pe0);
+          if (BEDGE > 1) pe1 = fma(dC[ks >> 1][ks & 1], we.y, pe1);
+        }
+      }
+      if constexpr (BEDGE > 0) {
+        pe0 += __shfl_xor_sync(0xffffffffu, pe0, 1);
+        pe0 += __shfl_xor_sync(0xffffffffu, pe0, 2);
+        if (BEDGE > 1) {
+          pe1 += __shfl_xor_sync(0xffffffffu, pe1, 1);
+          pe1 += __shfl_xor_sync(0xffffffffu, pe1, 2);
+        }
+        // lane c keeps input feature 8(NT-1)+c in register 0; everything else in the tile is padding
+        dn[NT - 1][0] = (c == 0) ? pe0 : (BEDGE > 1 && c == 1) ? pe1 : 0.0;
+        dn[NT - 1][1] = 0.0;
       }
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) {
@@ -722,25 +909,35 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
       }
       db ^= 1;
     }
-    // ---- layer 0: dW_0 = d_0^T [inputs, 1]
+    // ---- layer 0: publish d_0; its contraction dW_0 = d_0^T [inputs, 1] runs in the next tile's top stage (or after
+    // the loop).  D[db] was last read by the contraction two stages back, which every warp has left (they all arrived at
+    // the stage in between).
 #pragma unroll
     for (int jn = 0; jn < NT; jn++)
       *reinterpret_cast<double2*>(&sm.D[db][lrow * S + ((8 * jn + 2 * c) ^ gl)]) = make_double2(dC[jn][0], dC[jn][1]);
-    SYNC_ARRIVE();
-    finish_top(tile + gridDim.x, qn, zA, in0, in1);
-    SYNC_WAIT();
-    if (warp < NT) {
-#pragma unroll 4
-      for (int ks = 0; ks < KR; ks++)
-        dmma(g0[0], g0[1], sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)], sm.In[parity][(4 * ks + c) * SN + r]);
-    }
+    finish_top(qn, zA, in0, in1);
     db ^= 1;
     // the next tile's top-layer h is already in flight into H[hb^1]
     hb ^= 1;
   }
+  // ---- the last tile's layer-0 contraction
+  SYNC_ARRIVE();
+  cp_async_wait_all();
+  SYNC_WAIT();
+  if (warp < NT) {
+    double g0b[2] = {0.0, 0.0};
+    const double* Dp = sm.D[db ^ 1];
+    const double* Ip = sm.In[parity ^ 1];
+#pragma unroll 2
+    for (int ks = 0; ks < KR; ks += 2) {
+      dmma(g0[0], g0[1], Dp[(4 * ks + c) * S + ((8 * warp + r) ^ gc)], Ip[(4 * ks + c) * SN + r]);
+      dmma(g0b[0], g0b[1], Dp[(4 * ks + 4 + c) * S + ((8 * warp + r) ^ gc)], Ip[(4 * ks + 4 + c) * SN + r]);
+    }
+    g0[0] += g0b[0]; g0[1] += g0b[1];
+  }
 #undef SYNC_ARRIVE
 #undef SYNC_WAIT
-  cp_async_wait_all();
+  if (io.dbg && threadIdx.x == 0) io.dbg[3 * blockIdx.x + 1] = globaltimer_ns();
 
   // ---- write per-CTA partials (padded slot layout):
   //   part[cta] = [ L0: NT*8 x 8 | hidden l: (8NT x 8NT) each | out: 8 x 8NT ]

@@ -258,3 +258,45 @@ def test_roofline_formulas_match_the_survey_numbers():
     assert abs(r.element_bytes_per_qp("hex8", 3, 8) - 16.0) < 1e-12
     total = r.step_flops_per_qp_eval("hex8", 4, 3, 50, 4, 2146689 / 16777216)
     assert 6500 <= total <= 7100          # "~6.8 kflop per qp-eval" for EnergyLoss on Hex8 128^3
+
+
+def _tanh_rep_numpy(x):
+    """The arithmetic of pcx_mlp.cuh:tanh_rep replayed in numpy (fma emulated in 80-bit extended precision, the
+    reciprocal seed truncated to ~20 bits like MUFU.RCP64H), with the 2^(j/64) table parsed from the header."""
+    src = open(os.path.join(ROOT, "pancax_b200", "csrc", "pcx_mlp.cuh")).read()
+    tab = src[src.index("g_exp2_tab[EXP2_TAB_N] = {"):]
+    tab = np.array([float.fromhex(t) for t in re.findall(r"0x1\.[0-9a-f]+p\+0", tab[:tab.index("};")])])
+    assert tab.size == 128 and abs(tab[64] - np.sqrt(2.0)) < 1e-15
+    T64 = tab[::2]
+    L = np.longdouble
+
+    def fma(a, b, c):
+        return np.asarray(L(a) * L(b) + L(c), dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    a = np.minimum(np.abs(x), 22.0 + 2.0 ** -16)          # integer clamp on the high word: at most 22 + 2^-16
+    MAGIC, C = 6755399441055744.0, float.fromhex("-0x1.71547652b82fep+7")
+    t = fma(a, C, MAGIC)
+    k = (t - MAGIC).astype(np.int64)
+    s = fma(a, C, -k.astype(np.float64))
+    coef = [float.fromhex(h) for h in ("0x1.5d87fe78a6731p-40", "0x1.3b2ab6fba4e77p-31", "0x1.c6b08d704a0c0p-23",
+                                       "0x1.ebfbdff82c58fp-15", "0x1.62e42fefa39efp-7")]
+    p = np.full_like(x, coef[0])
+    for c in coef[1:] + [1.0]:
+        p = fma(p, s, c)
+    m = T64[k & 63] * p
+    n = k >> 6
+    E = np.ldexp(m, n)
+    den = 1.0 + E
+    r0 = np.ldexp(np.floor(np.ldexp(1.0 / den, 20)), -20)      # ~2^-20 seed
+    e = fma(-den, r0, 1.0)
+    r1 = fma(r0, fma(e, e, e), r0)
+    q = fma(-2.0 * E, r1, 1.0)
+    return np.copysign(q, x)
+
+
+def test_forward_kernel_tanh_arithmetic_is_accurate_to_3e16():
+    xs = np.concatenate([np.linspace(-25.0, 25.0, 200001), np.array([0.0, -0.0, 1e-300, -1e-300, 1e-9, 40.0, -1e6, 21.9999, 22.0001]),
+                         np.random.default_rng(0).standard_normal(100000) * 3.0])
+    ref = np.tanh(xs.astype(np.longdouble)).astype(np.float64)
+    err = np.abs(_tanh_rep_numpy(xs) - ref)
+    assert err.max() <= 3.0e-16, err.max()
