@@ -54,11 +54,52 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
       : "d"(a), "d"(b));
 }
 
+// the same, pinned in program order relative to other volatile asm (the scheduler-token acquire / release below)
+__device__ __forceinline__ void dmma_v(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void token_acquire(int* tok) {   // one lane spins, the warp follows
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(tok);
+    int old;
+    do {
+      asm volatile("atom.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "r"(a) : "memory");
+      if (old != 0) __nanosleep(40);
+    } while (old != 0);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void token_release(int* tok) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(tok);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0) : "memory");
+  }
+}
+
 __device__ __forceinline__ void st_cs_f64x2(double* p, double a, double b) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 __device__ __forceinline__ void st_cs_f32x2_fwd(float* p, float a, float b) {
   asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+// read-only global load pinned in program order relative to the other volatile asm of a kernel (the streaming
+// stores): ptxas otherwise sinks a load whose value is only needed an iteration later down to its use
+__device__ __forceinline__ double ld_nc_early(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+// (raw - lo) / scale of fields.py:80-86, bit-identical to the plain division; a ZERO numerator (t = 0, nodes on the
+// lower faces) would send the whole warp through the division's slow-path subroutine (ncu r2: a CALL on half of the row
+// groups), so those lanes divide 1 instead and select 0
+__device__ __forceinline__ double normalise(double raw, double lo, double scale) {
+  const double num = raw - lo;
+  const bool z = num == 0.0;
+  const double q = (z ? 1.0 : num) / scale;
+  return z ? num : q;      // keeps the sign of a zero numerator, like the division
 }
 __device__ __forceinline__ double2 ld_cs_f64x2(const double* p) {
   double2 r;
@@ -392,10 +433,18 @@ __device__ __forceinline__ double tanh_rep(double x, const double* __restrict__ 
 // TV = 0: tanh_tb (single 128-entry table); TV = 1: tanh_rep (replicated conflict-free table, 13 FP64 instructions);
 // TV = 2 (tuning): replicated table with tanh_tb's clamp / range reduction
 constexpr int fwd_table_doubles(int tv) { return tv ? EXP2_REP_N * EXP2_REP_COPIES : EXP2_TAB_N; }
-template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV = 1, int NTHR = 256>
+// LOCK = 1 (one CTA of 16 warps per SM): at most ONE warp per scheduler is inside a hidden layer's DMMA loop at a time.
+// Measured (tools/pipe_mix.cu): the FP64 datapath is arbitrated in favour of DMMA -- two warps issuing DMMAs starve the
+// DFMA (tanh) warps of the same scheduler to 0.4 % of their stand-alone rate, ONE leaves them 37 % of the pipe -- so
+// without the token the warps of a scheduler fall into lock step (all in the tanh phase, all in the DMMA phase) and
+// nothing overlaps the latency-bound parts (loads, stores, address arithmetic) of a row group.
+template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV = 1, int NTHR = 256, int LOCK = 0>
 __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
+  __shared__ int dtoken[4];
+  if (threadIdx.x < 4) dtoken[threadIdx.x] = 0;
+  int* const mytoken = &dtoken[(threadIdx.x >> 5) & 3];   // warp w of a CTA runs on scheduler w & 3
   if (io.dbg && threadIdx.x == 0) { io.dbg[3 * blockIdx.x] = globaltimer_ns(); unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); io.dbg[3 * blockIdx.x + 2] = sm; }
   double* sw = reinterpret_cast<double*>(smem_raw);
   double* stab = sw + (s.pBO - s.pF0);          // exp2 table behind the weight fragments
@@ -457,8 +506,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
   };
   auto load_raw = [&](int m) -> double {
     if (rowN[m] >= io.n) return in_min;      // normalises to 0
-    if (is_x) return io.x[nodeN[m] * io.x_stride + c];
-    if (is_t) return io.nn_mod > 0 ? io.times[tqN[m]] : (io.trow ? io.trow[rowN[m] * io.x_stride] : io.t);
+    if (is_x) return ld_nc_early(io.x + nodeN[m] * io.x_stride + c);
+    if (is_t) return io.nn_mod > 0 ? ld_nc_early(io.times + tqN[m]) : (io.trow ? ld_nc_early(io.trow + rowN[m] * io.x_stride) : io.t);
     return 0.0;
   };
   long long g = warp_id;
@@ -468,7 +517,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
 #pragma unroll
   for (int m = 0; m < MT; m++) rawn[m] = load_raw(m);
 
-  for (; g < ngroups; g = gnext, gnext = grab(g)) {
+  for (; g < ngroups;) {
+    const long long gnext2 = grab(gnext);   // two groups ahead: the atomic's round trip is covered by a whole group
     const long long row0 = g * (8 * MT);
     double h[MT][NT][2], acc[MT][NT][2];
     // ---- layer 0
@@ -479,14 +529,14 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
     for (int m = 0; m < MT; m++) {
       const double rw = rawn[m];
       rawn[m] = load_raw(m);
-      a0[m] = (rw - in_min) / in_scale;
+      a0[m] = normalise(rw, in_min, in_scale);
       const long long row = row0 + 8 * m + r;
 #pragma unroll
       for (int x = 0; x < 2; x++) {
         const int oi = 2 * c + x;
         const bool ok = io.u && row < io.n && oi < s.n_out;
-        bcA[m][x] = (ok && io.bc_a) ? io.bc_a[row * s.n_out + oi] : 0.0;
-        bcB[m][x] = (ok && io.bc_b) ? io.bc_b[row * s.n_out + oi] : 1.0;
+        bcA[m][x] = (ok && io.bc_a) ? ld_nc_early(io.bc_a + row * s.n_out + oi) : 0.0;
+        bcB[m][x] = (ok && io.bc_b) ? ld_nc_early(io.bc_b + row * s.n_out + oi) : 1.0;
       }
     }
 #pragma unroll
@@ -555,13 +605,18 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
 #pragma unroll
       for (int m = 0; m < MT; m++) pe[m][0] = pe[m][1] = 0.0;
       const double2* fe = reinterpret_cast<const double2*>(pk + s.pFE + (long long)i * KSP * 8) + c;
+      if constexpr (LOCK) token_acquire(mytoken);
 #pragma unroll
       for (int ks = 0; ks < KS; ks++) {
+        if constexpr (LOCK) { if (ks == KS - 1) token_release(mytoken); }   // the last k-step overlaps the next holder's start
 #pragma unroll
         for (int jn = 0; jn < NTD; jn++) {
           const double bf = fh[(ks * NT + jn) * 32 + lane];
 #pragma unroll
-          for (int m = 0; m < MT; m++) dmma(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
+          for (int m = 0; m < MT; m++) {
+            if constexpr (LOCK) dmma_v(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
+            else dmma(acc[m][jn][0], acc[m][jn][1], h[m][ks >> 1][ks & 1], bf);
+          }
         }
         if constexpr (NEDGE > 0) {
           const double2 we = fe[ks * 4];
@@ -621,6 +676,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
         }
       }
     }
+    g = gnext;
+    gnext = gnext2;
   }
   if (io.dbg) {
     __syncthreads();
@@ -769,7 +826,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
   auto finish_top = [&](const TopRaw& q, double& zA, double& v0, double& v1) {
     zA = q.g * q.b;
     // fields.py:80-88: inputs = hstack(x_norm, t_norm)  (same arithmetic as the forward kernel)
-    v0 = (q.x - in_min) / in_scale;
+    v0 = normalise(q.x, in_min, in_scale);
     v1 = (4 + c == s.n_in) ? 1.0 : 0.0;
     if (c == s.n_in) v0 = 1.0;  // n_in < 4
     if (!q.live) { zA = 0.0; v0 = 0.0; v1 = 0.0; }

@@ -30,10 +30,8 @@ eng = get_engine(problem, params)
 eng.set_option("cull_null_steps", 0)
 w = params.fields.networks.weights
 VARIANTS = [("default_r2", dict(tune_fwd_variant=12)),
-            ("fwd_320_threads", dict(tune_fwd_variant=13)),
-            ("fwd_384_threads", dict(tune_fwd_variant=14)),
-            ("no_l2_prefetch", dict(tune_fwd_variant=12, tune_l2pf=0)),
-            ("default_again", dict(tune_fwd_variant=12, tune_l2pf=1))]
+            ("fwd_static_stride", dict(tune_fwd_dynamic=0)),
+            ("default_again", dict(tune_fwd_dynamic=1))]
 ref = None
 
 
