@@ -529,7 +529,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "null_step_culling": culled, "tf32_adjoint": tf32,
         "strong_scaling": strong_leg, "residual_sharded": resid_leg,
     }
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -597,7 +597,39 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample,
                             "host_cpus": os.cpu_count()},
            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    _emit(out)
+
+
+class _CleanStdout:
+    """stdout carries exactly ONE JSON line: everything else a library writes to fd 1 while the benchmark runs (NCCL's
+    "NCCL version ..." banner goes to stdout when NCCL_DEBUG is set by the launcher) is diverted to stderr, and the
+    line is written to the real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        os.write(self.real, (line.rstrip("\n") + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+_OUT = None
+
+
+def _emit(obj):
+    line = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(line)
+    else:
+        print(line)
 
 
 def main():
@@ -618,12 +650,16 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): n^3 elements per GPU; strong: one n^3 block cut into z slabs")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        if not torch.cuda.is_available():
-            raise SystemExit("bench.py: no CUDA device; pancax_b200 has no CPU path (use --impl reference for the CPU arm)")
-        run_ours(args)
+    global _OUT
+    with _CleanStdout() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            if not torch.cuda.is_available():
+                raise SystemExit("bench.py: no CUDA device; pancax_b200 has no CPU path (use --impl reference for the CPU arm)")
+            run_ours(args)
+        _OUT = None
 
 
 if __name__ == "__main__":

@@ -289,6 +289,15 @@ int pcx_loss_finish(pcx_handle* h, const pcx_loss_desc* loss, const double* f_fu
                     double replicated_scale, double* loss_out, double* aux, double* g_weights, double* g_props,
                     void* stream);
 
+/* Pack / unpack kernels of the exchange between pcx_loss_begin and pcx_loss_mid: rows idx[0..n) (distinct node ids) of
+ * f [nt][nn][ndof] <-> a contiguous buffer [nt][n][ndof].  pcx_scatter_rows: accumulate = 0 overwrites (in = NULL: zeros),
+ * accumulate = 1 adds.  The caller sends the packed rows to the shards that share those nodes (ncclSend/Recv between
+ * neighbours) and adds what it receives in ascending shard order, so every sharer ends with bit-identical sums. */
+int pcx_gather_rows(const double* f, int64_t nt, int64_t nn, int32_t ndof, const int64_t* idx, int64_t n, double* out,
+                    void* stream);
+int pcx_scatter_rows(double* f, int64_t nt, int64_t nn, int32_t ndof, const int64_t* idx, int64_t n, const double* in,
+                     int32_t accumulate, void* stream);
+
 /* FullFieldDataLoss value + weight gradient on one batch -- data_loss_functions.py:13-24.
  *   loss: device scalar = weight * mean((u - outputs)^2). */
 int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const double* pts,

@@ -86,7 +86,7 @@ SYMBOLS = [
     "pcx_element_fields", "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
     "pcx_num_state_variables", "pcx_get_state", "pcx_set_option", "pcx_set_ownership", "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish",
     "pcx_points_jet", "pcx_strong_form_loss_and_grad", "pcx_launch_count", "pcx_adam_step", "pcx_adam_step_sched", "pcx_profile_enable", "pcx_profile_collect",
-    "pcx_measure_dmma_peak", "pcx_reserve",
+    "pcx_measure_dmma_peak", "pcx_reserve", "pcx_gather_rows", "pcx_scatter_rows",
 ]
 
 
@@ -140,6 +140,8 @@ def load():
     lib.pcx_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.pcx_measure_dmma_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
     lib.pcx_reserve.argtypes = [vp, i32, i64]
+    lib.pcx_gather_rows.argtypes = [vp, i64, i64, i32, vp, i64, vp, vp]
+    lib.pcx_scatter_rows.argtypes = [vp, i64, i64, i32, vp, i64, vp, i32, vp]
     for name in SYMBOLS:
         if name not in ("pcx_last_error", "pcx_num_weights", "pcx_num_trainable_props",
                         "pcx_num_qp", "pcx_launch_count", "pcx_nq", "pcx_nnpe", "pcx_nd",

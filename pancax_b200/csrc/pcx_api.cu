@@ -1877,6 +1877,49 @@ extern "C" int pcx_adam_step_sched(double* params, const double* grads, double* 
   return PCX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ ABI: shard exchange helpers
+// pack / unpack of the shared-node rows of f [nt][nn][ndof] for the neighbour exchange of the sharded residual losses
+__global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ f, long long nn, int ndof, const long long* __restrict__ idx,
+                                                     long long n, double* __restrict__ out) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n * ndof) return;
+  const long long t = blockIdx.y, row = k / ndof;
+  const int i = (int)(k - row * ndof);
+  out[(t * n + row) * ndof + i] = f[(t * nn + idx[row]) * ndof + i];
+}
+__global__ void __launch_bounds__(256) k_scatter_rows(double* __restrict__ f, long long nn, int ndof, const long long* __restrict__ idx,
+                                                      long long n, const double* __restrict__ in, int accumulate) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n * ndof) return;
+  const long long t = blockIdx.y, row = k / ndof;
+  const int i = (int)(k - row * ndof);
+  double* dst = f + (t * nn + idx[row]) * ndof + i;      // idx holds distinct rows: no two threads share a destination
+  const double v = in ? in[(t * n + row) * ndof + i] : 0.0;
+  *dst = accumulate ? *dst + v : v;
+}
+
+extern "C" int pcx_gather_rows(const double* f, int64_t nt, int64_t nn, int32_t ndof, const int64_t* idx, int64_t n, double* out,
+                               void* stream) {
+  if (n <= 0 || nt <= 0) return PCX_OK;
+  if (!f || !idx || !out || ndof < 1) return fail(PCX_ERR_INVALID, "pcx_gather_rows: bad argument");
+  dim3 grid((unsigned)((n * ndof + 255) / 256), (unsigned)nt);
+  k_gather_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(f, nn, ndof, (const long long*)idx, n, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PCX_ERR_CUDA, "k_gather_rows launch failed: %s", cudaGetErrorString(e));
+  return PCX_OK;
+}
+
+extern "C" int pcx_scatter_rows(double* f, int64_t nt, int64_t nn, int32_t ndof, const int64_t* idx, int64_t n, const double* in,
+                                int32_t accumulate, void* stream) {
+  if (n <= 0 || nt <= 0) return PCX_OK;
+  if (!f || !idx || ndof < 1) return fail(PCX_ERR_INVALID, "pcx_scatter_rows: bad argument");
+  dim3 grid((unsigned)((n * ndof + 255) / 256), (unsigned)nt);
+  k_scatter_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(f, nn, ndof, (const long long*)idx, n, in, accumulate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PCX_ERR_CUDA, "k_scatter_rows launch failed: %s", cudaGetErrorString(e));
+  return PCX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ ABI: profiling helpers
 extern "C" int pcx_profile_enable(pcx_handle* h, int on) {
   if (!h) return fail(PCX_ERR_INVALID, "null handle");

@@ -74,13 +74,17 @@ def get_engine(problem, params, deterministic: bool = True) -> Engine:
     fld = params.fields
     net = fld.networks
     shard = getattr(problem, "shard", None)
-    if shard is not None and getattr(shard, "x_mins", None) is not None:
+    if shard is not None and getattr(shard, "x_mins", None) is not None and getattr(fld, "_shard_bounds_seen", None) is not shard:
         # fields.py:70-71 normalises with the bounds of the WHOLE mesh.  A Field built on a shard took the shard's
         # own bounds from problem.coords: every rank would then evaluate a different u(x, t) from the same weights.
-        # A Field whose bounds were set by hand to something else is left alone.
-        loc_lo, loc_hi = np.min(problem.coords, axis=0), np.max(problem.coords, axis=0)
+        # A Field whose bounds were set by hand to something else is left alone.  Checked once per (Field, shard): the
+        # reduction over the coordinates costs milliseconds and this function runs on every loss call.
+        if getattr(shard, "local_bounds", None) is None:
+            shard.local_bounds = (problem.coords.min(axis=0), problem.coords.max(axis=0))
+        loc_lo, loc_hi = shard.local_bounds
         if np.array_equal(fld.x_mins, loc_lo) and np.array_equal(fld.x_maxs, loc_hi):
             fld.x_mins, fld.x_maxs = shard.x_mins.copy(), shard.x_maxs.copy()
+        fld._shard_bounds_seen = shard
     # everything baked into the pcx_handle at set-up is part of the key; the wrapper itself (not its id(), which can
     # be reused after garbage collection) is held by the key
     key = (net.n_inputs, net.n_outputs, net.n_neurons, net.n_layers, net.use_final_bias,

@@ -105,11 +105,14 @@ class ShardPlan:
     shared_slot  : their slot in the (sorted) global list of shared nodes
     n_shared     : length of that global list
     owned        : bool mask over local nodes; a shared node is owned by the lowest shard holding it
+    peers        : {other shard -> local indices of the nodes shared with it, in ascending global-id order (the same
+                   order on both sides)}: the neighbour exchange sends / receives exactly these rows
     """
 
-    def __init__(self, shared_local, shared_slot, n_shared, owned, n_shards, index):
+    def __init__(self, shared_local, shared_slot, n_shared, owned, n_shards, index, peers=None):
         self.shared_local, self.shared_slot = shared_local, shared_slot
         self.n_shared, self.owned, self.n_shards, self.index = n_shared, owned, n_shards, index
+        self.peers = {} if peers is None else peers
 
     def order_owned_first(self, unknown_idx, reaction_nodes, ndof):
         """Reorder dof / node lists so the entries owned by this shard come first (what
@@ -144,11 +147,19 @@ def make_shard_plans(l2g_all):
     owner = np.full(shared_ids.size, -1, dtype=np.int64)
     for r in reversed(range(n)):
         owner[slots[r]] = r
+    # pairwise neighbour lists: slots present on both shards, ascending (= ascending global id), as local indices
+    peers = [dict() for _ in range(n)]
+    for r in range(n):
+        for q in range(r + 1, n):
+            common, ir, iq = np.intersect1d(slots[r], slots[q], assume_unique=True, return_indices=True)
+            if common.size:
+                peers[r][q] = locs[r][ir].astype(np.int64)
+                peers[q][r] = locs[q][iq].astype(np.int64)
     plans = []
     for r, l2g in enumerate(l2g_all):
         owned = np.ones(len(l2g), dtype=bool)
         owned[locs[r]] = owner[slots[r]] == r
-        plans.append(ShardPlan(locs[r], slots[r], int(shared_ids.size), owned, n, r))
+        plans.append(ShardPlan(locs[r], slots[r], int(shared_ids.size), owned, n, r, peers[r]))
     return plans
 
 
@@ -162,26 +173,76 @@ def make_shard_plan(local_to_global):
 
 
 class ShardExchange:
-    """The two exchanges of the phased loss over torch.distributed (NCCL on GPUs, gloo in the CPU
-    tests): pack the shared-node rows, ONE allreduce, unpack; then ONE allreduce of nt*2 scalars.
-    Both run on the current stream without host synchronisation."""
+    """The two exchanges of the phased loss over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+    sum_shared: NEIGHBOUR exchange of the shared-node rows of f -- each shard packs the rows it shares with a peer
+    (library kernel pcx_gather_rows), sends them to that peer only and receives the peer's (ncclSend / ncclRecv through
+    batch_isend_irecv: one fused NCCL group), then rebuilds the rows as the sum of all sharers' contributions in ASCENDING
+    SHARD ORDER (pcx_scatter_rows), so every sharer holds bit-identical values.  A z-slab partition talks to two
+    neighbours about one plane each; round 1 allreduced the global list of all shared nodes on every rank.
+    sum_scalars: ONE allreduce of nt*2 scalars.  Everything runs on the current stream without host synchronisation."""
 
     def __init__(self, plan: ShardPlan, device):
         self.plan, self.n_shards = plan, plan.n_shards
+        self.device = torch.device(device)
         self.loc = torch.as_tensor(plan.shared_local, dtype=torch.long, device=device)
-        self.slot = torch.as_tensor(plan.shared_slot, dtype=torch.long, device=device)
-        self._buf = None
+        self.peer_idx = {q: torch.as_tensor(ix, dtype=torch.long, device=device) for q, ix in sorted(plan.peers.items())}
+        self._bufs = None
+
+    # ---- pack / unpack: library kernels on the GPU, torch indexing on the host (gloo tests)
+    def _gather(self, f, idx, out):
+        if f.is_cuda:
+            from . import _lib
+            import ctypes as C
+            nt, nn, ndof = f.shape
+            _lib.check(_lib.load().pcx_gather_rows(C.c_void_p(f.data_ptr()), nt, nn, ndof, C.c_void_p(idx.data_ptr()), idx.numel(),
+                                                   C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:
+            out.copy_(f[:, idx])
+        return out
+
+    def _scatter(self, f, idx, src, accumulate):
+        if f.is_cuda:
+            from . import _lib
+            import ctypes as C
+            nt, nn, ndof = f.shape
+            _lib.check(_lib.load().pcx_scatter_rows(C.c_void_p(f.data_ptr()), nt, nn, ndof, C.c_void_p(idx.data_ptr()), idx.numel(),
+                                                    None if src is None else C.c_void_p(src.data_ptr()), 1 if accumulate else 0,
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        elif src is None:
+            f[:, idx] = 0.0
+        elif accumulate:
+            f[:, idx] += src
+        else:
+            f[:, idx] = src
 
     def sum_shared(self, f):
         if self.n_shards == 1 or self.plan.n_shared == 0:
             return f
         nt, _, ndof = f.shape
-        if self._buf is None or self._buf.shape != (nt, self.plan.n_shared, ndof):
-            self._buf = torch.empty(nt, self.plan.n_shared, ndof, dtype=f.dtype, device=f.device)
-        self._buf.zero_()
-        self._buf[:, self.slot] = f[:, self.loc]
-        dist.all_reduce(self._buf, op=dist.ReduceOp.SUM)
-        f[:, self.loc] = self._buf[:, self.slot]
+        if self._bufs is None or self._bufs[0].shape[0] != nt:
+            mine = torch.empty(nt, self.loc.numel(), ndof, dtype=f.dtype, device=f.device)
+            send = {q: torch.empty(nt, ix.numel(), ndof, dtype=f.dtype, device=f.device) for q, ix in self.peer_idx.items()}
+            recv = {q: torch.empty_like(b) for q, b in send.items()}
+            self._bufs = (mine, send, recv)
+        mine, send, recv = self._bufs
+        self._gather(f, self.loc, mine)                       # every send uses the ORIGINAL partial values
+        ops = []
+        for q, ix in self.peer_idx.items():
+            self._gather(f, ix, send[q])
+            ops.append(dist.P2POp(dist.isend, send[q], q))
+            ops.append(dist.P2POp(dist.irecv, recv[q], q))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self._scatter(f, self.loc, None, False)               # 0, then contributions in ascending shard order
+        me, done_me = self.plan.index, False
+        for q, ix in self.peer_idx.items():
+            if q > me and not done_me:
+                self._scatter(f, self.loc, mine, True)
+                done_me = True
+            self._scatter(f, ix, recv[q], True)
+        if not done_me:
+            self._scatter(f, self.loc, mine, True)
         return f
 
     def sum_scalars(self, rr):

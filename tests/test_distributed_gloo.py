@@ -127,3 +127,55 @@ def test_two_rank_shard_exchange():
     np.add.at(owners, l2g1[own1], 1)
     assert np.array_equal(owners[np.union1d(l2g0, l2g1)], np.ones(np.union1d(l2g0, l2g1).size, dtype=int))
     assert nuo0 == own0.sum() * 3 and nuo1 == own1.sum() * 3
+
+
+def _exchange3_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from pancax_b200 import parallel
+    from tests.cases import make_case
+    parallel.init_distributed()
+    case = make_case("quad4_neohookean", n=7, nt=3, width=12, depth=2)
+    conns = case.mesh["conns"][np.random.default_rng(5).permutation(case.mesh["conns"].shape[0])]   # shards interleave in space
+    ne = conns.shape[0]
+    lo, hi = (ne * rank) // world, (ne * (rank + 1)) // world
+    l2g = np.unique(conns[lo:hi])
+    plan = parallel.make_shard_plan(l2g)
+    ex = parallel.ShardExchange(plan, "cpu")
+    nt, ndof = 3, 2
+    rng = np.random.default_rng(100 + rank)
+    f = torch.as_tensor(rng.standard_normal((nt, l2g.size, ndof)))       # this shard's partial rows
+    part = f.clone()
+    ex.sum_shared(f)
+    q.put((rank, l2g, part.numpy(), f.numpy(), sorted(plan.peers)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_rank_neighbour_exchange_sums_in_ascending_shard_order():
+    """Neighbour exchange (isend / irecv of the rows shared with each peer): nodes shared by two AND by three shards end
+    with the sum of all sharers' partial rows, accumulated in ascending shard order -- bit-identical on every sharer."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange3_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    nglob = max(r[1].max() for r in res) + 1
+    total = np.zeros((3, nglob, 2))
+    count = np.zeros(nglob, dtype=int)
+    for rank, l2g, part, f, peers in res:          # ascending shard order, from zero: the canonical sum
+        total[:, l2g] += part
+        count[l2g] += 1
+    assert (count == 3).any() and (count == 2).any()
+    for rank, l2g, part, f, peers in res:
+        sh = count[l2g] > 1
+        assert np.array_equal(f[:, sh], total[:, l2g[sh]])          # bitwise
+        assert np.array_equal(f[:, ~sh], part[:, ~sh])
+        assert len(peers) == 2
