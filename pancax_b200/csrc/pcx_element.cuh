@@ -111,11 +111,24 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // (k_visco_qp).  Compile-time variants: as run-time branches they cost the plain kernels half of their speed in register spills.
 // resident CTAs per SM asked of the register allocator: the 3D sweeps want every register (1 -> 255 registers; 3 costs
 // Hex8 +47 % in spills), the 2D tangent sweep is 22 % faster with 3 (168 registers, 12 warps per SM) -- measured
-constexpr int elem_min_blocks(int nd, bool tangent) { return (nd == 2 && tangent) ? 3 : 0; }   // 0 = no request
+// r2: in 3D the element's nodal accumulators (24 doubles for Hex8) live in SHARED memory, transposed [slot][thread]
+// (conflict-free), instead of 48 registers held across the whole quadrature loop: with X / U (96 registers) they kept the
+// kernel at 255 registers = 8 warps per SM, where every DFMA waited out the latency of the one before it (ncu r1: FP64 pipe
+// 49 % active, 12 % occupancy).  PCX_ELEM3D_MINB resident CTAs per SM are then asked of the register allocator.
+#ifndef PCX_ELEM_QUNROLL
+#define PCX_ELEM_QUNROLL 1
+#endif
+#ifndef PCX_ELEM3D_MINB
+#define PCX_ELEM3D_MINB 2
+#endif
+__host__ __device__ constexpr bool elem_acc_smem(int nd) { return nd == 3 && PCX_ELEM3D_MINB > 0; }
+constexpr int elem_min_blocks(int nd, bool tangent) { return nd == 3 ? PCX_ELEM3D_MINB : (tangent ? 3 : 0); }   // 0 = no request
 template <int NNPE, int ND, int NDOF, int MODEL, bool TANGENT, int VAR = 0>
 __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
   constexpr int NTH = 128;
+  constexpr bool ACC_SMEM = elem_acc_smem(ND);
   __shared__ double sh[NTH / 32];
+  __shared__ double acc_s[ACC_SMEM ? NNPE * NDOF : 1][ACC_SMEM ? NTH : 1];
   const long long e = blockIdx.x * (long long)NTH + threadIdx.x;
   // per-time-step views
   struct {
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #pragma unroll
       for (int a = 0; a < NNPE; a++) cn[a] = __ldg(A.conns + e * NNPE + a);
     }
-    double X[NNPE][ND], U[NNPE][NDOF], acc[NNPE][NDOF];
+    double X[NNPE][ND], U[NNPE][NDOF], acc[ACC_SMEM ? 1 : NNPE][ACC_SMEM ? 1 : NDOF];
     double V[TANGENT ? NNPE : 1][NDOF];
 #pragma unroll
     for (int a = 0; a < NNPE; a++) {
@@ -166,11 +179,14 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #pragma unroll
       for (int i = 0; i < NDOF; i++) {
         U[a][i] = __ldg(A.us + (long long)cn[a] * NDOF + i);
-        acc[a][i] = 0.0;
+        if constexpr (ACC_SMEM) acc_s[a * NDOF + i][threadIdx.x] = 0.0;
+        else acc[a][i] = 0.0;
         if constexpr (TANGENT) V[a][i] = __ldg(A.v + (long long)cn[a] * NDOF + i);
       }
     }
 
+    constexpr int QU = (ND == 3) ? PCX_ELEM_QUNROLL : 1;
+#pragma unroll QU
     for (int q = 0; q < tab.nq; q++) {
       const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
       double J[ND * ND], Ji[ND * ND];
@@ -309,11 +325,14 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
         for (int a = 0; a < NNPE; a++)
 #pragma unroll
           for (int i = 0; i < NDOF; i++) {
-            double s = acc[a][i];
+            double s;
+            if constexpr (ACC_SMEM) s = acc_s[a * NDOF + i][threadIdx.x];
+            else s = acc[a][i];
 #pragma unroll
             for (int k = 0; k < ND; k++) s = fma(Q[i][k], dN[a * 3 + k], s);
             if constexpr (MODEL == 0 && !TANGENT) s = fma(JxW * su, tab.N[q * TAB_MAX_NNPE + a], s);
-            acc[a][i] = s;
+            if constexpr (ACC_SMEM) acc_s[a * NDOF + i][threadIdx.x] = s;
+            else acc[a][i] = s;
           }
       }
     }
@@ -323,12 +342,13 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #pragma unroll
         for (int a = 0; a < NNPE; a++)
 #pragma unroll
-          for (int i = 0; i < NDOF; i++) o[a * NDOF + i] = acc[a][i];
+          for (int i = 0; i < NDOF; i++) o[a * NDOF + i] = ACC_SMEM ? acc_s[a * NDOF + i][threadIdx.x] : acc[a][i];
       } else {
 #pragma unroll
         for (int a = 0; a < NNPE; a++)
 #pragma unroll
-          for (int i = 0; i < NDOF; i++) atomicAdd(A.f_atomic + (long long)cn[a] * NDOF + i, acc[a][i]);
+          for (int i = 0; i < NDOF; i++)
+            atomicAdd(A.f_atomic + (long long)cn[a] * NDOF + i, ACC_SMEM ? acc_s[a * NDOF + i][threadIdx.x] : acc[a][i]);
       }
     }
   }

@@ -415,6 +415,62 @@ __device__ __forceinline__ double tanh_rep(double x, const double* __restrict__ 
   return __hiloint2double((__double2hiint(q) & 0x7fffffff) | (xh & 0x80000000), __double2loint(q));
 }
 
+// The same arithmetic for N independent arguments, written STAGE BY STAGE (all range reductions, all table loads, one
+// Horner step for every argument at a time, all reciprocal seeds, ...): tanh is a ~20-deep dependent chain (DFMA latency
+// 8.4 cycles at 2.2 cycles issue, one LDS, one MUFU, one I2F), a warp issues in order, and left to itself ptxas
+// interleaved only two or three of the 14 chains of a layer -- the tanh phases of the forward kernel ran the FP64
+// pipe at 38 % (knock-out timing, profiles/r02_kernel_ab_8).  Results are bit-identical to tanh_rep.
+template <int N>
+__device__ __forceinline__ void tanh_rep_batch(const double (&x)[N], double (&y)[N], const double* __restrict__ T /* + (lane & 15) */) {
+  const double MAGIC = 6755399441055744.0;
+  const double C = -0x1.71547652b82fep+7;                          // -2 log2(e) * 64
+  int k[N];
+  double s[N], tb[N], p[N];
+#pragma unroll
+  for (int e = 0; e < N; e++) {
+    const int ah = min(__double2hiint(x[e]) & 0x7fffffff, 0x40360000);
+    const double a = __hiloint2double(ah, __double2loint(x[e]));
+    const double t = fma(a, C, MAGIC);
+    k[e] = __double2loint(t);
+    s[e] = fma(a, C, -(double)k[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < N; e++) tb[e] = T[(k[e] & (EXP2_REP_N - 1)) * EXP2_REP_COPIES];
+#pragma unroll
+  for (int e = 0; e < N; e++) p[e] = fma(0x1.5d87fe78a6731p-40, s[e], 0x1.3b2ab6fba4e77p-31);
+#pragma unroll
+  for (int e = 0; e < N; e++) p[e] = fma(p[e], s[e], 0x1.c6b08d704a0c0p-23);
+#pragma unroll
+  for (int e = 0; e < N; e++) p[e] = fma(p[e], s[e], 0x1.ebfbdff82c58fp-15);
+#pragma unroll
+  for (int e = 0; e < N; e++) p[e] = fma(p[e], s[e], 0x1.62e42fefa39efp-7);
+#pragma unroll
+  for (int e = 0; e < N; e++) p[e] = fma(p[e], s[e], 1.0);
+  double E2[N], den[N], r0[N];     // -2E, 1 + E, reciprocal seed
+#pragma unroll
+  for (int e = 0; e < N; e++) {
+    const double m = tb[e] * p[e];
+    const int n = k[e] >> 6;
+    const int mh = __double2hiint(m), ml = __double2loint(m);
+    const double E = __hiloint2double(mh + (n << 20), ml);
+    E2[e] = __hiloint2double((mh + ((n + 1) << 20)) ^ 0x80000000, ml);
+    den[e] = 1.0 + E;
+  }
+#pragma unroll
+  for (int e = 0; e < N; e++) r0[e] = rcp_approx_f64(den[e]);
+#pragma unroll
+  for (int e = 0; e < N; e++) den[e] = fma(-den[e], r0[e], 1.0);          // e
+#pragma unroll
+  for (int e = 0; e < N; e++) den[e] = fma(den[e], den[e], den[e]);       // e + e^2
+#pragma unroll
+  for (int e = 0; e < N; e++) r0[e] = fma(r0[e], den[e], r0[e]);          // r1
+#pragma unroll
+  for (int e = 0; e < N; e++) {
+    const double q = fma(E2[e], r0[e], 1.0);
+    y[e] = __hiloint2double((__double2hiint(q) & 0x7fffffff) | (__double2hiint(x[e]) & 0x80000000), __double2loint(q));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward.  One warp = MT tiles of 8 rows; grid-stride over row groups.  The forward weight
 // fragments [F0 | FB | FH | FO | FOB] are staged ONCE per CTA into shared memory with a bulk
@@ -583,8 +639,30 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
       // issues in order, so the DMMAs then queue behind the dependent DFMA chain of the tanh in front of them; as
       // separate phases one warp's DMMA phase is a clean stream of independent instructions that fills the pipe while
       // the other warps of the scheduler sit in their tanh chains.)
+      if constexpr (TV == 1 && MT == 1 && NE >= 4) {
+        // two stage-by-stage batches (register budget: one batch keeps ~8 registers per element in flight)
+        constexpr int NA = NE / 2, NB = NE - 1 - NA;      // elements [0, NA) and [NA, NE - 1); the last one separately
+        {
+          double xa[NA], ya[NA];
 #pragma unroll
-      for (int e = 0; e < NE; e++) activate(e);
+          for (int e = 0; e < NA; e++) xa[e] = acc[0][e >> 1][e & 1];
+          tanh_rep_batch<NA>(xa, ya, stab);
+#pragma unroll
+          for (int e = 0; e < NA; e++) h[0][e >> 1][e & 1] = ya[e];
+        }
+        {
+          double xb[NB], yb[NB];
+#pragma unroll
+          for (int e = 0; e < NB; e++) xb[e] = acc[0][(NA + e) >> 1][(NA + e) & 1];
+          tanh_rep_batch<NB>(xb, yb, stab);
+#pragma unroll
+          for (int e = 0; e < NB; e++) h[0][(NA + e) >> 1][(NA + e) & 1] = yb[e];
+        }
+        activate(NE - 1);     // all padding for width 50: no tanh
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; e++) activate(e);
+      }
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) store_tile(i, jn);
       if (i == s.depth - 1) break;

@@ -29,9 +29,7 @@ params = px.Parameters(problem, key=0, n_layers=4, n_neurons=50, device=device,
 eng = get_engine(problem, params)
 eng.set_option("cull_null_steps", 0)
 w = params.fields.networks.weights
-VARIANTS = [("default_r2", dict(tune_fwd_variant=12)),
-            ("fwd_static_stride", dict(tune_fwd_dynamic=0)),
-            ("default_again", dict(tune_fwd_dynamic=1))]
+VARIANTS = [("default", dict(tune_fwd_variant=12))]
 ref = None
 
 
