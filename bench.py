@@ -508,6 +508,16 @@ def run_ours(args):
                 "algorithmic_flop_per_row": algorithmic_flops_per_row_bwd(), "rows_per_step": eng.nn * nt,
                 "formulas": "pancax_b200/roofline.py",
                 "step_share": {k: round(v[0] / ms, 4) for k, v in prof.items() if v[1]}}
+    # the whole step against the same FP64 roof (algorithmic flop of SURVEY 8d / pancax_b200/roofline.py)
+    from pancax_b200 import roofline as _rf
+    step_flop = _rf.step_flops_per_qp_eval("hex8", MLP_IN, MLP_OUT, WIDTH, DEPTH, eng.nn / float(eng.ne * eng.nq)) * evals_per_rank
+    roofline["whole_step"] = {"algorithmic_gflop": step_flop / 1e9, "achieved_tflops": step_flop / (ms / args.steps * 1e-3) / 1e12,
+                              "frac_of_fp64_peak": step_flop / (ms / args.steps * 1e-3) / 1e12 / pk.value,
+                              "kernel_frac": {"mlp_forward": (algorithmic_flops_per_row_fwd() * rows_total / (prof["mlp_forward"][0] * 1e-3) / 1e12 / pk.value)
+                                              if prof["mlp_forward"][0] > 0 else None,
+                                              "element_force": (_rf.element_flops_per_qp("hex8", MLP_OUT) * evals_per_rank * args.steps /
+                                                                (prof["element_force"][0] * 1e-3) / 1e12 / pk.value)
+                                              if prof["element_force"][0] > 0 else None}}
     # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -584,9 +584,8 @@ static int pack_weights(pcx_handle* h, const double* w, cudaStream_t st) {
 
 static int reduce_wgrad(pcx_handle* h, int nparts, double* g, cudaStream_t st) {
   ProfScope ps(h, PCX_PROF_REDUCE_WGRAD, st);
-  const int thr = 128;
-  const int blocks = (int)((h->ms.nweights + thr - 1) / thr);
-  k_reduce_wgrad<<<blocks, thr, 0, st>>>(h->ms, h->part, h->part_stride, nparts, g);
+  const int blocks = (int)((h->ms.nweights + 63) / 64);
+  k_reduce_wgrad<<<blocks, 256, 0, st>>>(h->ms, h->part, h->part_stride, nparts, g);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }

@@ -1107,36 +1107,51 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
 }
 
 // Fixed-order sum over CTAs + un-padding into the flat equinox-order gradient.
-// One thread per real parameter.
-__global__ void k_reduce_wgrad(MlpShape s, const double* __restrict__ part, long long part_stride, int nparts,
-                               double* __restrict__ g) {
-  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (p >= s.nweights) return;
-  const int WPd = 8 * s.NT, W = s.width, D = s.depth;
-  // locate the layer
-  int layer = 0;
-  bool is_bias = false;
-  long long local = 0;
-  for (int i = 0; i <= D; i++) {
-    const int fin = (i == 0) ? s.n_in : W, fout = (i == D) ? s.n_out : W;
-    if (p >= s.offW[i] && p < s.offW[i] + (long long)fin * fout) { layer = i; is_bias = false; local = p - s.offW[i]; break; }
-    if (s.offB[i] >= 0 && p >= s.offB[i] && p < s.offB[i] + fout) { layer = i; is_bias = true; local = p - s.offB[i]; break; }
-  }
-  const int fin = (layer == 0) ? s.n_in : W;
-  const int o = is_bias ? (int)local : (int)(local / fin);
-  const int k = is_bias ? -1 : (int)(local % fin);
-  long long off;
-  if (layer == 0) {
-    off = (long long)feat_to_slot(o) * 8 + (is_bias ? s.n_in : k);
-  } else if (layer < D) {
-    off = (long long)WPd * 8 + (long long)(layer - 1) * WPd * WPd + (long long)feat_to_slot(o) * WPd +
-          feat_to_slot(is_bias ? W : k);
-  } else {
-    off = (long long)WPd * 8 + (long long)(D - 1) * WPd * WPd + (long long)o * WPd + feat_to_slot(is_bias ? W : k);
-  }
+// 64 parameters per block, 4 threads per parameter: thread (p, g) sums the partials q = g, g + 4, g + 8, ... with two
+// independent accumulators (even / odd terms), the four group sums are combined in the order g = 0..3 through shared
+// memory -- a fixed order, so the gradient stays bit-reproducible, at 4 x the memory-level parallelism of one thread
+// per parameter walking all 148 partials (r1: 19 us per step, 1.2 % of the step of a 2 M-point shard).
+__global__ void __launch_bounds__(256) k_reduce_wgrad(MlpShape s, const double* __restrict__ part, long long part_stride, int nparts,
+                                                      double* __restrict__ g) {
+  __shared__ double sh[4][64];
+  const int pl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const long long p = blockIdx.x * 64LL + pl;
   double acc = 0.0;
-  for (int q = 0; q < nparts; q++) acc += part[(long long)q * part_stride + off];
-  g[p] = acc;
+  if (p < s.nweights) {
+    const int WPd = 8 * s.NT, W = s.width, D = s.depth;
+    // locate the layer
+    int layer = 0;
+    bool is_bias = false;
+    long long local = 0;
+    for (int i = 0; i <= D; i++) {
+      const int fin = (i == 0) ? s.n_in : W, fout = (i == D) ? s.n_out : W;
+      if (p >= s.offW[i] && p < s.offW[i] + (long long)fin * fout) { layer = i; is_bias = false; local = p - s.offW[i]; break; }
+      if (s.offB[i] >= 0 && p >= s.offB[i] && p < s.offB[i] + fout) { layer = i; is_bias = true; local = p - s.offB[i]; break; }
+    }
+    const int fin = (layer == 0) ? s.n_in : W;
+    const int o = is_bias ? (int)local : (int)(local / fin);
+    const int k = is_bias ? -1 : (int)(local % fin);
+    long long off;
+    if (layer == 0) {
+      off = (long long)feat_to_slot(o) * 8 + (is_bias ? s.n_in : k);
+    } else if (layer < D) {
+      off = (long long)WPd * 8 + (long long)(layer - 1) * WPd * WPd + (long long)feat_to_slot(o) * WPd +
+            feat_to_slot(is_bias ? W : k);
+    } else {
+      off = (long long)WPd * 8 + (long long)(D - 1) * WPd * WPd + (long long)o * WPd + feat_to_slot(is_bias ? W : k);
+    }
+    double a0 = 0.0, a1 = 0.0;
+    int q = grp;
+    for (; q + 4 < nparts; q += 8) {
+      a0 += part[(long long)q * part_stride + off];
+      a1 += part[(long long)(q + 4) * part_stride + off];
+    }
+    if (q < nparts) a0 += part[(long long)q * part_stride + off];
+    acc = a0 + a1;
+  }
+  sh[grp][pl] = acc;
+  __syncthreads();
+  if (grp == 0 && p < s.nweights) g[p] = ((sh[0][pl] + sh[1][pl]) + sh[2][pl]) + sh[3][pl];
 }
 
 }  // namespace pcx
