@@ -103,7 +103,7 @@ struct pcx_handle {
   unsigned int* sched = nullptr;          // group counter of the forward kernel's dynamic scheduler
   int fwd_dynamic = 1;                    // PCX_OPT_TUNE_FWD_DYNAMIC
   unsigned long long* stamps = nullptr;   // tuning: per-CTA time stamps of the last MLP launch (PCX_OPT_TUNE_STAMPS)
-  int bwd_edge = 1;       // the same for the adjoint's delta chain; PCX_BWD_EDGE=0 disables
+  int bwd_edge = 2;       // the same for the adjoint: 1 = delta chain, 2 = + weight-gradient contraction (width 50); PCX_BWD_EDGE=0 disables
   int fwd_edge = 1;       // last (mostly padding) tile of the hidden layers on the FP64 vector pipe; PCX_FWD_EDGE=0 disables
   bool prof_on = false;
   struct ProfEv { int cat; cudaEvent_t e0, e1; };
@@ -394,15 +394,15 @@ static int launch_element(pcx_handle* h, bool tangent, int T, cudaStream_t st, c
   return PCX_OK;
 }
 
-template <int NT, int KODD, int DH, bool WSMEM, int BEDGE>
+template <int NT, int KODD, int DH, bool WSMEM, int BEDGE, int CE = 0>
 static int launch_mlp_bwd_e(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
   const size_t smem = sizeof(BwdSmem<NT, DH, WSMEM>);
   if (smem > 227 * 1024)
     return fail(PCX_ERR_UNSUPPORTED, "MLP %d x %d needs %zu bytes of shared memory in the adjoint kernel", h->ms.width,
                 h->ms.depth, smem);
   // per device and cheap: set it on every launch (a process may drive several devices)
-  CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM, BEDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_mlp_backward<NT, KODD, DH, WSMEM, BEDGE><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward<NT, KODD, DH, WSMEM, BEDGE, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mlp_backward<NT, KODD, DH, WSMEM, BEDGE, CE><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, io);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
@@ -411,6 +411,7 @@ static int launch_mlp_bwd_v(pcx_handle* h, int grid, cudaStream_t st, const MlpI
   // edge tile of the delta chain on the vector pipe when the last tile holds one or two real features (width 50: 48, 49)
   if constexpr (NT == 7 && KODD == 1 && DH > 0) {
     const int nedge = h->ms.width - 8 * (NT - 1);
+    if (h->bwd_edge >= 2 && nedge == 2) return launch_mlp_bwd_e<NT, KODD, DH, WSMEM, 2, 1>(h, grid, st, io);
     if (h->bwd_edge && nedge == 2) return launch_mlp_bwd_e<NT, KODD, DH, WSMEM, 2>(h, grid, st, io);
     if (h->bwd_edge && nedge == 1) return launch_mlp_bwd_e<NT, KODD, DH, WSMEM, 1>(h, grid, st, io);
   }

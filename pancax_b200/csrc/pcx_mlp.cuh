@@ -803,7 +803,17 @@ struct BwdSmem {
 // replaced by DFMAs on the lane-local A-fragment elements (row r, out feature 4ks+c) times the two weight columns
 // W[4ks+c][48..49] (one 16-byte read-only load per k-step, L1-resident) and a 2-step butterfly over the 4 lanes of a row:
 // 26 DFMA + 4 DADD + 8 SHFL instead of 13 DMMA.  BEDGE = 0: off.
-template <int NT, int KODD, int DH, bool WSMEM, int BEDGE = 0>
+//
+// CE = 1 (needs NT = 7, BEDGE = 2, i.e. width 50): the same treatment for the weight-gradient contraction.  Of the 7 x 7
+// blocks of a hidden layer's dW the 13 that touch the last tile are 5/8 or 6/8 padding (in slots 48 / 50 / ones = features
+// 48, 49 and the bias column; out slots 48 / 50).  They leave the tensor pipe: the 36 full blocks are shared 7 per warp
+// on warps 0-3 (out block w x in tiles 0..5 plus one block of out blocks 4 / 5) and 2 per warp on warps 4-7 -- 9 per
+// scheduler -- and warps 4-7 sum the edge entries with DFMAs, rows 16 (w-4) .. +15 each, lane l on the slot pair
+// (2l, 2l+1): dW[o][48|50|ones] += d[row][o] * (h48 | h50 | 1) and dW[48|50][i] += (d48 | d50) * h[row][i], one row per
+// k-step of the DMMA loop next to it.  Per hidden layer and 64-row tile 576 DMMA + 640 DFMA warp instructions instead of
+// 784 DMMA (algorithmic: 637.5 DMMA-equivalents); the accumulators reuse the registers of the dropped blocks.  The four
+// row-group partials of the edge sums are combined in fixed order through shared memory when the CTA finishes.
+template <int NT, int KODD, int DH, bool WSMEM, int BEDGE = 0, int CE = 0>
 __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   using SM = BwdSmem<NT, DH, WSMEM>;
   constexpr int ROWS = SM::ROWS, S = SM::S, SN = SM::SN;
@@ -811,6 +821,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
   constexpr int KS = 2 * NT - KODD;
   constexpr int KR = ROWS / 4;  // k-steps over rows in the weight-gradient contraction (even: ROWS = 8 (NT + 1))
   static_assert(BEDGE == 0 || KODD == 1, "the edge weights live in the unused last k-step of BH");
+  static_assert(CE == 0 || (NT == 7 && BEDGE == 2 && DH > 0), "contraction edge: width 50 only");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
@@ -1025,7 +1036,48 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
       // prefetch h for the next layer (or the next tile's top layer) into the buffer just released
       if (L > 1) prefetch_h(tile, L - 2, hb ^ 1);
       else prefetch_h(tile + gridDim.x, s.depth - 1, hb ^ 1);
-      if (warp < NT) {
+      if constexpr (CE) {
+        const double* Dt = sm.D[db];
+        const double* Ht = sm.H[hb];
+        if (warp < 4) {
+          // out block `warp` x in tiles 0..5, plus block (4 + warp/2, 4 + warp%2)
+          const int jrx = 4 + (warp >> 1);
+          const bool odd = warp & 1;
+#pragma unroll 4
+          for (int ks = 0; ks < KR; ks++) {
+            const double a = Dt[(4 * ks + c) * S + ((8 * warp + r) ^ gc)];
+            const double ax = Dt[(4 * ks + c) * S + ((8 * jrx + r) ^ gc)];
+            double b[NT - 1];
+#pragma unroll
+            for (int jc = 0; jc < NT - 1; jc++) b[jc] = Ht[(4 * ks + c) * S + ((8 * jc + r) ^ gc)];
+#pragma unroll
+            for (int jc = 0; jc < NT - 1; jc++) dmma(gH[L - 1][jc][0], gH[L - 1][jc][1], a, b[jc]);
+            dmma(gH[L - 1][NT - 1][0], gH[L - 1][NT - 1][1], ax, odd ? b[NT - 2] : b[NT - 3]);
+          }
+        } else {
+          // blocks (4 + (w-4)/2, 2 ((w-4)%2) + {0, 1}) and the edge sums of rows 16 (w-4) .. +15
+          const int w4 = warp - 4;
+          const int jr = 4 + (w4 >> 1), jc0 = 2 * (w4 & 1);
+          const int ecol = lane < 4 * (NT - 1) + 4 ? 2 * lane : 0;   // slot pair (2 lane, 2 lane + 1) of the 8 NT slots
+          constexpr int E0 = 8 * (NT - 1), E1 = 8 * (NT - 1) + 2;     // slots of features 48 and 49
+#pragma unroll 4
+          for (int ks = 0; ks < KR; ks++) {
+            const double a = Dt[(4 * ks + c) * S + ((8 * jr + r) ^ gc)];
+            dmma(gH[L - 1][0][0], gH[L - 1][0][1], a, Ht[(4 * ks + c) * S + ((8 * jc0 + r) ^ gc)]);
+            dmma(gH[L - 1][1][0], gH[L - 1][1][1], a, Ht[(4 * ks + c) * S + ((8 * jc0 + 8 + r) ^ gc)]);
+            const int row = 16 * w4 + ks, g = swz(row);
+            const double2 dv = *reinterpret_cast<const double2*>(&Dt[row * S + (ecol ^ g)]);
+            const double2 hv = *reinterpret_cast<const double2*>(&Ht[row * S + (ecol ^ g)]);
+            const double h48 = Ht[row * S + (E0 ^ g)], h50 = Ht[row * S + (E1 ^ g)];
+            const double d48 = Dt[row * S + (E0 ^ g)], d50 = Dt[row * S + (E1 ^ g)];
+            gH[L - 1][2][0] = fma(dv.x, h48, gH[L - 1][2][0]); gH[L - 1][2][1] = fma(dv.y, h48, gH[L - 1][2][1]);
+            gH[L - 1][3][0] = fma(dv.x, h50, gH[L - 1][3][0]); gH[L - 1][3][1] = fma(dv.y, h50, gH[L - 1][3][1]);
+            gH[L - 1][4][0] += dv.x;                           gH[L - 1][4][1] += dv.y;
+            gH[L - 1][5][0] = fma(hv.x, d48, gH[L - 1][5][0]); gH[L - 1][5][1] = fma(hv.y, d48, gH[L - 1][5][1]);
+            gH[L - 1][6][0] = fma(hv.x, d50, gH[L - 1][6][0]); gH[L - 1][6][1] = fma(hv.y, d50, gH[L - 1][6][1]);
+          }
+        }
+      } else if (warp < NT) {
 #pragma unroll 4
         for (int ks = 0; ks < KR; ks++) {
           const double a = sm.D[db][(4 * ks + c) * S + ((8 * warp + r) ^ gc)];
@@ -1079,7 +1131,60 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_mlp_backward(const __grid_
   double* P = io.part + (long long)blockIdx.x * io.part_stride;
   constexpr int WPd = 8 * NT;
   double* Po = P + WPd * 8 + (long long)DH * WPd * WPd;
-  if (warp < NT) {
+  if constexpr (CE) {
+    if (warp < NT) {
+      P[(8 * warp + r) * 8 + 2 * c] = g0[0];
+      P[(8 * warp + r) * 8 + 2 * c + 1] = g0[1];
+      Po[r * WPd + 8 * warp + 2 * c] = gO[0];
+      Po[r * WPd + 8 * warp + 2 * c + 1] = gO[1];
+    }
+    // edge sums: the four row-group partials of warps 4-7 meet in shared memory (the D tiles are free now)
+    double* scr = &sm.D[0][0];     // [w4][l][k = 0..4][64 slots]
+    static_assert(4 * DH * 5 * 64 <= 2 * ROWS * S, "edge scratch fits the D tiles");
+    __syncthreads();
+    if (warp >= 4) {
+#pragma unroll
+      for (int l = 0; l < DH; l++)
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          scr[(((warp - 4) * DH + l) * 5 + k) * 64 + 2 * lane] = gH[l][2 + k][0];
+          scr[(((warp - 4) * DH + l) * 5 + k) * 64 + 2 * lane + 1] = gH[l][2 + k][1];
+        }
+    }
+    __syncthreads();
+    constexpr int E0 = 8 * (NT - 1), E1 = 8 * (NT - 1) + 2;
+    for (int i = threadIdx.x; i < DH * 5 * WPd; i += blockDim.x) {
+      const int col = i % WPd, k = (i / WPd) % 5, l = i / (5 * WPd);
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) v += scr[((q * DH + l) * 5 + k) * 64 + col];
+      double* Pl = P + WPd * 8 + (long long)l * WPd * WPd;
+      if (k < 3) Pl[col * WPd + (k == 0 ? E0 : k == 1 ? E1 : ones_slot)] = v;     // dW[o = col][48 | 50 | ones]
+      else if (col < E0) Pl[(k == 3 ? E0 : E1) * WPd + col] = v;                  // dW[48 | 50][i = col]
+    }
+#pragma unroll
+    for (int l = 0; l < DH; l++) {
+      double* Pl = P + WPd * 8 + (long long)l * WPd * WPd;
+      if (warp < 4) {
+#pragma unroll
+        for (int jc = 0; jc < NT - 1; jc++) {
+          Pl[(8 * warp + r) * WPd + 8 * jc + 2 * c] = gH[l][jc][0];
+          Pl[(8 * warp + r) * WPd + 8 * jc + 2 * c + 1] = gH[l][jc][1];
+        }
+        const int jrx = 4 + (warp >> 1), jcx = 4 + (warp & 1);
+        Pl[(8 * jrx + r) * WPd + 8 * jcx + 2 * c] = gH[l][NT - 1][0];
+        Pl[(8 * jrx + r) * WPd + 8 * jcx + 2 * c + 1] = gH[l][NT - 1][1];
+      } else {
+        const int w4 = warp - 4;
+        const int jr = 4 + (w4 >> 1), jc0 = 2 * (w4 & 1);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          Pl[(8 * jr + r) * WPd + 8 * (jc0 + j) + 2 * c] = gH[l][j][0];
+          Pl[(8 * jr + r) * WPd + 8 * (jc0 + j) + 2 * c + 1] = gH[l][j][1];
+        }
+      }
+    }
+  } else if (warp < NT) {
     P[(8 * warp + r) * 8 + 2 * c] = g0[0];
     P[(8 * warp + r) * 8 + 2 * c + 1] = g0[1];
 #pragma unroll

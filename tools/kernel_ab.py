@@ -29,7 +29,8 @@ params = px.Parameters(problem, key=0, n_layers=4, n_neurons=50, device=device,
 eng = get_engine(problem, params)
 eng.set_option("cull_null_steps", 0)
 w = params.fields.networks.weights
-VARIANTS = [("default", dict(tune_fwd_variant=12))]
+VARIANTS = [("bwd_chain_edge+contraction_edge", dict(tune_bwd_edge=2)), ("bwd_warp_specialised", dict(tune_bwd_edge=3)),
+            ("bwd_edge2_again", dict(tune_bwd_edge=2)), ("bwd_ws_again", dict(tune_bwd_edge=3))]
 ref = None
 
 
