@@ -14,6 +14,7 @@
 #include "pcx_jet.cuh"
 #include "pcx_mlp.cuh"
 #include "pcx_mlp_tf32.cuh"
+#include "pcx_mlp_umma.cuh"
 
 using namespace pcx;
 
@@ -85,7 +86,7 @@ struct pcx_handle {
   bool vz_filled = false;                   // a path-dependent call has written the state history
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
                  const double* lam_in; double* lam_out; } vstep;
-  int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT
+  int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT: 1 = mma.sync kernel, 2 = tcgen05 contractions
   double *us = nullptr, *fe = nullptr, *f = nullptr, *v = nullptr, *ubar = nullptr;
   double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
   double *scal = nullptr;       // see SC_* offsets
@@ -480,12 +481,18 @@ static int launch_mlp_fwd_k(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
 }
 
 // TF32-adjoint mode: the activation planes are stored as fp32 in the same workspace (same element offsets)
+// the tcgen05 kernel covers 7 slot tiles (width 49..55) and 1..3 hidden->hidden layers; anything else in mode 2 runs the
+// mma.sync kernel
+static bool umma_adjoint(const pcx_handle* h) {
+  return h->tf32_adjoint == 2 && h->ms.NT == 7 && h->ms.depth >= 2 && h->ms.depth <= 4;
+}
 static MlpIO tf32_view(const pcx_handle* h, const MlpIO& io_in) {
   MlpIO io = io_in;
   if (h->tf32_adjoint && io.act) {
     io.act32 = reinterpret_cast<float*>(h->act) + (io.act - h->act);
     io.act = nullptr;
     io.pk32 = h->pk32;
+    io.act32_quad = umma_adjoint(h) ? 1 : 0;
   }
   return io;
 }
@@ -535,6 +542,17 @@ static int launch_mlp_bwd_tf32_nt(pcx_handle* h, int DH, int grid, cudaStream_t 
   }
 }
 
+template <int DH>
+static int launch_mlp_bwd_umma(pcx_handle* h, int grid, cudaStream_t st, const MlpIO& io) {
+  const size_t smem = sizeof(BwdUmmaSmem<DH>);
+  static_assert(sizeof(BwdUmmaSmem<DH>) <= 227 * 1024, "shared memory budget of the tcgen05 adjoint");
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_backward_umma<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaMemsetAsync(h->part, 0, (size_t)grid * h->part_stride * sizeof(double), st));   // partials are accumulated with RED
+  k_mlp_backward_umma<DH><<<grid, UMMA_THREADS, smem, st>>>(h->ms, io);
+  LAUNCH_CHECK(h);
+  return PCX_OK;
+}
+
 static int tf32_supported(const pcx_handle* h) {
   if (h->ms.NT > 7) return fail(PCX_ERR_UNSUPPORTED, "TF32 adjoint: MLP width %d not supported (n_neurons <= 55)", h->ms.width);
   return PCX_OK;
@@ -552,6 +570,13 @@ static int launch_mlp_bwd(pcx_handle* h, cudaStream_t st, const MlpIO& io_in, in
     if (rc) return rc;
     const MlpIO io = tf32_view(h, io_in);
     if (!io.act32) return fail(PCX_ERR_STATE, "TF32 adjoint launched without stored activations");
+    if (umma_adjoint(h)) {
+      switch (DH) {
+        case 1: return launch_mlp_bwd_umma<1>(h, grid, st, io);
+        case 2: return launch_mlp_bwd_umma<2>(h, grid, st, io);
+        case 3: return launch_mlp_bwd_umma<3>(h, grid, st, io);
+      }
+    }
     switch (h->ms.NT) {
       case 2: return launch_mlp_bwd_tf32_nt<2>(h, DH, grid, st, io);
       case 4: return launch_mlp_bwd_tf32_nt<4>(h, DH, grid, st, io);
@@ -795,7 +820,7 @@ extern "C" int pcx_set_option(pcx_handle* h, int32_t option, int64_t value) {
     case PCX_OPT_CULL_NULL_STEPS: h->cull_null_steps = value != 0; return PCX_OK;
     case PCX_OPT_TF32_ADJOINT:
       if (value && h->have_field) { int rc = tf32_supported(h); if (rc) return rc; }
-      h->tf32_adjoint = value != 0;
+      h->tf32_adjoint = value == 2 ? 2 : value != 0;
       return PCX_OK;
     // kernel-variant switches (tuning / A-B measurements; every variant computes the same function)
     case PCX_OPT_TUNE_FWD_TANH: h->fwd_tanh = (int)value; return PCX_OK;
@@ -845,7 +870,7 @@ extern "C" int pcx_set_field(pcx_handle* h, const pcx_field_desc* f) {
   h->bc_a = f->bc_a; h->bc_b = f->bc_b;
   h->have_field = true;
   if (const char* e = getenv("PCX_CULL_NULL_STEPS")) h->cull_null_steps = atoi(e) != 0;
-  if (const char* e = getenv("PCX_TF32_ADJOINT")) h->tf32_adjoint = atoi(e) != 0;
+  if (const char* e = getenv("PCX_TF32_ADJOINT")) h->tf32_adjoint = atoi(e) == 2 ? 2 : atoi(e) != 0;
   if (h->tf32_adjoint) { int rc = tf32_supported(h); if (rc) return rc; }
   int rc = find_null_steps(h);
   if (rc) return rc;

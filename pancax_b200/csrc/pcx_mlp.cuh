@@ -214,6 +214,7 @@ struct MlpIO {
   const double* g_u;    // backward: [n*n_out] cotangent on u
   double* act;          // activations [depth][NT][rows_cap][8] (nullptr: do not store)
   float* act32;         // TF32-adjoint mode: the same planes stored as fp32 instead (pcx_mlp_tf32.cuh)
+  int act32_quad;       // act32 in tcgen05 operand order [layer][row/4][tile j][slot%8][row%4] (pcx_mlp_umma.cuh)
   long long rows_cap;
   const double* pk;     // packed weights
   const float* pk32;    // TF32-adjoint mode: packed hi/lo chain weights (k_pack_weights_tf32)
@@ -620,9 +621,16 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
 #pragma unroll
         for (int m = 0; m < MT; m++) {
           const long long row = row0 + 8 * m + r;
-          if (row < io.n)
-            st_cs_f32x2_fwd(io.act32 + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, (float)h[m][jn][0],
-                            (float)h[m][jn][1]);
+          if (row < io.n) {
+            if (io.act32_quad) {   // K-major tcgen05 operand order: 4 consecutive rows of one slot are 16 contiguous bytes
+              float* q = io.act32 + (((long long)i * (io.rows_cap >> 2) + (row >> 2)) * NT + jn) * 32 + 8 * c + (row & 3);
+              __stcs(q, (float)h[m][jn][0]);
+              __stcs(q + 4, (float)h[m][jn][1]);
+            } else {
+              st_cs_f32x2_fwd(io.act32 + (((long long)i * NT + jn) * io.rows_cap + row) * 8 + 2 * c, (float)h[m][jn][0],
+                              (float)h[m][jn][1]);
+            }
+          }
         }
       } else if (io.act) {
 #pragma unroll

@@ -1,4 +1,4 @@
-"""A/B device-time measurements of kernel variants on the bench workload (C3: Hex8 n^3, nt = 2, every row evaluated).
+"""(TF32 modes) A/B device-time measurements of kernel variants on the bench workload (C3: Hex8 n^3, nt = 2, every row evaluated).
 One engine, the variants switched with pcx_set_option(PCX_OPT_TUNE_*); per-kernel-class times from CUDA events on the
 launching stream (pcx_profile_*).  Also checks that every variant returns the same loss / gradient as the baseline.
 
@@ -29,7 +29,8 @@ params = px.Parameters(problem, key=0, n_layers=4, n_neurons=50, device=device,
 eng = get_engine(problem, params)
 eng.set_option("cull_null_steps", 0)
 w = params.fields.networks.weights
-VARIANTS = [("default", dict(tune_bwd_edge=2))]
+VARIANTS = [("fp64", dict(tf32_adjoint=0)), ("tf32_mma_sync", dict(tf32_adjoint=1)), ("tf32_tcgen05", dict(tf32_adjoint=2)),
+            ("tf32_mma_sync_again", dict(tf32_adjoint=1)), ("tf32_tcgen05_again", dict(tf32_adjoint=2))]
 ref = None
 
 
