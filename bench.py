@@ -471,6 +471,34 @@ def run_ours(args):
                     "flush every 1024 rows) from fp32 activations; forward / element sweeps / loss stay fp64. NOT the "
                     "headline: value/e2e/roofline are the fp64 path."}
 
+    # the same mode with every contraction over rows on tcgen05.mma kind::tf32 / TMEM (PCX_OPT_TF32_ADJOINT = 2)
+    eng.set_option("tf32_adjoint", 2)
+    for _ in range(3):
+        step_device()
+    g32u = res.gw.clone()
+    eng.profile_enable(True)
+    eng.profile_collect()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    prof32u = eng.profile_collect()
+    eng.profile_enable(False)
+    eng.set_option("tf32_adjoint", 0)
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_u = float(t_ms.cpu()[0])
+    tf32["tcgen05"] = {"value": evals_per_rank * world * args.steps / (ms_u * 1e-3), "unit": "evals/s",
+                       "ms_per_step": ms_u / args.steps,
+                       "grad_rel_err_vs_fp64": float((torch.linalg.norm(g32u - g64) / torch.linalg.norm(g64)).cpu()),
+                       "kernel_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in prof32u.items() if v[1]},
+                       "note": "k_mlp_backward_umma: dW_L = d_L^T h_L, dW_out, dW_0 as tcgen05.mma kind::tf32 (M 64, N 56 / 8, "
+                               "K = 128 rows per tile, 3xTF32 into two TMEM accumulator sets, operands K-major straight from "
+                               "one 28 KB bulk copy per layer tile), delta chain on mma.sync"}
+
     # ---------------- strong scaling of the literal C3 and the sharded residual loss (C2), every N
     strong_leg = resid_leg = None
     if not args.no_extra_legs and args.scaling == "weak":

@@ -182,12 +182,15 @@ int pcx_destroy(pcx_handle* h);
  * rows, from fp32 copies of the hidden activations (BASELINE.json north_star item 4 / config C5).  The forward pass,
  * the element sweeps, the loss and aux stay fp64 and bit-identical; only d loss / d weights changes, by <= 1e-5
  * relative per leaf (north_star allows 1e-4).  Must not be toggled between a forward and its adjoint
- * (pcx_loss_begin / pcx_loss_finish). */
+ * (pcx_loss_begin / pcx_loss_finish).  Value 1: mma.sync.m16n8k8.tf32 kernel (csrc/pcx_mlp_tf32.cuh).  Value 2: every
+ * contraction over rows (dW_L = d_L^T h_L, dW_out, dW_0) on tcgen05.mma kind::tf32 with TMEM accumulators
+ * (csrc/pcx_mlp_umma.cuh; widths 49..55 with 2..4 hidden layers, other shapes run the value-1 kernel); same tolerance. */
 #define PCX_OPT_TF32_ADJOINT 2
 /* Kernel-variant switches for A/B measurements (tools/kernel_ab.py); every variant computes the same function to
  * rounding.  FWD_TANH: 1 (default) replicated conflict-free exp2 table + 13-instruction tanh, 0 single table, 2 replicated
- * table with the old range reduction.  FWD_EDGE / BWD_EDGE: 1 (default) the mostly-padding last feature tile of the hidden
- * layers on the FP64 vector pipe instead of the tensor pipe.  FWD_VARIANT: (row tiles per warp, min CTAs per SM) = 12|21|22. */
+ * table with the old range reduction.  FWD_EDGE / BWD_EDGE: the mostly-padding last feature tile of the hidden
+ * layers on the FP64 vector pipe instead of the tensor pipe (BWD_EDGE: 1 = delta chain, 2 (default) = + the 13 edge blocks of
+ * the weight-gradient contraction at width 50).  FWD_VARIANT: (row tiles per warp, min CTAs per SM) = 12|21|22. */
 #define PCX_OPT_TUNE_FWD_TANH    100
 #define PCX_OPT_TUNE_FWD_EDGE    101
 #define PCX_OPT_TUNE_BWD_EDGE    102

@@ -369,7 +369,8 @@ class Engine:
 
     def set_option(self, name, value):
         """``cull_null_steps``: skip the MLP on time steps whose Dirichlet table b is identically zero (exact).
-        ``tf32_adjoint``: adjoint through the MLP on the TF32 tensor cores (3xTF32, fp32 activations); loss and aux
+        ``tf32_adjoint``: adjoint through the MLP on the TF32 tensor cores (3xTF32, fp32 activations; 1 = mma.sync
+        kernel, 2 = contractions on tcgen05.mma kind::tf32 / TMEM); loss and aux
         unchanged, weight gradients within 1e-5 relative per leaf (PCX_OPT_TF32_ADJOINT)."""
         codes = {"cull_null_steps": 1, "tf32_adjoint": 2, "tune_fwd_tanh": 100, "tune_fwd_edge": 101, "tune_bwd_edge": 102,
                  "tune_fwd_variant": 103, "tune_stamps": 104, "tune_fwd_dynamic": 105, "tune_l2pf": 107}
