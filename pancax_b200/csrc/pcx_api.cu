@@ -441,10 +441,10 @@ static int launch_mlp_bwd_nt(pcx_handle* h, int DH, int grid, cudaStream_t st, c
   }
 }
 
-template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV, int NTHR = 256, int LOCK = 0>
+template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV, int NTHR = 256, int LOCK = 0, int QUAD = 0>
 static int launch_mlp_fwd_t(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + fwd_table_doubles(TV)) * sizeof(double);
-  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB, NEDGE, TV, NTHR, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward<NT, KODD, MT, MINB, NEDGE, TV, NTHR, LOCK, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
   const long long groups = (io.n + 8 * MT - 1) / (8 * MT);
   long long blocks = (groups + NTHR / 32 - 1) / (NTHR / 32);
@@ -454,7 +454,7 @@ static int launch_mlp_fwd_t(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   MlpIO iod = io;
   iod.sched = h->fwd_dynamic ? h->sched : nullptr;
   if (iod.sched) CUDA_TRY(cudaMemsetAsync(h->sched, 0, sizeof(unsigned int), st));
-  k_mlp_forward<NT, KODD, MT, MINB, NEDGE, TV, NTHR, LOCK><<<(int)blocks, NTHR, smem, st>>>(h->ms, iod);
+  k_mlp_forward<NT, KODD, MT, MINB, NEDGE, TV, NTHR, LOCK, QUAD><<<(int)blocks, NTHR, smem, st>>>(h->ms, iod);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }
@@ -466,6 +466,9 @@ static int launch_mlp_fwd_v(pcx_handle* h, cudaStream_t st, const MlpIO& io) {
   if constexpr (NT == 7 && MT == 1 && MINB == 2 && NEDGE == 2) {   // tuning: more warps per CTA (fewer registers each)
     if (h->fwd_variant == 15) return launch_mlp_fwd_t<NT, KODD, MT, 1, NEDGE, 1, 512, 0>(h, st, io);
     if (h->fwd_variant == 16) return launch_mlp_fwd_t<NT, KODD, MT, 1, NEDGE, 1, 512, 1>(h, st, io);
+  }
+  if constexpr (NT == 7) {   // fp32 activations in tcgen05 operand order (TF32 adjoint mode 2)
+    if (io.act32 && io.act32_quad) return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 1, 256, 0, 1>(h, st, io);
   }
   if (h->fwd_tanh == 1 && (smem1 + 1024) * MINB <= 227 * 1024) return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 1>(h, st, io);
   return launch_mlp_fwd_t<NT, KODD, MT, MINB, NEDGE, 0>(h, st, io);

@@ -495,7 +495,10 @@ constexpr int fwd_table_doubles(int tv) { return tv ? EXP2_REP_N * EXP2_REP_COPI
 // DFMA (tanh) warps of the same scheduler to 0.4 % of their stand-alone rate, ONE leaves them 37 % of the pipe -- so
 // without the token the warps of a scheduler fall into lock step (all in the tanh phase, all in the DMMA phase) and
 // nothing overlaps the latency-bound parts (loads, stores, address arithmetic) of a row group.
-template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV = 1, int NTHR = 256, int LOCK = 0>
+// QUAD = 1: the fp32 activations of the TF32 mode in tcgen05 operand order (MlpIO::act32_quad); a compile-time variant so
+// that the fp64 path keeps its register allocation (as a run-time branch it cost the default kernel 24 B of spills and
+// 0.18 ms at C3 size)
+template <int NT, int KODD, int MT, int MINB, int NEDGE, int TV = 1, int NTHR = 256, int LOCK = 0, int QUAD = 0>
 __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constant__ MlpShape s, const __grid_constant__ MlpIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_mlp_forward(const __grid_constan
         for (int m = 0; m < MT; m++) {
           const long long row = row0 + 8 * m + r;
           if (row < io.n) {
-            if (io.act32_quad) {   // K-major tcgen05 operand order: 4 consecutive rows of one slot are 16 contiguous bytes
+            if constexpr (QUAD) {   // K-major tcgen05 operand order: 4 consecutive rows of one slot are 16 contiguous bytes
               float* q = io.act32 + (((long long)i * (io.rows_cap >> 2) + (row >> 2)) * NT + jn) * 32 + 8 * c + (row & 3);
               __stcs(q, (float)h[m][jn][0]);
               __stcs(q + 4, (float)h[m][jn][1]);
