@@ -13,6 +13,7 @@
 #include "pcx_element.cuh"
 #include "pcx_jet.cuh"
 #include "pcx_mlp.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include "pcx_mlp_tf32.cuh"
 #include "pcx_mlp_umma.cuh"
 
@@ -113,13 +114,20 @@ struct pcx_handle {
 
 // optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py
 // to report the dominant kernel's average launch duration from inside the timed region.
+// Every kernel class of a step is bracketed by an NVTX range (header-only NVTX 3: a no-op unless a tool such as Nsight
+// Systems / ncu --nvtx is attached; the reference has no profiler hooks) and, when pcx_profile_enable is on, by
+// a pair of CUDA events on the launching stream.
+static const char* const kProfNames[PCX_PROF_NCLASS] = {"pcx:pack_weights", "pcx:mlp_forward", "pcx:element_force", "pcx:assemble",
+                                                        "pcx:element_tangent", "pcx:mlp_backward", "pcx:reduce_wgrad", "pcx:other"};
 struct ProfScope {
   pcx_handle* h; int cat; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
   ProfScope(pcx_handle* h_, int cat_, cudaStream_t st_) : h(h_), cat(cat_), st(st_) {
+    nvtxRangePushA(kProfNames[cat >= 0 && cat < PCX_PROF_NCLASS ? cat : PCX_PROF_NCLASS - 1]);
     if (h->prof_on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   }
   ~ProfScope() {
     if (e0) { cudaEventRecord(e1, st); h->prof_events.push_back({cat, e0, e1}); }
+    nvtxRangePop();
   }
 };
 

@@ -34,6 +34,10 @@ FULL_KEYS = [
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory wavefronts % of peak"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("smsp__sass_inst_executed_op_utcmma.sum", "tcgen05.mma instructions (UTCxMMA)"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor memory (TMEM) active %"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "tensor-core shared-memory operand wavefronts % of peak"),
+    ("sm__ops_path_tensor_op_hmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "mma.sync TF32 ops % of peak"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe throttle (warps/issue)"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall: wait (fixed latency)"),
@@ -47,6 +51,9 @@ FULL_KEYS = [
 
 
 def _raw_csv(path):
+    if path.endswith(".csv"):   # a raw page already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x.raw.csv
+        rows = list(csv.reader(open(path)))
+        return rows[0], rows[1], rows[2:]
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
