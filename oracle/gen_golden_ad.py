@@ -65,7 +65,9 @@ T0 = {"hex8_swanson": 0.25, "hex8_blatz_ko": 0.25, "quad4_blatz_ko_bounded": 0.2
       "quad4_hencky_pstress": 0.2}
 
 
-def main():
+def setup():
+    """Import the reference on the torch stand-in; returns build(case) -> (params, problem, leaves, raws), flat_grad and
+    the reference's loss classes (shared with oracle/gen_golden_visco_resid.py)."""
     sys.path.insert(0, ROOT)
     from oracle import refshim_torch as shim
     shim.import_reference(REF)
@@ -88,7 +90,6 @@ def main():
                   "gent": ("bulk_modulus", "shear_modulus", "Jm_parameter"),
                   "swanson": tuple(SWANSON_PROPS.keys()), "hencky": ("bulk_modulus", "shear_modulus"),
                   "blatz_ko": ("shear_modulus",)}
-    out = {}
 
     def build(case):
         mesh = case.mesh
@@ -164,6 +165,16 @@ def main():
         gw = torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1) for g, p in zip(gs[:len(leaves)], leaves)])
         gp = torch.cat([g.reshape(-1) for g in gs[len(leaves):]]) if raws else torch.zeros(0, dtype=torch.float64)
         return gw.numpy(), gp.numpy()
+
+    return dict(locals())
+
+
+def main():
+    S = setup()
+    build, flat_grad, make_case, LOSS_WEIGHTS = S["build"], S["flat_grad"], S["make_case"], S["LOSS_WEIGHTS"]
+    EnergyLoss, EnergyAndResidualLoss = S["EnergyLoss"], S["EnergyAndResidualLoss"]
+    EnergyResidualAndReactionLoss, FullFieldDataLoss = S["EnergyResidualAndReactionLoss"], S["FullFieldDataLoss"]
+    out = {}
 
     for name, n, nt, width, depth, q, kinds in CASES:
         case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q, t0=T0.get(name, 0.0))

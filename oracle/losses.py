@@ -168,18 +168,33 @@ def loss_value(problem: OracleProblem, loss: dict, w, pr):
         # threaded through the steps n = 1 .. nt-1.  dt: times[1]-times[0] for step 1, and -- the update at the END
         # of the body, :63 -- times[n-1]-times[n-2] for step n >= 2.
         from .physics import potential_energy_with_state
-        assert kind == "energy" and first == 1, "state variables: path-dependent EnergyLoss only"
+        assert first == 1, "state variables: path-dependent calls only"
         ne, nq, nb = conns.shape[0], len(pe.w), len(problem.prony[0])
         Z = torch.eye(3, dtype=F64).expand(ne, nq, nb, 3, 3).clone()
         ts = problem.times
         dt = float(ts[1] - ts[0])
-        energy = 0.0
+        energy, R, reaction = 0.0, 0.0, 0.0
         for n in range(1, nt):
             us = fld(coords, float(ts[n]))
-            pi, Z = potential_energy_with_state(phys, pe, coords, conns, us, Z, dt)
+            pi, Z_new = potential_energy_with_state(phys, pe, coords, conns, us, Z, dt)
             energy = energy + pi
+            if kind != "energy":
+                # :146-192, :242-276 with base.py:356-385: f = dPi/dus at FIXED old state (value_and_grad, argnums=3,
+                # has_aux); the residual norm / reaction still depend on the weights through the old state as well
+                (f,) = torch.autograd.grad(pi, us, create_graph=True)
+                R = R + residual_norm(f, torch.as_tensor(problem.unknown_idx, dtype=torch.long))
+                if kind == "energy_residual_reaction":
+                    rn = torch.as_tensor(problem.reaction_nodes, dtype=torch.long)
+                    r = reaction_force(f, rn, problem.reaction_dof)
+                    reaction = reaction + torch.square(r - float(problem.global_outputs[n]))
+            Z = Z_new
             dt = float(ts[n] - ts[n - 1])
-        return we * energy, dict(energy=energy.detach())
+        if kind == "energy":
+            return we * energy, dict(energy=energy.detach())
+        if kind == "energy_residual":
+            return we * energy + wr * (R / nt), dict(energy=energy.detach(), residual=(R / nt).detach())
+        return (we * energy + wr * (R / nt) + wg * (reaction / nt),
+                dict(energy=energy.detach(), residual=(R / nt).detach(), global_data_loss=(reaction / nt).detach()))
     for t in problem.times[first:]:
         us = fld(coords, float(t))                           # weak_form:42,208,304
         if kind == "energy":

@@ -220,3 +220,43 @@ def test_cuda_matches_reference_visco_path_dependent(cuda_device, name, n, nt, w
     case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q)
     for det in (True, False):
         _check_visco(run_engine_loss(case, "energy", deterministic=det, first_step=1), f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}")
+
+
+# ---------------------------------------------------------------- state variables under the residual / reaction losses
+# EnergyAndResidualLoss.path_dependent_call (weak_form_loss_functions.py:151-192) and
+# EnergyResidualAndReactionLoss.path_dependent_call (:242-276) with SimpleFeFv: goldens from the reference's own calls on
+# the stand-in (oracle/gen_golden_visco_resid.py) -- what examples/inverse_problems/mechanics/path-dependent runs.
+GV = np.load(os.path.join(os.path.dirname(__file__), "golden", "visco_resid.npz"))
+VISCO_RESID_CASES = [("hex8_visco_neohookean", 2, 4, 12, 2, 2), ("quad4_visco_gent", 3, 3, 12, 2, 2),
+                     ("hex8_visco_hencky", 2, 3, 8, 2, 2), ("tri3_visco_neohookean_bounded", 3, 3, 10, 2, 2)]
+RESID_KINDS = ["energy_residual", "energy_residual_reaction"]
+
+
+def _check_visco_resid(out, tag, kind):
+    L, aux, gw, gp = out
+    key = f"{tag}__{kind}__"
+    names = ["energy", "residual", "global_data_loss"][:2 if kind == "energy_residual" else 3]
+    assert abs(L - float(GV[key + "loss"])) <= TOL * abs(float(GV[key + "loss"])), (tag, kind, L, float(GV[key + "loss"]))
+    for i, nme in enumerate(names):
+        a = float(aux[nme]) if isinstance(aux, dict) else float(aux[i])
+        assert abs(a - float(GV[key + "aux_" + nme])) <= TOL * abs(float(GV[key + "aux_" + nme])), (tag, kind, nme)
+    assert rel(gw, GV[key + "gw"]) < TOL, (tag, kind, rel(gw, GV[key + "gw"]))
+    if GV[key + "gp"].size:
+        assert rel(gp, GV[key + "gp"]) < TOL, (tag, kind, gp, GV[key + "gp"])
+
+
+@pytest.mark.parametrize("kind", RESID_KINDS)
+@pytest.mark.parametrize("name,n,nt,width,depth,q", VISCO_RESID_CASES)
+def test_oracle_matches_reference_visco_residual_losses(name, n, nt, width, depth, q, kind):
+    case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q)
+    _check_visco_resid(run_oracle_loss(case, kind, first_step=1), f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}", kind)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", RESID_KINDS)
+@pytest.mark.parametrize("name,n,nt,width,depth,q", VISCO_RESID_CASES)
+def test_cuda_matches_reference_visco_residual_losses(cuda_device, name, n, nt, width, depth, q, kind):
+    case = make_case(name, n=n, nt=nt, width=width, depth=depth, q_order=q)
+    for det in (True, False):
+        _check_visco_resid(run_engine_loss(case, kind, deterministic=det, first_step=1),
+                           f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}", kind)
