@@ -133,8 +133,11 @@ typedef struct {
    * equilibrium model; n_prony > 0 adds that many non-equilibrium Prony branches (PronySeries.moduli /
    * .relaxation_times, base.py:20-28), each with a 3x3 viscous deformation gradient per quadrature point as state.
    * The shift factor is 1, as in the reference (simple_fefv.py:27).  value[] / bounded[] describe the equilibrium
-   * model's properties (trainable ones allowed).  Only the path-dependent EnergyLoss
-   * (pcx_loss_desc.first_step = 1, weak_form_loss_functions.py:48-72) is defined for a model with state. */
+   * model's properties (trainable ones allowed).  A model with state is defined for the path-dependent calls only
+   * (pcx_loss_desc.first_step = 1): EnergyLoss (weak_form_loss_functions.py:48-72), EnergyAndResidualLoss
+   * (:151-192) and EnergyResidualAndReactionLoss (:242-276) -- the internal force of a step is dPi/du at fixed old
+   * state (base.py:356-361), the gradient carries the second-order terms through the state history.  PlaneStress
+   * with a state model, the phased (sharded) calls and the op-level calls are refused for it. */
   int32_t n_prony;
   double  prony_moduli[PCX_MAX_PRONY];
   double  prony_times[PCX_MAX_PRONY];
@@ -147,8 +150,8 @@ typedef struct {
   double  reaction_weight;
   const double* global_outputs; /* DEVICE f64 [nt] (problem.global_data.outputs) or NULL; read by the kernels
                                    of the call, never staged (ABI v4; v3 took a host pointer)       */
-  int32_t first_step;         /* 0: path-independent call (vmap over all times); 1: the path-dependent call of a
-                                 model without state variables (weak_form_loss_functions.py:48-72,242-276): the
+  int32_t first_step;         /* 0: path-independent call (vmap over all times); 1: the path-dependent call
+                                 (weak_form_loss_functions.py:48-72,151-192,242-276; required for a model with state): the
                                  loop starts at time step 1 ("time step 0 is the initial condition"), residual and
                                  reaction terms are still divided by nt                                  */
 } pcx_loss_desc;

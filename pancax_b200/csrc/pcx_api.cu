@@ -86,7 +86,8 @@ struct pcx_handle {
   long long vz_per = 0;
   bool vz_filled = false;                   // a path-dependent call has written the state history
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
-                 const double* lam_in; double* lam_out; } vstep;
+                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; } vstep;   // mode: k_visco_qp MODE
+  double* vv = nullptr;                     // [nt][nn][ndof] v_t = dloss/df_t of every step (residual losses with state)
   int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT: 1 = mma.sync kernel, 2 = tcgen05 contractions
   double *us = nullptr, *fe = nullptr, *f = nullptr, *v = nullptr, *ubar = nullptr;
   double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
@@ -355,27 +356,29 @@ static int launch_element_m(int model, bool tangent, dim3 grid, cudaStream_t st,
 
 // SimpleFeFv: per-point sweep (+ scatter of the point fluxes in the reverse sweep)
 template <int NNPE, int ND, int NDOF, int MODEL>
-static void launch_visco_t(bool bwd, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
-  if (bwd) {
-    k_visco_qp<NNPE, ND, NDOF, MODEL, true><<<nblk_qp, 128, 0, st>>>(tab, a);
-    k_visco_scatter<NNPE, ND, NDOF><<<(unsigned)((a.ne + visco_scatter_epb<NNPE>() - 1) / visco_scatter_epb<NNPE>()), 128, 0, st>>>(tab, a);
-  } else {
-    k_visco_qp<NNPE, ND, NDOF, MODEL, false><<<nblk_qp, 128, 0, st>>>(tab, a);
+static void launch_visco_t(int mode, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+  switch (mode) {
+    case 0: k_visco_qp<NNPE, ND, NDOF, MODEL, 0><<<nblk_qp, 128, 0, st>>>(tab, a); break;
+    case 1: k_visco_qp<NNPE, ND, NDOF, MODEL, 1><<<nblk_qp, 128, 0, st>>>(tab, a); break;
+    case 2: k_visco_qp<NNPE, ND, NDOF, MODEL, 2><<<nblk_qp, 128, 0, st>>>(tab, a); break;
+    default: k_visco_qp<NNPE, ND, NDOF, MODEL, 3><<<nblk_qp, 128, 0, st>>>(tab, a); break;
   }
+  if (mode != 0)
+    k_visco_scatter<NNPE, ND, NDOF><<<(unsigned)((a.ne + visco_scatter_epb<NNPE>() - 1) / visco_scatter_epb<NNPE>()), 128, 0, st>>>(tab, a);
 }
 template <int NNPE, int ND, int NDOF>
-static int launch_visco_m(int model, bool bwd, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
+static int launch_visco_m(int model, int mode, int nblk_qp, int nblk_el, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {
   switch (model) {
-    case PCX_MODEL_NEOHOOKEAN: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_NEOHOOKEAN>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
-    case PCX_MODEL_GENT: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_GENT>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
-    case PCX_MODEL_SWANSON: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_SWANSON>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
-    case PCX_MODEL_HENCKY: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_HENCKY>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
-    case PCX_MODEL_BLATZ_KO: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_BLATZ_KO>(bwd, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_NEOHOOKEAN: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_NEOHOOKEAN>(mode, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_GENT: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_GENT>(mode, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_SWANSON: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_SWANSON>(mode, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_HENCKY: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_HENCKY>(mode, nblk_qp, nblk_el, st, tab, a); return 0;
+    case PCX_MODEL_BLATZ_KO: launch_visco_t<NNPE, ND, NDOF, PCX_MODEL_BLATZ_KO>(mode, nblk_qp, nblk_el, st, tab, a); return 0;
   }
   return -1;
 }
-static int launch_visco(pcx_handle* h, bool bwd, cudaStream_t st, const ElemArgs& a) {
-  ProfScope ps(h, PCX_PROF_ELEMENT_FORCE, st);
+static int launch_visco(pcx_handle* h, int bwd /* k_visco_qp MODE 0..3 */, cudaStream_t st, const ElemArgs& a) {
+  ProfScope ps(h, bwd == 3 ? PCX_PROF_ELEMENT_TANGENT : PCX_PROF_ELEMENT_FORCE, st);
   int rc;
   if (h->elem_type == PCX_ELEM_HEX8) rc = launch_visco_m<8, 3, 3>(h->phys.model, bwd, h->vnblk, h->nblk_el, st, h->tab, a);
   else if (h->elem_type == PCX_ELEM_QUAD4) rc = launch_visco_m<4, 2, 2>(h->phys.model, bwd, h->vnblk, h->nblk_el, st, h->tab, a);
@@ -644,6 +647,8 @@ static void free_ws(pcx_handle* h) {
   for (int i = 0; i < 2; i++) { if (h->vlam[i]) cudaFree(h->vlam[i]); h->vlam[i] = nullptr; }
   if (h->vq) cudaFree(h->vq);
   if (h->vpart) cudaFree(h->vpart);
+  if (h->vv) cudaFree(h->vv);
+  h->vv = nullptr;
   if (h->f33) cudaFree(h->f33);
   h->f33 = nullptr; h->f33_cap = 0;
   h->vz = nullptr; h->vus = nullptr; h->vq = nullptr; h->vpart = nullptr; h->vz_per = 0; h->vnblk = 0; h->vz_filled = false;
@@ -706,6 +711,7 @@ static int alloc_ws(pcx_handle* h) {
     if (h->T < h->nt) CUDA_TRY(cudaMalloc(&h->vus, (size_t)h->nt * h->nn * h->ndof * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vlam[1], (size_t)per * sizeof(double)));
+    if (h->unknown_idx) CUDA_TRY(cudaMalloc(&h->vv, (size_t)h->nt * h->nn * h->ndof * sizeof(double)));
     h->vz_per = per;
   }
   CUDA_TRY(cudaMalloc(&h->flags, sizeof(int)));
@@ -1045,16 +1051,20 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
   }
   if (h->phys.physics == PCX_PHYS_SOLID && h->phys.n_prony > 0) {
     if (!h->vstep.on || tangent)
-      return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
-                                       "only (pcx_loss_and_grad, kind = PCX_LOSS_ENERGY, first_step = 1)");
+      return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent losses only "
+                                       "(pcx_loss_and_grad with first_step = 1)");
     a.n_prony = h->phys.n_prony;
     for (int b = 0; b < a.n_prony; b++) { a.prony_kappa[b] = h->vstep.kappa[b]; a.prony_c[b] = h->vstep.c[b]; }
     a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
+    a.wpsi = h->vstep.wpsi;
     a.qbuf = h->vq;
     // the per-point sweep has its own grid: partials [vnblk] and [vnblk][PCX_MAX_PROPS]
     a.epart = want_energy ? h->vpart : nullptr;
     a.ppart = want_dp ? h->vpart + h->vnblk : nullptr;
-    if (T != 1 || want_force == (a.z_new != nullptr) || !h->vq)
+    const int mode = h->vstep.mode;
+    const bool ok = mode == 0 ? (!want_force && a.z_new) : mode == 1 ? (want_force && a.lam_in && a.lam_out)
+                  : mode == 2 ? (want_force && a.z_new) : (want_force && a.lam_in && a.lam_out && v);
+    if (T != 1 || !ok || !h->vq)
       return fail(PCX_ERR_STATE, "state-variable sweep: one time step per launch, forward (states) or reverse (forces)");
   }
   const long long ndofs = h->nn * h->ndof;
@@ -1065,7 +1075,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
       CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)T * ndofs * sizeof(double), st));
     }
   }
-  int rc = a.n_prony > 0 ? launch_visco(h, want_force, st, a) : launch_element(h, tangent, T, st, a);
+  int rc = a.n_prony > 0 ? launch_visco(h, h->vstep.mode, st, a) : launch_element(h, tangent, T, st, a);
   if (rc) return rc;
   if (want_force) {
     const long long n = (long long)T * ndofs;
@@ -1346,22 +1356,37 @@ __global__ void k_fill_identity33(double* __restrict__ z, long long nmat) {
 
 static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,
                                double* loss_out, double* aux, double* g_weights, double* g_props, cudaStream_t st) {
-  if (L->kind != PCX_LOSS_ENERGY || L->first_step != 1)
-    return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent EnergyLoss "
-                                     "only (kind = PCX_LOSS_ENERGY, first_step = 1)");
+  const int kind = L->kind;
+  if (kind < PCX_LOSS_ENERGY || kind > PCX_LOSS_ENERGY_RESIDUAL_REACTION) return fail(PCX_ERR_INVALID, "unknown loss kind %d", kind);
+  if (L->first_step != 1)
+    return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent losses only "
+                                     "(first_step = 1)");
+  if (h->phys.formulation == PCX_FORM_PLANE_STRESS)
+    return fail(PCX_ERR_UNSUPPORTED, "PlaneStress with a state-variable model is not supported");
   if (h->nt < 2) return fail(PCX_ERR_INVALID, "the path-dependent call needs at least two time steps");
+  // residual / reaction losses (weak_form_loss_functions.py:151-192,242-276): every step's internal force f_n = dPi_n/du_n
+  // at FIXED old state comes out of the forward sweep (k_visco_qp MODE 2), R_n / reaction_n / v_n = dloss/df_n right
+  // after it; the reverse sweep (MODE 3) adds the second-order terms d/deps (dPi_n/du_n, dPi_n/dz_{n-1})(u_n + eps v_n)
+  // to the cotangent of u_n and to the adjoint of the old state.
+  const bool resid = kind != PCX_LOSS_ENERGY;
+  if (resid && (!h->unknown_idx || !h->vv)) return fail(PCX_ERR_STATE, "residual losses need unknown_idx in pcx_mesh_desc");
+  if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION && (!h->reaction_nodes || !L->global_outputs))
+    return fail(PCX_ERR_STATE, "reaction loss needs reaction_nodes and global_outputs");
   // the MLP activations of every time step stay resident when the workspace holds them (one adjoint launch over all
   // rows at the end); otherwise each step's activations are recomputed right before its adjoint in the reverse sweep
   const bool resident = h->T >= h->nt;
   const bool want_grad = g_weights != nullptr;
   // trainable properties belong to the equilibrium model: the Prony branches and the state evolution do not depend on
-  // them, so d loss / d prop is the plain sum of JxW dpsi_eq/dp over the steps of the forward sweep
+  // them, so d loss / d prop is the plain sum of JxW dpsi_eq/dp over the steps of the forward sweep (plus, for the
+  // residual losses, the dual parts JxW d/deps dpsi_eq/dp (u + eps v) of the reverse sweep)
   const bool want_dp = want_grad && g_props != nullptr && h->ntrain > 0;
   const int nb = h->phys.n_prony, nt = h->nt;
   const long long per = h->ne * h->nq * (long long)nb * 9;
   if (!h->vz || h->vz_per != per) return fail(PCX_ERR_STATE, "state-variable workspace missing (pcx_set_physics / pcx_set_field allocate it)");
   int rc;
-  const double we = L->energy_weight;
+  const double we = L->energy_weight, wr = resid ? L->residual_weight : 0.0;
+  const double wg = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->reaction_weight : 0.0;
+  const double* gout = kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION ? L->global_outputs : nullptr;   // device [nt]
   const long long ndofs = h->nn * h->ndof;
   CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(h->scal, 0, SC_SIZE(h) * sizeof(double), st));
@@ -1386,18 +1411,39 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
       h->vstep.kappa[b] = G * ((1.0 - c) * (1.0 - c) + tau * c * c / (dt * dt));
     }
   };
-  struct VStepGuard { pcx_handle* h; ~VStepGuard() { h->vstep.on = false; } } vstep_guard{h};   // also on early error returns
+  struct VStepGuard { pcx_handle* h; ~VStepGuard() { h->vstep.on = false; h->vstep.mode = 0; h->vstep.wpsi = 1.0; } } vstep_guard{h};   // also on early error returns
   h->vstep.on = true;
+  h->vstep.wpsi = 1.0;
   rc = PCX_OK;
   for (int n = 1; n < nt && !rc; n++) {
     step_constants(n);
     h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = h->vz + (long long)n * per;
     h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
-    rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, nullptr, 1.0, nullptr, 0.0, true, want_dp, false, st);
+    h->vstep.mode = resid ? 2 : 0;
+    rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, resid ? h->f : nullptr, 1.0, nullptr, 0.0, true, want_dp, resid, st);
     if (!rc) rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
     if (!rc && want_dp)
       rc = reduce_rows(h, h->vpart + h->vnblk, h->vnblk, PCX_MAX_PROPS, h->phys.nprops, 1,
                        h->scal + SC_DPI(h) + (long long)n * PCX_MAX_PROPS, PCX_MAX_PROPS, st);
+    if (!rc && resid) {
+      if ((rc = resid_react(h, 1, h->f, h->scal + SC_RR(h), st))) break;
+      k_resid_coeffs<<<1, 64, 0, st>>>(n, 1, nt, wr, wg, h->scal + SC_RR(h), gout,
+                                       h->scal + SC_R(h), h->scal + SC_REACT(h), h->scal + SC_C1(h), h->scal + SC_C2(h));
+      LAUNCH_CHECK(h);
+      if (!want_grad) continue;
+      double* v_n = h->vv + (long long)n * ndofs;
+      CUDA_TRY(cudaMemsetAsync(v_n, 0, (size_t)ndofs * sizeof(double), st));
+      if (h->n_unknown > 0) {
+        k_make_v<<<(unsigned)((h->n_unknown + 255) / 256), 256, 0, st>>>(n, h->nn, h->ndof, h->f, h->unknown_idx, h->n_unknown,
+            h->reaction_nodes, h->n_reaction, h->reaction_dof, h->scal + SC_C1(h), h->scal + SC_C2(h), v_n, 0);
+        LAUNCH_CHECK(h);
+      }
+      if (kind == PCX_LOSS_ENERGY_RESIDUAL_REACTION && h->n_reaction > 0) {
+        k_make_v<<<(unsigned)((h->n_reaction + 255) / 256), 256, 0, st>>>(n, h->nn, h->ndof, h->f, h->unknown_idx, h->n_unknown,
+            h->reaction_nodes, h->n_reaction, h->reaction_dof, h->scal + SC_C1(h), h->scal + SC_C2(h), v_n, 1);
+        LAUNCH_CHECK(h);
+      }
+    }
   }
   bool first = true;
   if (!rc && want_grad) {
@@ -1408,8 +1454,16 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
       step_constants(n);
       h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = nullptr;
       h->vstep.lam_in = h->vlam[cur]; h->vstep.lam_out = h->vlam[cur ^ 1];
+      // EnergyLoss: the sweep runs with unit energy weight, the assembly scales by we (lam is the adjoint per unit we);
+      // residual losses: the sweep carries we itself (the second-order terms do not scale with it)
+      h->vstep.mode = resid ? 3 : 1;
+      h->vstep.wpsi = resid ? we : 1.0;
       double* ubar_n = resident ? h->ubar + (long long)n * ndofs : h->ubar;
-      rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, ubar_n, we, nullptr, 0.0, false, false, true, st);
+      rc = sweep(h, false, 1, us_all + (long long)n * ndofs, resid ? h->vv + (long long)n * ndofs : nullptr, ubar_n,
+                 resid ? 1.0 : we, nullptr, 0.0, false, resid && want_dp, true, st);
+      if (!rc && resid && want_dp)
+        rc = reduce_rows(h, h->vpart + h->vnblk, h->vnblk, PCX_MAX_PROPS, h->phys.nprops, 1,
+                         h->scal + SC_DFV(h) + (long long)n * PCX_MAX_PROPS, PCX_MAX_PROPS, st);
       cur ^= 1;
       if (!rc && !resident) {
         h->vstep.on = false;
@@ -1425,7 +1479,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     if (resident && (rc = field_backward_steps(h, 0, nt, h->ubar, g_weights, first, st))) return rc;
     if (first) CUDA_TRY(cudaMemsetAsync(g_weights, 0, h->ms.nweights * sizeof(double), st));
   }
-  k_finish<<<1, 32, 0, st>>>(PCX_LOSS_ENERGY, nt, we, 0.0, 0.0, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), nullptr,
+  k_finish<<<1, 32, 0, st>>>(kind, nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), gout,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
                              want_dp ? g_props : nullptr, 1.0, 1);
   LAUNCH_CHECK(h);

@@ -60,6 +60,7 @@ struct ElemArgs {
   const double* lam_in;
   double* lam_out;
   double* qbuf;            // [ne][nq][NDOF][ND] parent-space point fluxes (k_visco_qp -> k_visco_scatter)
+  double wpsi;             // k_visco_qp MODE 3: weight of the step's energy in the loss (the flux then carries every term)
 };
 
 template <int ND>
@@ -371,8 +372,15 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 // element's X/U/acc (72 doubles for Hex8) live across them and runs only ne threads, so it spills and under-fills the
 // machine.  Here a point's thread owns nothing but its point: geometry -> F -> branches -> (BWD) Q = JxW S J^-T in
 // parent space [ne][nq][NDOF][ND], which k_visco_scatter contracts with the parent gradients into the element vector.
-// BWD = false: z_old -> z_new, energy (and equilibrium property-gradient) partials per block.
-// BWD = true : z_old, lam_in -> lam_out, Q.
+// MODE 0: z_old -> z_new, energy (and equilibrium property-gradient) partials per block.
+// MODE 1: z_old, lam_in -> lam_out, Q  (reverse sweep of the path-dependent EnergyLoss).
+// MODE 2: MODE 0 plus the flux of the step's internal force f = dPi/du at FIXED old state (lam = 0 reverse branch): the
+//         forward sweep of the path-dependent residual / reaction losses (weak_form_loss_functions.py:151-192,242-276).
+// MODE 3: reverse sweep of those losses.  With v = dloss/df of this step on the nodes, the flux carries
+//         wpsi dpsi/dF + (adjoint of the new state pulled back) + d/deps dpsi/dF (u + eps v), and lam_out additionally
+//         d/deps dpsi/dFv_old (u + eps v) -- the second-order terms from ONE forward-mode (dual) evaluation of the
+//         equilibrium model and the closed-form tangent of the branch (fefv_branch); property-gradient partials are the
+//         dual parts of JxW dW/dp.
 // ----------------------------------------------------------------------------------------------
 #ifndef PCX_VISCO_MINB_BWD
 #define PCX_VISCO_MINB_BWD 3
@@ -380,8 +388,9 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #ifndef PCX_VISCO_MINB_FWD
 #define PCX_VISCO_MINB_FWD 4
 #endif
-template <int NNPE, int ND, int NDOF, int MODEL, bool BWD>
-__global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB_FWD) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+template <int NNPE, int ND, int NDOF, int MODEL, int MODE>
+__global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 0 ? PCX_VISCO_MINB_FWD : 2) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+  constexpr bool FLUX = MODE != 0;                  // a point flux Q is written
   constexpr int NTH = 128;
   __shared__ double sh[NTH / 32];
   const int nq = tab.nq;
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
 #pragma unroll
   for (int k = 0; k < PCX_MAX_PROPS; k++) props.p[k] = (k < A0.nprops) ? __ldg(A0.props_dev + k) : 0.0;
   props_derive<MODEL>(props);
-  const bool want_dp = !BWD && A0.ppart != nullptr;
+  const bool want_dp = MODE != 1 && A0.ppart != nullptr;
   double Wq = 0.0;
   double dps[PCX_MAX_PROPS];
 #pragma unroll
@@ -402,13 +411,19 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
     const long long e = t / nq;
     const int q = (int)(t - e * nq);
     const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
-    double J[ND * ND], Ji[ND * ND], Gu[NDOF][ND];
+    double J[ND * ND], Ji[ND * ND], Gu[NDOF][ND], Gv[MODE == 3 ? NDOF : 1][ND];
 #pragma unroll
     for (int k = 0; k < ND * ND; k++) J[k] = 0.0;
 #pragma unroll
     for (int i = 0; i < NDOF; i++)
 #pragma unroll
       for (int k = 0; k < ND; k++) Gu[i][k] = 0.0;
+    if constexpr (MODE == 3) {
+#pragma unroll
+      for (int i = 0; i < NDOF; i++)
+#pragma unroll
+        for (int k = 0; k < ND; k++) Gv[i][k] = 0.0;
+    }
 #pragma unroll
     for (int a = 0; a < NNPE; a++) {
       const long long n = __ldg(A0.conns + e * NNPE + a);
@@ -423,6 +438,11 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
         const double u = __ldg(A0.us + n * NDOF + i);
 #pragma unroll
         for (int k = 0; k < ND; k++) Gu[i][k] = fma(u, dN[a * 3 + k], Gu[i][k]);
+        if constexpr (MODE == 3) {
+          const double vv = __ldg(A0.v + n * NDOF + i);
+#pragma unroll
+          for (int k = 0; k < ND; k++) Gv[i][k] = fma(vv, dN[a * 3 + k], Gv[i][k]);
+        }
       }
     }
     const double detJ = inv_det<ND>(J, Ji);
@@ -438,26 +458,61 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
         F[3 * i + j] += s;
       }
     double W, P[9], dp[PCX_MAX_PROPS];
-    model_eval<MODEL, double>(F, props, W, P, dp, want_dp);   // equilibrium branch (simple_fefv.py:33-40)
     const long long zq = t * (long long)A0.n_prony * 9;
-    for (int b = 0; b < A0.n_prony; b++) {
-      double zo[9], zn[9], li[9], lo[9];
+    if constexpr (MODE == 3) {
+      double dF[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int i = 0; i < 9; i++) zo[i] = A0.z_old[zq + b * 9 + i];
-      if constexpr (BWD) {
+      for (int i = 0; i < NDOF; i++)
 #pragma unroll
-        for (int i = 0; i < 9; i++) li[i] = A0.lam_in[zq + b * 9 + i];
-        W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], nullptr, li, P, lo);
+        for (int j = 0; j < ND; j++) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < ND; k++) s = fma(Gv[i][k], Ji[j * ND + k], s);
+          dF[3 * i + j] = s;
+        }
+      {
+        Dual Fd[9], Wd, Pd[9], dpd[PCX_MAX_PROPS];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Fd[i] = Dual(F[i], dF[i]);
+        model_eval<MODEL, Dual>(Fd, props, Wd, Pd, dpd, want_dp);   // equilibrium branch, value + tangent along v
+        W = Wd.v;
+#pragma unroll
+        for (int i = 0; i < 9; i++) P[i] = fma(A0.wpsi, Pd[i].v, Pd[i].d);
+        if (want_dp) {
+#pragma unroll
+          for (int k = 0; k < PCX_MAX_PROPS; k++)
+            if (k < A0.nprops) dp[k] = dpd[k].d;
+        }
+      }
+      for (int b = 0; b < A0.n_prony; b++) {
+        double zo[9], li[9], lo[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) { zo[i] = A0.z_old[zq + b * 9 + i]; li[i] = A0.lam_in[zq + b * 9 + i]; }
+        W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], nullptr, li, P, lo, A0.wpsi, dF, P, lo);
 #pragma unroll
         for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = lo[i];
-      } else {
-        W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], zn, nullptr, nullptr, lo);
+      }
+    } else {
+      model_eval<MODEL, double>(F, props, W, P, dp, want_dp);   // equilibrium branch (simple_fefv.py:33-40)
+      for (int b = 0; b < A0.n_prony; b++) {
+        double zo[9], zn[9], li[9], lo[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
+        for (int i = 0; i < 9; i++) zo[i] = A0.z_old[zq + b * 9 + i];
+        if constexpr (MODE == 1) {
+#pragma unroll
+          for (int i = 0; i < 9; i++) li[i] = A0.lam_in[zq + b * 9 + i];
+          W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], nullptr, li, P, lo);
+#pragma unroll
+          for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = lo[i];
+        } else {
+          W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], zn, nullptr, MODE == 2 ? P : nullptr, lo);
+#pragma unroll
+          for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
+        }
       }
     }
     if (!(W == W) || fabs(W) > 1.0e300) bad = true;
-    if constexpr (BWD) {
+    if constexpr (FLUX) {
       double* Q = A0.qbuf + t * (NDOF * ND);
 #pragma unroll
       for (int i = 0; i < NDOF; i++)
@@ -468,7 +523,8 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
           for (int j = 0; j < ND; j++) s = fma(P[3 * i + j], Ji[j * ND + k], s);
           Q[i * ND + k] = s * JxW;
         }
-    } else {
+    }
+    if constexpr (MODE != 1) {
       Wq = JxW * W;
       if (want_dp) {
 #pragma unroll
@@ -478,7 +534,7 @@ __global__ void __launch_bounds__(128, BWD ? PCX_VISCO_MINB_BWD : PCX_VISCO_MINB
     }
   }
   if (bad) atomicOr(A0.flags, 1);
-  if constexpr (!BWD) {
+  if constexpr (MODE != 1) {
     if (A0.epart) {
       const double s = block_sum<NTH>(Wq, sh);
       if (threadIdx.x == 0) A0.epart[blockIdx.x] = s;

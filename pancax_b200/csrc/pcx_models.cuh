@@ -606,8 +606,19 @@ __device__ inline void mat33_mul_nt(const double* A, const double* B, double* C)
 
 // F, Fv_old: 3x3 row-major.  Fv_new / lam / S / lam_old may be null (forward sweep: Fv_new only; reverse sweep: the
 // last three).  Returns psi of the branch.
+//
+// Second order (residual / reaction losses of a model with state, weak_form_loss_functions.py:151-192,242-276): the
+// loss holds v . f with f = dPi/du at FIXED old state, so its gradient needs the derivative of (dpsi/dF, dpsi/dFv_old)
+// along dF = sum_a v_a (x) grad N_a -- the dual part of the lam = 0 reverse sweep.  With Cbar = kappa V diag(de_i / mu_i) V^T
+// = kappa [g(Ce) - eb Ce^-1], g(mu) = ln mu / (2 mu), eb = ln det Ce / 6, its directional derivative along
+// dCe = dFe^T Fe + Fe^T dFe is, in the eigenbasis (H = V^T dCe V),
+//   dCbar^_ij = kappa { [log1p(xr)/xr - 2 de_j] / (2 mu_i mu_j) H_ij - delta_ij (sum_k H_kk / (6 mu_k)) / mu_i },  xr = (mu_i - mu_j)/mu_j
+// (first divided differences of g merged with the eb Ce^-1 dCe Ce^-1 term; symmetric in i, j; the diagonal is the limit
+// xr -> 0) -- no eigenvector derivatives, nothing singular at repeated stretches.  Then dFebar = 2 (dFe Cbar + Fe dCbar),
+// dS += dFebar A^T, dlam_old -= A^T (dF^T Febar + F^T dFebar) A^T.  wpsi = cotangent of psi (the real part's scale).
 __device__ inline double fefv_branch(const double* F, const double* Fv_old, double kappa, double c, double* Fv_new,
-                                     const double* lam, double* S, double* lam_old) {
+                                     const double* lam, double* S, double* lam_old, double wpsi = 1.0,
+                                     const double* dF = nullptr, double* dS = nullptr, double* dlam_old = nullptr) {
   double cofv[9], A[9];
   cofactor3(Fv_old, cofv);
   const double detv = Fv_old[0] * cofv[0] + Fv_old[1] * cofv[1] + Fv_old[2] * cofv[2];
@@ -637,7 +648,7 @@ __device__ inline double fefv_branch(const double* F, const double* Fv_old, doub
     double Eh[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) Eh[i] = 0.0;
-    Eh[0] = 2.0 * kappa * de[0]; Eh[4] = 2.0 * kappa * de[1]; Eh[8] = 2.0 * kappa * de[2];
+    Eh[0] = 2.0 * kappa * wpsi * de[0]; Eh[4] = 2.0 * kappa * wpsi * de[1]; Eh[8] = 2.0 * kappa * wpsi * de[2];
     if (lam) {
       double M[9], T[9], Mh[9];
       mat33_mul_nt(lam, Fv_old, M);     // lam Fv_old^T
@@ -693,6 +704,53 @@ __device__ inline double fefv_branch(const double* F, const double* Fv_old, doub
     mat33_mul_nt(T1, A, T2);            // A^T Abar A^T
 #pragma unroll
     for (int i = 0; i < 9; i++) lam_old[i] -= T2[i];
+    if (dF) {
+      double dFe[9], dC[9], H[9], dCh[9], dCb[9], Cb0[9], Feb0[9], dFeb[9];
+      mat33_mul(dF, A, dFe);
+      mat33_mul_tn(Fe, dFe, T1);        // Fe^T dFe
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) dC[3 * i + j] = T1[3 * i + j] + T1[3 * j + i];
+      mat33_mul_tn(V, dC, T1);
+      mat33_mul(T1, V, H);              // V^T dCe V
+      const double deb = (H[0] * rmu[0] + H[4] * rmu[1] + H[8] * rmu[2]) * (1.0 / 6.0);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        dCh[4 * i] = kappa * rmu[i] * ((0.5 - de[i]) * rmu[i] * H[4 * i] - deb);
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+          const double xr = (mu[i] - mu[j]) * rmu[j];
+          const double cf = kappa * (((xr == 0.0) ? 1.0 : log1p(xr) / xr) - 2.0 * de[j]) * 0.5 * rmu[i] * rmu[j];
+          dCh[3 * i + j] = cf * H[3 * i + j];
+          dCh[3 * j + i] = cf * H[3 * j + i];
+        }
+      }
+      mat33_mul(V, dCh, T1);
+      mat33_mul_nt(T1, V, dCb);         // V dCh V^T
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          Cb0[3 * i + j] = kappa * (V[3 * i] * de[0] * rmu[0] * V[3 * j] + V[3 * i + 1] * de[1] * rmu[1] * V[3 * j + 1] +
+                                    V[3 * i + 2] * de[2] * rmu[2] * V[3 * j + 2]);
+      mat33_mul(Fe, Cb0, Feb0);
+      mat33_mul(dFe, Cb0, T1);
+      mat33_mul(Fe, dCb, T2);
+#pragma unroll
+      for (int i = 0; i < 9; i++) { Feb0[i] *= 2.0; dFeb[i] = 2.0 * (T1[i] + T2[i]); }
+      mat33_mul_nt(dFeb, A, T1);        // dFebar A^T
+#pragma unroll
+      for (int i = 0; i < 9; i++) dS[i] += T1[i];
+      mat33_mul_tn(dF, Feb0, T1);       // dF^T Febar
+      mat33_mul_tn(F, dFeb, T2);        // F^T dFebar
+#pragma unroll
+      for (int i = 0; i < 9; i++) T1[i] += T2[i];
+      mat33_mul_tn(A, T1, T2);
+      mat33_mul_nt(T2, A, T1);          // A^T dAbar A^T
+#pragma unroll
+      for (int i = 0; i < 9; i++) dlam_old[i] -= T1[i];
+    }
   }
   return psi;
 }

@@ -153,18 +153,20 @@ class PhysicsLossFunction(BaseLossFunction):
     def _weights(self):
         return dict(energy_weight=1.0, residual_weight=1.0, reaction_weight=1.0)
 
-    def _run(self, params, problem, want_grad):
+    def _run(self, params, problem, want_grad, path_dependent=None):
         first_step = 0
-        if getattr(self, "is_path_dependent", False):
-            # weak_form_loss_functions.py:48-72,242-276: the scan starts at time step 1.  Without state variables
-            # (every hyperelastic model here) that is the only difference from the path-independent call.
-            model = getattr(problem.physics, "constitutive_model", None)
-            if model is not None and model.num_state_variables != 0 and self.kind != "energy":
-                raise NotImplementedError("models with state variables: only the path-dependent EnergyLoss is on the B200 path")
-            if self.kind == "energy_residual":
-                raise AssertionError("EnergyAndResidualLoss: path-dependent call is disabled in the reference too "
-                                     "(weak_form_loss_functions.py:145-147)")
+        model = getattr(problem.physics, "constitutive_model", None)
+        has_state = model is not None and model.num_state_variables != 0
+        if getattr(self, "is_path_dependent", False) if path_dependent is None else path_dependent:
+            # weak_form_loss_functions.py:48-72,151-192,242-276: the scan starts at time step 1.  Without state variables
+            # that is the only difference from the path-independent call; with them (SimpleFeFv) the library threads the
+            # state through the steps and -- residual / reaction losses -- adds the second-order terms through the history.
+            if self.kind == "energy_residual" and path_dependent is None:
+                raise AssertionError("EnergyAndResidualLoss.__call__: the path-dependent case asserts in the reference too "
+                                     "(weak_form_loss_functions.py:145-147); call path_dependent_call")
             first_step = 1
+        elif has_state:
+            raise NotImplementedError("models with state variables need the path-dependent call (is_path_dependent=True)")
         eng = get_engine(problem, params, self.deterministic)
         gd = getattr(problem, "global_data", None)
         gout = None
@@ -232,7 +234,18 @@ class EnergyAndResidualLoss(PhysicsLossFunction):
         return dict(energy=aux[0], residual=aux[1])
 
     def path_independent_call(self, params, problem):
-        return self.__call__(params, problem)
+        loss, aux, _, _ = self._run(params, problem, False, path_dependent=False)
+        return loss[0], self._aux(aux)
+
+    def path_dependent_call(self, params, problem):
+        """weak_form_loss_functions.py:151-192: L = w_e sum_{n>=1} Pi_n + w_r sum_{n>=1} R_n / len(times), the state
+        threaded through the steps."""
+        loss, aux, _, _ = self._run(params, problem, False, path_dependent=True)
+        return loss[0], self._aux(aux)
+
+    def path_dependent_value_and_grad(self, params, problem):
+        loss, aux, gw, gp = self._run(params, problem, True, path_dependent=True)
+        return (loss[0], self._aux(aux)), Grads(gw, gp)
 
 
 class EnergyResidualAndReactionLoss(PhysicsLossFunction):

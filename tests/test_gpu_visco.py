@@ -7,7 +7,7 @@ Tolerance 1e-10 relative (fp64)."""
 import numpy as np
 import pytest
 
-from tests.cases import make_case, make_engine, run_engine_loss, run_oracle_loss
+from tests.cases import LOSS_WEIGHTS, make_case, make_engine, run_engine_loss, run_oracle_loss
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -85,8 +85,12 @@ def test_state_models_are_refused_elsewhere(cuda_device):
     with pytest.raises(PcxError, match="state variables"):
         eng.loss_and_grad("energy", case.weights, None)                       # path-independent call
     with pytest.raises(PcxError, match="state variables"):
-        eng.loss_and_grad("energy_residual", case.weights, None, first_step=1)
+        eng.loss_and_grad("energy_residual", case.weights, None)              # residual loss, path-independent call
     eng.close()
+    ps = make_case("quad4_visco_neohookean", n=3, nt=3, width=8, depth=2)
+    ps.formulation = "plane_stress"
+    with pytest.raises(PcxError, match="PlaneStress"):      # refused at pcx_set_physics
+        make_engine(ps)
 
 
 def test_public_api_example_hyper_visco(cuda_device):
@@ -185,3 +189,69 @@ def test_trainable_equilibrium_properties(cuda_device, name):
     assert abs(L - Lo) <= TOL * abs(Lo)
     assert rel(gw, gwo) < TOL
     assert gpo.size and rel(gp, gpo) < TOL, (gp, gpo)
+
+
+# ---------------------------------------------------------------- residual / reaction losses with state (second order)
+@pytest.mark.parametrize("deterministic", [True, False])
+@pytest.mark.parametrize("kind", ["energy_residual", "energy_residual_reaction"])
+@pytest.mark.parametrize("name,n,nt", [("hex8_visco_neohookean", 3, 4), ("hex8_visco_gent", 2, 3), ("hex8_visco_hencky", 2, 3),
+                                       ("hex8_visco_swanson", 2, 3), ("hex8_visco_blatz_ko", 2, 3),
+                                       ("quad4_visco_neohookean", 5, 5), ("tri3_visco_gent", 4, 3),
+                                       ("quad4_visco_gent_bounded", 4, 4)])
+def test_path_dependent_residual_losses_with_state(cuda_device, name, n, nt, kind, deterministic):
+    """EnergyAndResidualLoss / EnergyResidualAndReactionLoss.path_dependent_call (weak_form_loss_functions.py:151-192,
+    242-276) with SimpleFeFv: f_n = dPi_n/du_n at fixed old state, R_n and reaction_n from it, and the gradient with the
+    second-order terms through the state history (k_visco_qp MODE 2 / 3) against the oracle's double backward."""
+    case = make_case(name, n=n, nt=nt, width=16, depth=2)
+    L, aux, gw, gp = run_engine_loss(case, kind, deterministic=deterministic, first_step=1)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, kind, first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo), (L, Lo)
+    assert abs(aux[0] - float(auxo["energy"])) <= TOL * abs(float(auxo["energy"]))
+    assert abs(aux[1] - float(auxo["residual"])) <= TOL * abs(float(auxo["residual"]))
+    if kind == "energy_residual_reaction":
+        assert abs(aux[2] - float(auxo["global_data_loss"])) <= TOL * abs(float(auxo["global_data_loss"]))
+    assert rel(gw, gwo) < TOL, rel(gw, gwo)
+    if gpo.size:
+        assert rel(gp, gpo) < TOL, (gp, gpo)
+
+
+def test_residual_losses_with_state_value_only_recompute_and_zero_energy_weight(cuda_device, monkeypatch):
+    case = make_case("hex8_visco_neohookean", n=3, nt=4, width=12, depth=2)
+    eng = make_engine(case)
+    ref = run_engine_loss(case, "energy_residual_reaction", eng=eng, first_step=1)
+    loss, aux, _, _ = eng.loss_and_grad("energy_residual_reaction", case.weights, None, global_outputs=case.global_outputs,
+                                        want_grad=False, first_step=1, **LOSS_WEIGHTS)
+    assert float(loss.cpu()[0]) == ref[0]
+    # pure residual + reaction loss (energy weight 0): the flux then holds second-order terms only
+    got = run_engine_loss(case, "energy_residual_reaction", eng=eng, first_step=1, energy_weight=0.0)
+    exp = run_oracle_loss(case, "energy_residual_reaction", first_step=1, energy_weight=0.0)
+    assert abs(got[0] - exp[0]) <= TOL * abs(exp[0]) and rel(got[2], exp[2]) < TOL
+    eng.close()
+    monkeypatch.setenv("PCX_TCHUNK", "1")        # activations of one step resident: recompute mode
+    got = run_engine_loss(case, "energy_residual_reaction", first_step=1)
+    assert got[0] == ref[0] and rel(got[2], ref[2]) < 1e-13
+
+
+def test_public_api_inverse_path_dependent_visco(cuda_device):
+    """examples/inverse_problems/mechanics/path-dependent/script.py: SimpleFeFv with a trainable equilibrium shear
+    modulus, EnergyResidualAndReactionLoss(is_path_dependent=True) + Adam on a small mesh."""
+    import pancax_b200 as px
+    import torch
+    mesh = px.create_structured_mesh("hex8", 3)
+    times = np.linspace(0.0, 1.0, 4)
+    domain = px.VariationalDomain(mesh, times)
+    model = px.SimpleFeFv(px.NeoHookean(bulk_modulus=10.0, shear_modulus=px.BoundedProperty(0.01, 5.0, key=1)),
+                          px.PronySeries(moduli=[1.0, 0.5], relaxation_times=[10.0, 1.0]), px.WLF(C1=17.44, C2=51.6, theta_ref=60.0))
+    physics = px.SolidMechanics(model, px.ThreeDimensional())
+    bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_5") for c in range(3)]
+    gd = px.GlobalData.from_arrays(times, 0.3 * times, mesh.nodeSets["nset_5"], 1)
+    problem = px.InverseProblem(domain, physics, None, gd, dirichlet_bcs=bcs)
+    params = px.Parameters(problem, key=0, dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
+    loss_fn = px.EnergyResidualAndReactionLoss(is_path_dependent=True, residual_weight=10.0, reaction_weight=10.0)
+    opt = px.Adam(loss_fn, learning_rate=1e-3, has_aux=True)
+    st = opt.init(params)
+    l0 = None
+    for _ in range(20):
+        params, st, (loss, aux) = opt.step(params, st, problem)
+        l0 = float(loss) if l0 is None else l0
+    assert torch.isfinite(loss) and float(loss) < l0
