@@ -192,6 +192,15 @@ def visco(steps, device, n=64, nt=11):
     evals = n ** 3 * 8 * (nt - 1)     # the scan starts at step 1
     measure(f"visco: Hex8 {n}^3 ({n ** 3 * 8} qp) SimpleFeFv(NeoHookean, 1 Prony branch), nt={nt}, path-dependent EnergyLoss, "
             "MLP 4->50x4->3", problem, params, px.EnergyLoss(is_path_dependent=True), (), steps, evals)
+    # examples/inverse_problems/mechanics/path-dependent/script.py at scale: the residual + reaction loss on the same
+    # model (forward sweep with the step's internal force, reverse sweep with the second-order terms)
+    gd = px.GlobalData.from_arrays(times, 0.1 * times, mesh.nodeSets["nset_5"], 1)
+    problem = px.InverseProblem(domain, physics, None, gd, dirichlet_bcs=bcs)
+    params = px.Parameters(problem, key=0, n_layers=4, n_neurons=50, device=device,
+                           dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
+    measure(f"visco: Hex8 {n}^3 ({n ** 3 * 8} qp) SimpleFeFv(NeoHookean, 1 Prony branch), nt={nt}, path-dependent "
+            "EnergyResidualAndReactionLoss, MLP 4->50x4->3", problem, params,
+            px.EnergyResidualAndReactionLoss(is_path_dependent=True), (), steps, evals)
 
 
 def main():
