@@ -1703,7 +1703,7 @@ static void jet_free(pcx_handle* h) {
 static int jet_alloc(pcx_handle* h, long long n) {
   const int S = h->nd + 3;
   const long long per_row = ((long long)(2 * h->ms.depth + 1) * S * h->ms.NT * 8 + 2LL * S * h->ndof) * sizeof(double);
-  long long budget = 8LL << 30;
+  long long budget = 32LL << 30;   // of 180 GB HBM3e: 1 M points in 3D (24 KB of streams per point) stay in one chunk
   if (const char* e = getenv("PCX_JET_WORKSPACE_GB")) budget = (long long)(atof(e) * (1LL << 30));
   long long cap = budget / per_row;
   if (cap < 64) cap = 64;
@@ -1768,6 +1768,11 @@ static int jet_launch_nt(pcx_handle* h, int what, const JetIO& io, const JetWgra
   } else if (what == 1) {
     const size_t smem = (size_t)(h->ms.npacked - h->ms.pBO) * sizeof(double);
     if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
+    if (smem <= 100 * 1024) {        // two CTAs per SM (128 registers per thread)
+      blocks = (groups + 7) / 8;
+      if (blocks > 2 * h->sm_count) blocks = 2 * h->sm_count;
+      if (blocks < 1) blocks = 1;
+    }
     if (kodd) {
       CUDA_TRY(cudaFuncSetAttribute(k_jet_backward<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       k_jet_backward<NT, 1><<<(int)blocks, 256, smem, st>>>(h->ms, io);

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256, 1) k_jet_forward(const __grid_constant__ 
 // planes (for k_jet_wgrad) and leaves nothing else behind.  Transposed fragments [BO | BH] in smem.
 // ---------------------------------------------------------------------------------------------
 template <int NT, int KODD>
-__global__ void __launch_bounds__(256, 1) k_jet_backward(const __grid_constant__ MlpShape s, const __grid_constant__ JetIO io) {
+__global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__ MlpShape s, const __grid_constant__ JetIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
   double* sw = reinterpret_cast<double*>(smem_raw);
@@ -241,61 +241,50 @@ __global__ void __launch_bounds__(256, 1) k_jet_backward(const __grid_constant__
     for (int l = s.depth - 1; l >= 0; l--) {
       const double* postL = io.post + (long long)l * S * PL;
       double* preL = io.pre + (long long)l * S * PL;
-      double sv[NT][2], qb[NT][2], zb[NT][2], sq[NT][2];
       const double* adjQ = io.adj + (long long)(nd + 1) * PL;
       const double* adjT = io.adj + (long long)(nd + 2) * PL;
       double* preQ = preL + (long long)(nd + 1) * PL;
       double* preT = preL + (long long)(nd + 2) * PL;
-      // value stream + Laplacian + time streams
-#pragma unroll
+      // The coupling between the streams is local to a (tile, slot): one 8-wide tile at a time, so that nothing but
+      // the tile's own values is live here (r2: the arrays over all NT tiles kept the kernel at one 8-warp CTA per SM
+      // with exposed global-memory latency; per-tile scoping fits 128 registers = two CTAs per SM)
+#pragma unroll 1
       for (int jn = 0; jn < NT; jn++) {
         const double2 s2 = ld2(postL, jn), q2 = ld2(adjQ, jn), h2 = ld2(io.adj, jn);
         const double2 zq = ld2(preQ, jn), zt = ld2(preT, jn), tb = ld2(adjT, jn);
-        double oq[2], ot[2];
+        double2 zg[3], gb[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          if (j < nd) { zg[j] = ld2(preL + (long long)(1 + j) * PL, jn); gb[j] = ld2(io.adj + (long long)(1 + j) * PL, jn); }
+        double oq[2], ot[2], zb[2], og[3][2];
 #pragma unroll
         for (int x = 0; x < 2; x++) {
           const double sx = x ? s2.y : s2.x, qx = x ? q2.y : q2.x, hx = x ? h2.y : h2.x;
           const double zqx = x ? zq.y : zq.x, ztx = x ? zt.y : zt.x, tbx = x ? tb.y : tb.x;
           const double s1 = fma(-sx, sx, 1.0), s2d = -2.0 * sx * s1;
-          sv[jn][x] = sx; qb[jn][x] = qx; sq[jn][x] = 0.0;
-          zb[jn][x] = fma(s1, hx, s2d * fma(qx, zqx, tbx * ztx));
+          double z0 = fma(s1, hx, s2d * fma(qx, zqx, tbx * ztx));
+          double sq = 0.0;
           oq[x] = s1 * qx;
           ot[x] = s1 * tbx;
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+            if (j < nd) {
+              const double z = x ? zg[j].y : zg[j].x, gx = x ? gb[j].y : gb[j].x;
+              z0 = fma(s2d * gx, z, z0);
+              sq = fma(z, z, sq);
+              og[j][x] = fma(s1, gx, 2.0 * s2d * z * qx);
+            }
+          const double s3 = -2.0 * s1 * fma(-2.0 * sx, sx, s1);      // s''' = -2 s' (s' - 2 s^2)
+          zb[x] = fma(s3 * qx, sq, z0);
         }
         if (live) {
           *reinterpret_cast<double2*>(preQ + off(jn)) = make_double2(oq[0], oq[1]);
           *reinterpret_cast<double2*>(preT + off(jn)) = make_double2(ot[0], ot[1]);
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+            if (j < nd) *reinterpret_cast<double2*>(preL + (long long)(1 + j) * PL + off(jn)) = make_double2(og[j][0], og[j][1]);
+          *reinterpret_cast<double2*>(preL + off(jn)) = make_double2(zb[0], zb[1]);
         }
-      }
-      // gradient streams
-      for (int j = 0; j < nd; j++) {
-        double* preG = preL + (long long)(1 + j) * PL;
-        const double* adjG = io.adj + (long long)(1 + j) * PL;
-#pragma unroll
-        for (int jn = 0; jn < NT; jn++) {
-          const double2 zg = ld2(preG, jn), gb = ld2(adjG, jn);
-          double og[2];
-#pragma unroll
-          for (int x = 0; x < 2; x++) {
-            const double sx = sv[jn][x], z = x ? zg.y : zg.x, gx = x ? gb.y : gb.x;
-            const double s1 = fma(-sx, sx, 1.0), s2d = -2.0 * sx * s1;
-            zb[jn][x] = fma(s2d * gx, z, zb[jn][x]);
-            sq[jn][x] = fma(z, z, sq[jn][x]);
-            og[x] = fma(s1, gx, 2.0 * s2d * z * qb[jn][x]);
-          }
-          if (live) *reinterpret_cast<double2*>(preG + off(jn)) = make_double2(og[0], og[1]);
-        }
-      }
-#pragma unroll
-      for (int jn = 0; jn < NT; jn++) {
-#pragma unroll
-        for (int x = 0; x < 2; x++) {
-          const double sx = sv[jn][x];
-          const double s1 = fma(-sx, sx, 1.0);
-          const double s3 = -2.0 * s1 * fma(-2.0 * sx, sx, s1);      // s''' = -2 s' (s' - 2 s^2)
-          zb[jn][x] = fma(s3 * qb[jn][x], sq[jn][x], zb[jn][x]);
-        }
-        if (live) *reinterpret_cast<double2*>(preL + off(jn)) = make_double2(zb[jn][0], zb[jn][1]);
       }
       if (l == 0) break;
       // chain: adjoint of the previous layer's post-activation streams  pbar_s = zbar_s W_l

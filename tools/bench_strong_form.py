@@ -51,8 +51,9 @@ def main():
                       "ms_per_step": ms, "points_per_s": n / (ms * 1e-3), "kernel_launches_per_step": (eng.launch_count - l0) // reps,
                       "algorithmic_flop_per_point": flop_fwd + flop_bwd, "achieved_tflops": ach, "dmma_peak_tflops": pk.value,
                       "frac": ach / pk.value, "bound": "tensor (FP64 DMMA)",
-                      "note": "first correct path: streams round-trip through global planes between layers; "
-                              "unfused weight-gradient contraction per layer"}))
+                      "note": "streams round-trip through global planes between layers; unfused weight-gradient contraction "
+                              "per layer; r2: k_jet_backward's coupling stage scoped per 8-wide tile (128 registers, two CTAs "
+                              "per SM), 32 GB default jet workspace (1 M points in 3D = one chunk)"}))
     eng.close()
 
 
