@@ -339,8 +339,19 @@ static void launch_element_t(bool tangent, dim3 grid, cudaStream_t st, const Par
       }
     }
   }
-  if (tangent) k_element<NNPE, ND, NDOF, MODEL, true><<<grid, 128, 0, st>>>(tab, a);
-  else k_element<NNPE, ND, NDOF, MODEL, false><<<grid, 128, 0, st>>>(tab, a);
+  // 3D: nodal accumulators (and, force sweep, X / U) live in dynamic shared memory, [slot][thread]
+  constexpr int smem_t = elem_dyn_smem_bytes(NNPE, ND, NDOF, true), smem_f = elem_dyn_smem_bytes(NNPE, ND, NDOF, false);
+  if (tangent) {
+    if constexpr (smem_t > 40 * 1024) {      // static + dynamic above 48 KB needs the opt-in
+      cudaFuncSetAttribute(k_element<NNPE, ND, NDOF, MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t);   // per device: not cached
+    }
+    k_element<NNPE, ND, NDOF, MODEL, true><<<grid, 128, smem_t, st>>>(tab, a);
+  } else {
+    if constexpr (smem_f > 40 * 1024) {
+      cudaFuncSetAttribute(k_element<NNPE, ND, NDOF, MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
+    }
+    k_element<NNPE, ND, NDOF, MODEL, false><<<grid, 128, smem_f, st>>>(tab, a);
+  }
 }
 template <int NNPE, int ND, int NDOF>
 static int launch_element_m(int model, bool tangent, dim3 grid, cudaStream_t st, const ParentTab& tab, const ElemArgs& a) {

@@ -110,26 +110,70 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // true -> stiffness action K v (forward-mode duals through the same constitutive source).
 // VAR: 0 = plain; 1 = PlaneStress (2D solid: per-point root find).  SimpleFeFv has its own per-point kernels below
 // (k_visco_qp).  Compile-time variants: as run-time branches they cost the plain kernels half of their speed in register spills.
-// resident CTAs per SM asked of the register allocator: the 3D sweeps want every register (1 -> 255 registers; 3 costs
-// Hex8 +47 % in spills), the 2D tangent sweep is 22 % faster with 3 (168 registers, 12 warps per SM) -- measured
-// r2: in 3D the element's nodal accumulators (24 doubles for Hex8) live in SHARED memory, transposed [slot][thread]
-// (conflict-free), instead of 48 registers held across the whole quadrature loop: with X / U (96 registers) they kept the
-// kernel at 255 registers = 8 warps per SM, where every DFMA waited out the latency of the one before it (ncu r1: FP64 pipe
-// 49 % active, 12 % occupancy).  PCX_ELEM3D_MINB resident CTAs per SM are then asked of the register allocator.
+// Register budget of the 3D sweeps (measured, tools/elem_ab.cu, profiles/r02_elem_ab.jsonl; Hex8 128^3 x 2 steps, NeoHookean):
+//   r1  everything in registers (X, U, accumulators: 144 registers + the constitutive chain): 255 registers, 8 warps per SM,
+//       every DFMA waits out the latency of the one before it (ncu: FP64 pipe 49 % active)                        1.64 ms
+//   r2a accumulators in shared memory [slot][thread], X / U in registers (236 registers, 8 warps)                     1.61 ms
+//   r2b FORCE sweep: X / U in shared memory, re-read per quadrature point as 24 conflict-free LDS.128 ([pair][thread][2]
+//       planes, asm volatile so that the compiler does not hoist them back into registers), accumulators in registers:
+//       166 registers = 3 CTAs = 12 warps per SM                                                                      1.30 ms
+//       (same with LDS.64 planes 1.35; U only + accumulators in shared memory 1.46; X, U AND accumulators in shared memory
+//       1.55: the read-modify-write of the accumulators is what hurts; 4 CTAs per SM at 128 registers spill: 1.73;
+//       two quadrature points per iteration: 1.54).  Results are bit-identical across the variants.
+//       Other models, same change: Gent 1.99 -> 1.65, Swanson 2.72 -> 2.32 (340 B of spills at 168 registers and still ahead),
+//       Hencky 3.17 -> 2.52 ms.
+//   r2b TANGENT sweep (dual numbers; X, U and the direction V in shared memory, 72 KB per CTA, 3 CTAs per SM; one time step):
+//       NeoHookean 1.075 -> 1.00 ms, Hencky 2.27 -> 1.92 ms (2 CTAs per SM: 0.97 / 2.11).
+//   2D: everything in registers; the tangent sweep is 22 % faster with 3 CTAs per SM.
 #ifndef PCX_ELEM_QUNROLL
 #define PCX_ELEM_QUNROLL 1
 #endif
 #ifndef PCX_ELEM3D_MINB
-#define PCX_ELEM3D_MINB 2
+#define PCX_ELEM3D_MINB 3          // force sweep (PCX_ELEM3D_MINB_T: tangent sweep)
 #endif
-__host__ __device__ constexpr bool elem_acc_smem(int nd) { return nd == 3 && PCX_ELEM3D_MINB > 0; }
-constexpr int elem_min_blocks(int nd, bool tangent) { return nd == 3 ? PCX_ELEM3D_MINB : (tangent ? 3 : 0); }   // 0 = no request
+// PCX_ELEM3D_XU_SMEM (force sweep): 0 = X / U in registers; 1 = U in shared memory; 2 = X and U ([slot][thread] planes,
+// LDS.64); 3 = X and U in [pair][thread][2] planes read with LDS.128
+#ifndef PCX_ELEM3D_XU_SMEM
+#define PCX_ELEM3D_XU_SMEM 3
+#endif
+#ifndef PCX_ELEM3D_ACC_SMEM
+#define PCX_ELEM3D_ACC_SMEM 0      // force sweep: nodal accumulators in shared memory (PCX_ELEM3D_ACC_SMEM_T: tangent sweep)
+#endif
+#ifndef PCX_ELEM3D_ACC_SMEM_T
+#define PCX_ELEM3D_ACC_SMEM_T 0
+#endif
+__host__ __device__ constexpr bool elem_acc_smem(int nd, bool tangent) { return nd == 3 && (tangent ? PCX_ELEM3D_ACC_SMEM_T : PCX_ELEM3D_ACC_SMEM); }
+#ifndef PCX_ELEM3D_XU_SMEM_T
+#define PCX_ELEM3D_XU_SMEM_T 3     // tangent sweep: 0 or 3 (X, U and V in [pair][thread][2] planes)
+#endif
+#ifndef PCX_ELEM3D_MINB_T
+#define PCX_ELEM3D_MINB_T 3
+#endif
+__host__ __device__ constexpr int elem_xu_smem(int nd, bool tangent) { return nd == 3 ? (tangent ? PCX_ELEM3D_XU_SMEM_T : PCX_ELEM3D_XU_SMEM) : 0; }
+// bytes of dynamic shared memory a k_element launch needs (128 threads per CTA)
+__host__ __device__ constexpr int elem_dyn_smem_bytes(int nnpe, int nd, int ndof, bool tangent) {
+  return ((elem_acc_smem(nd, tangent) ? nnpe * ndof : 0) + (elem_xu_smem(nd, tangent) >= 1 ? nnpe * ndof : 0) +
+          (elem_xu_smem(nd, tangent) >= 2 ? nnpe * nd : 0) + (elem_xu_smem(nd, tangent) == 3 && tangent ? nnpe * ndof : 0)) * 128 * (int)sizeof(double);
+}
+constexpr int elem_min_blocks(int nd, bool tangent) { return nd == 3 ? (tangent ? PCX_ELEM3D_MINB_T : PCX_ELEM3D_MINB) : (tangent ? 3 : 0); }   // 0 = no request
+// 128-bit shared-memory load of two consecutive doubles; asm volatile: re-issued per quadrature point, never hoisted
+__device__ __forceinline__ void lds_v2(const double* p, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned)__cvta_generic_to_shared(p)));
+}
 template <int NNPE, int ND, int NDOF, int MODEL, bool TANGENT, int VAR = 0>
 __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
   constexpr int NTH = 128;
-  constexpr bool ACC_SMEM = elem_acc_smem(ND);
+  constexpr bool ACC_SMEM = elem_acc_smem(ND, TANGENT);
   __shared__ double sh[NTH / 32];
-  __shared__ double acc_s[ACC_SMEM ? NNPE * NDOF : 1][ACC_SMEM ? NTH : 1];
+  constexpr int XU = elem_xu_smem(ND, TANGENT);
+  // dynamic shared memory (elem_dyn_smem_bytes): [slot][thread] planes of the accumulators, then U, then X
+  extern __shared__ __align__(16) double elem_dyn_s[];
+  double (*acc_s)[NTH] = reinterpret_cast<double (*)[NTH]>(elem_dyn_s);
+  double (*u_s)[NTH] = reinterpret_cast<double (*)[NTH]>(elem_dyn_s + (ACC_SMEM ? NNPE * NDOF : 0) * NTH);
+  double (*x_s)[NTH] = reinterpret_cast<double (*)[NTH]>(elem_dyn_s + ((ACC_SMEM ? NNPE * NDOF : 0) + (XU >= 1 ? NNPE * NDOF : 0)) * NTH);
+  constexpr int UOFF = (ACC_SMEM ? NNPE * NDOF : 0) * NTH, XOFF = UOFF + (XU >= 1 ? NNPE * NDOF : 0) * NTH;   // XU == 3: [pair][thread][2]
+  constexpr int VOFF = XOFF + (XU >= 2 ? NNPE * ND : 0) * NTH;                                                  // tangent, XU == 3
+  constexpr bool V_SMEM = TANGENT && XU == 3;
   const long long e = blockIdx.x * (long long)NTH + threadIdx.x;
   // per-time-step views
   struct {
@@ -171,18 +215,29 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #pragma unroll
       for (int a = 0; a < NNPE; a++) cn[a] = __ldg(A.conns + e * NNPE + a);
     }
-    double X[NNPE][ND], U[NNPE][NDOF], acc[ACC_SMEM ? 1 : NNPE][ACC_SMEM ? 1 : NDOF];
-    double V[TANGENT ? NNPE : 1][NDOF];
+    double X[XU >= 2 ? 1 : NNPE][XU >= 2 ? 1 : ND], U[XU >= 1 ? 1 : NNPE][XU >= 1 ? 1 : NDOF], acc[ACC_SMEM ? 1 : NNPE][ACC_SMEM ? 1 : NDOF];
+    double V[TANGENT && !V_SMEM ? NNPE : 1][NDOF];
+#define PCX_X(a, j) (XU >= 2 ? *reinterpret_cast<const volatile double*>(&x_s[(a) * ND + (j)][threadIdx.x]) : X[XU >= 2 ? 0 : (a)][XU >= 2 ? 0 : (j)])
+#define PCX_U(a, i) (XU == 3 ? *reinterpret_cast<const volatile double*>(&elem_dyn_s[UOFF + ((((a) * NDOF + (i)) >> 1) * NTH + threadIdx.x) * 2 + (((a) * NDOF + (i)) & 1)]) : XU >= 1 ? *reinterpret_cast<const volatile double*>(&u_s[(a) * NDOF + (i)][threadIdx.x]) : U[XU >= 1 ? 0 : (a)][XU >= 1 ? 0 : (i)])
 #pragma unroll
     for (int a = 0; a < NNPE; a++) {
 #pragma unroll
-      for (int j = 0; j < ND; j++) X[a][j] = __ldg(A.coords + (long long)cn[a] * ND + j);
+      for (int j = 0; j < ND; j++) {
+        const double xv = __ldg(A.coords + (long long)cn[a] * ND + j);
+        if constexpr (XU == 3) elem_dyn_s[XOFF + (((a * ND + j) >> 1) * NTH + threadIdx.x) * 2 + ((a * ND + j) & 1)] = xv;
+        else if constexpr (XU == 2) x_s[a * ND + j][threadIdx.x] = xv;
+        else X[a][j] = xv;
+      }
 #pragma unroll
       for (int i = 0; i < NDOF; i++) {
-        U[a][i] = __ldg(A.us + (long long)cn[a] * NDOF + i);
+        const double uv = __ldg(A.us + (long long)cn[a] * NDOF + i);
+        if constexpr (XU == 3) elem_dyn_s[UOFF + (((a * NDOF + i) >> 1) * NTH + threadIdx.x) * 2 + ((a * NDOF + i) & 1)] = uv;
+        else if constexpr (XU >= 1) u_s[a * NDOF + i][threadIdx.x] = uv;
+        else U[a][i] = uv;
         if constexpr (ACC_SMEM) acc_s[a * NDOF + i][threadIdx.x] = 0.0;
         else acc[a][i] = 0.0;
-        if constexpr (TANGENT) V[a][i] = __ldg(A.v + (long long)cn[a] * NDOF + i);
+        if constexpr (V_SMEM) elem_dyn_s[VOFF + (((a * NDOF + i) >> 1) * NTH + threadIdx.x) * 2 + ((a * NDOF + i) & 1)] = __ldg(A.v + (long long)cn[a] * NDOF + i);
+        else if constexpr (TANGENT) V[a][i] = __ldg(A.v + (long long)cn[a] * NDOF + i);
       }
     }
 
@@ -192,14 +247,30 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
       const double* dN = tab.dN + q * (TAB_MAX_NNPE * 3);
       double J[ND * ND], Ji[ND * ND];
 #pragma unroll
-      for (int k = 0; k < ND; k++)
+      for (int k = 0; k < ND * ND; k++) J[k] = 0.0;
+      if constexpr (XU == 3) {
 #pragma unroll
-        for (int j = 0; j < ND; j++) {
-          double s = 0.0;
+        for (int p = 0; p < NNPE * ND / 2; p++) {
+          double xv[2];
+          lds_v2(elem_dyn_s + XOFF + (p * NTH + threadIdx.x) * 2, xv[0], xv[1]);
 #pragma unroll
-          for (int a = 0; a < NNPE; a++) s = fma(dN[a * 3 + k], X[a][j], s);
-          J[k * ND + j] = s;
+          for (int h = 0; h < 2; h++) {
+            const int a = (2 * p + h) / ND, j = (2 * p + h) % ND;
+#pragma unroll
+            for (int k = 0; k < ND; k++) J[k * ND + j] = fma(dN[a * 3 + k], xv[h], J[k * ND + j]);
+          }
         }
+      } else {
+#pragma unroll
+        for (int a = 0; a < NNPE; a++)
+#pragma unroll
+          for (int j = 0; j < ND; j++) {
+            // shared-memory copies are re-read per quadrature point (volatile: not hoisted back into registers)
+            const double xv = PCX_X(a, j);
+#pragma unroll
+            for (int k = 0; k < ND; k++) J[k * ND + j] = fma(dN[a * 3 + k], xv, J[k * ND + j]);
+          }
+      }
       const double detJ = inv_det<ND>(J, Ji);
       const double JxW = detJ * tab.w[q];
       // parent-space gradient of u (and of v)
@@ -208,16 +279,36 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #pragma unroll
       for (int i = 0; i < NDOF; i++)
 #pragma unroll
-        for (int k = 0; k < ND; k++) {
-          double s = 0.0, sv = 0.0;
+        for (int k = 0; k < ND; k++) { Gu[i][k] = 0.0; if constexpr (TANGENT) Gv[i][k] = 0.0; }
+      if constexpr (XU == 3) {
 #pragma unroll
-          for (int a = 0; a < NNPE; a++) {
-            s = fma(U[a][i], dN[a * 3 + k], s);
-            if constexpr (TANGENT) sv = fma(V[a][i], dN[a * 3 + k], sv);
+        for (int p = 0; p < NNPE * NDOF / 2; p++) {
+          double uv[2], vv[2] = {0.0, 0.0};
+          lds_v2(elem_dyn_s + UOFF + (p * NTH + threadIdx.x) * 2, uv[0], uv[1]);
+          if constexpr (V_SMEM) lds_v2(elem_dyn_s + VOFF + (p * NTH + threadIdx.x) * 2, vv[0], vv[1]);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int a = (2 * p + h) / NDOF, i = (2 * p + h) % NDOF;
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+              Gu[i][k] = fma(uv[h], dN[a * 3 + k], Gu[i][k]);
+              if constexpr (V_SMEM) Gv[i][k] = fma(vv[h], dN[a * 3 + k], Gv[i][k]);
+            }
           }
-          Gu[i][k] = s;
-          if constexpr (TANGENT) Gv[i][k] = sv;
         }
+      } else {
+#pragma unroll
+        for (int a = 0; a < NNPE; a++)
+#pragma unroll
+          for (int i = 0; i < NDOF; i++) {
+            const double uv = PCX_U(a, i);
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+              Gu[i][k] = fma(uv, dN[a * 3 + k], Gu[i][k]);
+              if constexpr (TANGENT) Gv[i][k] = fma(V[a][i], dN[a * 3 + k], Gv[i][k]);
+            }
+          }
+      }
       // H[i][j] = sum_k Gu[i][k] Ji[j][k]
       double H[NDOF][ND], dH[TANGENT ? NDOF : 1][ND];
 #pragma unroll
@@ -243,7 +334,7 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
         if constexpr (!TANGENT) {
           double uq = 0.0, w = 0.0;
 #pragma unroll
-          for (int a = 0; a < NNPE; a++) uq = fma(tab.N[q * TAB_MAX_NNPE + a], U[a][0], uq);
+          for (int a = 0; a < NNPE; a++) uq = fma(tab.N[q * TAB_MAX_NNPE + a], PCX_U(a, 0), uq);
 #pragma unroll
           for (int j = 0; j < ND; j++) { w = fma(H[0][j], H[0][j], w); S[0][j] = H[0][j]; }
           Wsum = fma(JxW, 0.5 * w - fq * uq, Wsum);
@@ -353,6 +444,8 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
       }
     }
   }
+#undef PCX_X
+#undef PCX_U
   if (bad) atomicOr(A.flags, 1);
   if (A.epart) {
     const double t = block_sum<NTH>(Wsum, sh);
