@@ -482,10 +482,13 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #define PCX_VISCO_MINB_FWD 4
 #endif
 #ifndef PCX_VISCO_MINB_FWDF
-#define PCX_VISCO_MINB_FWDF 3     // MODE 2 (196 registers unconstrained)
+#define PCX_VISCO_MINB_FWDF 3     // MODE 2 (196 registers unconstrained; 2 CTAs per SM: 5.59 ms per step of 10 sweeps at 2.1 M points, 3: 4.14)
+#endif
+#ifndef PCX_VISCO_MINB_BWDT
+#define PCX_VISCO_MINB_BWDT 3     // MODE 3 (254 registers unconstrained)
 #endif
 template <int NNPE, int ND, int NDOF, int MODEL, int MODE>
-__global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 0 ? PCX_VISCO_MINB_FWD : MODE == 2 ? PCX_VISCO_MINB_FWDF : 2) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
+__global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 0 ? PCX_VISCO_MINB_FWD : MODE == 2 ? PCX_VISCO_MINB_FWDF : PCX_VISCO_MINB_BWDT) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
   constexpr bool FLUX = MODE != 0;                  // a point flux Q is written
   constexpr int NTH = 128;
   __shared__ double sh[NTH / 32];
