@@ -1769,6 +1769,11 @@ static int jet_launch_nt(pcx_handle* h, int what, const JetIO& io, const JetWgra
   if (what == 0) {
     const size_t smem = (size_t)(h->ms.pBO - h->ms.pF0 + EXP2_TAB_N) * sizeof(double);
     if (smem > 200 * 1024) return fail(PCX_ERR_UNSUPPORTED, "MLP too large for the shared-memory weight stage (%zu bytes)", smem);
+    if (PCX_JET_FWD_MINB >= 2 && smem <= 100 * 1024) {        // two CTAs per SM (128 registers per thread)
+      blocks = (groups + 7) / 8;
+      if (blocks > 2 * h->sm_count) blocks = 2 * h->sm_count;
+      if (blocks < 1) blocks = 1;
+    }
     if (kodd) {
       CUDA_TRY(cudaFuncSetAttribute(k_jet_forward<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       k_jet_forward<NT, 1><<<(int)blocks, 256, smem, st>>>(h->ms, io);
