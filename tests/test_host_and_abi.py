@@ -300,3 +300,38 @@ def test_forward_kernel_tanh_arithmetic_is_accurate_to_3e16():
     ref = np.tanh(xs.astype(np.longdouble)).astype(np.float64)
     err = np.abs(_tanh_rep_numpy(xs) - ref)
     assert err.max() <= 3.0e-16, err.max()
+
+
+def test_data_containers_from_csv(tmp_path):
+    """pancax/data.py:11-35,86-105,118-243: CSV headers are stripped, n_time_steps counts the distinct times, the loader
+    yields shuffled FULL batches, GlobalData resamples the record onto n_time_steps and refuses repeated / decreasing times."""
+    import pancax_b200 as px
+    from pancax_b200.data import (FullFieldData, FullFieldDataLoader, GlobalData, GlobalDataTimesNotStrictlyIncreasingException,
+                                  GlobalDataTimesNotUniqueException)
+    rng = np.random.default_rng(0)
+    ff = tmp_path / "dic.csv"
+    rows = np.column_stack([rng.uniform(0, 1, (30, 2)), np.repeat([0.0, 0.5, 1.0], 10), rng.standard_normal((30, 2))])
+    ff.write_text(" x , y ,t, u_x ,u_y\n" + "\n".join(",".join(f"{v:.17g}" for v in r) for r in rows))
+    data = FullFieldData(str(ff), ["x", "y", "t"], ["u_x", "u_y"])
+    assert len(data) == 30 and data.n_time_steps == 3 and data.inputs.flags.c_contiguous
+    # pandas' default (fast) float parser, like the reference: within an ulp or two of the written value
+    assert np.allclose(data.inputs, rows[:, :3], rtol=1e-14, atol=0) and np.allclose(data.outputs, rows[:, 3:], rtol=1e-14, atol=0)
+    batches = list(FullFieldDataLoader(data).dataloader(8))
+    assert len(batches) == 3 and all(b[0].shape == (8, 3) and b[1].shape == (8, 2) for b in batches)
+    seen = np.concatenate([b[0] for b in batches])
+    assert len({tuple(r) for r in seen}) == 24                      # no row twice within an epoch
+    mesh = px.create_structured_mesh("quad4", 3)
+    gd_file = tmp_path / "global.csv"
+    gd_file.write_text("time, disp , force\n0.0,0.0,0.0\n1.0,0.1,2.0\n2.0,0.2,3.0\n")
+    gd = GlobalData(str(gd_file), "time", "disp", "force", mesh, 1, "y", 5, interpolate=True)
+    assert gd.n_time_steps == 5 and gd.reaction_dof == 1 and gd.n_nodes == len(mesh.nodeSets[list(mesh.nodeSets)[0]])
+    assert np.allclose(gd.times, np.linspace(0, 2, 5)) and np.allclose(gd.outputs, [0.0, 1.0, 2.0, 2.5, 3.0])
+    assert np.allclose(gd.displacements, np.linspace(0, 0.2, 5))
+    with pytest.raises(ValueError):
+        GlobalData(str(gd_file), "time", "disp", "force", mesh, 1, 1, 5)
+    gd_file.write_text("time,disp,force\n0.0,0.0,0.0\n1.0,0.1,2.0\n1.0,0.2,3.0\n")
+    with pytest.raises(GlobalDataTimesNotUniqueException):
+        GlobalData(str(gd_file), "time", "disp", "force", mesh, 1, "x", 3)
+    gd_file.write_text("time,disp,force\n0.0,0.0,0.0\n2.0,0.1,2.0\n1.0,0.2,3.0\n")
+    with pytest.raises(GlobalDataTimesNotStrictlyIncreasingException):
+        GlobalData(str(gd_file), "time", "disp", "force", mesh, 1, "x", 3)
