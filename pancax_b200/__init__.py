@@ -20,7 +20,8 @@ from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E
 from .domains import CollocationDomain, VariationalDomain  # noqa: F401,E402
 from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, write_exodus_mesh  # noqa: F401,E402
 from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, EnergyLoss,  # noqa: F401,E402
-                             EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss)
+                             EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss,
+                             UserDefinedLossFunction)
 from .networks import MLP, Field, Parameters  # noqa: F401,E402
 from .optimizers import LBFGS, Adam  # noqa: F401,E402
 from .physics_kernels import HeatEquation, PlaneStrain, PlaneStress, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402

@@ -24,6 +24,60 @@ class Grads:
     def __add__(self, other):
         return Grads(self.fields + other.fields, self.props + other.props)
 
+    def scaled(self, c):
+        return Grads(self.fields * c, self.props * c)
+
+
+class TracedLoss:
+    """A loss value that carries d(value)/d(weights, properties): what the built-in losses return while a
+    UserDefinedLossFunction is being differentiated.  The reference lets jax trace the user's Python function
+    (loss_functions/utils.py:30-34, optimizers.py:77-88); here the function is EXECUTED once and the arithmetic it does on
+    the built-in losses' values (+, -, *, /, unary -, with numbers or with each other) is differentiated by the chain
+    rule on this object -- the built-in losses and their gradients themselves are the library's fused CUDA calls."""
+
+    def __init__(self, value, grads: Grads):
+        self.value, self.grads = value, grads
+
+    @staticmethod
+    def _split(other):
+        return (other.value, other.grads) if isinstance(other, TracedLoss) else (other, None)
+
+    def __add__(self, other):
+        v, g = self._split(other)
+        return TracedLoss(self.value + v, self.grads if g is None else self.grads + g)
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return TracedLoss(-self.value, self.grads.scaled(-1.0))
+
+    def __sub__(self, other):
+        v, g = self._split(other)
+        return TracedLoss(self.value - v, self.grads if g is None else self.grads + g.scaled(-1.0))
+
+    def __rsub__(self, other):
+        return (-self) + other
+
+    def __mul__(self, other):
+        v, g = self._split(other)
+        if g is None:
+            return TracedLoss(self.value * v, self.grads.scaled(v))
+        return TracedLoss(self.value * v, self.grads.scaled(v) + g.scaled(self.value))      # product rule
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        v, g = self._split(other)
+        if g is None:
+            return TracedLoss(self.value / v, self.grads.scaled(1.0 / v))
+        return TracedLoss(self.value / v, self.grads.scaled(1.0 / v) + g.scaled(-self.value / (v * v)))
+
+    def __float__(self):
+        return float(self.value)
+
+
+_TRACING = [False]      # set while UserDefinedLossFunction.value_and_grad runs the user's function
+
 
 def _wrap_bc(bc_func, ndof):
     """Accept batched wrappers (x (N,nd), t, z (N,ndof)) -- pancax_b200.bvps -- and, for small
@@ -193,6 +247,9 @@ class PhysicsLossFunction(BaseLossFunction):
         raise NotImplementedError
 
     def __call__(self, params, problem, *args):
+        if _TRACING[0]:
+            (loss, aux), grads = self.value_and_grad(params, problem, *args)
+            return TracedLoss(loss, grads), aux
         loss, aux, _, _ = self._run(params, problem, False)
         return loss[0], self._aux(aux)
 
@@ -290,6 +347,9 @@ class FullFieldDataLoss(BaseLossFunction):
                                             weight=self.weight)
 
     def __call__(self, params, problem, inputs, outputs):
+        if _TRACING[0]:
+            (loss, aux), grads = self.value_and_grad(params, problem, inputs, outputs)
+            return TracedLoss(loss, grads), aux
         loss, _ = self._run(params, problem, inputs, outputs)
         return loss[0], {"field_data_loss": loss[0] / self.weight if self.weight else loss[0]}
 
@@ -378,5 +438,30 @@ class CombineLossFunctions(BaseLossFunction):
 
 
 class UserDefinedLossFunction(BaseLossFunction):
+    """loss_functions/utils.py:30-34: ``func(params, problem, *args) -> (loss, aux)`` written by the user.  Every shipped
+    example builds it from the library's own loss functions (examples/inverse_problems/mechanics/path-dependent/
+    script.py:121-127: ``loss_1 + loss_2`` of an EnergyResidualAndReactionLoss and a FullFieldDataLoss), and that is what
+    runs here: the function is executed, the built-in losses inside it run as the fused CUDA calls and hand back values
+    that carry their gradients (TracedLoss), and the arithmetic between them is differentiated by the chain rule.  A
+    function that computes its loss some other way (from params / problem directly) has no gradient on this path and
+    is refused -- there is no tracing compiler and no CPU fallback behind it."""
+
     def __init__(self, func):
-        raise NotImplementedError("user-defined Python losses cannot run on the B200 path (no fallback)")
+        self.func = func
+
+    def __call__(self, params, problem, *args):
+        return self.func(params, problem, *args)
+
+    def value_and_grad(self, params, problem, *args):
+        if _TRACING[0]:
+            raise RuntimeError("UserDefinedLossFunction.value_and_grad is not re-entrant")
+        _TRACING[0] = True
+        try:
+            out = self.func(params, problem, *args)
+        finally:
+            _TRACING[0] = False
+        loss, aux = out if isinstance(out, tuple) else (out, {})
+        if not isinstance(loss, TracedLoss):
+            raise NotImplementedError("the user-defined loss must be an arithmetic combination (+ - * /) of the library's loss "
+                                      "functions evaluated on (params, problem): anything else has no gradient on the B200 path")
+        return (loss.value, aux), loss.grads

@@ -148,6 +148,59 @@ def test_inverse_problem_combined_loss_and_adam(cuda_device):
     assert st.epoch == 3
 
 
+def test_user_defined_loss_function_of_builtin_losses(cuda_device):
+    """loss_functions/utils.py:30-34 as the reference's inverse examples use it (examples/inverse_problems/mechanics/
+    path-dependent/script.py:121-127, vanilla/example_v2.py): a Python function that adds the built-in losses.  The
+    function is executed, the built-in losses inside it are the fused CUDA calls, the arithmetic between their values is
+    differentiated by the chain rule (TracedLoss): same value / aux / gradient as CombineLossFunctions, and weighted /
+    product combinations against the hand-applied chain rule; a loss that is not built from them is refused."""
+    import torch
+    import pancax_b200 as px
+    prob, params = _build("quad4", n=6, nt=3, bounded=True, inverse=True)
+    rng = np.random.default_rng(1)
+    nb = 128
+    inputs = np.column_stack([rng.uniform(0, 1, (nb, 2)), rng.choice(prob.times, nb)])
+    outputs = 0.05 * rng.standard_normal((nb, 2))
+    phys = px.EnergyResidualAndReactionLoss(energy_weight=1.0, residual_weight=25.0, reaction_weight=2.5)
+    data = px.FullFieldDataLoss(weight=10.0)
+
+    def loss_function(params, problem, inputs, outputs):
+        loss_1, aux_1 = phys(params, problem)
+        loss_2, aux_2 = data(params, problem, inputs, outputs)
+        aux_1.update(aux_2)
+        return loss_1 + loss_2, aux_1
+
+    user = px.UserDefinedLossFunction(loss_function)
+    comb = px.CombineLossFunctions(phys, data)
+    (Lu, au), gu = user.value_and_grad(params, prob, inputs, outputs)
+    (Lc, ac), gc = comb.value_and_grad(params, prob, inputs, outputs)
+    assert float(Lu) == float(Lc) and set(au) == set(ac)
+    assert torch.equal(gu.fields, gc.fields) and torch.equal(gu.props, gc.props)
+    Lv, av = user(params, prob, inputs, outputs)                     # plain call: values only
+    assert abs(float(Lv) - float(Lc)) <= 1e-14 * abs(float(Lc)) and not isinstance(Lv, px.loss_functions.TracedLoss)
+
+    def weighted(params, problem, inputs, outputs):
+        l1, a1 = phys(params, problem)
+        l2, a2 = data(params, problem, inputs, outputs)
+        return 0.5 * l1 - l2 / 4.0 + 3.0 + l1 * l2, a1
+
+    (Lw, _), gw = px.UserDefinedLossFunction(weighted).value_and_grad(params, prob, inputs, outputs)
+    (L1, _), g1 = phys.value_and_grad(params, prob)
+    (L2, _), g2 = data.value_and_grad(params, prob, inputs, outputs)
+    L1f, L2f = float(L1), float(L2)
+    assert abs(float(Lw) - (0.5 * L1f - L2f / 4.0 + 3.0 + L1f * L2f)) <= 1e-13 * abs(float(Lw))
+    exp_w = (0.5 + L2f) * g1.fields + (-0.25 + L1f) * g2.fields
+    exp_p = (0.5 + L2f) * g1.props + (-0.25 + L1f) * g2.props
+    assert rel(gw.fields.cpu().numpy(), exp_w.cpu().numpy()) < 1e-13 and rel(gw.props.cpu().numpy(), exp_p.cpu().numpy()) < 1e-13
+    # the optimiser takes it like any other loss (optimizers.py:77-107)
+    opt = px.Adam(user, learning_rate=1e-3, has_aux=True)
+    st = opt.init(params)
+    params, st, (loss, aux) = opt.step(params, st, prob, inputs, outputs)
+    assert torch.isfinite(loss) and "reactions" in aux and st.epoch == 1
+    with pytest.raises(NotImplementedError):
+        px.UserDefinedLossFunction(lambda p, pr: (torch.zeros(()), {})).value_and_grad(params, prob)
+
+
 def test_trainer_reduces_energy_and_checkpoints(cuda_device, tmp_path):
     import pancax_b200 as px
     prob, params = _build("quad4", n=8, nt=2, t0=0.0)

@@ -335,3 +335,19 @@ def test_data_containers_from_csv(tmp_path):
     gd_file.write_text("time,disp,force\n0.0,0.0,0.0\n2.0,0.1,2.0\n1.0,0.2,3.0\n")
     with pytest.raises(GlobalDataTimesNotStrictlyIncreasingException):
         GlobalData(str(gd_file), "time", "disp", "force", mesh, 1, "x", 3)
+
+
+def test_traced_loss_arithmetic_is_the_chain_rule():
+    """loss_functions.TracedLoss (what UserDefinedLossFunction differentiates): + - * / between traced values and numbers."""
+    import torch
+    from pancax_b200.loss_functions import Grads, TracedLoss
+    a = TracedLoss(torch.tensor(2.0, dtype=torch.float64), Grads(torch.tensor([1.0, 0.0], dtype=torch.float64), torch.tensor([0.5], dtype=torch.float64)))
+    b = TracedLoss(torch.tensor(-3.0, dtype=torch.float64), Grads(torch.tensor([0.0, 2.0], dtype=torch.float64), torch.tensor([1.0], dtype=torch.float64)))
+    f = 2.0 * a - b / 4.0 + 1.5 - a * b + (1.0 - a) / b
+    va, vb = 2.0, -3.0
+    assert abs(float(f) - (2 * va - vb / 4 + 1.5 - va * vb + (1 - va) / vb)) < 1e-15
+    dfa = 2.0 - vb - 1.0 / vb
+    dfb = -0.25 - va - (1 - va) / vb ** 2
+    assert torch.allclose(f.grads.fields, dfa * a.grads.fields + dfb * b.grads.fields, rtol=1e-15, atol=1e-15)
+    assert torch.allclose(f.grads.props, dfa * a.grads.props + dfb * b.grads.props, rtol=1e-15, atol=1e-15)
+    assert isinstance(sum([a, b]), TracedLoss) and float(-a) == -2.0
