@@ -138,6 +138,13 @@ class SimpleFeFv:
     def initial_state(self):
         return np.tile(np.eye(3).ravel(), self.num_prony_terms())
 
+    # bookkeeping of the flat state vector (hyperviscoelasticity/base.py:11-16)
+    def extract_scalar(self, state, start_index: int):
+        return state[start_index]
+
+    def extract_tensor(self, state, start_index: int):
+        return np.asarray(state)[start_index:start_index + 9].reshape((3, 3))
+
     def properties(self):
         return self.eq_model.properties()
 

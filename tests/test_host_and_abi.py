@@ -351,3 +351,19 @@ def test_traced_loss_arithmetic_is_the_chain_rule():
     assert torch.allclose(f.grads.fields, dfa * a.grads.fields + dfb * b.grads.fields, rtol=1e-15, atol=1e-15)
     assert torch.allclose(f.grads.props, dfa * a.grads.props + dfb * b.grads.props, rtol=1e-15, atol=1e-15)
     assert isinstance(sum([a, b]), TracedLoss) and float(-a) == -2.0
+
+
+def test_simple_fefv_state_bookkeeping():
+    """test/constitutive_models/test_hyperviscoelastic.py:18-118 of the reference: initial_state is one identity per
+    Prony branch, extract_tensor slices the flat state vector branch by branch."""
+    import pancax_b200 as px
+    model = px.SimpleFeFv(px.NeoHookean(bulk_modulus=1000.0, shear_modulus=0.855),
+                          px.PronySeries(moduli=[1.0, 2.0, 3.0], relaxation_times=[1.0, 10.0, 100.0]),
+                          px.WLF(C1=17.44, C2=51.6, theta_ref=60.0))
+    assert model.num_prony_terms() == 3 and model.num_state_variables == 27
+    assert np.array_equal(model.initial_state(), np.tile([1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0], 3))
+    state = np.linspace(1.0, 27.0, 27)
+    for k in range(3):
+        assert np.array_equal(model.extract_tensor(state, 9 * k), np.arange(9 * k + 1.0, 9 * k + 10.0).reshape(3, 3))
+        assert np.array_equal(state.reshape((3, 3, 3))[k], model.extract_tensor(state, 9 * k))
+    assert model.extract_scalar(state, 4) == 5.0 and model.bulk_modulus == 1000.0
