@@ -26,9 +26,17 @@ class Physics:
         self.prony = prony    # (moduli, relaxation_times): SimpleFeFv around `model` (simple_fefv.py:11-14)
 
     def energy_density_with_state(self, grad_u, Z_old, dt):
-        """(psi (ne, nq), Z_new (ne, nq, nb, 3, 3)) -- SolidMechanics.energy with a SimpleFeFv model."""
-        return models.simple_fefv_energy(self.model, self.modify_field_gradient(grad_u), self.props, Z_old, dt,
-                                         self.prony[0], self.prony[1])
+        """(psi (ne, nq), Z_new (ne, nq, nb, 3, 3)) -- SolidMechanics.energy with a SimpleFeFv model.  PlaneStress
+        (solid_mechanics.py:49-71): the root find runs on the stress of the WHOLE model at fixed old state --
+        cauchy_stress = jacfwd(energy)[0] F^T / J with energy = (psi_eq + sum psi_neq, Z_new), mechanics/base.py:10-17,
+        112-118 -- so the out-of-plane gradient depends on grad_u AND on the old state."""
+        if self.formulation == "plane_stress":
+            def psi_of(H3):
+                return models.simple_fefv_energy(self.model, H3, self.props, Z_old, dt, self.prony[0], self.prony[1])[0]
+            H3 = plane_stress_gradient(self.model, grad_u, self.props, energy_fn=psi_of)
+        else:
+            H3 = self.modify_field_gradient(grad_u)
+        return models.simple_fefv_energy(self.model, H3, self.props, Z_old, dt, self.prony[0], self.prony[1])
 
     def energy_density(self, x_q, u_q, grad_u):
         """(ne, nq) energy density.  solid_mechanics.py:102-109 / poisson.py:16-19."""
@@ -50,7 +58,7 @@ class Physics:
         raise ValueError(self.formulation)
 
 
-def plane_stress_gradient(model, grad_u, props):
+def plane_stress_gradient(model, grad_u, props, energy_fn=None):
     """PlaneStress.modify_field_gradient (solid_mechanics.py:49-71): the out-of-plane entry x = grad_u_33 is the
     root of sigma_33(x) = 0, found by scalar_root_find.find_root (Newton safeguarded by bisection, guess 0.05,
     bracket [-0.99, 10], x_tol 1e-13; math/scalar_root_find.py:18-160) and differentiated by the implicit function
@@ -61,8 +69,11 @@ def plane_stress_gradient(model, grad_u, props):
     E33 = torch.zeros(3, 3, dtype=F64)
     E33[2, 2] = 1.0
 
+    # energy_fn(H3) -> psi: the energy the stress is taken of (a model with state: psi at FIXED old state, differentiable
+    # w.r.t. that state through its closure); default: the hyperelastic model
     def g_and_dg(H2, x, create_graph):
-        W = models.energy(model, models.tensor_2D_to_3D(H2) + x[..., None, None] * E33, props)
+        H3 = models.tensor_2D_to_3D(H2) + x[..., None, None] * E33
+        W = models.energy(model, H3, props) if energy_fn is None else energy_fn(H3)
         (g,) = torch.autograd.grad(W.sum(), x, create_graph=True)
         (dg,) = torch.autograd.grad(g.sum(), x, create_graph=create_graph)
         return g, dg

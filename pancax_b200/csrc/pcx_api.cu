@@ -86,8 +86,9 @@ struct pcx_handle {
   long long vz_per = 0;
   bool vz_filled = false;                   // a path-dependent call has written the state history
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
-                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; } vstep;   // mode: k_visco_qp MODE
+                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; double* f33 = nullptr; } vstep;   // mode: k_visco_qp MODE
   double* vv = nullptr;                     // [nt][nn][ndof] v_t = dloss/df_t of every step (residual losses with state)
+  double *vf33 = nullptr, *vscr = nullptr;   // PlaneStress with state: roots F_33 [nt][ne*nq]; MODE 5 scratch [ne*nq*n_prony*9]
   int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT: 1 = mma.sync kernel, 2 = tcgen05 contractions
   double *us = nullptr, *fe = nullptr, *f = nullptr, *v = nullptr, *ubar = nullptr;
   double *epart = nullptr, *ppart = nullptr, *rpart = nullptr;
@@ -267,7 +268,7 @@ __global__ void k_finish(int kind, int nt, double we, double wr, double wg, cons
                          const double* __restrict__ sc_R, const double* __restrict__ sc_re, const double* __restrict__ gout,
                          const double* __restrict__ dpi, const double* __restrict__ dfv, const double* __restrict__ props_dev,
                          pcx_physics_desc d, const int* __restrict__ flags, double* __restrict__ loss, double* __restrict__ aux,
-                         double* __restrict__ g_props, double rep, int t_first = 0) {
+                         double* __restrict__ g_props, double rep, int t_first = 0, int add_dfv = 0) {
   // rep: weight of the terms every shard computes identically (R, reaction loss, reactions): 1 for a
   // whole mesh, 1/n_shards for a shard, so that SUM over shards of (loss, aux) is the global value
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -298,6 +299,7 @@ __global__ void k_finish(int kind, int nt, double we, double wr, double wg, cons
       for (int t = 0; t < nt; t++) {
         s += we * dpi[t * PCX_MAX_PROPS + i];
         if (kind != PCX_LOSS_ENERGY) s += dfv[t * PCX_MAX_PROPS + i];
+        else if (add_dfv) s += we * dfv[t * PCX_MAX_PROPS + i];   // PlaneStress with state: implicit-function part, per unit weight
       }
       g_props[k++] = s * props_dev[PCX_MAX_PROPS + i];
     }
@@ -372,9 +374,11 @@ static void launch_visco_t(int mode, int nblk_qp, int nblk_el, cudaStream_t st, 
     case 0: k_visco_qp<NNPE, ND, NDOF, MODEL, 0><<<nblk_qp, 128, 0, st>>>(tab, a); break;
     case 1: k_visco_qp<NNPE, ND, NDOF, MODEL, 1><<<nblk_qp, 128, 0, st>>>(tab, a); break;
     case 2: k_visco_qp<NNPE, ND, NDOF, MODEL, 2><<<nblk_qp, 128, 0, st>>>(tab, a); break;
-    default: k_visco_qp<NNPE, ND, NDOF, MODEL, 3><<<nblk_qp, 128, 0, st>>>(tab, a); break;
+    case 3: k_visco_qp<NNPE, ND, NDOF, MODEL, 3><<<nblk_qp, 128, 0, st>>>(tab, a); break;
+    case 4: if constexpr (ND == 2) k_visco_qp<NNPE, ND, NDOF, MODEL, 4><<<nblk_qp, 128, 0, st>>>(tab, a); break;   // PlaneStress
+    default: if constexpr (ND == 2) k_visco_qp<NNPE, ND, NDOF, MODEL, 5><<<nblk_qp, 128, 0, st>>>(tab, a); break;
   }
-  if (mode != 0)
+  if (mode != 0 && mode != 4)
     k_visco_scatter<NNPE, ND, NDOF><<<(unsigned)((a.ne + visco_scatter_epb<NNPE>() - 1) / visco_scatter_epb<NNPE>()), 128, 0, st>>>(tab, a);
 }
 template <int NNPE, int ND, int NDOF>
@@ -660,6 +664,9 @@ static void free_ws(pcx_handle* h) {
   if (h->vpart) cudaFree(h->vpart);
   if (h->vv) cudaFree(h->vv);
   h->vv = nullptr;
+  if (h->vf33) cudaFree(h->vf33);
+  if (h->vscr) cudaFree(h->vscr);
+  h->vf33 = nullptr; h->vscr = nullptr;
   if (h->f33) cudaFree(h->f33);
   h->f33 = nullptr; h->f33_cap = 0;
   h->vz = nullptr; h->vus = nullptr; h->vq = nullptr; h->vpart = nullptr; h->vz_per = 0; h->vnblk = 0; h->vz_filled = false;
@@ -723,6 +730,10 @@ static int alloc_ws(pcx_handle* h) {
     CUDA_TRY(cudaMalloc(&h->vlam[0], (size_t)per * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->vlam[1], (size_t)per * sizeof(double)));
     if (h->unknown_idx) CUDA_TRY(cudaMalloc(&h->vv, (size_t)h->nt * h->nn * h->ndof * sizeof(double)));
+    if (h->phys.formulation == PCX_FORM_PLANE_STRESS) {
+      CUDA_TRY(cudaMalloc(&h->vf33, (size_t)h->nt * h->ne * h->nq * sizeof(double)));
+      CUDA_TRY(cudaMalloc(&h->vscr, (size_t)per * sizeof(double)));
+    }
     h->vz_per = per;
   }
   CUDA_TRY(cudaMalloc(&h->flags, sizeof(int)));
@@ -808,7 +819,6 @@ extern "C" int pcx_set_physics(pcx_handle* h, const pcx_physics_desc* p) {
     if (p->n_prony > 0) {
       for (int b = 0; b < p->n_prony; b++)
         if (!(p->prony_times[b] > 0.0)) return fail(PCX_ERR_INVALID, "Prony relaxation time %d must be positive", b);
-      if (p->formulation == PCX_FORM_PLANE_STRESS) return fail(PCX_ERR_UNSUPPORTED, "PlaneStress with a state-variable model is not on the B200 path");
     }
   } else return fail(PCX_ERR_INVALID, "unknown physics %d", p->physics);
   h->phys = *p;
@@ -1068,13 +1078,18 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
     for (int b = 0; b < a.n_prony; b++) { a.prony_kappa[b] = h->vstep.kappa[b]; a.prony_c[b] = h->vstep.c[b]; }
     a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
     a.wpsi = h->vstep.wpsi;
+    a.f33_out = nullptr; a.f33_in = nullptr;
+    if (h->vstep.mode == 4) a.f33_out = h->vstep.f33;
+    if (h->vstep.mode == 5) { a.f33_in = h->vstep.f33; a.vscr = h->vscr; }
     a.qbuf = h->vq;
     // the per-point sweep has its own grid: partials [vnblk] and [vnblk][PCX_MAX_PROPS]
     a.epart = want_energy ? h->vpart : nullptr;
     a.ppart = want_dp ? h->vpart + h->vnblk : nullptr;
     const int mode = h->vstep.mode;
     const bool ok = mode == 0 ? (!want_force && a.z_new) : mode == 1 ? (want_force && a.lam_in && a.lam_out)
-                  : mode == 2 ? (want_force && a.z_new) : (want_force && a.lam_in && a.lam_out && v);
+                  : mode == 2 ? (want_force && a.z_new) : mode == 3 ? (want_force && a.lam_in && a.lam_out && v)
+                  : mode == 4 ? (!want_force && a.z_new && a.f33_out && h->nd == 2)
+                  : (want_force && a.lam_in && a.lam_out && a.f33_in && a.vscr && h->nd == 2);
     if (T != 1 || !ok || !h->vq)
       return fail(PCX_ERR_STATE, "state-variable sweep: one time step per launch, forward (states) or reverse (forces)");
   }
@@ -1372,8 +1387,12 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   if (L->first_step != 1)
     return fail(PCX_ERR_UNSUPPORTED, "a model with state variables (SimpleFeFv) is defined for the path-dependent losses only "
                                      "(first_step = 1)");
-  if (h->phys.formulation == PCX_FORM_PLANE_STRESS)
-    return fail(PCX_ERR_UNSUPPORTED, "PlaneStress with a state-variable model is not supported");
+  // PlaneStress with state: the per-point root find runs on the total stress at fixed old state (k_visco_qp MODE 4 / 5);
+  // under the residual losses its gradient needs third derivatives of the energy: refused
+  const bool pstress = h->phys.formulation == PCX_FORM_PLANE_STRESS;
+  if (pstress && kind != PCX_LOSS_ENERGY)
+    return fail(PCX_ERR_UNSUPPORTED, "PlaneStress with a state-variable model is defined for the path-dependent EnergyLoss only");
+  if (pstress && (!h->vf33 || !h->vscr || h->nd != 2)) return fail(PCX_ERR_STATE, "PlaneStress state workspace missing");
   if (h->nt < 2) return fail(PCX_ERR_INVALID, "the path-dependent call needs at least two time steps");
   // residual / reaction losses (weak_form_loss_functions.py:151-192,242-276): every step's internal force f_n = dPi_n/du_n
   // at FIXED old state comes out of the forward sweep (k_visco_qp MODE 2), R_n / reaction_n / v_n = dloss/df_n right
@@ -1430,7 +1449,8 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     step_constants(n);
     h->vstep.z_old = h->vz + (long long)(n - 1) * per; h->vstep.z_new = h->vz + (long long)n * per;
     h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
-    h->vstep.mode = resid ? 2 : 0;
+    h->vstep.mode = resid ? 2 : pstress ? 4 : 0;
+    h->vstep.f33 = pstress ? h->vf33 + (long long)n * h->ne * h->nq : nullptr;
     rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, resid ? h->f : nullptr, 1.0, nullptr, 0.0, true, want_dp, resid, st);
     if (!rc) rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
     if (!rc && want_dp)
@@ -1467,12 +1487,13 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
       h->vstep.lam_in = h->vlam[cur]; h->vstep.lam_out = h->vlam[cur ^ 1];
       // EnergyLoss: the sweep runs with unit energy weight, the assembly scales by we (lam is the adjoint per unit we);
       // residual losses: the sweep carries we itself (the second-order terms do not scale with it)
-      h->vstep.mode = resid ? 3 : 1;
+      h->vstep.mode = resid ? 3 : pstress ? 5 : 1;
+      h->vstep.f33 = pstress ? h->vf33 + (long long)n * h->ne * h->nq : nullptr;
       h->vstep.wpsi = resid ? we : 1.0;
       double* ubar_n = resident ? h->ubar + (long long)n * ndofs : h->ubar;
       rc = sweep(h, false, 1, us_all + (long long)n * ndofs, resid ? h->vv + (long long)n * ndofs : nullptr, ubar_n,
-                 resid ? 1.0 : we, nullptr, 0.0, false, resid && want_dp, true, st);
-      if (!rc && resid && want_dp)
+                 resid ? 1.0 : we, nullptr, 0.0, false, (resid || pstress) && want_dp, true, st);
+      if (!rc && (resid || pstress) && want_dp)
         rc = reduce_rows(h, h->vpart + h->vnblk, h->vnblk, PCX_MAX_PROPS, h->phys.nprops, 1,
                          h->scal + SC_DFV(h) + (long long)n * PCX_MAX_PROPS, PCX_MAX_PROPS, st);
       cur ^= 1;
@@ -1492,7 +1513,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
   }
   k_finish<<<1, 32, 0, st>>>(kind, nt, we, wr, wg, h->scal + SC_PI(h), h->scal + SC_R(h), h->scal + SC_REACT(h), gout,
                              h->scal + SC_DPI(h), h->scal + SC_DFV(h), h->props_dev, h->phys, h->flags, loss_out, aux,
-                             want_dp ? g_props : nullptr, 1.0, 1);
+                             want_dp ? g_props : nullptr, 1.0, 1, pstress ? 1 : 0);
   LAUNCH_CHECK(h);
   return PCX_OK;
 }

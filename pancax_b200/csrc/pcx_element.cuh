@@ -61,6 +61,7 @@ struct ElemArgs {
   double* lam_out;
   double* qbuf;            // [ne][nq][NDOF][ND] parent-space point fluxes (k_visco_qp -> k_visco_scatter)
   double wpsi;             // k_visco_qp MODE 3: weight of the step's energy in the loss (the flux then carries every term)
+  double* vscr;            // k_visco_qp MODE 5: scratch [ne][nq][n_prony][9] (tangent of the old-state adjoint along E_33)
 };
 
 template <int ND>
@@ -474,6 +475,12 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 //         d/deps dpsi/dFv_old (u + eps v) -- the second-order terms from ONE forward-mode (dual) evaluation of the
 //         equilibrium model and the closed-form tangent of the branch (fefv_branch); property-gradient partials are the
 //         dual parts of JxW dW/dp.
+// MODE 4 / 5 (2D, PlaneStress with state, path-dependent EnergyLoss): MODE 0 / 1 with the out-of-plane stretch from the
+//         per-point root of the TOTAL P_33 at fixed old state (plane_stress_visco_solve; the roots are kept per step in
+//         f33_out / f33_in).  The reverse sweep adds the implicit-function terms: with G_33 = dL/dF_33 of the point
+//         (energy + adjoint of the new state) and the tangent (dP, dlam_old) of the lam = 0 branch along dF = E_33,
+//         mu = -G_33 / dP_33, flux += mu dP_2D, lam_out += mu dlam_old, property partials mu d(dW/dp)
+//         (dx/dF_ij = -dP_ij/dP_33 by the symmetry of the Hessian, dx/dz = -d(dpsi/dz)/dF_33 / dP_33).
 // ----------------------------------------------------------------------------------------------
 #ifndef PCX_VISCO_MINB_BWD
 #define PCX_VISCO_MINB_BWD 3
@@ -489,7 +496,8 @@ __global__ void __launch_bounds__(128, elem_min_blocks(ND, TANGENT)) k_element(c
 #endif
 template <int NNPE, int ND, int NDOF, int MODEL, int MODE>
 __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 0 ? PCX_VISCO_MINB_FWD : MODE == 2 ? PCX_VISCO_MINB_FWDF : PCX_VISCO_MINB_BWDT) k_visco_qp(const __grid_constant__ ParentTab tab, const __grid_constant__ ElemArgs A0) {
-  constexpr bool FLUX = MODE != 0;                  // a point flux Q is written
+  constexpr bool FLUX = MODE != 0 && MODE != 4;     // a point flux Q is written
+  constexpr bool REV = MODE == 1 || MODE == 5;      // no energy partials
   constexpr int NTH = 128;
   __shared__ double sh[NTH / 32];
   const int nq = tab.nq;
@@ -500,7 +508,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 
 #pragma unroll
   for (int k = 0; k < PCX_MAX_PROPS; k++) props.p[k] = (k < A0.nprops) ? __ldg(A0.props_dev + k) : 0.0;
   props_derive<MODEL>(props);
-  const bool want_dp = MODE != 1 && A0.ppart != nullptr;
+  const bool want_dp = MODE != 1 && A0.ppart != nullptr;   // MODE 5: the implicit-function part of the property gradient
   double Wq = 0.0;
   double dps[PCX_MAX_PROPS];
 #pragma unroll
@@ -591,6 +599,55 @@ __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 
 #pragma unroll
         for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = lo[i];
       }
+    } else if constexpr (MODE == 4 && ND == 2) {
+      const double* zo = A0.z_old + zq;
+      if (!plane_stress_visco_solve<MODEL>(F, props, A0.n_prony, zo, A0.prony_kappa, A0.prony_c)) bad = true;
+      if (A0.f33_out) A0.f33_out[t] = F[8];
+      model_eval<MODEL, double>(F, props, W, P, dp, want_dp);
+      for (int b = 0; b < A0.n_prony; b++) {
+        double zn[9], lo[9];
+        W += fefv_branch(F, zo + b * 9, A0.prony_kappa[b], A0.prony_c[b], zn, nullptr, nullptr, lo);
+#pragma unroll
+        for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
+      }
+    } else if constexpr (MODE == 5 && ND == 2) {
+      const double* zo = A0.z_old + zq;
+      F[8] = A0.f33_in[t];
+      double dPt[9];
+      {
+        Dual Fd[9], Wd, Pd[9], dpd[PCX_MAX_PROPS];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Fd[i] = Dual(F[i], i == 8 ? 1.0 : 0.0);
+        model_eval<MODEL, Dual>(Fd, props, Wd, Pd, dpd, want_dp);
+        W = Wd.v;
+#pragma unroll
+        for (int i = 0; i < 9; i++) { P[i] = Pd[i].v; dPt[i] = Pd[i].d; }
+        if (want_dp) {
+#pragma unroll
+          for (int k = 0; k < PCX_MAX_PROPS; k++)
+            if (k < A0.nprops) dp[k] = dpd[k].d;
+        }
+      }
+      const double dF[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0};
+      for (int b = 0; b < A0.n_prony; b++) {
+        double li[9], lo[9], dlo[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) { li[i] = A0.lam_in[zq + b * 9 + i]; dlo[i] = 0.0; }
+        W += fefv_branch(F, zo + b * 9, A0.prony_kappa[b], A0.prony_c[b], nullptr, li, P, lo, 1.0, dF, dPt, dlo);
+#pragma unroll
+        for (int i = 0; i < 9; i++) { A0.lam_out[zq + b * 9 + i] = lo[i]; A0.vscr[zq + b * 9 + i] = dlo[i]; }
+      }
+      const double mu = -P[8] / dPt[8];
+#pragma unroll
+      for (int i = 0; i < 9; i++) P[i] = fma(mu, dPt[i], P[i]);
+      for (int b = 0; b < A0.n_prony; b++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = fma(mu, A0.vscr[zq + b * 9 + i], A0.lam_out[zq + b * 9 + i]);
+      if (want_dp) {
+#pragma unroll
+        for (int k = 0; k < PCX_MAX_PROPS; k++)
+          if (k < A0.nprops) dp[k] *= mu;
+      }
     } else {
       model_eval<MODEL, double>(F, props, W, P, dp, want_dp);   // equilibrium branch (simple_fefv.py:33-40)
       for (int b = 0; b < A0.n_prony; b++) {
@@ -624,7 +681,7 @@ __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 
         }
     }
     if constexpr (MODE != 1) {
-      Wq = JxW * W;
+      if constexpr (!REV) Wq = JxW * W;
       if (want_dp) {
 #pragma unroll
         for (int k = 0; k < PCX_MAX_PROPS; k++)

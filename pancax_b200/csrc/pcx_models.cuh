@@ -832,4 +832,60 @@ __device__ inline void plane_stress_tangent(Dual* Fd, const Props& pr, Dual& W, 
   Fd[8].d = dx;
 }
 
+// ------------------------------------------------------------------ PlaneStress with a model with state (SimpleFeFv)
+// The reference's root find runs on the Cauchy stress of the WHOLE model at fixed old state (solid_mechanics.py:49-71 with
+// mechanics/base.py:10-17,112-118: cauchy_stress = jacfwd(energy)[0] F^T / J, energy = psi_eq + sum_b psi_b), so here
+//   g(x)  = P_33 = dpsi_eq/dF_33 + sum_b S_b,33          (S_b: the lam = 0 reverse branch of fefv_branch)
+//   g'(x) = its tangent along dF = E_33                    (dual evaluation of the equilibrium model + fefv_branch's closed-form tangent)
+// and the same safeguarded Newton iteration as plane_stress_solve.  F: in-plane entries set; on exit F[8] = 1 + x.
+// zo: the old viscous deformation gradients [n_prony][9].
+template <int MODEL>
+__device__ inline void plane_stress_visco_g(const double* F, const Props& pr, int n_prony, const double* zo, const double* kappa,
+                                            const double* cc, double& g, double& dg) {
+  Dual Fd[9], W, P[9], dp[PCX_MAX_PROPS];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Fd[i] = Dual(F[i], i == 8 ? 1.0 : 0.0);
+  model_eval<MODEL, Dual>(Fd, pr, W, P, dp, false);
+  g = P[8].v;
+  dg = P[8].d;
+  const double dF[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0};
+  for (int b = 0; b < n_prony; b++) {
+    double S[9], lo[9], dS[9], dlo[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) S[i] = dS[i] = dlo[i] = 0.0;
+    fefv_branch(F, zo + 9 * b, kappa[b], cc[b], nullptr, nullptr, S, lo, 1.0, dF, dS, dlo);
+    g += S[8];
+    dg += dS[8];
+  }
+}
+
+template <int MODEL>
+__device__ inline bool plane_stress_visco_solve(double* F, const Props& pr, int n_prony, const double* zo, const double* kappa,
+                                                const double* cc) {
+  const double j2 = F[0] * F[4] - F[1] * F[3];
+  double lo = -0.99, hi = 10.0;
+  double x = fmin(fmax(1.0 / j2 - 1.0, lo), hi);
+  if (!(x == x)) x = 0.05;
+  bool ok = false;
+  double dx_prev = 1.0e300;
+#pragma unroll 1
+  for (int it = 0; it < 60; it++) {
+    F[8] = 1.0 + x;
+    double g, dg;
+    plane_stress_visco_g<MODEL>(F, pr, n_prony, zo, kappa, cc, g, dg);
+    if (g < 0.0) lo = x; else hi = x;
+    double xn = x - g / dg;
+    const double slack = 8.0 * 2.220446049250313e-16 * fmax(1.0, fabs(x));
+    if (dg > 0.0 && xn <= lo && xn >= lo - slack) xn = lo;
+    else if (dg > 0.0 && xn >= hi && xn <= hi + slack) xn = hi;
+    else if (!(xn > lo) || !(xn < hi) || !(dg > 0.0)) xn = 0.5 * (lo + hi);
+    const double dx = fabs(xn - x);
+    x = xn;
+    if (dx < 1.0e-15 || (dx < 1.0e-13 && dx > 0.75 * dx_prev)) { ok = true; break; }
+    dx_prev = dx;
+  }
+  F[8] = 1.0 + x;
+  return ok;
+}
+
 }  // namespace pcx

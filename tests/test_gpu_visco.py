@@ -87,10 +87,11 @@ def test_state_models_are_refused_elsewhere(cuda_device):
     with pytest.raises(PcxError, match="state variables"):
         eng.loss_and_grad("energy_residual", case.weights, None)              # residual loss, path-independent call
     eng.close()
-    ps = make_case("quad4_visco_neohookean", n=3, nt=3, width=8, depth=2)
-    ps.formulation = "plane_stress"
-    with pytest.raises(PcxError, match="PlaneStress"):      # refused at pcx_set_physics
-        make_engine(ps)
+    ps = make_case("quad4_visco_neohookean_pstress", n=3, nt=3, width=8, depth=2)
+    eng = make_engine(ps)
+    with pytest.raises(PcxError, match="PlaneStress"):      # third derivatives of the energy: EnergyLoss only
+        eng.loss_and_grad("energy_residual", ps.weights, None, first_step=1)
+    eng.close()
 
 
 def test_public_api_example_hyper_visco(cuda_device):
@@ -255,3 +256,24 @@ def test_public_api_inverse_path_dependent_visco(cuda_device):
         params, st, (loss, aux) = opt.step(params, st, problem)
         l0 = float(loss) if l0 is None else l0
     assert torch.isfinite(loss) and float(loss) < l0
+
+
+# ---------------------------------------------------------------- PlaneStress with state (path-dependent EnergyLoss)
+@pytest.mark.parametrize("deterministic", [True, False])
+@pytest.mark.parametrize("name,n,nt", [("quad4_visco_neohookean_pstress", 4, 4), ("tri3_visco_gent_pstress_bounded", 4, 3),
+                                       ("quad4_visco_hencky_pstress", 3, 3), ("quad4_visco_swanson_pstress", 3, 3),
+                                       ("tri3_visco_neohookean_pstress_bounded", 3, 4)])
+def test_plane_stress_with_state(cuda_device, name, n, nt, deterministic):
+    """PlaneStress.modify_field_gradient (solid_mechanics.py:49-71) with SimpleFeFv: the per-point root find runs on the
+    Cauchy stress of the whole model at fixed old state, so the out-of-plane stretch depends on the displacement gradient
+    AND on the old viscous state (k_visco_qp MODE 4); the reverse sweep (MODE 5) adds the implicit-function terms to the
+    point flux, to the adjoint of the old state and to the property gradient.  Against the oracle (differentiable Newton
+    steps on the same root)."""
+    case = make_case(name, n=n, nt=nt, width=12, depth=2)
+    L, aux, gw, gp = run_engine_loss(case, "energy", deterministic=deterministic, first_step=1)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, "energy", first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo), (L, Lo)
+    assert rel(gw, gwo) < TOL, rel(gw, gwo)
+    if gpo.size:
+        assert rel(gp, gpo) < TOL, (gp, gpo)
+    assert aux[3] == 0.0          # every root find converged
