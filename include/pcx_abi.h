@@ -137,7 +137,9 @@ typedef struct {
    * (pcx_loss_desc.first_step = 1): EnergyLoss (weak_form_loss_functions.py:48-72), EnergyAndResidualLoss
    * (:151-192) and EnergyResidualAndReactionLoss (:242-276) -- the internal force of a step is dPi/du at fixed old
    * state (base.py:356-361), the gradient carries the second-order terms through the state history.  PlaneStress
-   * with a state model, the phased (sharded) calls and the op-level calls are refused for it. */
+   * with a state model (the root find then runs on the total stress at fixed old state, solid_mechanics.py:49-71) is
+   * defined under the EnergyLoss; under the residual losses, in the phased (sharded) calls and in the op-level calls
+   * a state model is refused. */
   int32_t n_prony;
   double  prony_moduli[PCX_MAX_PRONY];
   double  prony_times[PCX_MAX_PRONY];
