@@ -238,7 +238,7 @@ def make_shard_engines(case, n_shards, deterministic=True, scramble=False):
                      deterministic=deterministic)
         eng.set_ownership(n_uo, n_ro)
         props = [(p[0], p[1]) if isinstance(p, tuple) else p for p in case.props]
-        eng.set_physics("solid", case.model, case.formulation, props)
+        eng.set_physics("solid", case.model, case.formulation, props, prony=case.prony)
         a, b = tabulate_bc(bc, coords[nodes], case.times, case.ndof)
         eng.set_field(*case.mlp, bc_a=a, bc_b=b, x_min=coords.min(0), x_max=coords.max(0))   # GLOBAL bounds
         engines.append(eng)

@@ -277,3 +277,24 @@ def test_plane_stress_with_state(cuda_device, name, n, nt, deterministic):
     if gpo.size:
         assert rel(gp, gpo) < TOL, (gp, gpo)
     assert aux[3] == 0.0          # every root find converged
+
+
+@pytest.mark.parametrize("name,n,nt,shards", [("hex8_visco_neohookean", 4, 4, 2), ("quad4_visco_gent_bounded", 6, 3, 3),
+                                              ("quad4_visco_neohookean_pstress", 5, 3, 2)])
+def test_state_models_on_element_shards_sum_to_the_whole_mesh(cuda_device, name, n, nt, shards):
+    """SURVEY 8e for models with state: the viscous states belong to the quadrature points of a shard's own elements and
+    the field at a node is a pure function of (x, t, theta), so the path-dependent EnergyLoss needs no exchange -- the
+    shards' (loss, gradient, property gradient) add up to the whole-mesh values (what the packed allreduce does)."""
+    from tests.cases import make_shard_engines
+    case = make_case(name, n=n, nt=nt, width=12, depth=2)
+    L, aux, gw, gp = run_engine_loss(case, "energy", first_step=1)
+    engines, _ = make_shard_engines(case, shards, scramble=True)
+    Ls, gws, gps = 0.0, 0.0, 0.0
+    for eng in engines:
+        l, a, g, p = run_engine_loss(case, "energy", eng=eng, first_step=1)
+        Ls, gws, gps = Ls + l, gws + g, gps + p
+        eng.close()
+    assert abs(Ls - L) <= 1e-13 * abs(L)
+    assert rel(gws, gw) < 1e-12
+    if np.size(gp):
+        assert rel(gps, gp) < 1e-12
