@@ -86,7 +86,7 @@ struct pcx_handle {
   long long vz_per = 0;
   bool vz_filled = false;                   // a path-dependent call has written the state history
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
-                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; double* f33 = nullptr; } vstep;   // mode: k_visco_qp MODE
+                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; double* f33 = nullptr; const double* f33_prev = nullptr; } vstep;   // mode: k_visco_qp MODE
   double* vv = nullptr;                     // [nt][nn][ndof] v_t = dloss/df_t of every step (residual losses with state)
   double *vf33 = nullptr, *vscr = nullptr;   // PlaneStress with state: roots F_33 [nt][ne*nq]; MODE 5 scratch [ne*nq*n_prony*9]
   int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT: 1 = mma.sync kernel, 2 = tcgen05 contractions
@@ -1079,7 +1079,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
     a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
     a.wpsi = h->vstep.wpsi;
     a.f33_out = nullptr; a.f33_in = nullptr;
-    if (h->vstep.mode == 4) a.f33_out = h->vstep.f33;
+    if (h->vstep.mode == 4) { a.f33_out = h->vstep.f33; a.f33_in = h->vstep.f33_prev; }   // f33_in: start of the root find
     if (h->vstep.mode == 5) { a.f33_in = h->vstep.f33; a.vscr = h->vscr; }
     a.qbuf = h->vq;
     // the per-point sweep has its own grid: partials [vnblk] and [vnblk][PCX_MAX_PROPS]
@@ -1451,6 +1451,7 @@ static int visco_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const doub
     h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
     h->vstep.mode = resid ? 2 : pstress ? 4 : 0;
     h->vstep.f33 = pstress ? h->vf33 + (long long)n * h->ne * h->nq : nullptr;
+    h->vstep.f33_prev = (pstress && n > 1) ? h->vf33 + (long long)(n - 1) * h->ne * h->nq : nullptr;
     rc = sweep(h, false, 1, us_all + (long long)n * ndofs, nullptr, resid ? h->f : nullptr, 1.0, nullptr, 0.0, true, want_dp, resid, st);
     if (!rc) rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, h->scal + SC_PI(h) + n, 1, st);
     if (!rc && want_dp)

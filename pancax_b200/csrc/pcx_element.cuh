@@ -601,7 +601,8 @@ __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 
       }
     } else if constexpr (MODE == 4 && ND == 2) {
       const double* zo = A0.z_old + zq;
-      if (!plane_stress_visco_solve<MODEL>(F, props, A0.n_prony, zo, A0.prony_kappa, A0.prony_c)) bad = true;
+      const double x_prev = A0.f33_in ? A0.f33_in[t] - 1.0 : __longlong_as_double(0x7ff8000000000000LL);   // previous step's root
+      if (!plane_stress_visco_solve<MODEL>(F, props, A0.n_prony, zo, A0.prony_kappa, A0.prony_c, x_prev)) bad = true;
       if (A0.f33_out) A0.f33_out[t] = F[8];
       model_eval<MODEL, double>(F, props, W, P, dp, want_dp);
       for (int b = 0; b < A0.n_prony; b++) {

@@ -10,7 +10,7 @@ host-mirror API, in both adjoint modes (fp64 DMMA / TF32 tensor cores).  One JSO
 
   R3D 3D residual / reaction loss on Hex8 100^3 (NeoHookean / Swanson / Hencky): the stiffness-action sweep in 3D
 
-    python tools/bench_configs.py [--cases c2,c4,c5,visco,r3d,pstress] [--c5-n 50,100,159,252] [--steps 5]
+    python tools/bench_configs.py [--cases c2,c4,c5,visco,visco2d,r3d,pstress] [--c5-n 50,100,159,252] [--steps 5]
 
 Every (time step, node) row is evaluated (null-step culling off), deterministic assembly, CUDA events on the
 launching stream, inputs resident.  Not the bench.py contract: no e2e / CPU arm here."""
@@ -203,6 +203,26 @@ def visco(steps, device, n=64, nt=11):
             px.EnergyResidualAndReactionLoss(is_path_dependent=True), (), steps, evals)
 
 
+def visco_pstress(steps, device, n=512, nt=11):
+    """C2's mesh with SimpleFeFv under PlaneStress (per-point root find on the total stress at fixed old state) and plane
+    strain, path-dependent EnergyLoss."""
+    mesh = px.create_structured_mesh("quad4", (n, n), lengths=(1.0, 1.0))
+    times = np.linspace(0.0, 1.0, nt)
+    domain = px.VariationalDomain(mesh, times, q_order=2)
+    model = px.SimpleFeFv(px.NeoHookean(bulk_modulus=10.0, shear_modulus=0.855),
+                          px.PronySeries(moduli=[1.0], relaxation_times=[10.0]), px.WLF(C1=17.44, C2=51.6, theta_ref=60.0))
+    for form_name, form in (("plane strain", px.PlaneStrain()), ("plane stress", px.PlaneStress())):
+        physics = px.SolidMechanics(model, form)
+        bcs = [px.DirichletBC(component=c, nset_name=s) for s in ("nset_3", "nset_1") for c in range(2)]
+        problem = px.ForwardProblem(domain, physics, dirichlet_bcs=bcs)
+        params = px.Parameters(problem, key=0, n_layers=3, n_neurons=50, device=device,
+                               dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 2))
+        measure(f"visco 2D: Quad4 {n}^2 ({n * n * 4} qp) SimpleFeFv(NeoHookean, 1 Prony branch) {form_name}, nt={nt}, "
+                "path-dependent EnergyLoss, MLP 3->50x3->2", problem, params, px.EnergyLoss(is_path_dependent=True), (), steps,
+                n * n * 4 * (nt - 1))
+        problem._engines.clear()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="c2,c4,c5")
@@ -221,6 +241,8 @@ def main():
         c5(args.steps, device, [int(x) for x in args.c5_n.split(",")])
     if "visco" in cases:
         visco(args.steps, device)
+    if "visco2d" in cases:
+        visco_pstress(args.steps, device)
     if "r3d" in cases:
         r3d(args.steps, device)
     if "pstress" in cases:
