@@ -796,10 +796,12 @@ __device__ inline bool plane_stress_solve(double* F, const Props& pr) {
     else if (dg > 0.0 && xn >= hi && xn <= hi + slack) xn = hi;
     else if (!(xn > lo) || !(xn < hi) || !(dg > 0.0)) xn = 0.5 * (lo + hi);   // bisection step (rtsafe)
     const double dx = fabs(xn - x);
+    const bool newton = xn != 0.5 * (lo + hi);
     x = xn;
     // converged: step below 1e-15, or below 1e-13 and no longer contracting (a bisection step halves it) -- the quadratic phase has hit the rounding
-    // floor of P_33 (a few 1e-16 through the eigen decomposition of Hencky), where steps only jitter
-    if (dx < 1.0e-15 || (dx < 1.0e-13 && dx > 0.75 * dx_prev)) { ok = true; break; }
+    // floor of P_33 (a few 1e-16 through the eigen decomposition of Hencky), where steps only jitter; or (r2) an accepted
+    // Newton step below 3e-8, whose remaining error (g''/2g') dx^2 is below 1e-15: the confirming evaluation is not run
+    if ((newton && dx < 3.0e-8) || dx < 1.0e-15 || (dx < 1.0e-13 && dx > 0.75 * dx_prev)) { ok = true; break; }
     dx_prev = dx;
   }
   F[8] = 1.0 + x;
