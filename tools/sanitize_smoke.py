@@ -24,5 +24,11 @@ for name, n, nt, kind in (("hex8_neohookean", 7, 3, "energy"), ("quad4_neohookea
             ref = gw
         print(name, kind, "tf32_adjoint", mode, "loss", L, "grad rel", float(np.linalg.norm(gw - ref) / np.linalg.norm(ref)), flush=True)
     eng.close()
+# models with state: path-dependent energy / residual + reaction losses (k_visco_qp MODE 0-3), PlaneStress with state (MODE 4 / 5)
+for name, n, nt, kind in (("hex8_visco_neohookean", 3, 3, "energy"), ("hex8_visco_neohookean", 3, 3, "energy_residual_reaction"),
+                          ("quad4_visco_gent_bounded", 5, 3, "energy_residual"), ("quad4_visco_neohookean_pstress", 5, 3, "energy")):
+    case = make_case(name, n=n, nt=nt, width=16, depth=2)
+    L, aux, gw, gp = run_engine_loss(case, kind, first_step=1)
+    print(name, kind, "loss", L, "|grad|", float(np.linalg.norm(gw)), flush=True)
 torch.cuda.synchronize()
 print("done", flush=True)
