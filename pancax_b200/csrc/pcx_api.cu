@@ -1735,7 +1735,7 @@ static void jet_free(pcx_handle* h) {
 
 static int jet_alloc(pcx_handle* h, long long n) {
   const int S = h->nd + 3;
-  const long long per_row = ((long long)(2 * h->ms.depth + 1) * S * h->ms.NT * 8 + 2LL * S * h->ndof) * sizeof(double);
+  const long long per_row = ((long long)(2 * h->ms.depth) * S * h->ms.NT * 8 + 2LL * S * h->ndof) * sizeof(double);
   long long budget = 32LL << 30;   // of 180 GB HBM3e: 1 M points in 3D (24 KB of streams per point) stay in one chunk
   if (const char* e = getenv("PCX_JET_WORKSPACE_GB")) budget = (long long)(atof(e) * (1LL << 30));
   long long cap = budget / per_row;
@@ -1747,7 +1747,7 @@ static int jet_alloc(pcx_handle* h, long long n) {
   const long long PL = (long long)h->ms.NT * want * 8;
   CUDA_TRY(cudaMalloc(&h->jet_post, (size_t)h->ms.depth * S * PL * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->jet_pre, (size_t)h->ms.depth * S * PL * sizeof(double)));
-  CUDA_TRY(cudaMalloc(&h->jet_adj, (size_t)S * PL * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->jet_adj, (size_t)2 * h->sm_count * 8 * S * h->ms.NT * 64 * sizeof(double)));   // one slot per resident warp (2 CTAs x 8 warps per SM)
   CUDA_TRY(cudaMalloc(&h->jet_zjet, (size_t)want * S * h->ndof * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->jet_obar, (size_t)want * S * h->ndof * sizeof(double)));
   h->jet_rows_cap = want;

@@ -22,7 +22,8 @@
 //   POST[l][s]  post-activation streams of hidden layer l (inputs of layer l+1 / of the output layer)
 //   PRE[l][s]   forward: pre-activation streams W g_j, W q, W tau (s >= 1; s = 0 unused: s itself is POST[l][0])
 //               backward: overwritten in place by the adjoints zbar_s of the pre-activations (all s)
-//   ADJ[s]      adjoint of the post-activation streams of the layer being processed (scratch, S planes)
+//   ADJ         adjoint of the post-activation streams of the layer being processed: scratch, one
+//               [S][NT][8 rows][8 slots] slot per resident warp of k_jet_backward (L2-resident)
 // Adjoint of one layer (given hbar+, gbar_j+, qbar+, taubar+), s''' = -2 s' (s' - 2 s^2):
 //     zbar_q   = s' qbar+                     zbar_tau = s' taubar+
 //     zbar_g_j = s' gbar_j+ + 2 s'' (W g_j) qbar+
@@ -43,7 +44,7 @@ struct JetIO {
   long long rows_cap;     // plane row capacity
   double* post;           // POST planes: [depth][S] planes
   double* pre;            // PRE / ZBAR planes: [depth][S] planes
-  double* adj;            // ADJ planes: [S]
+  double* adj;            // ADJ scratch: [warps of k_jet_backward][S][NT][64]
   double* zjet;           // forward out: [n][S][n_out]   raw network jet (before the Dirichlet wrapper)
   const double* obar;     // backward in: [n][S][n_out]   adjoint of zjet
   const double* pk;       // packed weights
@@ -226,26 +227,42 @@ __global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__
     const long long row = g * 8 + r;
     const bool live = row < io.n;
     auto off = [&](int jn) { return ((long long)jn * io.rows_cap + row) * 8 + 2 * c; };
+    // PRE / POST planes stream through once (evict-first), the ADJ scratch is kept (L2 evict-last policy): without the
+    // hints the 9 GB of plane traffic pushed the scratch out of L2 between its write and its read half of the time
     auto ld2 = [&](const double* plane, int jn) {
-      return live ? *reinterpret_cast<const double2*>(plane + off(jn)) : make_double2(0.0, 0.0);
+      return live ? __ldcs(reinterpret_cast<const double2*>(plane + off(jn))) : make_double2(0.0, 0.0);
+    };
+    auto st2 = [&](double* plane, int jn, double a, double b) { __stcs(reinterpret_cast<double2*>(plane + off(jn)), make_double2(a, b)); };
+    // ADJ scratch (r2): one slot per RESIDENT warp, [stream][tile][8 rows][8 slots], reused for every group the warp
+    // walks -- 21.5 KB x 2 368 warps = 51 MB that stay in the 126 MB L2 instead of S planes over all rows written to and
+    // read back from HBM once per layer (ncu: the kernel moved 9.8 GB per 262 144 points at 5.5 TB/s, more than half of
+    // it this scratch).  Each lane only ever reads what it wrote itself.
+    double* const adjw = io.adj + warp_id * ((long long)S * NT * 64) + r * 8 + 2 * c;
+    auto adjp = [&](int st, int jn) { return adjw + ((long long)st * NT + jn) * 64; };
+    uint64_t keep;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    auto ldadj = [&](int st, int jn) {
+      double2 v = make_double2(0.0, 0.0);
+      if (live) asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(adjp(st, jn)), "l"(keep));
+      return v;
+    };
+    auto stadj = [&](int st, int jn, double a, double b) {
+      asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(adjp(st, jn)), "d"(a), "d"(b), "l"(keep) : "memory");
     };
     // ---- top: adjoint of the last hidden layer's post-activation streams  pbar_s = obar_s W_out
     for (int st = 0; st < S; st++) {
       double zA = 0.0;
       if (live && c < s.n_out) zA = io.obar[(row * S + st) * s.n_out + c];
-      double* dst = io.adj + (long long)st * PL;
 #pragma unroll
       for (int jn = 0; jn < NT; jn++) {
         double a0 = 0.0, a1 = 0.0;
         dmma(a0, a1, zA, wBO[jn * 32 + lane]);
-        if (live) *reinterpret_cast<double2*>(dst + off(jn)) = make_double2(a0, a1);
+        if (live) stadj(st, jn, a0, a1);
       }
     }
     for (int l = s.depth - 1; l >= 0; l--) {
       const double* postL = io.post + (long long)l * S * PL;
       double* preL = io.pre + (long long)l * S * PL;
-      const double* adjQ = io.adj + (long long)(nd + 1) * PL;
-      const double* adjT = io.adj + (long long)(nd + 2) * PL;
       double* preQ = preL + (long long)(nd + 1) * PL;
       double* preT = preL + (long long)(nd + 2) * PL;
       // The coupling between the streams is local to a (tile, slot): one 8-wide tile at a time, so that nothing but
@@ -253,12 +270,12 @@ __global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__
       // with exposed global-memory latency; per-tile scoping fits 128 registers = two CTAs per SM)
 #pragma unroll 1
       for (int jn = 0; jn < NT; jn++) {
-        const double2 s2 = ld2(postL, jn), q2 = ld2(adjQ, jn), h2 = ld2(io.adj, jn);
-        const double2 zq = ld2(preQ, jn), zt = ld2(preT, jn), tb = ld2(adjT, jn);
+        const double2 s2 = ld2(postL, jn), q2 = ldadj(nd + 1, jn), h2 = ldadj(0, jn);
+        const double2 zq = ld2(preQ, jn), zt = ld2(preT, jn), tb = ldadj(nd + 2, jn);
         double2 zg[3], gb[3];
 #pragma unroll
         for (int j = 0; j < 3; j++)
-          if (j < nd) { zg[j] = ld2(preL + (long long)(1 + j) * PL, jn); gb[j] = ld2(io.adj + (long long)(1 + j) * PL, jn); }
+          if (j < nd) { zg[j] = ld2(preL + (long long)(1 + j) * PL, jn); gb[j] = ldadj(1 + j, jn); }
         double oq[2], ot[2], zb[2], og[3][2];
 #pragma unroll
         for (int x = 0; x < 2; x++) {
@@ -281,12 +298,12 @@ __global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__
           zb[x] = fma(s3 * qx, sq, z0);
         }
         if (live) {
-          *reinterpret_cast<double2*>(preQ + off(jn)) = make_double2(oq[0], oq[1]);
-          *reinterpret_cast<double2*>(preT + off(jn)) = make_double2(ot[0], ot[1]);
+          st2(preQ, jn, oq[0], oq[1]);
+          st2(preT, jn, ot[0], ot[1]);
 #pragma unroll
           for (int j = 0; j < 3; j++)
-            if (j < nd) *reinterpret_cast<double2*>(preL + (long long)(1 + j) * PL + off(jn)) = make_double2(og[j][0], og[j][1]);
-          *reinterpret_cast<double2*>(preL + off(jn)) = make_double2(zb[0], zb[1]);
+            if (j < nd) st2(preL + (long long)(1 + j) * PL, jn, og[j][0], og[j][1]);
+          st2(preL, jn, zb[0], zb[1]);
         }
       }
       if (l == 0) break;
@@ -305,10 +322,9 @@ __global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__
         for (int ks = 0; ks < KS; ks++)
 #pragma unroll
           for (int jn = 0; jn < NT; jn++) dmma(dn[jn][0], dn[jn][1], dC[ks >> 1][ks & 1], bh[(ks * NT + jn) * 32 + lane]);
-        double* dst = io.adj + (long long)st * PL;
         if (live) {
 #pragma unroll
-          for (int jn = 0; jn < NT; jn++) *reinterpret_cast<double2*>(dst + off(jn)) = make_double2(dn[jn][0], dn[jn][1]);
+          for (int jn = 0; jn < NT; jn++) stadj(st, jn, dn[jn][0], dn[jn][1]);
         }
       }
     }

@@ -53,7 +53,7 @@ def main():
                       "frac": ach / pk.value, "bound": "tensor (FP64 DMMA)",
                       "note": "streams round-trip through global planes between layers; unfused weight-gradient contraction "
                               "per layer; r2: k_jet_backward's coupling stage scoped per 8-wide tile (128 registers, two CTAs "
-                              "per SM), 32 GB default jet workspace (1 M points in 3D = one chunk)"}))
+                              "per SM), ADJ scratch = one L2-resident slot per resident warp, 32 GB default jet workspace (1 M points in 3D = one chunk)"}))
     eng.close()
 
 
