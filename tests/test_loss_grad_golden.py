@@ -260,3 +260,20 @@ def test_cuda_matches_reference_visco_residual_losses(cuda_device, name, n, nt, 
     for det in (True, False):
         _check_visco_resid(run_engine_loss(case, kind, deterministic=det, first_step=1),
                            f"{name}_n{n}_nt{nt}_w{width}_d{depth}_q{q}", kind)
+
+
+# ---------------------------------------------------------------- PlaneStress with state: no golden (the reference's own
+# call does not finish on the stand-in) -- the oracle's gradient is checked against central differences of
+# its own loss, and the CUDA path against the oracle (tests/test_gpu_visco.py::test_plane_stress_with_state)
+@pytest.mark.parametrize("name", ["tri3_visco_gent_pstress_bounded", "quad4_visco_neohookean_pstress"])
+def test_oracle_plane_stress_with_state_gradient_is_consistent(name):
+    case = make_case(name, n=2, nt=3, width=8, depth=2)
+    L, aux, gw, gp = run_oracle_loss(case, "energy", first_step=1)
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal(gw.shape)
+    d /= np.linalg.norm(d)
+    h = 1e-6
+    Lp = run_oracle_loss(case, "energy", weights=case.weights + h * d, first_step=1)[0]
+    Lm = run_oracle_loss(case, "energy", weights=case.weights - h * d, first_step=1)[0]
+    fd = (Lp - Lm) / (2 * h)
+    assert abs(fd - gw @ d) <= 1e-6 * max(abs(fd), 1e-3), (fd, gw @ d)
