@@ -86,8 +86,10 @@ typedef struct {
   int64_t n_reaction;         /* len(global_data.reaction_nodes); 0 if unused                  */
   const double*  coords;      /* device, f64 [nn*nd] row-major (mesh.coords)                   */
   const int32_t* conns;       /* device, i32 [ne*nnpe] row-major, 0-based (mesh.conns)          */
-  const int64_t* unknown_idx; /* device, i64 [n_unknown], dof id = node*ndof+comp, or NULL      */
-  const int32_t* reaction_nodes; /* device, i32 [n_reaction], or NULL                          */
+  const int64_t* unknown_idx; /* device, i64 [n_unknown], dof id = node*ndof+comp, or NULL (residual losses unused).
+                                 A non-NULL pointer with n_unknown = 0 is the empty list: every dof constrained, R = 0
+                                 with a zero gradient (what jnp.linalg.norm of an empty slice gives)            */
+  const int32_t* reaction_nodes; /* device, i32 [n_reaction], or NULL; non-NULL with n_reaction = 0: reaction = 0 */
   int32_t nt;                 /* number of time steps (len(domain.times))                       */
   int32_t deterministic;      /* 1: node-centric fixed-order force assembly; 0: fp64 atomics    */
   const double* times;        /* HOST, f64 [nt]                                                 */

@@ -97,16 +97,20 @@ class Engine:
         with torch.cuda.device(dev):
             self.coords = torch.from_numpy(coords).to(dev)
             self.conns = torch.from_numpy(conns).to(dev)
-            self.unknown_idx = None if unknown_idx is None else \
-                torch.from_numpy(np.ascontiguousarray(unknown_idx, dtype=np.int64)).to(dev)
-            self.reaction_nodes = None if reaction_nodes is None else \
-                torch.from_numpy(np.ascontiguousarray(reaction_nodes, dtype=np.int32)).to(dev)
+            # an EMPTY index list is not a missing one (every dof constrained: R = 0; no reaction nodes: reaction = 0,
+            # as jnp.linalg.norm / jnp.sum of an empty slice give): the library gets a valid pointer and a zero count
+            def _dev(a, dt):
+                a = np.ascontiguousarray(a, dtype=dt)
+                return torch.from_numpy(a if a.size else np.zeros(1, dtype=dt)).to(dev)
+            self.n_unknown = 0 if unknown_idx is None else int(np.size(unknown_idx))
+            self.n_reaction = 0 if reaction_nodes is None else int(np.size(reaction_nodes))
+            self.unknown_idx = None if unknown_idx is None else _dev(unknown_idx, np.int64)
+            self.reaction_nodes = None if reaction_nodes is None else _dev(reaction_nodes, np.int32)
             md = MeshDesc()
             md.elem_type, md.q_order, md.ndof = ELEM[elem], self.q_order, self.ndof
             md.reaction_dof = int(reaction_dof)
             md.ne, md.nn = self.ne, self.nn
-            md.n_unknown = 0 if self.unknown_idx is None else self.unknown_idx.numel()
-            md.n_reaction = 0 if self.reaction_nodes is None else self.reaction_nodes.numel()
+            md.n_unknown, md.n_reaction = self.n_unknown, self.n_reaction
             md.coords, md.conns = self.coords.data_ptr(), self.conns.data_ptr()
             md.unknown_idx = None if self.unknown_idx is None else self.unknown_idx.data_ptr()
             md.reaction_nodes = None if self.reaction_nodes is None else self.reaction_nodes.data_ptr()

@@ -335,3 +335,40 @@ def test_null_step_culling_is_exact(cuda_device, name, kind):
     if p0.size:
         assert rel(p1, p0) < 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["hex8_neohookean", "quad4_neohookean", "tri3_neohookean_bounded"])
+@pytest.mark.parametrize("kind", ["energy", "energy_residual", "energy_residual_reaction"])
+def test_single_element_single_time_step_all_dofs_constrained(cuda_device, name, kind):
+    """Smallest inputs: ONE element, ONE time step.  Every node of a one-element mesh sits on a Dirichlet node set, so
+    unknownIndices is EMPTY (not missing): R = ||f[[]]|| = 0 with a zero gradient, as jnp.linalg.norm of an empty slice
+    gives; energy and reaction terms remain."""
+    case = make_case(name, n=1, nt=1, width=9, depth=1, t0=0.5)
+    assert case.unknown_idx.size == 0
+    L, aux, gw, gp = run_engine_loss(case, kind)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, kind)
+    assert abs(L - Lo) <= TOL * abs(Lo)
+    assert rel(gw, gwo) < TOL
+    if kind != "energy":
+        assert aux[1] == 0.0 and float(auxo["residual"]) == 0.0
+    if gpo.size:
+        assert rel(gp, gpo) < TOL
+
+
+def test_full_field_data_loss_single_row(cuda_device):
+    """A batch of ONE DIC row (ragged tail batches of a data loader)."""
+    import torch
+    from oracle import losses as ol
+    from tests.cases import oracle_problem
+    case = make_case("quad4_neohookean", n=3, nt=2, width=10, depth=2)
+    eng = make_engine(case)
+    inp, out = np.array([[0.3, 0.6, 0.5]]), np.array([[0.01, -0.02]])
+    from pancax_b200 import tabulate_bc
+    from tests.cases import engine_bc
+    bc = engine_bc(case)
+    a = bc(inp[:, :2], inp[:, 2], np.zeros((1, 2)))
+    b = bc(inp[:, :2], inp[:, 2], np.ones((1, 2))) - a
+    loss, gw = eng.field_data_loss_and_grad(torch.as_tensor(case.weights, device="cuda"), inp, out, a, b, weight=2.0)
+    Lo, gwo = ol.full_field_data_loss_and_grad(oracle_problem(case), case.weights, inp, out, weight=2.0)
+    assert abs(float(loss[0]) - Lo) <= TOL * abs(Lo) and rel(gw.cpu().numpy(), gwo) < TOL
+    eng.close()
