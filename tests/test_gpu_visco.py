@@ -298,3 +298,24 @@ def test_state_models_on_element_shards_sum_to_the_whole_mesh(cuda_device, name,
     assert rel(gws, gw) < 1e-12
     if np.size(gp):
         assert rel(gps, gp) < 1e-12
+
+
+@pytest.mark.parametrize("nb,kind", [(1, "energy"), (3, "energy_residual_reaction"), (20, "energy"), (20, "energy_residual")])
+def test_prony_series_lengths_and_two_time_steps(cuda_device, nb, kind):
+    """1, 3 (the reference's test_hyperviscoelastic.py fixture) and PCX_MAX_PRONY = 20 branches, nt = 2 (ONE active step of
+    the scan): forward / reverse sweeps loop over the branches, the state arrays scale with them."""
+    case = make_case("hex8_visco_neohookean", n=2, nt=2, width=10, depth=2)
+    rng = np.random.default_rng(nb)
+    case.prony = (list(rng.uniform(0.2, 2.0, nb)), list(10.0 ** rng.uniform(-1.0, 2.0, nb)))
+    L, aux, gw, gp = run_engine_loss(case, kind, first_step=1)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, kind, first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo), (L, Lo)
+    assert rel(gw, gwo) < TOL, rel(gw, gwo)
+
+
+def test_more_than_max_prony_branches_is_refused(cuda_device):
+    from pancax_b200._lib import PcxError
+    case = make_case("hex8_visco_neohookean", n=2, nt=2, width=10, depth=2)
+    case.prony = ([1.0] * 21, [1.0] * 21)
+    with pytest.raises((PcxError, ValueError, AssertionError, IndexError)):
+        make_engine(case)
