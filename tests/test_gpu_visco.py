@@ -319,3 +319,18 @@ def test_more_than_max_prony_branches_is_refused(cuda_device):
     case.prony = ([1.0] * 21, [1.0] * 21)
     with pytest.raises((PcxError, ValueError, AssertionError, IndexError)):
         make_engine(case)
+
+
+@pytest.mark.parametrize("name,q", [("hex8_visco_neohookean", 1), ("quad4_visco_gent", 1), ("quad4_visco_gent", 3), ("tri3_visco_neohookean", 1),
+                                    ("quad4_visco_neohookean_pstress", 3)])
+@pytest.mark.parametrize("kind", ["energy", "energy_residual_reaction"])
+def test_state_models_on_other_quadrature_orders(cuda_device, name, q, kind):
+    """Hex8 / Quad4 / Tri3 with 1 point and Quad4 with 9 points per element (quadrature_rules.py:109-245): the per-point
+    sweeps and the flux scatter take nq from the parent table."""
+    if "pstress" in name and kind != "energy":
+        pytest.skip("PlaneStress with state: EnergyLoss only")
+    case = make_case(name, n=3, nt=3, width=10, depth=2, q_order=q)
+    L, aux, gw, gp = run_engine_loss(case, kind, first_step=1)
+    Lo, auxo, gwo, gpo = run_oracle_loss(case, kind, first_step=1)
+    assert abs(L - Lo) <= TOL * abs(Lo), (L, Lo)
+    assert rel(gw, gwo) < TOL, rel(gw, gwo)
