@@ -334,6 +334,20 @@ class FullFieldDataLoss(BaseLossFunction):
     def _run(self, params, problem, inputs, outputs):
         eng = get_engine(problem, params)
         inputs = np.asarray(inputs, dtype=np.float64)
+        frac = 1.0
+        shard = getattr(problem, "shard", None)
+        if shard is not None and shard.plan.n_shards > 1:
+            # the batch rows are sharded over the ranks (rows rank, rank + R, ...); w * mean over the WHOLE batch
+            # = sum over ranks of (w n_r / N) * mean over the rank's rows, so the returned values are PARTIAL and add up in
+            # the packed allreduce like the weak-form losses (the field is a function of (x, t, theta): any rank can
+            # evaluate any row)
+            n_all = inputs.shape[0]
+            inputs = inputs[shard.plan.index::shard.plan.n_shards]
+            outputs = np.asarray(outputs, dtype=np.float64)[shard.plan.index::shard.plan.n_shards]
+            frac = inputs.shape[0] / n_all
+            if inputs.shape[0] == 0:
+                z = torch.zeros(1, dtype=torch.float64, device=params.fields.networks.weights.device)
+                return z, torch.zeros_like(params.fields.networks.weights), 0.0
         nd = problem.n_dims
         a = b = None
         bc = params.fields.dirichlet_bc_func
@@ -343,18 +357,19 @@ class FullFieldDataLoss(BaseLossFunction):
             z0 = np.zeros((inputs.shape[0], problem.n_dofs))
             a = g(xs, ts, z0)
             b = g(xs, ts, z0 + 1.0) - a
-        return eng.field_data_loss_and_grad(params.fields.networks.weights, inputs, outputs, a, b,
-                                            weight=self.weight)
+        loss, gw = eng.field_data_loss_and_grad(params.fields.networks.weights, inputs, outputs, a, b,
+                                                weight=self.weight * frac)
+        return loss, gw, frac
 
     def __call__(self, params, problem, inputs, outputs):
         if _TRACING[0]:
             (loss, aux), grads = self.value_and_grad(params, problem, inputs, outputs)
             return TracedLoss(loss, grads), aux
-        loss, _ = self._run(params, problem, inputs, outputs)
+        loss, _, _ = self._run(params, problem, inputs, outputs)
         return loss[0], {"field_data_loss": loss[0] / self.weight if self.weight else loss[0]}
 
     def value_and_grad(self, params, problem, inputs, outputs):
-        loss, gw = self._run(params, problem, inputs, outputs)
+        loss, gw, _ = self._run(params, problem, inputs, outputs)
         aux = {"field_data_loss": loss[0] / self.weight if self.weight else loss[0]}
         return (loss[0], aux), Grads(gw, torch.zeros_like(params.prop_raw))
 

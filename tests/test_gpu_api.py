@@ -201,6 +201,31 @@ def test_user_defined_loss_function_of_builtin_losses(cuda_device):
         px.UserDefinedLossFunction(lambda p, pr: (torch.zeros(()), {})).value_and_grad(params, prob)
 
 
+def test_full_field_data_loss_batch_rows_shard_over_ranks(cuda_device):
+    """FullFieldDataLoss on a sharded problem takes rows rank, rank + R, ... of the batch with the weight
+    scaled by n_r / N, so the ranks' partial (loss, gradient) ADD UP to the whole-batch values in the packed allreduce
+    (ranks faked here by swapping the shard descriptor; 5 ranks on 13 rows: ragged and short shards)."""
+    import torch
+    import pancax_b200 as px
+    from pancax_b200.parallel import ShardInfo, ShardPlan
+    prob, params = _build("quad4", n=5, nt=3, bounded=False, inverse=True)
+    rng = np.random.default_rng(2)
+    for nb, R in ((13, 5), (3, 4)):                      # the second: fewer rows than ranks (an empty shard)
+        inputs = np.column_stack([rng.uniform(0, 1, (nb, 2)), rng.choice(prob.times, nb)])
+        outputs = 0.05 * rng.standard_normal((nb, 2))
+        lf = px.FullFieldDataLoss(weight=7.0)
+        prob.shard = None
+        (L, _), g = lf.value_and_grad(params, prob, inputs, outputs)
+        Ls, gs = 0.0, 0.0
+        for r in range(R):
+            prob.shard = ShardInfo(ShardPlan(None, None, 0, None, R, r), None)
+            (l, _), gr = lf.value_and_grad(params, prob, inputs, outputs)
+            Ls, gs = Ls + float(l), gs + gr.fields
+        prob.shard = None
+        assert abs(Ls - float(L)) <= 1e-13 * abs(float(L))
+        assert float((gs - g.fields).norm() / g.fields.norm()) < 1e-12
+
+
 def test_trainer_reduces_energy_and_checkpoints(cuda_device, tmp_path):
     import pancax_b200 as px
     prob, params = _build("quad4", n=8, nt=2, t0=0.0)
