@@ -372,3 +372,30 @@ def test_full_field_data_loss_single_row(cuda_device):
     Lo, gwo = ol.full_field_data_loss_and_grad(oracle_problem(case), case.weights, inp, out, weight=2.0)
     assert abs(float(loss[0]) - Lo) <= TOL * abs(Lo) and rel(gw.cpu().numpy(), gwo) < TOL
     eng.close()
+
+
+@pytest.mark.parametrize("name,kind", [("quad4_neohookean", "energy_residual_reaction"), ("hex8_gent", "energy"),
+                                       ("hex8_visco_neohookean", "energy_residual")])
+def test_mlp_with_final_bias(cuda_device, name, kind):
+    """networks/mlp.py:61-79: ``use_final_bias=True`` (MLPBasis and user networks) -- one more leaf [.., Wout, bout] in the
+    equinox order; forward, adjoint and (TF32 mode) the bias gradient of the output layer."""
+    from oracle import losses as ol
+    from oracle.field import flatten_mlp, init_mlp
+    from tests.cases import LOSS_WEIGHTS
+    case = make_case(name, n=3, nt=3 if "visco" in name else 2, width=12, depth=2, t0=0.0 if "visco" in name else 0.3)
+    n_in, n_out, width, depth = case.mlp
+    w = flatten_mlp(init_mlp(n_in, n_out, width, depth, seed=3, use_final_bias=True))
+    assert w.size == case.weights.size + n_out
+    case.weights, case.mlp = w, (n_in, n_out, width, depth, True)
+    first = 1 if "visco" in name else 0
+    eng = make_engine(case)
+    op = oracle_problem(case)
+    op.mlp.use_final_bias = True
+    Lo, auxo, gwo, gpo = ol.loss_and_grad(op, dict(kind=kind, first_step=first, **LOSS_WEIGHTS), w, None)
+    for mode, tol in ((0, TOL), (1, 1e-5)):
+        eng.set_option("tf32_adjoint", mode)
+        loss, aux, gw, gp = eng.loss_and_grad(kind, w, None, global_outputs=case.global_outputs, first_step=first, **LOSS_WEIGHTS)
+        assert abs(float(loss[0]) - Lo) <= TOL * abs(Lo)
+        assert rel(gw.cpu().numpy(), gwo) < tol, (mode, rel(gw.cpu().numpy(), gwo))
+        assert rel(gw.cpu().numpy()[-n_out:], gwo[-n_out:]) < max(tol, 1e-5 if mode else TOL)      # the final-bias leaf
+    eng.close()
