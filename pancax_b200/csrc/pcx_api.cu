@@ -1843,19 +1843,20 @@ static int jet_launch(pcx_handle* h, int what, const JetIO& io, const JetWgradAr
   return fail(PCX_ERR_UNSUPPORTED, "MLP width %d not supported", h->ms.width);
 }
 
-static JetIO jet_io(pcx_handle* h, const double* pts, long long n) {
+// S: nd + 3 streams, or nd + 2 when the d/dt stream is not needed (workspaces are sized for nd + 3)
+static JetIO jet_io(pcx_handle* h, const double* pts, long long n, int S) {
   JetIO io;
   memset(&io, 0, sizeof(io));
   io.pts = pts; io.n = n; io.rows_cap = h->jet_rows_cap;
   io.post = h->jet_post; io.pre = h->jet_pre; io.adj = h->jet_adj; io.zjet = h->jet_zjet; io.obar = h->jet_obar;
-  io.pk = h->pk; io.S = h->nd + 3; io.nd = h->nd;
+  io.pk = h->pk; io.S = S; io.nd = h->nd;
   return io;
 }
 
-static JetPointArgs jet_point_args(pcx_handle* h, long long n, const double* tab, long long o) {
+static JetPointArgs jet_point_args(pcx_handle* h, long long n, const double* tab, long long o, int S) {
   JetPointArgs a;
   memset(&a, 0, sizeof(a));
-  a.zjet = h->jet_zjet; a.n = n; a.S = h->nd + 3; a.nd = h->nd; a.n_out = h->ndof;
+  a.zjet = h->jet_zjet; a.n = n; a.S = S; a.nd = h->nd; a.n_out = h->ndof;
   a.tab = tab ? tab + o * h->ndof * 2 * (h->nd + 3) : nullptr;
   return a;
 }
@@ -1870,9 +1871,10 @@ extern "C" int pcx_points_jet(pcx_handle* h, const double* weights, const double
   if ((rc = pack_weights(h, weights, st))) return rc;
   for (long long o = 0; o < n; o += h->jet_rows_cap) {
     const long long m = (n - o < h->jet_rows_cap) ? n - o : h->jet_rows_cap;
-    JetIO io = jet_io(h, pts + o * (h->nd + 1), m);
+    const int S = u_t ? h->nd + 3 : h->nd + 2;      // no d/dt stream when u_t is not asked for
+    JetIO io = jet_io(h, pts + o * (h->nd + 1), m, S);
     if ((rc = jet_launch(h, 0, io, nullptr, 0, st))) return rc;
-    JetPointArgs a = jet_point_args(h, m, tab, o);
+    JetPointArgs a = jet_point_args(h, m, tab, o, S);
     a.c_t = 0.0; a.c_lap = 0.0; a.scale = 0.0;
     a.u = u ? u + o * h->ndof : nullptr;
     a.grad_u = grad_u ? grad_u + o * h->ndof * h->nd : nullptr;
@@ -1896,7 +1898,8 @@ extern "C" int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weight
   const long long nchunks = (n + h->jet_rows_cap - 1) / h->jet_rows_cap;
   const int pgrid = 256;
   if ((rc = pack_weights(h, weights, st))) return rc;
-  const int S = h->nd + 3, NT = h->ms.NT, WPd = 8 * NT, DH = h->ms.depth - 1;
+  const int S = (c_t != 0.0) ? h->nd + 3 : h->nd + 2;   // Poisson (c_t = 0): the d/dt stream is not carried
+  const int NT = h->ms.NT, WPd = 8 * NT, DH = h->ms.depth - 1;
   const long long PL = (long long)NT * h->jet_rows_cap * 8;
   const double scale = weight / ((double)n * h->ndof);       // weight * mean over (points, dofs)
   bool first = true;
@@ -1904,9 +1907,9 @@ extern "C" int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weight
   for (long long o = 0; o < n; o += h->jet_rows_cap, chunk++) {
     const long long m = (n - o < h->jet_rows_cap) ? n - o : h->jet_rows_cap;
     const double* p = pts + o * (h->nd + 1);
-    JetIO io = jet_io(h, p, m);
+    JetIO io = jet_io(h, p, m, S);
     if ((rc = jet_launch(h, 0, io, nullptr, 0, st))) return rc;
-    JetPointArgs a = jet_point_args(h, m, tab, o);
+    JetPointArgs a = jet_point_args(h, m, tab, o, S);
     a.c_t = c_t; a.c_lap = c_lap; a.scale = scale;
     a.src = src ? src + o * h->ndof : nullptr;
     a.target = target ? target + o * h->ndof : nullptr;

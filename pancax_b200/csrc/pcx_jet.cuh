@@ -53,7 +53,8 @@ struct JetIO {
 
 __device__ __forceinline__ long long plane_elems(int NT, long long rows_cap) { return (long long)NT * rows_cap * 8; }
 
-// stream index helpers: 0 = value, 1..nd = d/dx_j, nd+1 = Laplacian, nd+2 = d/dt
+// stream index helpers: 0 = value, 1..nd = d/dx_j, nd+1 = Laplacian, nd+2 = d/dt.  S = nd + 3, or nd + 2 when the caller
+// needs no time derivative (Poisson: c_t = 0): the d/dt stream, a sixth of the work in 3D, is then not carried at all
 // ---------------------------------------------------------------------------------------------
 // Forward jet.  256 threads, grid-stride over groups of 8 points; forward fragments + exp2 table in smem.
 // ---------------------------------------------------------------------------------------------
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256, PCX_JET_FWD_MINB) k_jet_forward(const __g
       }
       // ---------------- derivative streams (order: g_0.., then tau, then q which needs sum_j (W g_j)^2)
       for (int pass = 1; pass < S; pass++) {
-        const int st = pass <= nd ? pass : (pass == nd + 1 ? nd + 2 : nd + 1);   // g_j..., tau, q
+        const int st = pass <= nd ? pass : (S == nd + 3 && pass == nd + 1 ? nd + 2 : nd + 1);   // g_j..., (tau,) q
         if (l == 0) {
           // inputs of layer 0: d x_hat_j / d x_j = 1 / x_scale_j, d t_hat / d t = 1 / t_scale, Laplacian stream 0
           double a = 0.0;
@@ -265,13 +266,15 @@ __global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__
       double* preL = io.pre + (long long)l * S * PL;
       double* preQ = preL + (long long)(nd + 1) * PL;
       double* preT = preL + (long long)(nd + 2) * PL;
+      const bool has_t = S == nd + 3;
       // The coupling between the streams is local to a (tile, slot): one 8-wide tile at a time, so that nothing but
       // the tile's own values is live here (r2: the arrays over all NT tiles kept the kernel at one 8-warp CTA per SM
       // with exposed global-memory latency; per-tile scoping fits 128 registers = two CTAs per SM)
 #pragma unroll 1
       for (int jn = 0; jn < NT; jn++) {
         const double2 s2 = ld2(postL, jn), q2 = ldadj(nd + 1, jn), h2 = ldadj(0, jn);
-        const double2 zq = ld2(preQ, jn), zt = ld2(preT, jn), tb = ldadj(nd + 2, jn);
+        const double2 zq = ld2(preQ, jn);
+        const double2 zt = has_t ? ld2(preT, jn) : make_double2(0.0, 0.0), tb = has_t ? ldadj(nd + 2, jn) : make_double2(0.0, 0.0);
         double2 zg[3], gb[3];
 #pragma unroll
         for (int j = 0; j < 3; j++)
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(256, 2) k_jet_backward(const __grid_constant__
         }
         if (live) {
           st2(preQ, jn, oq[0], oq[1]);
-          st2(preT, jn, ot[0], ot[1]);
+          if (has_t) st2(preT, jn, ot[0], ot[1]);
 #pragma unroll
           for (int j = 0; j < 3; j++)
             if (j < nd) st2(preL + (long long)(1 + j) * PL, jn, og[j][0], og[j][1]);
@@ -528,7 +531,8 @@ __global__ void __launch_bounds__(256) k_jet_point(const __grid_constant__ JetPo
     const long long row = k / A.n_out;
     const int i = (int)(k - row * A.n_out);
     const double* zj = A.zjet + row * S * A.n_out + i;     // stride n_out between streams
-    const double z = zj[0], lz = zj[(long long)(nd + 1) * A.n_out], zt = zj[(long long)(nd + 2) * A.n_out];
+    const bool has_t = S == nd + 3;
+    const double z = zj[0], lz = zj[(long long)(nd + 1) * A.n_out], zt = has_t ? zj[(long long)(nd + 2) * A.n_out] : 0.0;
     double a = 0.0, b = 1.0, la = 0.0, lb = 0.0, at = 0.0, bt = 0.0;
     double da[3] = {0.0, 0.0, 0.0}, db[3] = {0.0, 0.0, 0.0};
     if (A.tab) {
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(256) k_jet_point(const __grid_constant__ JetPo
       ob[0] = fma(lb, lapb, bt * utb);
       for (int j = 0; j < nd; j++) ob[(long long)(1 + j) * A.n_out] = 2.0 * db[j] * lapb;
       ob[(long long)(nd + 1) * A.n_out] = b * lapb;
-      ob[(long long)(nd + 2) * A.n_out] = b * utb;
+      if (has_t) ob[(long long)(nd + 2) * A.n_out] = b * utb;
     }
   }
   if (A.part) {

@@ -229,3 +229,25 @@ def test_strong_form_loss_through_the_public_api(cuda_device):
         params, st, loss = opt.step(params, st, problem)
         l0 = float(loss) if l0 is None else l0
     assert float(loss) < 0.5 * l0
+
+
+@pytest.mark.gpu
+def test_jet_without_the_time_stream_is_bit_identical(cuda_device):
+    """The d/dt stream is only carried when somebody asks for it (pcx_points_jet with u_t = NULL, strong-form losses with
+    c_t = 0: Poisson): u, grad u and the Laplacian -- and a Poisson-type loss with its gradient -- are bit-identical to the
+    six-stream evaluation with the time terms switched off by a zero coefficient downstream."""
+    import torch
+    from tests.cases import make_case, make_engine
+    case = make_case("poisson_hex8", n=3, nt=2, width=20, depth=3)
+    eng = make_engine(case)
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(0.05, 0.95, (777, 4))
+    w = torch.as_tensor(case.weights, device=eng.device)
+    u6, g6, l6, _ = eng.points_jet(w, pts)
+    u5, g5, l5, none = eng.points_jet(w, pts, want=("u", "grad_u", "lap_u"))
+    assert none is None and torch.equal(u5, u6) and torch.equal(g5, g6) and torch.equal(l5, l6)
+    # loss: c_t = 0 drops the stream; a denormal-small c_t keeps it with no measurable contribution
+    L5, _, gw5 = eng.strong_form_loss_and_grad(w, pts, 0.0, 0.7, 2.0)
+    L6, _, gw6 = eng.strong_form_loss_and_grad(w, pts, 1e-300, 0.7, 2.0)
+    assert float(L5[0]) == float(L6[0]) and float((gw5 - gw6).norm()) <= 1e-15 * float(gw6.norm())
+    eng.close()

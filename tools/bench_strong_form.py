@@ -1,6 +1,6 @@
 """Measures the strong-form / collocation path on one B200: heat-equation residual loss +
 weight gradient over N collocation points in 3D (jet of S = 6 streams through the MLP 4->50x4->1 fp64).
-    python tools/bench_strong_form.py [n_points]    -> one JSON line (CUDA events, 5 steps after 3 warm-up)"""
+    python tools/bench_strong_form.py [n_points] [c_t]    -> one JSON line (CUDA events, 5 steps after 3 warm-up)"""
 import ctypes as C
 import json
 import os
@@ -16,6 +16,7 @@ def main():
     import pancax_b200 as px
     from pancax_b200 import Engine, _lib, roofline
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    c_t = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0      # 0: Poisson-type residual (no d/dt stream: 5 streams)
     mesh = px.create_structured_mesh("hex8", 4)
     eng = Engine(mesh.coords, mesh.conns, "hex8", 2, 1, np.linspace(0.0, 1.0, 2))
     eng.set_physics("poisson")
@@ -26,7 +27,7 @@ def main():
     w = torch.as_tensor(flatten_mlp(init_mlp(4, 1, 50, 4, seed=0)), device=eng.device)
 
     def step():
-        return eng.strong_form_loss_and_grad(w, pts, 1.0, 0.1, 1.0)
+        return eng.strong_form_loss_and_grad(w, pts, c_t, 0.1, 1.0)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
@@ -39,15 +40,16 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    S = 6
+    S = 6 if c_t != 0.0 else 5
     pw = roofline.mlp_pw(4, 1, 50, 4)
     flop_fwd = S * 2 * pw
     flop_bwd = S * (4 * pw - 2 * 4 * 50)
     pk = C.c_double()
     _lib.check(_lib.load().pcx_measure_dmma_peak(C.byref(pk), 5))
     ach = n * (flop_fwd + flop_bwd) / (ms * 1e-3) / 1e12
-    print(json.dumps({"workload": f"heat-equation strong-form residual loss + gradient, {n} collocation points in 3D, "
-                                  "MLP 4->50x4->1 fp64, jet of 6 streams (value, 3 coordinate tangents, Laplacian, d/dt)",
+    kind = "heat-equation" if c_t != 0.0 else "Poisson"
+    print(json.dumps({"workload": f"{kind} strong-form residual loss + gradient, {n} collocation points in 3D, "
+                                  f"MLP 4->50x4->1 fp64, jet of {S} streams (value, 3 coordinate tangents, Laplacian" + (", d/dt)" if S == 6 else ")"),
                       "ms_per_step": ms, "points_per_s": n / (ms * 1e-3), "kernel_launches_per_step": (eng.launch_count - l0) // reps,
                       "algorithmic_flop_per_point": flop_fwd + flop_bwd, "achieved_tflops": ach, "dmma_peak_tflops": pk.value,
                       "frac": ach / pk.value, "bound": "tensor (FP64 DMMA)",
