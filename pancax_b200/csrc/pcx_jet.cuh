@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, PCX_JET_FWD_MINB) k_jet_forward(const __g
             else o[x] = s1 * fma(-2.0 * sx, sq[jn][x], z);        // s' z + s'' sumsq, s'' = -2 s s'
           }
           if (live) {
-            *reinterpret_cast<double2*>(preS + off(jn)) = make_double2(acc[jn][0], acc[jn][1]);
+            __stcs(reinterpret_cast<double2*>(preS + off(jn)), make_double2(acc[jn][0], acc[jn][1]));   // read next by the adjoint only: streamed
             *reinterpret_cast<double2*>(postS + off(jn)) = make_double2(o[0], o[1]);
           }
         }
