@@ -1819,14 +1819,21 @@ static int jet_launch_nt(pcx_handle* h, int what, const JetIO& io, const JetWgra
       k_jet_backward<NT, 0><<<(int)blocks, 256, smem, st>>>(h->ms, io);
     }
   } else {
-    const size_t smem = (size_t)4 * 8 * (NT + 1) * 64 * sizeof(double);
     const int grid = h->bwd_grid;
 #define PCX_WG(M)                                                                                                       \
   do {                                                                                                                  \
+    const size_t smem = jet_wgrad_smem<NT, M>();                                                                        \
     CUDA_TRY(cudaFuncSetAttribute(k_jet_wgrad<NT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     k_jet_wgrad<NT, M><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, *wa);                                                   \
   } while (0)
-    if (mode == 0) PCX_WG(0); else if (mode == 1) PCX_WG(1); else PCX_WG(2);
+    if (mode == 0) PCX_WG(0);
+    else if (mode == 1) PCX_WG(1);
+    else if (mode == 2) PCX_WG(2);
+    else {   // mode 3: layer 0 (wa[0], MODE 2) and the output layer (wa[1], MODE 1) side by side in one launch
+      const size_t smem = jet_wgrad_smem<NT, 1>() > jet_wgrad_smem<NT, 2>() ? jet_wgrad_smem<NT, 1>() : jet_wgrad_smem<NT, 2>();
+      CUDA_TRY(cudaFuncSetAttribute(k_jet_wgrad_io<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_jet_wgrad_io<NT><<<dim3(grid, 2), 32 * (NT + 1), smem, st>>>(h->ms, wa[0], wa[1]);
+    }
 #undef PCX_WG
   }
   LAUNCH_CHECK(h);
@@ -1924,18 +1931,18 @@ extern "C" int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weight
     memset(&wa, 0, sizeof(wa));
     wa.n = m; wa.rows_cap = h->jet_rows_cap; wa.S = S; wa.nd = h->nd; wa.n_out = h->ndof; wa.n_in = h->ms.n_in;
     wa.ones_slot = feat_to_slot(h->ms.width); wa.part = h->part; wa.part_stride = h->part_stride; wa.pts = p;
-    // layer 0
-    wa.Z = h->jet_pre; wa.P = nullptr; wa.sec_off = 0;
-    if ((rc = jet_launch(h, 2, io, &wa, 2, st))) return rc;
+    // layer 0 and the output layer: one launch, two CTAs per SM (k_jet_wgrad_io)
+    JetWgradArgs wio[2] = {wa, wa};
+    wio[0].Z = h->jet_pre; wio[0].P = nullptr; wio[0].sec_off = 0;
+    wio[1].Z = h->jet_obar; wio[1].P = h->jet_post + (long long)DH * S * PL;
+    wio[1].sec_off = (long long)WPd * 8 + (long long)DH * WPd * WPd;
+    if ((rc = jet_launch(h, 2, io, wio, 3, st))) return rc;
     for (int l = 1; l <= DH; l++) {
       wa.Z = h->jet_pre + (long long)l * S * PL;
       wa.P = h->jet_post + (long long)(l - 1) * S * PL;
       wa.sec_off = (long long)WPd * 8 + (long long)(l - 1) * WPd * WPd;
       if ((rc = jet_launch(h, 2, io, &wa, 0, st))) return rc;
     }
-    wa.Z = h->jet_obar; wa.P = h->jet_post + (long long)DH * S * PL;
-    wa.sec_off = (long long)WPd * 8 + (long long)DH * WPd * WPd;
-    if ((rc = jet_launch(h, 2, io, &wa, 1, st))) return rc;
     if ((rc = reduce_wgrad(h, h->bwd_grid, first ? g_weights : h->gtmp, st))) return rc;
     if (!first) {
       const int thr = 256;

@@ -356,12 +356,19 @@ struct JetWgradArgs {
   long long sec_off;      // offset of this layer's section inside a record
 };
 
+// tile row strides: 64 doubles for a full plane tile; the 8-column operands (MODE 1: Z = obar, MODE 2: P = input vector)
+// take 16 (columns 0..7 XOR the swizzle {0, 4, 8, 12}), which lets two of those CTAs share an SM (k_jet_wgrad_io)
+template <int MODE> __host__ __device__ constexpr int jet_wgrad_sz() { return MODE == 1 ? 16 : 64; }
+template <int MODE> __host__ __device__ constexpr int jet_wgrad_sp() { return MODE == 2 ? 16 : 64; }
+template <int NT, int MODE> __host__ __device__ constexpr size_t jet_wgrad_smem() {
+  return (size_t)2 * 8 * (NT + 1) * (jet_wgrad_sz<MODE>() + jet_wgrad_sp<MODE>()) * sizeof(double);
+}
+
 template <int NT, int MODE>
-__global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_constant__ MlpShape s, const __grid_constant__ JetWgradArgs A) {
-  constexpr int NW = NT + 1, ROWS = 8 * NW, SS = 64, KR = ROWS / 4;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* Zt = reinterpret_cast<double*>(smem_raw);            // [2][ROWS*SS]
-  double* Pt = Zt + 2 * ROWS * SS;                             // [2][ROWS*SS]
+__device__ __forceinline__ void jet_wgrad_body(const MlpShape& s, const JetWgradArgs& A, unsigned char* smem_raw) {
+  constexpr int NW = NT + 1, ROWS = 8 * NW, SZ = jet_wgrad_sz<MODE>(), SP = jet_wgrad_sp<MODE>(), KR = ROWS / 4;
+  double* Zt = reinterpret_cast<double*>(smem_raw);            // [2][ROWS*SZ]
+  double* Pt = Zt + 2 * ROWS * SZ;                             // [2][ROWS*SP]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, c = lane & 3;
   const int lrow = warp * 8 + r;
@@ -382,19 +389,19 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_con
     const long long row = tile * ROWS + lrow;
     const bool ok = w < nwork && row < A.n;
     const long long rr = ok ? row : 0;
-    double* zt = Zt + buf * ROWS * SS;
-    double* pt = Pt + buf * ROWS * SS;
+    double* zt = Zt + buf * ROWS * SZ;
+    double* pt = Pt + buf * ROWS * SP;
     if constexpr (MODE != 1) {
       const double* zp = A.Z + (long long)st * PL;
 #pragma unroll
       for (int jn = 0; jn < NT; jn++)
-        cp_async16(&zt[lrow * SS + ((8 * jn + 2 * c) ^ gl)], zp + ((long long)jn * A.rows_cap + rr) * 8 + 2 * c, ok);
+        cp_async16(&zt[lrow * SZ + ((8 * jn + 2 * c) ^ gl)], zp + ((long long)jn * A.rows_cap + rr) * 8 + 2 * c, ok);
     }
     if constexpr (MODE != 2) {
       const double* pp = A.P + (long long)st * PL;
 #pragma unroll
       for (int jn = 0; jn < NT; jn++)
-        cp_async16(&pt[lrow * SS + ((8 * jn + 2 * c) ^ gl)], pp + ((long long)jn * A.rows_cap + rr) * 8 + 2 * c, ok);
+        cp_async16(&pt[lrow * SP + ((8 * jn + 2 * c) ^ gl)], pp + ((long long)jn * A.rows_cap + rr) * 8 + 2 * c, ok);
     }
     cp_async_commit();
     if constexpr (MODE == 1) {        // Z tile columns 0..7 = obar[row][st][o]
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_con
         if (2 * c < A.n_out) v0 = A.Z[(row * A.S + st) * A.n_out + 2 * c];
         if (2 * c + 1 < A.n_out) v1 = A.Z[(row * A.S + st) * A.n_out + 2 * c + 1];
       }
-      *reinterpret_cast<double2*>(&zt[lrow * SS + ((2 * c) ^ gl)]) = make_double2(v0, v1);
+      *reinterpret_cast<double2*>(&zt[lrow * SZ + ((2 * c) ^ gl)]) = make_double2(v0, v1);
     }
     if constexpr (MODE == 2) {        // P tile columns 0..7 = input vector of stream st
       double v0 = 0.0, v1 = 0.0;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_con
         }
         if (x == 0) v0 = v; else v1 = v;
       }
-      *reinterpret_cast<double2*>(&pt[lrow * SS + ((2 * c) ^ gl)]) = make_double2(v0, v1);
+      *reinterpret_cast<double2*>(&pt[lrow * SP + ((2 * c) ^ gl)]) = make_double2(v0, v1);
     }
   };
 
@@ -435,38 +442,38 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_con
     const long long tile = w - (long long)st * ntiles;
     const bool live = tile * ROWS + lrow < A.n;
     cp_async_wait_all();
-    double* zt = Zt + buf * ROWS * SS;
-    double* pt = Pt + buf * ROWS * SS;
-    if (MODE != 2 && st == 0 && live && c == ((A.ones_slot & 7) >> 1)) pt[lrow * SS + (A.ones_slot ^ gl)] = 1.0;
+    double* zt = Zt + buf * ROWS * SZ;
+    double* pt = Pt + buf * ROWS * SP;
+    if (MODE != 2 && st == 0 && live && c == ((A.ones_slot & 7) >> 1)) pt[lrow * SP + (A.ones_slot ^ gl)] = 1.0;
     __syncthreads();          // tile `buf` complete; everybody is done reading tile `buf^1`
     load(w + gridDim.x, buf ^ 1);
     if constexpr (MODE == 0) {
       if (warp < NT) {
 #pragma unroll 4
         for (int ks = 0; ks < KR; ks++) {
-          const double a = zt[(4 * ks + c) * SS + ((8 * warp + r) ^ gc)];
+          const double a = zt[(4 * ks + c) * SZ + ((8 * warp + r) ^ gc)];
 #pragma unroll
-          for (int jc = 0; jc < NT - 1; jc++) dmma(acc[jc][0], acc[jc][1], a, pt[(4 * ks + c) * SS + ((8 * jc + r) ^ gc)]);
+          for (int jc = 0; jc < NT - 1; jc++) dmma(acc[jc][0], acc[jc][1], a, pt[(4 * ks + c) * SP + ((8 * jc + r) ^ gc)]);
         }
       } else {
 #pragma unroll 4
         for (int ks = 0; ks < KR; ks++) {
-          const double b = pt[(4 * ks + c) * SS + ((8 * (NT - 1) + r) ^ gc)];
+          const double b = pt[(4 * ks + c) * SP + ((8 * (NT - 1) + r) ^ gc)];
 #pragma unroll
-          for (int jr = 0; jr < NT; jr++) dmma(acc[jr][0], acc[jr][1], zt[(4 * ks + c) * SS + ((8 * jr + r) ^ gc)], b);
+          for (int jr = 0; jr < NT; jr++) dmma(acc[jr][0], acc[jr][1], zt[(4 * ks + c) * SZ + ((8 * jr + r) ^ gc)], b);
         }
       }
     } else if constexpr (MODE == 1) {
       if (warp < NT) {
 #pragma unroll 4
         for (int ks = 0; ks < KR; ks++)
-          dmma(acc[0][0], acc[0][1], zt[(4 * ks + c) * SS + (r ^ gc)], pt[(4 * ks + c) * SS + ((8 * warp + r) ^ gc)]);
+          dmma(acc[0][0], acc[0][1], zt[(4 * ks + c) * SZ + (r ^ gc)], pt[(4 * ks + c) * SP + ((8 * warp + r) ^ gc)]);
       }
     } else {
       if (warp < NT) {
 #pragma unroll 4
         for (int ks = 0; ks < KR; ks++)
-          dmma(acc[0][0], acc[0][1], zt[(4 * ks + c) * SS + ((8 * warp + r) ^ gc)], pt[(4 * ks + c) * SS + (r ^ gc)]);
+          dmma(acc[0][0], acc[0][1], zt[(4 * ks + c) * SZ + ((8 * warp + r) ^ gc)], pt[(4 * ks + c) * SP + (r ^ gc)]);
       }
     }
   }
@@ -498,6 +505,23 @@ __global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_con
       P[(8 * warp + r) * 8 + 2 * c + 1] = acc[0][1];
     }
   }
+}
+
+template <int NT, int MODE>
+__global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_constant__ MlpShape s, const __grid_constant__ JetWgradArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  jet_wgrad_body<NT, MODE>(s, A, smem_raw);
+}
+
+// Layer 0 (MODE 2, blockIdx.y = 0) and the output layer (MODE 1, blockIdx.y = 1) in ONE launch: both are small contractions
+// that stream whole planes for a handful of DMMAs (ncu r2: 19 % / 15 % DMMA, 8 warps per SM, 0.21 + 0.27 ms back to back
+// at 262 144 points); with their narrow operand tiles they fit two to an SM and run side by side.
+template <int NT>
+__global__ void __launch_bounds__(32 * (NT + 1), 2) k_jet_wgrad_io(const __grid_constant__ MlpShape s, const __grid_constant__ JetWgradArgs A2,
+                                                                   const __grid_constant__ JetWgradArgs A1) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (blockIdx.y == 0) jet_wgrad_body<NT, 2>(s, A2, smem_raw);
+  else jet_wgrad_body<NT, 1>(s, A1, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
