@@ -1798,10 +1798,10 @@ static int jet_launch_nt(pcx_handle* h, int what, const JetIO& io, const JetWgra
     }
     if (kodd) {
       CUDA_TRY(cudaFuncSetAttribute(k_jet_forward<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      k_jet_forward<NT, 1><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+      k_jet_forward<NT, 1><<<(int)blocks, PCX_JET_FWD_THREADS, smem, st>>>(h->ms, io);
     } else {
       CUDA_TRY(cudaFuncSetAttribute(k_jet_forward<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      k_jet_forward<NT, 0><<<(int)blocks, 256, smem, st>>>(h->ms, io);
+      k_jet_forward<NT, 0><<<(int)blocks, PCX_JET_FWD_THREADS, smem, st>>>(h->ms, io);
     }
   } else if (what == 1) {
     const size_t smem = (size_t)(h->ms.npacked - h->ms.pBO) * sizeof(double);

@@ -58,11 +58,14 @@ __device__ __forceinline__ long long plane_elems(int NT, long long rows_cap) { r
 // ---------------------------------------------------------------------------------------------
 // Forward jet.  256 threads, grid-stride over groups of 8 points; forward fragments + exp2 table in smem.
 // ---------------------------------------------------------------------------------------------
+#ifndef PCX_JET_FWD_THREADS
+#define PCX_JET_FWD_THREADS 256   // measured: 384 threads (12 warps per SM, 168 registers, no spills) is neutral -- 18.5 vs 18.4 ms per 1 M points
+#endif
 #ifndef PCX_JET_FWD_MINB
 #define PCX_JET_FWD_MINB 1     // measured: 2 CTAs per SM (128 registers, 88 B of spills) 21.6 ms per 1 M points against 20.0 ms
 #endif
 template <int NT, int KODD>
-__global__ void __launch_bounds__(256, PCX_JET_FWD_MINB) k_jet_forward(const __grid_constant__ MlpShape s, const __grid_constant__ JetIO io) {
+__global__ void __launch_bounds__(PCX_JET_FWD_THREADS, PCX_JET_FWD_MINB) k_jet_forward(const __grid_constant__ MlpShape s, const __grid_constant__ JetIO io) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t wbar;
   double* sw = reinterpret_cast<double*>(smem_raw);

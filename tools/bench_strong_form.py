@@ -23,8 +23,15 @@ def main():
     eng.set_field(4, 1, 50, 4)
     rng = np.random.default_rng(0)
     pts = torch.as_tensor(rng.uniform(0.0, 1.0, (n, 4)), device=eng.device)
-    from oracle.field import flatten_mlp, init_mlp
-    w = torch.as_tensor(flatten_mlp(init_mlp(4, 1, 50, 4, seed=0)), device=eng.device)
+    # weights U(+-1/sqrt(fan_in)) in equinox leaf order [W0, b0, ..., Wout] (no final bias)
+    sizes = [4, 50, 50, 50, 50, 1]
+    leaves = []
+    for i in range(len(sizes) - 1):
+        lim = 1.0 / np.sqrt(sizes[i])
+        leaves.append(rng.uniform(-lim, lim, sizes[i + 1] * sizes[i]))
+        if i < len(sizes) - 2:
+            leaves.append(rng.uniform(-lim, lim, sizes[i + 1]))
+    w = torch.as_tensor(np.concatenate(leaves), device=eng.device)
 
     def step():
         return eng.strong_form_loss_and_grad(w, pts, c_t, 0.1, 1.0)
