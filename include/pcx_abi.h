@@ -320,7 +320,8 @@ int pcx_field_data_loss_and_grad(pcx_handle* h, const double* weights, const dou
  * (forward-mode coordinate tangents through the MLP on the FP64 tensor pipe).
  *   pts [n*(nd+1)] rows (x..., t); tab [n*ndof*2*(nd+3)] or NULL: the Dirichlet wrapper u = a + b z (fields.py:101)
  *   and its derivatives at the points, per (point, dof): (a, d_j a.., lap a, a_t, b, d_j b.., lap b, b_t); NULL = identity.
- *   Outputs (any may be NULL): u [n*ndof], grad_u [n*ndof*nd], lap_u [n*ndof], u_t [n*ndof]. */
+ *   Outputs (any may be NULL): u [n*ndof], grad_u [n*ndof*nd], lap_u [n*ndof], u_t [n*ndof].  The d/dt stream (one of
+ *   nd + 3) is carried only when u_t is asked for; the other outputs are bit-identical either way. */
 int pcx_points_jet(pcx_handle* h, const double* weights, const double* pts, const double* tab, int64_t n,
                    double* u, double* grad_u, double* lap_u, double* u_t, void* stream);
 
@@ -330,7 +331,7 @@ int pcx_points_jet(pcx_handle* h, const double* weights, const double* pts, cons
  * StrongFormResidualLoss (strong_form_loss_functions.py:8-27) when every time step carries the same points;
  * `target` is the collocation example's `outputs` (NULL = 0).  src / target [n*ndof] or NULL.
  *   loss_out: device scalar; resid_out [n*ndof] (r before the target is subtracted) or NULL; g_weights
- *   [pcx_num_weights] or NULL (value only). */
+ *   [pcx_num_weights] or NULL (value only).  c_t == 0 (no time term in the residual): the d/dt stream is not carried. */
 int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weights, const double* pts, const double* tab,
                                   const double* src, const double* target, int64_t n, double c_t, double c_lap,
                                   double weight, double* loss_out, double* resid_out, double* g_weights, void* stream);
