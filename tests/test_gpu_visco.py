@@ -334,3 +334,14 @@ def test_state_models_on_other_quadrature_orders(cuda_device, name, q, kind):
     Lo, auxo, gwo, gpo = run_oracle_loss(case, kind, first_step=1)
     assert abs(L - Lo) <= TOL * abs(Lo), (L, Lo)
     assert rel(gw, gwo) < TOL, rel(gw, gwo)
+
+
+@pytest.mark.parametrize("name,kind", [("hex8_visco_neohookean", "energy_residual_reaction"), ("quad4_visco_gent_bounded", "energy_residual"),
+                                       ("quad4_visco_neohookean_pstress", "energy")])
+def test_state_model_losses_repeat_bitwise(cuda_device, name, kind):
+    """Deterministic assembly: two evaluations of the same step (fresh engines) agree bit for bit -- fixed-order block
+    partials, CSR assembly of the point fluxes, fixed-order weight-gradient reduction."""
+    case = make_case(name, n=4, nt=4, width=16, depth=2)
+    a = run_engine_loss(case, kind, first_step=1)
+    b = run_engine_loss(case, kind, first_step=1)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
