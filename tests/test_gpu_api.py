@@ -416,6 +416,8 @@ def test_post_processor_writes_reference_layout(cuda_device, tmp_path):
     ("quad4_neohookean", "energy_residual_reaction", 0),
     ("quad4_neohookean_pstress", "energy_residual_reaction", 0),     # PlaneStress: root workspace sized at set-up
     ("hex8_visco_neohookean", "energy", 1),                          # SimpleFeFv: state history sized at set-up
+    ("hex8_visco_neohookean", "energy_residual_reaction", 1),        # ... with the per-step v_t buffers of the residual losses
+    ("quad4_visco_neohookean_pstress", "energy", 1),                 # ... and the per-step roots / scratch of PlaneStress with state
     ("hex8_neohookean", "energy_residual_reaction", 0),
 ])
 def test_loss_and_grad_is_cuda_graph_capturable(cuda_device, name, kind, first_step):
