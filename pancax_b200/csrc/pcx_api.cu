@@ -699,7 +699,7 @@ static int alloc_ws(pcx_handle* h) {
   CUDA_TRY(cudaMalloc(&h->pk, s.npacked * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->pk32, tf32_pack_floats(s.NT, s.depth) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&h->act, act_per_row * h->rows_cap));
-  CUDA_TRY(cudaMalloc(&h->part, h->part_stride * h->bwd_grid * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->part, 2 * h->part_stride * h->bwd_grid * sizeof(double)));   // 2x: the jet contractions run two CTAs per SM
   CUDA_TRY(cudaMalloc(&h->us, h->rows_cap * h->ndof * sizeof(double)));   // rows_cap >= T*nn
   CUDA_TRY(cudaMalloc(&h->f, T * ndofs * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->v, T * ndofs * sizeof(double)));
@@ -1819,14 +1819,20 @@ static int jet_launch_nt(pcx_handle* h, int what, const JetIO& io, const JetWgra
       k_jet_backward<NT, 0><<<(int)blocks, 256, smem, st>>>(h->ms, io);
     }
   } else {
-    const int grid = h->bwd_grid;
+    // every jet contraction launch writes 2 * bwd_grid partial records (two CTAs per SM); k_reduce_wgrad sums them all
+    const int grid = 2 * h->bwd_grid;
 #define PCX_WG(M)                                                                                                       \
   do {                                                                                                                  \
     const size_t smem = jet_wgrad_smem<NT, M>();                                                                        \
     CUDA_TRY(cudaFuncSetAttribute(k_jet_wgrad<NT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     k_jet_wgrad<NT, M><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, *wa);                                                   \
   } while (0)
-    if (mode == 0) PCX_WG(0);
+    if (mode == 0) {
+      constexpr int NB = PCX_JET_WGRAD_HIDDEN_NBUF;
+      const size_t smem = jet_wgrad_smem<NT, 0, NB>();
+      CUDA_TRY(cudaFuncSetAttribute(k_jet_wgrad<NT, 0, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_jet_wgrad<NT, 0, NB><<<grid, 32 * (NT + 1), smem, st>>>(h->ms, *wa);
+    }
     else if (mode == 1) PCX_WG(1);
     else if (mode == 2) PCX_WG(2);
     else {   // mode 3: layer 0 (wa[0], MODE 2) and the output layer (wa[1], MODE 1) side by side in one launch
@@ -1943,7 +1949,7 @@ extern "C" int pcx_strong_form_loss_and_grad(pcx_handle* h, const double* weight
       wa.sec_off = (long long)WPd * 8 + (long long)(l - 1) * WPd * WPd;
       if ((rc = jet_launch(h, 2, io, &wa, 0, st))) return rc;
     }
-    if ((rc = reduce_wgrad(h, h->bwd_grid, first ? g_weights : h->gtmp, st))) return rc;
+    if ((rc = reduce_wgrad(h, 2 * h->bwd_grid, first ? g_weights : h->gtmp, st))) return rc;
     if (!first) {
       const int thr = 256;
       k_axpby<<<(int)((h->ms.nweights + thr - 1) / thr), thr, 0, st>>>(h->ms.nweights, 1.0, g_weights, 1.0, h->gtmp, g_weights);

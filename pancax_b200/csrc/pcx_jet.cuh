@@ -363,15 +363,20 @@ struct JetWgradArgs {
 // take 16 (columns 0..7 XOR the swizzle {0, 4, 8, 12}), which lets two of those CTAs share an SM (k_jet_wgrad_io)
 template <int MODE> __host__ __device__ constexpr int jet_wgrad_sz() { return MODE == 1 ? 16 : 64; }
 template <int MODE> __host__ __device__ constexpr int jet_wgrad_sp() { return MODE == 2 ? 16 : 64; }
-template <int NT, int MODE> __host__ __device__ constexpr size_t jet_wgrad_smem() {
-  return (size_t)2 * 8 * (NT + 1) * (jet_wgrad_sz<MODE>() + jet_wgrad_sp<MODE>()) * sizeof(double);
+// NBUF = 2: tiles double-buffered inside the CTA (one CTA per SM for full tiles: 131 KB).  NBUF = 1 (hidden layers,
+// PCX_JET_WGRAD_HIDDEN_NBUF): one buffer, 64 KB, TWO CTAs per SM -- the other CTA's DMMAs cover this one's loads.
+#ifndef PCX_JET_WGRAD_HIDDEN_NBUF
+#define PCX_JET_WGRAD_HIDDEN_NBUF 1
+#endif
+template <int NT, int MODE, int NBUF = 2> __host__ __device__ constexpr size_t jet_wgrad_smem() {
+  return (size_t)NBUF * 8 * (NT + 1) * (jet_wgrad_sz<MODE>() + jet_wgrad_sp<MODE>()) * sizeof(double);
 }
 
-template <int NT, int MODE>
+template <int NT, int MODE, int NBUF = 2>
 __device__ __forceinline__ void jet_wgrad_body(const MlpShape& s, const JetWgradArgs& A, unsigned char* smem_raw) {
   constexpr int NW = NT + 1, ROWS = 8 * NW, SZ = jet_wgrad_sz<MODE>(), SP = jet_wgrad_sp<MODE>(), KR = ROWS / 4;
-  double* Zt = reinterpret_cast<double*>(smem_raw);            // [2][ROWS*SZ]
-  double* Pt = Zt + 2 * ROWS * SZ;                             // [2][ROWS*SP]
+  double* Zt = reinterpret_cast<double*>(smem_raw);            // [NBUF][ROWS*SZ]
+  double* Pt = Zt + NBUF * ROWS * SZ;                          // [NBUF][ROWS*SP]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, c = lane & 3;
   const int lrow = warp * 8 + r;
@@ -439,17 +444,21 @@ __device__ __forceinline__ void jet_wgrad_body(const MlpShape& s, const JetWgrad
   };
 
   int buf = 0;
-  load(blockIdx.x, 0);
-  for (long long w = blockIdx.x; w < nwork; w += gridDim.x, buf ^= 1) {
+  if constexpr (NBUF == 2) load(blockIdx.x, 0);
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x, buf ^= (NBUF - 1)) {
     const int st = (int)(w / ntiles);
     const long long tile = w - (long long)st * ntiles;
     const bool live = tile * ROWS + lrow < A.n;
+    if constexpr (NBUF == 1) {
+      __syncthreads();        // everybody is done reading the tile of the previous work item
+      load(w, 0);
+    }
     cp_async_wait_all();
     double* zt = Zt + buf * ROWS * SZ;
     double* pt = Pt + buf * ROWS * SP;
     if (MODE != 2 && st == 0 && live && c == ((A.ones_slot & 7) >> 1)) pt[lrow * SP + (A.ones_slot ^ gl)] = 1.0;
     __syncthreads();          // tile `buf` complete; everybody is done reading tile `buf^1`
-    load(w + gridDim.x, buf ^ 1);
+    if constexpr (NBUF == 2) load(w + gridDim.x, buf ^ 1);
     if constexpr (MODE == 0) {
       if (warp < NT) {
 #pragma unroll 4
@@ -510,10 +519,10 @@ __device__ __forceinline__ void jet_wgrad_body(const MlpShape& s, const JetWgrad
   }
 }
 
-template <int NT, int MODE>
-__global__ void __launch_bounds__(32 * (NT + 1), 1) k_jet_wgrad(const __grid_constant__ MlpShape s, const __grid_constant__ JetWgradArgs A) {
+template <int NT, int MODE, int NBUF = 2>
+__global__ void __launch_bounds__(32 * (NT + 1), NBUF == 1 ? 2 : 1) k_jet_wgrad(const __grid_constant__ MlpShape s, const __grid_constant__ JetWgradArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  jet_wgrad_body<NT, MODE>(s, A, smem_raw);
+  jet_wgrad_body<NT, MODE, NBUF>(s, A, smem_raw);
 }
 
 // Layer 0 (MODE 2, blockIdx.y = 0) and the output layer (MODE 1, blockIdx.y = 1) in ONE launch: both are small contractions
