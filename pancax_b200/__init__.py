@@ -17,7 +17,7 @@ from .bvps import BiaxialLinearRamp, SimpleShearLinearRamp, UniaxialTensionLinea
 from .constitutive_models import (BlatzKo, BoundedProperty, FixedProperty, Gent, Hencky, NeoHookean,  # noqa: F401,E402
                                   PronySeries, SimpleFeFv, Swanson, WLF)
 from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E402
-from .domains import CollocationDomain, VariationalDomain  # noqa: F401,E402
+from .domains import CollocationDataLoader, CollocationDomain, VariationalDomain  # noqa: F401,E402
 from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, write_exodus_mesh  # noqa: F401,E402
 from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, EnergyLoss,  # noqa: F401,E402
                              EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss,

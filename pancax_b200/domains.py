@@ -69,3 +69,24 @@ class CollocationDomain:
         """All (x..., t) rows, time-major: what CollocationDataLoader assembles (domains.py:96-110)."""
         nn = self.coords.shape[0]
         return np.column_stack([np.tile(self.coords, (len(self.times), 1)), np.repeat(self.times, nn)])
+
+
+class CollocationDataLoader:
+    """pancax/domains.py:88-130: shuffled full batches of the collocation rows (x..., t) of a CollocationDomain -- all
+    mesh nodes at every time, time-major -- with zero targets of ``num_fields`` columns (the trailing partial batch is
+    dropped)."""
+
+    def __init__(self, domain: CollocationDomain, num_fields: int) -> None:
+        self.inputs = domain.collocation_points()
+        self.outputs = np.zeros((self.inputs.shape[0], num_fields))
+        self.indices = np.arange(self.inputs.shape[0])
+
+    def __len__(self):
+        return self.inputs.shape[0]
+
+    def dataloader(self, batch_size: int):
+        order = np.random.permutation(self.indices)
+        for b in range(len(self) // batch_size):
+            rows = order[b * batch_size:(b + 1) * batch_size]
+            yield self.inputs[rows], self.outputs[rows]
+

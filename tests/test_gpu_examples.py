@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ("hyperelastic_3d.py", ["8", "10"], "wrote"),
     ("viscoelastic_3d.py", ["6", "11"], "10 "),
     ("inverse_path_dependent.py", ["8", "3"], "done 3"),
+    ("poisson_collocation.py", ["12", "30"], "residual loss"),
 ])
 def test_example_runs(cuda_device, tmp_path, script, args, expect):
     env = dict(os.environ, PANCAX_WORKDIR=str(tmp_path))

@@ -251,3 +251,16 @@ def test_jet_without_the_time_stream_is_bit_identical(cuda_device):
     L6, _, gw6 = eng.strong_form_loss_and_grad(w, pts, 1e-300, 0.7, 2.0)
     assert float(L5[0]) == float(L6[0]) and float((gw5 - gw6).norm()) <= 1e-15 * float(gw6.norm())
     eng.close()
+
+
+def test_collocation_data_loader():
+    """pancax/domains.py:88-130: rows (x..., t) of every node at every time with zero targets, shuffled FULL batches."""
+    import pancax_b200 as px
+    mesh = px.create_structured_mesh("quad4", 3)
+    dom = px.CollocationDomain(mesh, np.linspace(0.0, 1.0, 3))
+    dl = px.CollocationDataLoader(dom, num_fields=2)
+    assert len(dl) == 48 and dl.inputs.shape == (48, 3) and dl.outputs.shape == (48, 2) and not dl.outputs.any()
+    assert np.array_equal(dl.inputs, dom.collocation_points())
+    batches = list(dl.dataloader(10))
+    assert len(batches) == 4 and all(b[0].shape == (10, 3) and b[1].shape == (10, 2) for b in batches)
+    assert len({tuple(r) for b in batches for r in b[0]}) == 40
