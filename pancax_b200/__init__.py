@@ -19,12 +19,15 @@ from .constitutive_models import (BlatzKo, BoundedProperty, FixedProperty, Gent,
 from .data import FullFieldData, FullFieldDataLoader, GlobalData  # noqa: F401,E402
 from .domains import CollocationDataLoader, CollocationDomain, VariationalDomain  # noqa: F401,E402
 from .fem import DofManager, Mesh, create_structured_mesh, read_exodus_mesh, write_exodus_mesh  # noqa: F401,E402
+from .history_writer import EnsembleHistoryWriter, HistoryWriter  # noqa: F401,E402
 from .loss_functions import (CombineLossFunctions, EnergyAndResidualLoss, EnergyLoss,  # noqa: F401,E402
                              EnergyResidualAndReactionLoss, FullFieldDataLoss, StrongFormResidualLoss,
                              UserDefinedLossFunction)
 from .networks import MLP, Field, Parameters  # noqa: F401,E402
 from .optimizers import LBFGS, Adam  # noqa: F401,E402
-from .physics_kernels import HeatEquation, PlaneStrain, PlaneStress, Poisson, SolidMechanics, ThreeDimensional  # noqa: F401,E402
+from .physics_kernels import (BaseEnergyFormPhysics, BaseStrongFormPhysics, HeatEquation, PlaneStrain, PlaneStress,  # noqa: F401,E402
+                              Poisson, SolidMechanics, ThreeDimensional)
 from .post_processor import ExodusPostProcessor, PostProcessor  # noqa: F401,E402
 from .problems import ForwardProblem, InverseProblem  # noqa: F401,E402
 from .trainer import Trainer  # noqa: F401,E402
+from .utils import find_data_file, find_mesh_file  # noqa: F401,E402

@@ -367,3 +367,30 @@ def test_simple_fefv_state_bookkeeping():
         assert np.array_equal(model.extract_tensor(state, 9 * k), np.arange(9 * k + 1.0, 9 * k + 10.0).reshape(3, 3))
         assert np.array_equal(state.reshape((3, 3, 3))[k], model.extract_tensor(state, 9 * k))
     assert model.extract_scalar(state, 4) == 5.0 and model.bulk_modulus == 1000.0
+
+
+def test_history_writers_and_file_finders(tmp_path):
+    """pancax/history_writer.py:44-151 and utils.py:14-55: the loss history of a training loop as CSV (scalar aux entries,
+    property_k columns from ``props``, one file per ensemble member) and the example scripts' file look-up."""
+    import torch
+    import pancax_b200 as px
+    hw = px.HistoryWriter(str(tmp_path / "hist" / "history.csv"), log_every=2, write_every=4)
+    for epoch in range(6):
+        loss = (torch.tensor(1.0 / (epoch + 1), dtype=torch.float64),
+                {"energy": torch.tensor(2.0 * epoch, dtype=torch.float64), "reactions": torch.zeros(3),
+                 "props": {"bulk_modulus": 10.0, "shear_modulus": torch.tensor(0.5 + epoch)}})
+        hw.write_history(loss, epoch)
+    rows = (tmp_path / "hist" / "history.csv").read_text().strip().splitlines()
+    assert rows[0] == "energy,property_0,property_1,epoch,loss" and len(rows) == 1 + 3          # epochs 0, 2, 4 written at 4
+    assert rows[-1].split(",") == ["8.0", "10.0", "4.5", "4", "0.2"]
+    ew = px.EnsembleHistoryWriter(str(tmp_path / "ens"), 2, log_every=1, write_every=1)
+    ew.write_history((torch.tensor([1.0, 2.0]), {"energy": torch.tensor([3.0, 4.0])}), 0)
+    assert (tmp_path / "ens_1.csv").read_text().strip().splitlines() == ["energy,epoch,loss", "4.0,0,2.0"]
+    # file finders look next to the CALLING file and in its data / mesh sub-directory
+    here = os.path.dirname(os.path.abspath(__file__))
+    assert str(px.find_data_file("cases.py")) == os.path.join(here, "cases.py")          # next to the caller
+    assert str(px.find_mesh_file("cases.py")) == os.path.join(here, "cases.py")
+    with pytest.raises(px.utils.MeshFileNotFoundException):
+        px.find_mesh_file("no_such_mesh.g")
+    with pytest.raises(px.utils.DataFileNotFoundException):
+        px.find_data_file("no_such_data.csv")
