@@ -1,98 +1,95 @@
-"""Loss-history logging of the training loops: the interface of pancax/history_writer.py (HistoryWriter :44-105,
-EnsembleHistoryWriter :108-151) -- ``write_history(loss, epoch)`` with ``loss = (value, aux)`` as the optimisers return
-it, columns ``epoch``, ``loss``, every scalar aux entry, ``property_k`` / ``dproperty_k`` for the ``props`` / ``dprops``
-entries -- on plain Python lists and the csv module (values may be torch tensors on the GPU: ``float()`` reads them)."""
+"""Loss-history logging of the training loops, with the call interface of pancax/history_writer.py (HistoryWriter
+:44-105, EnsembleHistoryWriter :108-151): ``write_history(loss, epoch)`` takes ``loss = (value, aux)`` as the optimisers
+return it and keeps, every ``log_every`` epochs, the columns ``epoch``, ``loss``, every scalar aux entry and
+``property_k`` / ``dproperty_k`` for the ``props`` / ``dprops`` entries; every ``write_every`` epochs the table goes to a
+CSV file.  Values may be torch tensors on the GPU (one ``.item()`` read per logged value); vector-valued aux entries
+(the reactions per time step) are not columns."""
 from __future__ import annotations
 
 import csv
 from pathlib import Path
-from typing import List
+
+_PROP_COLUMNS = {"props": "property_", "dprops": "dproperty_"}
 
 
-def _scalar(v):
+def _number(v) -> float:
     return float(v.item()) if hasattr(v, "item") else float(v)
 
 
-def _prop_values(val):
-    """``props`` as the losses report them: a dict name -> value (CombineLossFunctions(with_props=True)) or a sequence."""
-    return list(val.values()) if isinstance(val, dict) else list(val)
+def _is_scalar(v) -> bool:
+    return not hasattr(v, "numel") or v.numel() == 1
 
 
-class BaseHistoryWriter:
-    def __init__(self, log_every: int, write_every: int) -> None:
-        self.log_every, self.write_every = int(log_every), int(write_every)
+def _columns(aux, member=None):
+    """(column name, value) pairs of one aux dict; ``member`` selects an ensemble member's slice of stacked entries."""
+    for key, val in aux.items():
+        if member is not None:
+            val = val[member]
+        if key in _PROP_COLUMNS:
+            items = val.values() if isinstance(val, dict) else val
+            for k, p in enumerate(items):
+                yield f"{_PROP_COLUMNS[key]}{k}", _number(p)
+        elif _is_scalar(val):
+            yield key, _number(val)
 
-    def write_history(self, loss, epoch: int) -> None:
-        if epoch % self.log_every == 0:
-            self.write_aux_values(loss)
-            self.write_epoch(epoch)
-            self.write_loss(loss)
-        if epoch % self.write_every == 0:
-            self.to_csv()
 
-
-class HistoryWriter(BaseHistoryWriter):
+class HistoryWriter:
     def __init__(self, history_file: str, log_every: int, write_every: int) -> None:
-        super().__init__(log_every, write_every)
         self.history_file = Path(history_file)
-        self.data_dict = {}
+        self.log_every, self.write_every = int(log_every), int(write_every)
+        self.data_dict = {}                  # column name -> values, in first-seen order
 
-    def write_data(self, key: str, val: float) -> None:
+    # -- the reference's fine-grained calls
+    def write_data(self, key: str, val) -> None:
         self.data_dict.setdefault(key, []).append(val)
 
-    def write_aux_values(self, loss) -> None:
-        for key, val in loss[1].items():
-            if key in ("props", "dprops"):
-                for k, p in enumerate(_prop_values(val)):
-                    self.write_data(("property_" if key == "props" else "dproperty_") + str(k), _scalar(p))
-            elif not hasattr(val, "numel") or val.numel() == 1:
-                self.write_data(key, _scalar(val))          # vector-valued aux entries (reactions per step) are not columns
+    def write_aux_values(self, loss, member=None) -> None:
+        for name, value in _columns(loss[1], member):
+            self.write_data(name, value)
 
     def write_epoch(self, epoch) -> None:
         self.write_data("epoch", int(epoch))
 
-    def write_loss(self, loss) -> None:
-        self.write_data("loss", _scalar(loss[0]))
+    def write_loss(self, loss, member=None) -> None:
+        self.write_data("loss", _number(loss[0] if member is None else loss[0][member]))
+
+    # -- one call per epoch
+    def write_history(self, loss, epoch: int) -> None:
+        if epoch % self.log_every == 0:
+            self.log(loss, epoch)
+        if epoch % self.write_every == 0:
+            self.to_csv()
+
+    def log(self, loss, epoch: int, member=None) -> None:
+        self.write_aux_values(loss, member)
+        self.write_epoch(epoch)
+        self.write_loss(loss, member)
 
     def to_csv(self) -> None:
-        keys = list(self.data_dict)
-        n = max((len(v) for v in self.data_dict.values()), default=0)
+        names = list(self.data_dict)
+        depth = max((len(col) for col in self.data_dict.values()), default=0)
         self.history_file.parent.mkdir(parents=True, exist_ok=True)
         with open(self.history_file, "w", newline="") as f:
-            w = csv.writer(f)
-            w.writerow(keys)
-            for i in range(n):
-                w.writerow([self.data_dict[k][i] if i < len(self.data_dict[k]) else "" for k in keys])
+            out = csv.writer(f)
+            out.writerow(names)
+            out.writerows([self.data_dict[c][i] if i < len(self.data_dict[c]) else "" for c in names] for i in range(depth))
 
 
-class EnsembleHistoryWriter(BaseHistoryWriter):
+class EnsembleHistoryWriter:
     """One CSV per ensemble member (``{base_name}_{n}.csv``); ``loss`` = (stacked values, stacked aux) as
     ``Adam.ensemble_step`` returns them."""
 
     def __init__(self, base_name: str, n_pinns: int, log_every: int, write_every: int) -> None:
-        super().__init__(log_every, write_every)
-        self.history_writers: List[HistoryWriter] = [HistoryWriter(f"{base_name}_{n}.csv", log_every, write_every)
-                                                     for n in range(n_pinns)]
+        self.log_every, self.write_every = int(log_every), int(write_every)
+        self.history_writers = [HistoryWriter(f"{base_name}_{n}.csv", log_every, write_every) for n in range(n_pinns)]
 
-    def write_aux_values(self, loss) -> None:
-        for key, val in loss[1].items():
-            for n, writer in enumerate(self.history_writers):
-                if key == "props":
-                    for k, p in enumerate(_prop_values(val[n])):
-                        writer.write_data(f"property_{k}", _scalar(p))
-                else:
-                    v = val[n]
-                    if not hasattr(v, "numel") or v.numel() == 1:
-                        writer.write_data(key, _scalar(v))
-
-    def write_epoch(self, epoch) -> None:
-        for writer in self.history_writers:
-            writer.write_epoch(epoch)
-
-    def write_loss(self, loss) -> None:
-        for n, writer in enumerate(self.history_writers):
-            writer.write_data("loss", _scalar(loss[0][n]))
+    def write_history(self, loss, epoch: int) -> None:
+        if epoch % self.log_every == 0:
+            for n, member in enumerate(self.history_writers):
+                member.log(loss, epoch, member=n)
+        if epoch % self.write_every == 0:
+            self.to_csv()
 
     def to_csv(self) -> None:
-        for writer in self.history_writers:
-            writer.to_csv()
+        for member in self.history_writers:
+            member.to_csv()
