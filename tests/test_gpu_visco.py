@@ -345,3 +345,18 @@ def test_state_model_losses_repeat_bitwise(cuda_device, name, kind):
     a = run_engine_loss(case, kind, first_step=1)
     b = run_engine_loss(case, kind, first_step=1)
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_state_model_residual_loss_with_the_tf32_adjoint(cuda_device, mode):
+    """PCX_OPT_TF32_ADJOINT (1: mma.sync, 2: tcgen05 contraction) only changes the adjoint through the MLP: the loss and aux
+    of the state-model residual + reaction loss stay bit-identical, the weight gradient moves by <= 1e-5 per the stated
+    tolerance."""
+    case = make_case("hex8_visco_neohookean", n=3, nt=4, width=50, depth=4)
+    eng = make_engine(case)
+    L, aux, gw, _ = run_engine_loss(case, "energy_residual_reaction", eng=eng, first_step=1)
+    eng.set_option("tf32_adjoint", mode)
+    L32, aux32, gw32, _ = run_engine_loss(case, "energy_residual_reaction", eng=eng, first_step=1)
+    eng.close()
+    assert L32 == L and np.array_equal(aux32, aux)
+    assert rel(gw32, gw) < 1e-5 and np.any(gw32 != gw)
