@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PCX_ABI_VERSION 4
+#define PCX_ABI_VERSION 5
 
 /* error codes */
 #define PCX_OK               0
@@ -256,6 +256,17 @@ int pcx_energy_force(pcx_handle* h, const double* prop_raw, const double* us, do
  *   (mechanics/base.py:112-118).  Any output may be NULL. */
 int pcx_element_fields(pcx_handle* h, const double* prop_raw, const double* us, double* F, double* I1_bar,
                        double* P, void* stream);
+
+/* one time step of a model with state variables (SimpleFeFv) at a GIVEN old state -- the op-level calls of the reference
+ * for such a model: physics.potential_energy(params, domain, t, us, state_old, dt) -> (Pi, state_new)
+ * (pancax/physics_kernels/base.py:349-354), potential_energy_and_internal_force(..., state_old, dt) (f = dPi/du at fixed
+ * old state, base.py:356-361) and the post-processor's element_pp(pk1_stress)(..., us, theta, state_old, dt)
+ * (base.py:24-74, constitutive_models/mechanics/base.py:112-118; driven step by step in post_processor.py:244-354,470-490).
+ *   state_old, state_new [ne*nq*n_prony*9] (must not alias), dt >= 0 (dt = 0, the post-processor's step 0: the reference
+ *   evaluates 0/0 there; the limit dt -> 0 is returned), Pi device scalar or NULL, f [nn*ndof] or NULL,
+ *   P [ne*nq*9] (3x3 row-major) or NULL.  PlaneStress: PCX_ERR_UNSUPPORTED. */
+int pcx_state_step(pcx_handle* h, const double* prop_raw, const double* us, const double* state_old, double dt,
+                   double* state_new, double* Pi, double* f, double* P, void* stream);
 
 /* tangent-stiffness action Kv = d/d(eps) f(us + eps v): the second-order term the reference gets
  * by differentiating through value_and_grad in base.py:363-385.  g_props = d<f,v>/d prop_raw or NULL. */

@@ -32,7 +32,7 @@ from pancax_b200._lib import (ELEM, FORM, LOSS, MODEL, PCX_AUX_FIXED, PHYS_POISS
 FFI_TARGETS = ("PcxElementGeometry", "PcxFieldForward", "PcxFieldBackward", "PcxPointsForward", "PcxPointsBackward",
                "PcxEnergyForce", "PcxStiffnessAction", "PcxResidualReaction", "PcxElementFields", "PcxLossAndGrad",
                "PcxLossBegin", "PcxLossMid", "PcxLossFinish", "PcxFieldDataLossAndGrad", "PcxPointsJet",
-               "PcxStrongFormLossAndGrad", "PcxGetState", "PcxAdamStep", "PcxAdamStepSched")
+               "PcxStrongFormLossAndGrad", "PcxGetState", "PcxStateStep", "PcxAdamStep", "PcxAdamStepSched")
 _registered = False
 
 

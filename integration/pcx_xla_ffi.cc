@@ -155,6 +155,13 @@ ffi::Error StrongFormLossAndGradImpl(cudaStream_t s, int64_t h, double c_t, doub
 ffi::Error GetStateImpl(cudaStream_t s, int64_t h, int32_t t_idx, RF64 state) {
   return pcx_err(pcx_get_state(H(h), t_idx, state->typed_data(), s));
 }
+// one time step of a state-variable model at a given old state: physics.potential_energy(params, domain, t, us, state_old, dt)
+// -> (Pi, state_new), the internal force at fixed old state and element_pp(pk1_stress) (physics_kernels/base.py:24-74,349-361)
+ffi::Error StateStepImpl(cudaStream_t s, int64_t h, double dt, F64 prop_raw, F64 us, F64 state_old, RF64 state_new, RF64 Pi,
+                         RF64 f, RF64 P) {
+  return pcx_err(pcx_state_step(H(h), opt(prop_raw), us.typed_data(), state_old.typed_data(), dt, state_new->typed_data(),
+                                opt(Pi), opt(f), opt(P), s));
+}
 // optax.chain(scale_by_adam, scale_by_schedule, scale(-1)) + apply_updates (pancax/optimizers.py:142-180).  params / mu /
 // nu are updated in place by the ABI: declare input_output_aliases={0: 0, 2: 1, 3: 2} in ffi_call; without aliasing the
 // inputs are first copied into the outputs.
@@ -232,6 +239,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(PcxStrongFormLossAndGrad, StrongFormLossAndGradImp
                               PCX_BIND().Attr<double>("c_t").Attr<double>("c_lap").Attr<double>("weight").Attr<int32_t>("want_grad")
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PcxGetState, GetStateImpl, PCX_BIND().Attr<int32_t>("t_idx").Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(PcxStateStep, StateStepImpl,
+                              PCX_BIND().Attr<double>("dt").Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PcxAdamStep, AdamStepImpl,
                               ffi::Ffi::Bind().Ctx<Stream>().Attr<int64_t>("count").Attr<double>("lr").Attr<double>("b1")
                                   .Attr<double>("b2").Attr<double>("eps")

@@ -86,7 +86,7 @@ SYMBOLS = [
     "pcx_element_fields", "pcx_residual_reaction", "pcx_loss_and_grad", "pcx_field_data_loss_and_grad",
     "pcx_num_state_variables", "pcx_get_state", "pcx_set_option", "pcx_set_ownership", "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish",
     "pcx_points_jet", "pcx_strong_form_loss_and_grad", "pcx_launch_count", "pcx_adam_step", "pcx_adam_step_sched", "pcx_profile_enable", "pcx_profile_collect",
-    "pcx_measure_dmma_peak", "pcx_reserve", "pcx_gather_rows", "pcx_scatter_rows",
+    "pcx_measure_dmma_peak", "pcx_reserve", "pcx_gather_rows", "pcx_scatter_rows", "pcx_state_step",
 ]
 
 
@@ -129,6 +129,7 @@ def load():
     lib.pcx_num_state_variables.argtypes = [vp]
     lib.pcx_num_state_variables.restype = i64
     lib.pcx_get_state.argtypes = [vp, i32, vp, vp]
+    lib.pcx_state_step.argtypes = [vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp]
     lib.pcx_set_ownership.argtypes = [vp, i64, i64]
     lib.pcx_loss_begin.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp]
     lib.pcx_loss_mid.argtypes = [vp, vp, vp, vp]

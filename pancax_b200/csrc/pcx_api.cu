@@ -86,7 +86,7 @@ struct pcx_handle {
   long long vz_per = 0;
   bool vz_filled = false;                   // a path-dependent call has written the state history
   struct VStep { bool on = false; double kappa[PCX_MAX_PRONY], c[PCX_MAX_PRONY]; const double* z_old; double* z_new;
-                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; double* f33 = nullptr; const double* f33_prev = nullptr; } vstep;   // mode: k_visco_qp MODE
+                 const double* lam_in; double* lam_out; int mode = 0; double wpsi = 1.0; double* f33 = nullptr; const double* f33_prev = nullptr; double* pp_P = nullptr; } vstep;   // mode: k_visco_qp MODE
   double* vv = nullptr;                     // [nt][nn][ndof] v_t = dloss/df_t of every step (residual losses with state)
   double *vf33 = nullptr, *vscr = nullptr;   // PlaneStress with state: roots F_33 [nt][ne*nq]; MODE 5 scratch [ne*nq*n_prony*9]
   int tf32_adjoint = 0;         // PCX_OPT_TF32_ADJOINT / env PCX_TF32_ADJOINT: 1 = mma.sync kernel, 2 = tcgen05 contractions
@@ -1078,6 +1078,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
     for (int b = 0; b < a.n_prony; b++) { a.prony_kappa[b] = h->vstep.kappa[b]; a.prony_c[b] = h->vstep.c[b]; }
     a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
     a.wpsi = h->vstep.wpsi;
+    a.pp_P = h->vstep.mode == 2 ? h->vstep.pp_P : nullptr;
     a.f33_out = nullptr; a.f33_in = nullptr;
     if (h->vstep.mode == 4) { a.f33_out = h->vstep.f33; a.f33_in = h->vstep.f33_prev; }   // f33_in: start of the root find
     if (h->vstep.mode == 5) { a.f33_in = h->vstep.f33; a.vscr = h->vscr; }
@@ -1529,6 +1530,44 @@ extern "C" int pcx_get_state(pcx_handle* h, int32_t t_idx, double* state, void* 
   CUDA_TRY(cudaMemcpyAsync(state, h->vz + (long long)t_idx * h->vz_per, (size_t)h->vz_per * sizeof(double), cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
   return PCX_OK;
+}
+
+// One time step of a model with state variables at a GIVEN old state: what the reference's op-level calls evaluate for
+// SimpleFeFv -- physics.potential_energy(params, domain, t, us, state_old, dt) -> (Pi, state_new) (base.py:349-354),
+// potential_energy_and_internal_force (f = dPi/du at fixed old state, base.py:356-361) and the post-processor's
+// element_pp(pk1_stress) = jacfwd(energy)(grad_u, theta, state_old, dt) (base.py:24-74, mechanics/base.py:112-118).
+// k_visco_qp MODE 2 computes all of them in one pass over the quadrature points.
+extern "C" int pcx_state_step(pcx_handle* h, const double* prop_raw, const double* us, const double* state_old, double dt,
+                              double* state_new, double* Pi, double* f, double* P, void* stream) {
+  NEED_READY(h);
+  if (h->phys.physics != PCX_PHYS_SOLID || h->phys.n_prony <= 0)
+    return fail(PCX_ERR_STATE, "pcx_state_step: the constitutive model has no state variables (use pcx_energy_force / pcx_element_fields)");
+  if (h->phys.formulation == PCX_FORM_PLANE_STRESS)
+    return fail(PCX_ERR_UNSUPPORTED, "pcx_state_step: PlaneStress with a state-variable model is defined for the path-dependent EnergyLoss only");
+  if (!us || !state_old || !state_new) return fail(PCX_ERR_INVALID, "pcx_state_step: us / state_old / state_new is null");
+  if (state_old == state_new) return fail(PCX_ERR_INVALID, "pcx_state_step: state_new must not alias state_old");
+  if (!(dt >= 0.0)) return fail(PCX_ERR_INVALID, "pcx_state_step: dt must be >= 0, got %g", dt);
+  if (!h->vq || !h->vpart || !h->f) return fail(PCX_ERR_STATE, "state-variable workspace missing (pcx_set_physics / pcx_set_field allocate it)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = set_props(h, prop_raw, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+  for (int b = 0; b < h->phys.n_prony; b++) {
+    const double G = h->phys.prony_moduli[b], tau = h->phys.prony_times[b];
+    const double c = dt / (tau + dt);   // simple_fefv.py:104-108
+    h->vstep.c[b] = c;
+    // psi_neq + dissipation = kappa |dev Ee_trial|^2 (simple_fefv.py:82-95); at dt = 0 the reference divides 0 by 0
+    // (Dv = delta_Ev / dt): the limit tau / (tau + dt)^2 of the dissipation factor is taken here
+    h->vstep.kappa[b] = G * ((1.0 - c) * (1.0 - c) + (dt > 0.0 ? tau * c * c / (dt * dt) : 1.0 / tau));
+  }
+  struct VStepGuard { pcx_handle* h; ~VStepGuard() { h->vstep.on = false; h->vstep.mode = 0; h->vstep.wpsi = 1.0; h->vstep.pp_P = nullptr; } } vstep_guard{h};
+  h->vstep.on = true; h->vstep.wpsi = 1.0; h->vstep.mode = 2;
+  h->vstep.z_old = state_old; h->vstep.z_new = state_new; h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
+  h->vstep.f33 = nullptr; h->vstep.f33_prev = nullptr; h->vstep.pp_P = P;
+  rc = sweep(h, false, 1, us, nullptr, f ? f : h->f, 1.0, nullptr, 0.0, true, false, true, st);
+  if (rc) return rc;
+  if (Pi) rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, Pi, 1, st);
+  return rc;
 }
 
 extern "C" int pcx_loss_and_grad(pcx_handle* h, const pcx_loss_desc* L, const double* weights, const double* prop_raw,

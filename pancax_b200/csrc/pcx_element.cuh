@@ -62,6 +62,7 @@ struct ElemArgs {
   double* qbuf;            // [ne][nq][NDOF][ND] parent-space point fluxes (k_visco_qp -> k_visco_scatter)
   double wpsi;             // k_visco_qp MODE 3: weight of the step's energy in the loss (the flux then carries every term)
   double* vscr;            // k_visco_qp MODE 5: scratch [ne][nq][n_prony][9] (tangent of the old-state adjoint along E_33)
+  double* pp_P;            // k_visco_qp MODE 2: [ne][nq][9] PK1 stress d psi / d grad_u at fixed old state, or nullptr (pcx_state_step)
 };
 
 template <int ND>
@@ -665,6 +666,12 @@ __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 
           W += fefv_branch(F, zo, A0.prony_kappa[b], A0.prony_c[b], zn, nullptr, MODE == 2 ? P : nullptr, lo);
 #pragma unroll
           for (int i = 0; i < 9; i++) A0.z_new[zq + b * 9 + i] = zn[i];
+        }
+      }
+      if constexpr (MODE == 2) {
+        if (A0.pp_P) {
+#pragma unroll
+          for (int i = 0; i < 9; i++) A0.pp_P[t * 9 + i] = P[i];
         }
       }
     }

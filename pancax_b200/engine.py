@@ -371,6 +371,35 @@ class Engine:
         check(self.lib.pcx_get_state(self.h, int(t_idx), _ptr(out), _stream()))
         return out
 
+    def initial_state(self):
+        """``constitutive_model.initial_state()`` at every quadrature point (simple_fefv.py:72-75): Fv = I per Prony
+        branch, (ne, nq, n_prony*9)."""
+        ns = int(self.lib.pcx_num_state_variables(self.h))
+        if ns <= 0:
+            raise ValueError("the constitutive model has no state variables")
+        z = self._empty(self.ne, self.nq, ns // 9, 9)
+        z.zero_()
+        z[..., 0::4] = 1.0
+        return z.reshape(self.ne, self.nq, ns)
+
+    def state_step(self, us, state_old, dt, prop_raw=None, want_force=True, want_P=True):
+        """One time step of a state-variable model at a given old state (pcx_state_step): (Pi, state_new, f, P) =
+        ``physics.potential_energy(params, domain, t, us, state_old, dt)`` (base.py:349-354), the internal force at
+        fixed old state (base.py:356-361) and ``element_pp(pk1_stress)`` (ne, nq, 3, 3)."""
+        u, pr, zo = self._dev(us), self._dev(prop_raw), self._dev(state_old)
+        ns = int(self.lib.pcx_num_state_variables(self.h))
+        if ns <= 0:
+            raise ValueError("the constitutive model has no state variables (use energy_force / element_fields)")
+        if zo.numel() != self.ne * self.nq * ns:
+            raise ValueError(f"state_old has {zo.numel()} entries, expected (ne, nq, {ns})")
+        zn = self._empty(self.ne, self.nq, ns)
+        Pi = self._empty(1)
+        f = self._empty(self.nn, self.ndof) if want_force else None
+        P = self._empty(self.ne, self.nq, 3, 3) if want_P else None
+        check(self.lib.pcx_state_step(self.h, _ptr(pr), _ptr(u), _ptr(zo), float(dt), _ptr(zn), _ptr(Pi), _ptr(f), _ptr(P),
+                                      _stream()))
+        return Pi, zn, f, P
+
     def set_option(self, name, value):
         """``cull_null_steps``: skip the MLP on time steps whose Dirichlet table b is identically zero (exact).
         ``tf32_adjoint``: adjoint through the MLP on the TF32 tensor cores (3xTF32, fp32 activations; 1 = mma.sync

@@ -209,28 +209,43 @@ class ExodusPostProcessor(BasePostProcessor):
                 for q in range(nq):
                     elem_vars[f"{comp}_{q + 1}"] = np.empty((nt, eng.ne))
         want = set(self.element_variables)
-        if "state_variables" in want:
-            # the state history of the path-dependent call (weak_form_loss_functions.py:48-72), kept by the library
+        # models with state variables: the reference threads the state through the steps (post_processor.py:470-490:
+        # dt = 0 at step 0, then times[n] - times[n-1]) and evaluates internal_force / pk1_stress / state_variables
+        # from the step's OLD state (:262-266,273-279,312-316) -- one pcx_state_step per time step here
+        ns = int(eng.lib.pcx_num_state_variables(eng.h))
+        stepwise = ns > 0 and getattr(problem.physics.formulation, "name", "") != "plane_stress"
+        state_old = eng.initial_state() if stepwise else None
+        if "state_variables" in want and not stepwise:
+            # PlaneStress with state: the state history of the path-dependent call (weak_form_loss_functions.py:48-72),
+            # kept by the library
             eng.loss_and_grad("energy", w, pr, want_grad=False, first_step=1)
         for n in range(nt):
             us = eng.field_forward(w, n)
+            f_state = P_state = None
+            if stepwise:
+                dt = 0.0 if n == 0 else float(problem.times[n] - problem.times[n - 1])
+                _, state_new, f_state, P_state = eng.state_step(us, state_old, dt, pr,
+                                                                want_force="internal_force" in self.node_variables,
+                                                                want_P="pk1_stress" in want)
             if "field_values" in self.node_variables:
                 u = us.cpu().numpy()
                 for i, nm in enumerate(names["field_values"]):
                     node_vars[nm][n] = u[:, i]
             if "internal_force" in self.node_variables:
-                _, f, _ = eng.energy_force(us, pr)
+                f = f_state if stepwise else eng.energy_force(us, pr)[1]
                 f = f.cpu().numpy()
                 for i, nm in enumerate(names["internal_force"]):
                     node_vars[nm][n] = f[:, i]
             if "state_variables" in want:
-                z = eng.get_state(n).cpu().numpy()                       # (ne, nq, ns)
+                z = (state_new if stepwise else eng.get_state(n)).cpu().numpy()      # (ne, nq, ns)
                 for c, comp in enumerate(names["state_variables"]):
                     for q in range(nq):
                         elem_vars[f"{comp}_{q + 1}"][n] = z[:, q, c]
             if want - {"state_variables"}:
                 F, I1b, P = eng.element_fields(us, pr, want_F="deformation_gradient" in want,
-                                               want_I1bar="I1_bar" in want, want_P="pk1_stress" in want)
+                                               want_I1bar="I1_bar" in want, want_P="pk1_stress" in want and not stepwise)
+                if stepwise:
+                    P = P_state
                 for v, arr in (("deformation_gradient", F), ("I1_bar", I1b), ("pk1_stress", P)):
                     if v not in want:
                         continue
@@ -238,6 +253,8 @@ class ExodusPostProcessor(BasePostProcessor):
                     for c, comp in enumerate(names[v]):
                         for q in range(nq):
                             elem_vars[f"{comp}_{q + 1}"][n] = a[:, q, c]
+            if stepwise:
+                state_old = state_new
         return node_vars, elem_vars
 
     def write_outputs(self, params, problem) -> None:

@@ -158,10 +158,23 @@ def test_state_variables_output(cuda_device, tmp_path):
     params = px.Parameters(problem, 0, n_layers=2, n_neurons=12, dirichlet_bc_func=px.UniaxialTensionLinearRamp(0.5, 1.0, "y", 3))
     pp = px.PostProcessor(mesh, "exodus")
     out = str(tmp_path / "visco.e")
-    pp.init(params, problem, out, node_variables=["field_values"], element_variables=["deformation_gradient", "state_variables"])
+    pp.init(params, problem, out, node_variables=["field_values", "internal_force"],
+            element_variables=["deformation_gradient", "state_variables", "pk1_stress"])
     pp.write_outputs(params, problem)
     pp.close()
     _, nod, el = read_exodus_results(out)
+    # internal_force / pk1_stress of a state model: evaluated step by step from the step's old state (pcx_state_step),
+    # as the reference's _write_step_outputs does (post_processor.py:244-354)
+    from pancax_b200.loss_functions import get_engine
+    e2 = get_engine(problem, params)
+    wts = params.fields.networks.weights
+    z = e2.initial_state()
+    for n in range(3):
+        _, z, f_n, P_n = e2.state_step(e2.field_forward(wts, n), z, 0.0 if n == 0 else float(times[n] - times[n - 1]))
+        assert np.allclose(el["P_yy_3"][n], P_n[:, 2, 1, 1].cpu().numpy(), rtol=1e-12, atol=1e-14)
+        assert np.allclose(nod["internal_force_y"][n], f_n[:, 1].cpu().numpy(), rtol=1e-12, atol=1e-14)
+        assert np.allclose(el["state_variable_5_2"][n], z[:, 1, 4].cpu().numpy(), rtol=1e-12, atol=1e-14)
+    assert np.abs(el["P_yy_3"][2]).max() > 1e-3
     assert "displ_x" in nod and "state_variable_1_1" in el and "state_variable_9_8" in el and "F_xx_1" in el
     assert np.allclose(el["state_variable_1_1"][0], 1.0) and np.allclose(el["state_variable_2_1"][0], 0.0)
     assert not np.allclose(el["state_variable_1_1"][2], 1.0)          # the viscous stretch has evolved by the last step
@@ -360,3 +373,68 @@ def test_state_model_residual_loss_with_the_tf32_adjoint(cuda_device, mode):
     eng.close()
     assert L32 == L and np.array_equal(aux32, aux)
     assert rel(gw32, gw) < 1e-5 and np.any(gw32 != gw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n", [("hex8_visco_neohookean", 3), ("hex8_visco_hencky", 2), ("quad4_visco_gent_bounded", 4),
+                                    ("tri3_visco_swanson", 4)])
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_state_step_matches_oracle(cuda_device, name, n, deterministic):
+    """pcx_state_step = the reference's op-level calls for a state-variable model at a GIVEN old state:
+    physics.potential_energy(params, domain, t, us, state_old, dt) -> (Pi, state_new) (base.py:349-354), the internal force
+    at fixed old state (base.py:356-361) and element_pp(pk1_stress) = jacfwd(energy)(grad_u, theta, state_old, dt)
+    (base.py:24-74, mechanics/base.py:112-118), against the oracle's autograd from a non-trivial old state (two steps)."""
+    import torch
+    from oracle import losses as ol
+    from oracle.physics import element_interpolants, potential_energy_with_state
+    from tests.cases import oracle_problem
+    case = make_case(name, n=n, nt=3, width=12, depth=2)
+    eng = make_engine(case, deterministic=deterministic)
+    prob = oracle_problem(case)
+    w, pr = ol._leaves(prob, case.weights, case.prop_raw)
+    fld, phys, pe = ol._build(prob, w, pr)
+    coords, conns = torch.as_tensor(prob.coords), torch.as_tensor(prob.conns, dtype=torch.long)
+    nb = len(case.prony[0])
+    Z = torch.eye(3, dtype=torch.float64).expand(eng.ne, eng.nq, nb, 3, 3).clone()
+    z = eng.initial_state()
+    assert np.array_equal(z.cpu().numpy(), Z.reshape(eng.ne, eng.nq, nb * 9).numpy())
+    prop_raw = case.prop_raw if eng.n_train else None
+    for step, dt in ((1, 0.3), (2, 0.7)):
+        us = fld(coords, float(case.times[step])).detach().clone().requires_grad_(True)
+        X_el, U_el = coords[conns], us[conns]
+        _, _, grad_u, JxW = element_interpolants(pe, X_el, U_el)
+        grad_u.retain_grad()
+        W, Z_new = phys.energy_density_with_state(grad_u, Z, dt)
+        Pi = (JxW * W).sum()
+        (f,) = torch.autograd.grad(Pi, us, retain_graph=True)
+        H3 = phys.modify_field_gradient(grad_u.detach()).clone().requires_grad_(True)
+        from oracle import models
+        psi = models.simple_fefv_energy(phys.model, H3, phys.props, Z, dt, phys.prony[0], phys.prony[1])[0]
+        (P,) = torch.autograd.grad(psi.sum(), H3)
+        Pi_o, Z_chk = potential_energy_with_state(phys, pe, coords, conns, us.detach(), Z, dt)
+        Pi = Pi.detach()
+        assert abs(float(Pi_o) - float(Pi)) <= 1e-14 * abs(float(Pi))
+        pi_g, zn, f_g, P_g = eng.state_step(us.detach().numpy(), z, dt, prop_raw)
+        assert abs(float(pi_g) - float(Pi)) <= 1e-12 * abs(float(Pi))
+        assert rel(zn.cpu().numpy(), Z_new.detach().reshape(eng.ne, eng.nq, nb * 9).numpy()) < 1e-12
+        assert rel(f_g.cpu().numpy(), f.numpy()) < 1e-10
+        assert rel(P_g.cpu().numpy(), P.numpy()) < 1e-10
+        # outputs are optional; the state is advanced the same way
+        _, zn2, f2, P2 = eng.state_step(us.detach().numpy(), z, dt, prop_raw, want_force=False, want_P=False)
+        assert f2 is None and P2 is None and torch.equal(zn2, zn)
+        Z, z = Z_new.detach(), zn
+    # dt = 0 (the post-processor's step 0): finite, state unchanged
+    pi0, z0, _, P0 = eng.state_step(us.detach().numpy(), z, 0.0, prop_raw)
+    assert np.isfinite(float(pi0)) and bool(torch.isfinite(P0).all()) and rel(z0.cpu().numpy(), z.cpu().numpy()) < 1e-14
+    with pytest.raises(Exception, match="dt must be"):
+        eng.state_step(us.detach().numpy(), z, -1.0, prop_raw)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_state_step_refused_without_state(cuda_device):
+    case = make_case("hex8_neohookean", n=2, nt=2, width=12, depth=2)
+    eng = make_engine(case)
+    with pytest.raises(Exception, match="no state variables"):
+        eng.state_step(np.zeros((eng.nn, 3)), np.zeros((eng.ne, eng.nq, 9)), 0.1)
+    eng.close()

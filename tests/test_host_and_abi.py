@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pcx_abi.h but not exported"
     assert sorted(_lib.SYMBOLS) == declared
-    assert lib.pcx_abi_version() == 4
+    assert lib.pcx_abi_version() == 5
     assert lib.pcx_last_error() is not None
 
 

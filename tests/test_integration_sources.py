@@ -36,12 +36,12 @@ def test_every_compute_entry_point_has_a_handler_and_is_registered():
     shim = open(os.path.join(ROOT, "integration", "pcx_xla_ffi.cc")).read()
     py = open(os.path.join(ROOT, "integration", "kernels_b200.py")).read()
     handlers = re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", shim)
-    assert len(handlers) == len(set(handlers)) >= 19
+    assert len(handlers) == len(set(handlers)) >= 20
     targets = re.search(r"FFI_TARGETS = \((.*?)\)", py, re.S).group(1)
     assert sorted(re.findall(r'"(\w+)"', targets)) == sorted(handlers)
     compute = ["pcx_element_geometry", "pcx_field_forward", "pcx_field_backward", "pcx_points_forward", "pcx_points_backward",
                "pcx_energy_force", "pcx_stiffness_action", "pcx_residual_reaction", "pcx_element_fields", "pcx_loss_and_grad",
                "pcx_loss_begin", "pcx_loss_mid", "pcx_loss_finish", "pcx_field_data_loss_and_grad", "pcx_points_jet",
-               "pcx_strong_form_loss_and_grad", "pcx_get_state", "pcx_adam_step", "pcx_adam_step_sched"]
+               "pcx_strong_form_loss_and_grad", "pcx_get_state", "pcx_state_step", "pcx_adam_step", "pcx_adam_step_sched"]
     for sym in compute:
         assert re.search(r"\b%s\(" % sym, shim), f"{sym} has no XLA-FFI handler"
