@@ -438,3 +438,38 @@ def test_state_step_refused_without_state(cuda_device):
     with pytest.raises(Exception, match="no state variables"):
         eng.state_step(np.zeros((eng.nn, 3)), np.zeros((eng.ne, eng.nq, 9)), 0.1)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_state_step_is_cuda_graph_capturable(cuda_device):
+    """pcx_state_step keeps the ABI's contract (no allocation, synchronisation or host staging inside a compute call):
+    captured on a handle that has never run, replayed with new displacements / old state in the caller's buffers."""
+    import torch
+    case = make_case("hex8_visco_neohookean", n=3, nt=3, width=12, depth=2)
+    warm, eng = make_engine(case), make_engine(case)
+    w = torch.as_tensor(case.weights, device=eng.device)
+    us = warm.field_forward(w, 2).clone()
+    z = warm.initial_state()
+    _, z1, _, _ = warm.state_step(us * 0.5, z, 0.4)
+    ref = [o.clone() for o in warm.state_step(us, z1, 0.3)]
+    zbuf = z1.clone()
+    torch.cuda.synchronize()
+    g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            out = eng.state_step(us, zbuf, 0.3)
+    torch.cuda.current_stream().wait_stream(s)
+    for o in out:
+        o.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(out, ref))
+    us.mul_(1.1)
+    zbuf.copy_(z)
+    g.replay()
+    torch.cuda.synchronize()
+    ref2 = warm.state_step(us, z, 0.3)
+    assert all(torch.equal(a, b) for a, b in zip(out, ref2))
+    eng.close()
+    warm.close()
