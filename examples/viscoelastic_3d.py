@@ -35,11 +35,13 @@ for epoch in range(epochs):
     if epoch % 10 == 0:
         print(epoch, float(loss[0]), flush=True)
 
-# results like the reference's script: nodal displacements, deformation gradient and the state variables (Fv)
+# results like the reference's script: nodal displacements, deformation gradient and the state variables (Fv); plus the
+# internal force and the PK1 stress, evaluated step by step from each step's old state (pcx_state_step)
 out = os.path.join(os.environ.get("PANCAX_WORKDIR", "/tmp/pancax_b200_example"), "output_visco.e")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 pp = PostProcessor(mesh, "exodus")
-pp.init(params, problem, out, node_variables=["field_values"], element_variables=["deformation_gradient", "state_variables"])
+pp.init(params, problem, out, node_variables=["field_values", "internal_force"],
+        element_variables=["deformation_gradient", "state_variables", "pk1_stress"])
 pp.write_outputs(params, problem)
 pp.close()
 print("wrote", out)
