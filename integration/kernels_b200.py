@@ -236,6 +236,16 @@ def potential_energy_and_internal_force(h: Handle, prop_raw, us):
     return pf(prop_raw, us)
 
 
+def state_step(h: Handle, prop_raw, us, state_old, dt, n_state: int):
+    """One step of a state-variable model at a given old state (PcxStateStep, no VJP: the post-processor's and the
+    op-level forward calls): (Pi, state_new (ne, nq, n_state), f (nn, ndof), P (ne, nq, 3, 3)) of
+    physics.potential_energy / potential_energy_and_internal_force / element_pp(pk1_stress), base.py:24-74,349-361."""
+    outs = (_f64(h.ne, h.nq, n_state), _f64(), _f64(h.nn, h.ndof), _f64(h.ne, h.nq, 3, 3))
+    z_new, Pi, f, P = jax.ffi.ffi_call("PcxStateStep", outs)(prop_raw, us, jnp.reshape(state_old, (h.ne, h.nq, n_state)),
+                                                            handle=np.int64(h.ptr), dt=np.float64(dt))
+    return Pi, z_new, f, P
+
+
 def residual_and_reaction(h: Handle, f):
     out = jax.ffi.ffi_call("PcxResidualReaction", _f64(2))(f, handle=np.int64(h.ptr))
     return out[0], out[1]
@@ -318,6 +328,10 @@ def install(problem, params, deterministic: bool = True, ffi_so: str = "libpcx_x
         raw = jnp.concatenate([jnp.ravel(p.prop_val) for p in jax.tree_util.tree_leaves(
             prm.physics.constitutive_model, is_leaf=lambda x: hasattr(x, "prop_val")) if hasattr(p, "prop_val")]) \
             if h.n_train else _empty()
+        n_state = int(getattr(physics.constitutive_model, "num_state_variables", 0))
+        if n_state > 0:      # SimpleFeFv: forward evaluation at the given old state (the losses go through S3)
+            Pi, state_new, f, _ = state_step(h, raw, us, state_old, dt, n_state)
+            return (Pi, state_new), f
         Pi, f = potential_energy_and_internal_force(h, raw, us)
         return (Pi, state_old), f
     object.__setattr__(physics, "vmap_field_values", vmap_field_values)
