@@ -399,9 +399,13 @@ class StrongFormResidualLoss(BaseLossFunction):
             return eng._dev(pts), eng._dev(tab), eng._dev(src)
         if inputs is None:          # every (time step, node): static, tabulated once per problem
             cache = problem._engines.setdefault("_strong_form_static", {})
-            if id(params.fields.dirichlet_bc_func) not in cache:
-                cache[id(params.fields.dirichlet_bc_func)] = tables(problem.domain.collocation_points())
-            pts, tab, src = cache[id(params.fields.dirichlet_bc_func)]
+            # keyed by id() but holding the wrapper itself: an id() reused after garbage collection cannot pair another
+            # wrapper with these tables
+            bc = params.fields.dirichlet_bc_func
+            hit = cache.get(id(bc))
+            if hit is None or hit[0] is not bc:
+                hit = cache[id(bc)] = (bc, tables(problem.domain.collocation_points()))
+            pts, tab, src = hit[1]
         else:
             pts, tab, src = tables(np.ascontiguousarray(inputs, dtype=np.float64))
         c_t, c_lap = phys.strong_form_coefficients()
