@@ -264,7 +264,8 @@ int pcx_element_fields(pcx_handle* h, const double* prop_raw, const double* us, 
  * (base.py:24-74, constitutive_models/mechanics/base.py:112-118; driven step by step in post_processor.py:244-354,470-490).
  *   state_old, state_new [ne*nq*n_prony*9] (must not alias), dt >= 0 (dt = 0, the post-processor's step 0: the reference
  *   evaluates 0/0 there; the limit dt -> 0 is returned), Pi device scalar or NULL, f [nn*ndof] or NULL,
- *   P [ne*nq*9] (3x3 row-major) or NULL.  PlaneStress: PCX_ERR_UNSUPPORTED. */
+ *   P [ne*nq*9] (3x3 row-major) or NULL.  PlaneStress (solid_mechanics.py:49-71): the out-of-plane stretch of every
+ *   point is the root of the total sigma_33 at the given old state; f and P are evaluated at those roots. */
 int pcx_state_step(pcx_handle* h, const double* prop_raw, const double* us, const double* state_old, double dt,
                    double* state_new, double* Pi, double* f, double* P, void* stream);
 

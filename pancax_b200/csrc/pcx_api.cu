@@ -1078,7 +1078,7 @@ static int sweep(pcx_handle* h, bool tangent, int T, const double* us, const dou
     for (int b = 0; b < a.n_prony; b++) { a.prony_kappa[b] = h->vstep.kappa[b]; a.prony_c[b] = h->vstep.c[b]; }
     a.z_old = h->vstep.z_old; a.z_new = h->vstep.z_new; a.lam_in = h->vstep.lam_in; a.lam_out = h->vstep.lam_out;
     a.wpsi = h->vstep.wpsi;
-    a.pp_P = h->vstep.mode == 2 ? h->vstep.pp_P : nullptr;
+    a.pp_P = (h->vstep.mode == 2 || h->vstep.mode == 5) ? h->vstep.pp_P : nullptr;
     a.f33_out = nullptr; a.f33_in = nullptr;
     if (h->vstep.mode == 4) { a.f33_out = h->vstep.f33; a.f33_in = h->vstep.f33_prev; }   // f33_in: start of the root find
     if (h->vstep.mode == 5) { a.f33_in = h->vstep.f33; a.vscr = h->vscr; }
@@ -1542,8 +1542,9 @@ extern "C" int pcx_state_step(pcx_handle* h, const double* prop_raw, const doubl
   NEED_READY(h);
   if (h->phys.physics != PCX_PHYS_SOLID || h->phys.n_prony <= 0)
     return fail(PCX_ERR_STATE, "pcx_state_step: the constitutive model has no state variables (use pcx_energy_force / pcx_element_fields)");
-  if (h->phys.formulation == PCX_FORM_PLANE_STRESS)
-    return fail(PCX_ERR_UNSUPPORTED, "pcx_state_step: PlaneStress with a state-variable model is defined for the path-dependent EnergyLoss only");
+  const bool pstress = h->phys.formulation == PCX_FORM_PLANE_STRESS;
+  if (pstress && (!h->vf33 || !h->vscr || !h->vlam[0] || !h->vlam[1] || h->nd != 2))
+    return fail(PCX_ERR_STATE, "PlaneStress state workspace missing");
   if (!us || !state_old || !state_new) return fail(PCX_ERR_INVALID, "pcx_state_step: us / state_old / state_new is null");
   if (state_old == state_new) return fail(PCX_ERR_INVALID, "pcx_state_step: state_new must not alias state_old");
   if (!(dt >= 0.0)) return fail(PCX_ERR_INVALID, "pcx_state_step: dt must be >= 0, got %g", dt);
@@ -1564,6 +1565,20 @@ extern "C" int pcx_state_step(pcx_handle* h, const double* prop_raw, const doubl
   h->vstep.on = true; h->vstep.wpsi = 1.0; h->vstep.mode = 2;
   h->vstep.z_old = state_old; h->vstep.z_new = state_new; h->vstep.lam_in = nullptr; h->vstep.lam_out = nullptr;
   h->vstep.f33 = nullptr; h->vstep.f33_prev = nullptr; h->vstep.pp_P = P;
+  if (pstress) {
+    // PlaneStress (solid_mechanics.py:49-71): MODE 4 finds the out-of-plane stretch of every point on the total stress at
+    // fixed old state and gives (Pi, state_new); the force / stress at those roots is the MODE 5 reverse sweep with a
+    // zero adjoint of the new state (its implicit-function term vanishes at the root: P_33 = 0)
+    h->vstep.mode = 4; h->vstep.f33 = h->vf33;
+    rc = sweep(h, false, 1, us, nullptr, nullptr, 1.0, nullptr, 0.0, true, false, false, st);
+    if (rc) return rc;
+    if (Pi && (rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, Pi, 1, st))) return rc;
+    if (!f && !P) return PCX_OK;
+    const long long per = h->ne * h->nq * (long long)h->phys.n_prony * 9;
+    CUDA_TRY(cudaMemsetAsync(h->vlam[0], 0, (size_t)per * sizeof(double), st));
+    h->vstep.mode = 5; h->vstep.lam_in = h->vlam[0]; h->vstep.lam_out = h->vlam[1];
+    return sweep(h, false, 1, us, nullptr, f ? f : h->f, 1.0, nullptr, 0.0, false, false, true, st);
+  }
   rc = sweep(h, false, 1, us, nullptr, f ? f : h->f, 1.0, nullptr, 0.0, true, false, true, st);
   if (rc) return rc;
   if (Pi) rc = reduce_rows(h, h->vpart, h->vnblk, 1, 1, 1, Pi, 1, st);

@@ -62,7 +62,7 @@ struct ElemArgs {
   double* qbuf;            // [ne][nq][NDOF][ND] parent-space point fluxes (k_visco_qp -> k_visco_scatter)
   double wpsi;             // k_visco_qp MODE 3: weight of the step's energy in the loss (the flux then carries every term)
   double* vscr;            // k_visco_qp MODE 5: scratch [ne][nq][n_prony][9] (tangent of the old-state adjoint along E_33)
-  double* pp_P;            // k_visco_qp MODE 2: [ne][nq][9] PK1 stress d psi / d grad_u at fixed old state, or nullptr (pcx_state_step)
+  double* pp_P;            // k_visco_qp MODE 2 / 5: [ne][nq][9] PK1 stress d psi / d grad_u at fixed old state, or nullptr (pcx_state_step)
 };
 
 template <int ND>
@@ -642,6 +642,10 @@ __global__ void __launch_bounds__(128, MODE == 1 ? PCX_VISCO_MINB_BWD : MODE == 
       const double mu = -P[8] / dPt[8];
 #pragma unroll
       for (int i = 0; i < 9; i++) P[i] = fma(mu, dPt[i], P[i]);
+      if (A0.pp_P) {          // pcx_state_step: PK1 stress at the plane-stress root (lam_in = 0)
+#pragma unroll
+        for (int i = 0; i < 9; i++) A0.pp_P[t * 9 + i] = P[i];
+      }
       for (int b = 0; b < A0.n_prony; b++)
 #pragma unroll
         for (int i = 0; i < 9; i++) A0.lam_out[zq + b * 9 + i] = fma(mu, A0.vscr[zq + b * 9 + i], A0.lam_out[zq + b * 9 + i]);

@@ -213,12 +213,8 @@ class ExodusPostProcessor(BasePostProcessor):
         # dt = 0 at step 0, then times[n] - times[n-1]) and evaluates internal_force / pk1_stress / state_variables
         # from the step's OLD state (:262-266,273-279,312-316) -- one pcx_state_step per time step here
         ns = int(eng.lib.pcx_num_state_variables(eng.h))
-        stepwise = ns > 0 and getattr(problem.physics.formulation, "name", "") != "plane_stress"
+        stepwise = ns > 0
         state_old = eng.initial_state() if stepwise else None
-        if "state_variables" in want and not stepwise:
-            # PlaneStress with state: the state history of the path-dependent call (weak_form_loss_functions.py:48-72),
-            # kept by the library
-            eng.loss_and_grad("energy", w, pr, want_grad=False, first_step=1)
         for n in range(nt):
             us = eng.field_forward(w, n)
             f_state = P_state = None
@@ -237,7 +233,7 @@ class ExodusPostProcessor(BasePostProcessor):
                 for i, nm in enumerate(names["internal_force"]):
                     node_vars[nm][n] = f[:, i]
             if "state_variables" in want:
-                z = (state_new if stepwise else eng.get_state(n)).cpu().numpy()      # (ne, nq, ns)
+                z = state_new.cpu().numpy()                                          # (ne, nq, ns)
                 for c, comp in enumerate(names["state_variables"]):
                     for q in range(nq):
                         elem_vars[f"{comp}_{q + 1}"][n] = z[:, q, c]

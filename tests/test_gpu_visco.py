@@ -377,7 +377,8 @@ def test_state_model_residual_loss_with_the_tf32_adjoint(cuda_device, mode):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n", [("hex8_visco_neohookean", 3), ("hex8_visco_hencky", 2), ("quad4_visco_gent_bounded", 4),
-                                    ("tri3_visco_swanson", 4)])
+                                    ("tri3_visco_swanson", 4), ("quad4_visco_neohookean_pstress", 4),
+                                    ("tri3_visco_gent_pstress", 4)])
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_state_step_matches_oracle(cuda_device, name, n, deterministic):
     """pcx_state_step = the reference's op-level calls for a state-variable model at a GIVEN old state:
@@ -407,8 +408,13 @@ def test_state_step_matches_oracle(cuda_device, name, n, deterministic):
         W, Z_new = phys.energy_density_with_state(grad_u, Z, dt)
         Pi = (JxW * W).sum()
         (f,) = torch.autograd.grad(Pi, us, retain_graph=True)
-        H3 = phys.modify_field_gradient(grad_u.detach()).clone().requires_grad_(True)
         from oracle import models
+        if phys.formulation == "plane_stress":      # PK1 stress at the root of the total sigma_33 at fixed old state
+            from oracle.physics import plane_stress_gradient
+            H3 = plane_stress_gradient(phys.model, grad_u.detach(), phys.props, energy_fn=lambda H: models.simple_fefv_energy(
+                phys.model, H, phys.props, Z, dt, phys.prony[0], phys.prony[1])[0]).detach().clone().requires_grad_(True)
+        else:
+            H3 = phys.modify_field_gradient(grad_u.detach()).clone().requires_grad_(True)
         psi = models.simple_fefv_energy(phys.model, H3, phys.props, Z, dt, phys.prony[0], phys.prony[1])[0]
         (P,) = torch.autograd.grad(psi.sum(), H3)
         Pi_o, Z_chk = potential_energy_with_state(phys, pe, coords, conns, us.detach(), Z, dt)
