@@ -236,6 +236,13 @@ def potential_energy_and_internal_force(h: Handle, prop_raw, us):
     return pf(prop_raw, us)
 
 
+def element_fields(h: Handle, prop_raw, us):
+    """(F (ne, nq, 3, 3), I1_bar (ne, nq), P (ne, nq, 3, 3)) at the quadrature points: the element_pp wrappers behind the
+    post-processor's deformation_gradient / I1_bar / pk1_stress (physics_kernels/base.py:24-158)."""
+    outs = (_f64(h.ne, h.nq, 3, 3), _f64(h.ne, h.nq), _f64(h.ne, h.nq, 3, 3))
+    return jax.ffi.ffi_call("PcxElementFields", outs)(prop_raw, us, handle=np.int64(h.ptr))
+
+
 def state_step(h: Handle, prop_raw, us, state_old, dt, n_state: int):
     """One step of a state-variable model at a given old state (PcxStateStep, no VJP: the post-processor's and the
     op-level forward calls): (Pi, state_new (ne, nq, n_state), f (nn, ndof), P (ne, nq, 3, 3)) of
@@ -298,12 +305,14 @@ def adam_step(params, grads, mu, nu, count, lr, b1=0.9, b2=0.999, eps=1e-8):
         eps=np.float64(eps))
 
 
-# ------------------------------------------------------------------------------------------------ hooks S1-S3
+# ------------------------------------------------------------------------------------------------ hooks S1-S4
 def install(problem, params, deterministic: bool = True, ffi_so: str = "libpcx_xla_ffi.so") -> Handle:
     """Opt-in: after this call the pancax objects of `problem` evaluate on the B200 library.
     S1 BasePhysics.vmap_field_values   (physics_kernels/base.py:248-250)  -> field_values
     S2 BaseEnergyFormPhysics.potential_energy_and_internal_force (base.py:356-361) -> potential_energy_and_internal_force
     S3 AbstractOptimizer._single_step  (optimizers.py:77-107) -> loss_and_grad when the loss is a built-in weak-form loss
+    S4 physics.var_name_to_method[...]["method"] of the element variables (solid_mechanics.py:115-170) -> element_fields /
+       state_step (the post-processor's per-step calls, post_processor.py:305-316)
     The reference classes are patched per instance (object.__setattr__ on the eqx.Module), nothing global."""
     import equinox as eqx
     from pancax.loss_functions.weak_form_loss_functions import (EnergyAndResidualLoss, EnergyLoss,
@@ -337,6 +346,29 @@ def install(problem, params, deterministic: bool = True, ffi_so: str = "libpcx_x
     object.__setattr__(physics, "vmap_field_values", vmap_field_values)
     if ref_pe_force is not None:
         object.__setattr__(physics, "potential_energy_and_internal_force", pe_and_force)
+
+    # S4: the element variables of the post-processor (post_processor.py:305-316 calls
+    # physics.var_name_to_method[var]["method"](params, problem, time, us, theta, state_old, dt))
+    def _raw(prm):
+        return jnp.concatenate([jnp.ravel(p.prop_val) for p in jax.tree_util.tree_leaves(
+            prm.physics.constitutive_model, is_leaf=lambda x: hasattr(x, "prop_val")) if hasattr(p, "prop_val")]) \
+            if h.n_train else _empty()
+
+    def _pp(which):
+        def method(prm, prob, t, us, theta, state_old, dt, *args):
+            n_state = int(getattr(physics.constitutive_model, "num_state_variables", 0))
+            if which == "state_variables":
+                return state_step(h, _raw(prm), us, state_old, dt, n_state)[1]
+            if which == "pk1_stress" and n_state > 0:
+                return state_step(h, _raw(prm), us, state_old, dt, n_state)[3]
+            F, I1b, P = element_fields(h, _raw(prm), us)
+            return {"deformation_gradient": F, "I1_bar": I1b, "pk1_stress": P}[which]
+        return method
+    table = getattr(physics, "var_name_to_method", None)
+    if isinstance(table, dict) and hasattr(physics, "constitutive_model"):
+        for var in ("deformation_gradient", "I1_bar", "pk1_stress", "state_variables"):
+            if var in table:
+                table[var]["method"] = _pp(var)
 
     kinds = {EnergyLoss: "energy", EnergyAndResidualLoss: "energy_residual",
              EnergyResidualAndReactionLoss: "energy_residual_reaction"}
