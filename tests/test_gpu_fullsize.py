@@ -205,3 +205,49 @@ def test_c2_plane_stress_at_full_size(cuda_device):
     b = float((torch.as_tensor(v, device=Kw.device) * Kw).sum())
     assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
     eng.close()
+
+
+def test_c3_mesh_state_step_patch_test_and_directional_derivative(cuda_device):
+    """pcx_state_step (a SimpleFeFv step at a given old state) on the C3 mesh (Hex8 128^3, 16.8 M quadrature points, two
+    Prony branches).  Patch test against the reference's OWN per-point values (tests/golden/state_step.npz): with the
+    affine displacement u = H X and the same old state at every point, Pi = psi vol, every point's new state and PK1
+    stress are the golden ones and the interior nodal forces vanish; then, for a random displacement and the evolved
+    state, the central difference of Pi along a direction equals <f, direction> (f = dPi/du at FIXED old state,
+    base.py:356-361); deterministic mode repeats bit for bit."""
+    import os
+    import pancax_b200 as px
+    from pancax_b200 import Engine
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "state_step.npz"))
+    mesh = px.create_structured_mesh("hex8", 128)
+    X = np.asarray(mesh.coords, dtype=np.float64)
+    eng = Engine(X, mesh.conns, "hex8", 2, 3, np.linspace(0.0, 1.0, 2))
+    moduli, taus = g["neohookean__prony"]
+    eng.set_physics("solid", "neohookean", "three_dimensional", [float(p) for p in g["neohookean__props"]],
+                    prony=(list(moduli), list(taus)))
+    eng.set_field(4, 3, 50, 4)
+    k = 1
+    H, Z, dt = g["neohookean__grad_u"][k], g["neohookean__Z_old"][k], float(g["neohookean__dt"][k])
+    psi, Zn, Pg = g["neohookean__psi"][k], g["neohookean__Z_new"][k], g["neohookean__P"][k]
+    z_old = torch.as_tensor(Z.reshape(-1), device=eng.device).expand(eng.ne, eng.nq, Z.size).contiguous()
+    us = torch.as_tensor(X @ H.T, device=eng.device)
+    Pi, zn, f, P = eng.state_step(us, z_old, dt)
+    Pi2, zn2, f2, P2 = eng.state_step(us, z_old, dt)
+    assert torch.equal(Pi, Pi2) and torch.equal(zn, zn2) and torch.equal(f, f2) and torch.equal(P, P2)
+    assert abs(float(Pi) - psi) <= 1e-11 * abs(psi)                                   # vol = 1
+    assert float((zn - torch.as_tensor(Zn.reshape(-1), device=eng.device)).abs().max()) <= 1e-10
+    assert float((P - torch.as_tensor(Pg, device=eng.device)).abs().max()) <= 1e-9 * np.abs(Pg).max()
+    interior = torch.as_tensor(np.all((X > 1e-9) & (X < 1.0 - 1e-9), axis=1), device=eng.device)
+    assert float(f[interior].abs().max()) <= 1e-11 * np.abs(Pg).max() / 128 ** 2
+    assert abs(float(f.sum())) <= 1e-9
+    # directional derivative at fixed old state, from the evolved state
+    rng = np.random.default_rng(5)
+    u1 = us + torch.as_tensor(2e-4 * rng.standard_normal(X.shape), device=eng.device)
+    d = torch.as_tensor(rng.standard_normal(X.shape), device=eng.device)
+    d /= d.norm()
+    _, _, f1, _ = eng.state_step(u1, zn, 0.4, want_P=False)
+    h = 1e-4
+    Pp = float(eng.state_step(u1 + h * d, zn, 0.4, want_force=False, want_P=False)[0])
+    Pm = float(eng.state_step(u1 - h * d, zn, 0.4, want_force=False, want_P=False)[0])
+    fd, an = (Pp - Pm) / (2 * h), float((f1 * d).sum())
+    assert abs(fd - an) <= 1e-6 * max(abs(an), float(f1.norm()) * 1e-3), (fd, an)
+    eng.close()
