@@ -514,3 +514,36 @@ def test_state_step_matches_reference_points(cuda_device, model):
         # so check the resultant instead: the nodal forces sum to zero
         assert np.abs(f.cpu().numpy().sum(0)).max() <= 1e-12 * max(1.0, np.abs(Pg).max())
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["neohookean", "gent", "swanson", "hencky"])
+def test_plane_stress_state_step_matches_reference_points(cuda_device, model):
+    """PlaneStress with a state-variable model against the REFERENCE's own formulation, point by point: the `ps_` arrays
+    of tests/golden/state_step.npz hold PlaneStress.modify_field_gradient (solid_mechanics.py:49-71: find_root on
+    sigma_33 of the whole model at fixed old state) followed by SimpleFeFv.energy / pk1_stress at that root.  One Quad4
+    element with the affine displacement u = H X and the same old state at every quadrature point (k_visco_qp MODE 4 / 5
+    through pcx_state_step)."""
+    import os
+    import pancax_b200 as px
+    from pancax_b200 import Engine
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "state_step.npz"))
+    mesh = px.create_structured_mesh("quad4", 1)
+    X = np.asarray(mesh.coords, dtype=np.float64)
+    eng = Engine(X, mesh.conns, "quad4", 2, 2, np.linspace(0.0, 1.0, 3))
+    moduli, taus = g[f"{model}__prony"]
+    eng.set_physics("solid", model, "plane_stress", [float(p) for p in g[f"{model}__ps_props"]],
+                    prony=(list(moduli), list(taus)))
+    eng.set_field(3, 2, 8, 2)
+    _, JxW, _ = eng.element_geometry(want_grad_N=False, want_xq=False)
+    area = float(JxW.sum())
+    for k in range(g[f"{model}__ps_grad_u"].shape[0]):
+        H, Z, dt = g[f"{model}__ps_grad_u"][k], g[f"{model}__ps_Z_old"][k], float(g[f"{model}__ps_dt"][k])
+        z_old = np.broadcast_to(Z.reshape(1, 1, -1), (eng.ne, eng.nq, Z.size)).copy()
+        Pi, zn, f, P = eng.state_step(X @ H.T, z_old, dt)
+        psi, Zn, Pg = g[f"{model}__ps_psi"][k], g[f"{model}__ps_Z_new"][k], g[f"{model}__ps_P"][k]
+        assert abs(float(Pi) - psi * area) <= 1e-10 * abs(psi * area)
+        assert np.abs(zn.cpu().numpy() - Zn.reshape(1, 1, -1)).max() <= 1e-10
+        assert np.abs(P.cpu().numpy() - Pg[None, None]).max() <= 1e-10 * max(1.0, np.abs(Pg).max())
+        assert np.abs(f.cpu().numpy().sum(0)).max() <= 1e-12 * max(1.0, np.abs(Pg).max())
+    eng.close()

@@ -334,3 +334,25 @@ def test_simple_fefv_point_step_matches_reference(model):
         # through the closed-form eigen decomposition it already has: they agree to ~3e-11 (measured), the bar is 1e-10
         assert np.abs(Zn.detach().numpy() - g[f"{model}__Z_new"][k]).max() <= 1e-10
         assert np.abs(P.numpy() - g[f"{model}__P"][k]).max() <= 1e-12 * max(1.0, np.abs(g[f"{model}__P"][k]).max())
+
+
+@pytest.mark.parametrize("model", ["neohookean", "gent", "swanson", "hencky"])
+def test_plane_stress_with_state_point_step_matches_reference(model):
+    """PlaneStress + SimpleFeFv: the oracle's root find on the total sigma_33 at fixed old state against the reference's
+    OWN PlaneStress.modify_field_gradient (solid_mechanics.py:49-71, scalar_root_find.find_root) followed by its energy /
+    pk1_stress, point by point (tests/golden/state_step.npz, the `ps_` arrays)."""
+    from oracle.physics import plane_stress_gradient
+    g = load("state_step.npz")
+    props = dict(zip(om.MODELS[model][1], [float(p) for p in g[f"{model}__ps_props"]]))
+    moduli, taus = (list(x) for x in g[f"{model}__prony"])
+    for k in range(g[f"{model}__ps_grad_u"].shape[0]):
+        H2, Z, dt = T(g[f"{model}__ps_grad_u"][k]), T(g[f"{model}__ps_Z_old"][k]), float(g[f"{model}__ps_dt"][k])
+        H3 = plane_stress_gradient(model, H2[None, None], props, energy_fn=lambda H: om.simple_fefv_energy(
+            model, H, props, Z[None, None], dt, moduli, taus)[0])[0, 0].detach()
+        assert abs(float(H3[2, 2]) - g[f"{model}__ps_grad_u_33"][k]) <= 1e-11
+        Hk = H3.clone().requires_grad_(True)
+        psi, Zn = om.simple_fefv_energy(model, Hk, props, Z, dt, moduli, taus)
+        (P,) = torch.autograd.grad(psi, Hk)
+        assert abs(float(psi.detach()) - g[f"{model}__ps_psi"][k]) <= 1e-11 * abs(g[f"{model}__ps_psi"][k])
+        assert np.abs(Zn.detach().numpy() - g[f"{model}__ps_Z_new"][k]).max() <= 1e-10
+        assert np.abs(P.numpy() - g[f"{model}__ps_P"][k]).max() <= 1e-10 * max(1.0, np.abs(g[f"{model}__ps_P"][k]).max())
